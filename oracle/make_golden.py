@@ -1,0 +1,148 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the LIVE reference (build container only).
+
+Usage:  python oracle/make_golden.py            (needs /root/reference; cv2 4.13)
+
+Every array written here is an OUTPUT OF THE REFERENCE'S OWN CODE (mdir/cirtorch
+functions, or the cv2/numpy calls at the reference's call sites) on the seeded
+inputs of oracle/synth.py.  tests/test_oracle_golden.py checks oracle/oracle.py
+against them; the -m gpu tests check the CUDA path against them.  The reference
+tree cannot travel to the GPU box, these fixtures do.
+"""
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+from oracle import ref_import, synth  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def main():
+    ref_import.import_reference()
+    import cv2
+    import torch
+    import torch.nn as nn
+    from cirtorch.layers.pooling import GeM, MAC, SPoC
+    from cirtorch.layers.normalization import L2N
+    from cirtorch.networks.imageretrievalnet import ImageRetrievalNet
+    from cirtorch.utils.whiten import whitenapply
+    from cirtorch.utils.evaluate import compute_map, compute_map_and_print
+    from mdir.components.data.wrapper import CirMultiscaleAggregation, CirtorchWhiten
+    from mdir.components.data.transform.functional import ChannelClahe
+
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+
+    # ---- 1. pooling + L2N (cirtorch/layers/pooling.py, normalization.py) -------
+    pool = {}
+    with torch.no_grad():
+        for si, shape in enumerate(synth.POOL_SHAPES):
+            for kind in ("relu", "signed", "zeros"):
+                x = torch.from_numpy(synth.fmap(shape, 100 + si, kind))
+                tag = "s%d_%s" % (si, kind)
+                pool[tag + "_mac"] = MAC()(x).numpy()
+                pool[tag + "_spoc"] = SPoC()(x).numpy()
+                pool[tag + "_l2n_mac"] = L2N()(MAC()(x)).numpy()
+                for p in synth.POOL_PS:
+                    pool[tag + "_gem_p%g" % p] = GeM(p=p)(x).numpy()
+                    pool[tag + "_l2n_gem_p%g" % p] = L2N()(GeM(p=p)(x)).numpy()
+    np.savez_compressed(os.path.join(OUT, "pooling.npz"), **pool)
+
+    # ---- 2. ImageRetrievalNet tail + multiscale + Lw head --------------------------
+    head = {}
+    C = 128
+    lwd = synth.lw(C, 7)
+    head["lw_m"] = lwd["m"]
+    head["lw_P"] = lwd["P"]
+    scales_hw = [(32, 24), (23, 17), (16, 12)]
+    with torch.no_grad():
+        for pooling, mod in (("gem", lambda p: GeM(p=p)), ("mac", lambda p: MAC()), ("spoc", lambda p: SPoC())):
+            for p in (3.0, 2.9137):
+                if pooling != "gem" and p != 3.0:
+                    continue
+                meta = {"architecture": "identity", "local_whitening": False, "pooling": pooling, "regional": False,
+                        "whitening": False, "mean": [0, 0, 0], "std": [1, 1, 1], "outputdim": C, "out_channels": C}
+                net = ImageRetrievalNet([nn.Identity()], None, mod(p), None, meta).eval()
+                for img in range(3):
+                    outs = []
+                    for s, (h, w) in enumerate(scales_hw):
+                        x = torch.from_numpy(synth.fmap((1, C, h, w), 200 + 10 * img + s, "relu"))
+                        o = net(x)                                            # (C,1)
+                        head["tail_%s_p%g_i%d_s%d" % (pooling, p, img, s)] = o.numpy()
+                        outs.append(o)
+                    ms = CirMultiscaleAggregation(True, torch.device("cpu"))
+                    v = ms.postprocess([o.clone() for o in outs], net, False)  # msp rule + aggregate_tensor
+                    head["agg_%s_p%g_i%d" % (pooling, p, img)] = v.numpy()
+                    v1 = CirMultiscaleAggregation([1], torch.device("cpu")).postprocess([outs[0].clone()], net, False)
+                    head["agg1_%s_p%g_i%d" % (pooling, p, img)] = v1.numpy()
+                    for dims in (None, 64, 32):
+                        wh = CirtorchWhiten.__new__(CirtorchWhiten)
+                        wh.device = torch.device("cpu")
+                        wh.P = torch.tensor(lwd["P"], dtype=torch.float32)
+                        wh.m = torch.tensor(lwd["m"], dtype=torch.float32)
+                        wh.dimensions = dims or wh.P.shape[0]
+                        head["wh_%s_p%g_i%d_d%s" % (pooling, p, img, dims)] = wh.postprocess(v.clone(), net, None).numpy()
+    # whitenapply (cirtorch/utils/whiten.py:4-12), fp64 batch
+    X = synth.descriptors(40, C, 9).T.astype(np.float64)
+    head["whitenapply_X"] = X
+    head["whitenapply_full"] = whitenapply(X, lwd["m"], lwd["P"])
+    head["whitenapply_d48"] = whitenapply(X, lwd["m"], lwd["P"], 48)
+    np.savez_compressed(os.path.join(OUT, "head.npz"), **head)
+
+    # ---- 3. CLAHE: cv2 at the reference call site (transform/functional.py:114-117) -
+    clahe = {}
+    for key, hw, dist, clip, seed in synth.clahe_cases():
+        img = synth.image_u8(hw, dist, seed)
+        out = cv2.createCLAHE(clipLimit=int(clip), tileGridSize=(8, 8)).apply(img)
+        clahe["in_sha_" + key] = np.array(synth.sha(img))
+        if hw in synth.CLAHE_SMALL:
+            clahe["out_" + key] = out
+        clahe["out_sha_" + key] = np.array(synth.sha(out))
+    # non-square grid and the float wrapper ChannelClahe.apply
+    img = synth.image_u8((127, 93), "gamma", 77)
+    clahe["grid4x6_127x93"] = cv2.createCLAHE(clipLimit=3, tileGridSize=(4, 6)).apply(img)
+    chan = (synth.image_u8((200, 150), "gamma", 78).astype(np.float32) + np.float32(0.37)) / np.float32(255.3)
+    clahe["channelclahe_200x150"] = ChannelClahe(4, 8).apply(chan)
+    np.savez_compressed(os.path.join(OUT, "clahe.npz"), **clahe)
+
+    # ---- 4. similarity / ranks / mAP (cirscore.py:69-71, evaluate.py) ---------------
+    srch = {}
+    db = synth.descriptors(500, 64, 11, clusters=20)
+    q, src = synth.planted_queries(db, 12, 12)
+    vecs, qvecs = np.ascontiguousarray(db.T), np.ascontiguousarray(q.T)
+    sc = np.dot(vecs.T, qvecs)
+    rk = np.argsort(-sc, axis=0)                       # the reference's (unstable) call
+    srch["scores"] = sc
+    srch["ranks_ref_unstable"] = rk
+    srch["ranks_stable"] = np.argsort(-sc, axis=0, kind="stable")
+    sct = np.round(sc * 20).astype(np.float32) / 20     # tie-heavy, includes +-0
+    srch["scores_ties"] = sct
+    srch["ranks_ties_stable"] = np.argsort(-sct, axis=0, kind="stable")
+    gnd = synth.gnd_okjunk(500, 12, 13, empty_every=5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m, aps, pr, prs = compute_map(rk, gnd, [1, 5, 10])
+        srch["okjunk_map"] = np.array(m)
+        srch["okjunk_aps"] = aps
+        srch["okjunk_pr"] = pr
+        srch["okjunk_prs"] = prs
+        gnd2 = synth.gnd_emh(500, 12, 14)
+        avg, per = compute_map_and_print("roxford5k", rk, gnd2)
+    for k_, v_ in avg.items():
+        srch["emh_" + k_] = np.array(v_)
+    for k_, v_ in per.items():
+        srch["emh_" + k_] = v_
+    np.savez_compressed(os.path.join(OUT, "search.npz"), **srch)
+
+    for f in sorted(os.listdir(OUT)):
+        print("%-14s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()
