@@ -1,0 +1,158 @@
+/*
+ * mdir_b200.h -- C ABI of libmdir_b200.so: hand-written sm_100a kernels for the
+ * post-backbone retrieval hot path of jenicek/mdir.
+ *
+ * The reference is pure Python and has NO FFI; its plug-in mechanism is four dict
+ * registries.  Every entry point below therefore cites the
+ * reference Python call it replaces (file:line relative to the reference root);
+ * INTEGRATION.md shows the ctypes stub a maintainer would add on the reference
+ * side.  Conventions: plain device pointers + sizes + a cudaStream_t passed as
+ * void*; no allocation, no synchronisation, no torch types; every function
+ * returns 0 on success, a positive cudaError_t, or a negative MDIR_E_* code, and
+ * mdir_last_error() describes the last failure on the calling thread.
+ */
+#ifndef MDIR_B200_H
+#define MDIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDIR_ABI_VERSION 1
+
+#define MDIR_E_ARG      (-1)   /* invalid argument (shape/alignment/range) */
+#define MDIR_E_DRIVER   (-2)   /* driver entry point (cuTensorMapEncodeTiled) unavailable */
+#define MDIR_E_DEVICE   (-3)   /* not an sm_100 device */
+
+int         mdir_abi_version(void);
+const char* mdir_last_error(void);
+/* 0 when the current device is compute capability 10.x with >= 148 SMs usable. */
+int         mdir_device_check(void);
+
+/* ---------------------------------------------------------------- pooling ---
+ * kind: 0 = GeM, 1 = MAC, 2 = SPoC.
+ * Replaces LF.gem / LF.mac / LF.spoc
+ *   (mdir/external/cirtorch/layers/functional.py:11-22) called by
+ *   GeM/MAC/SPoC.forward (mdir/external/cirtorch/layers/pooling.py:12-47).
+ * x holds n_maps feature maps; map i is C contiguous planes of hw[i] floats
+ * starting at x + off[i] (floats).  off/hw are DEVICE arrays; both NULL means a
+ * uniform (n_maps, C, hw_uniform) NCHW batch.  out: (n_maps, C) fp32.         */
+#define MDIR_POOL_GEM  0
+#define MDIR_POOL_MAC  1
+#define MDIR_POOL_SPOC 2
+int mdir_pool(int kind, const float* x, const int64_t* off, const int32_t* hw,
+              int n_maps, int C, int hw_uniform, float p, float eps,
+              float* out, void* stream);
+
+/* L2N over dim=1 of an (N, C, inner) tensor: x / (||x||_2 + eps)
+ * Replaces LF.l2n (cirtorch/layers/functional.py:130-131).                    */
+int mdir_l2n(const float* x, int N, int C, int inner, float eps, float* out, void* stream);
+
+/* Per image: L2N each of S pooled vectors (eps added to the norm), then
+ * v = (sum_s o_s^msp / S)^(1/msp); v /= ||v|| (no eps); optionally v -= m.
+ * Replaces ImageRetrievalNet.forward's norm(pool(o)) (cirtorch/networks/
+ * imageretrievalnet.py:107) + CirMultiscaleAggregation.aggregate_tensor
+ * (mdir/components/data/wrapper.py:109-119) + the centring of
+ * CirtorchWhiten.postprocess (wrapper.py:194).
+ * pooled: (n_img, S, C); m: (C) or NULL; out: (n_img, C).
+ * l2n_eps < 0 means the S vectors are already L2-normalised (skip that step). */
+int mdir_ms_aggregate(const float* pooled, int n_img, int S, int C, float l2n_eps,
+                      float msp, const float* m, float* out, void* stream);
+
+/* out[n, j] = sum_d P[j, d] * (v[n, d] - m[d]) for j < dims, then (optionally)
+ * out[n, :] /= (||out[n, :]||_2 + renorm_eps)  when renorm_eps >= 0.
+ * Replaces CirtorchWhiten.postprocess (wrapper.py:193-195) and, batched,
+ * whitenapply (mdir/external/cirtorch/utils/whiten.py:4-12).
+ * v: (n, D); m: (D) or NULL; P: (>=dims, D) row-major fp32; out: (n, dims).   */
+int mdir_whiten_project(const float* v, const float* m, int n, int D, const float* P, int dims,
+                        float renorm_eps, float* out, void* stream);
+
+/* ------------------------------------------------------------------ CLAHE ---
+ * Bit-exact cv2.createCLAHE(clipLimit=clip, tileGridSize=(tiles_x,tiles_y)).apply
+ * on a batch of ragged 8UC1 images.  Replaces ChannelClahe.apply's cv2 call
+ * (mdir/components/data/transform/functional.py:109-117).
+ * descs: DEVICE array of n_img descriptors (byte offsets into src/dst).
+ * ws: device workspace of mdir_clahe_workspace_bytes() bytes (the per-tile LUTs). */
+typedef struct {
+    int64_t src_off;    /* byte offset of pixel (0,0) in src */
+    int64_t dst_off;    /* byte offset of pixel (0,0) in dst */
+    int32_t H, W;
+    int32_t src_pitch;  /* bytes between rows */
+    int32_t dst_pitch;
+} mdir_image_desc;
+size_t mdir_clahe_workspace_bytes(int n_img, int tiles_x, int tiles_y);
+int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_desc* descs,
+                  int n_img, int max_H, int max_W, double clip, int tiles_x, int tiles_y,
+                  void* ws, void* stream);
+
+/* ------------------------------------------------------- similarity search ---
+ * Replaces np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0)
+ * (mdir/components/optim/score/cirscore.py:69-70).
+ *
+ * Descriptor matrices on the device are ROW-major (n, D) bf16 ("K-major"), D % 8
+ * == 0.  mdir_pack_bf16 converts from fp32, optionally from the reference's
+ * (D, n) column-per-image layout (cirtorch/networks/imageretrievalnet.py:291).  */
+int mdir_pack_bf16(const float* src, int64_t n, int D, int src_is_Dxn, uint16_t* dst, void* stream);
+
+/* One streaming pass of the database against <= 128 resident queries on
+ * tcgen05/TMEM tiles fed by TMA (256 db rows per tile, fp32 accumulate).
+ *   mode MDIR_SCAN_DENSE   : write every score, out[q * dense_ld + row]
+ *   mode MDIR_SCAN_SAMPLE  : only tiles t = j*sample_stride (j < n_sample), written
+ *                            compactly: out[q * dense_ld + j*256 + r]
+ *   mode MDIR_SCAN_FILTER  : all tiles EXCEPT the sample tiles (n_sample may be 0);
+ *                            a score is appended to cand[q] iff its 64-bit key
+ *                            (mdir key order: score desc, index asc) <= tau[q].
+ * cand: (n_q, cap) u64 keys, cand_count: (n_q) u32 (caller zeroes it; counts may
+ * exceed cap -- entries beyond cap are dropped and the caller must re-threshold).
+ * Keys carry idx_base + row so shards emit global indices.                      */
+#define MDIR_SCAN_DENSE  0
+#define MDIR_SCAN_SAMPLE 1
+#define MDIR_SCAN_FILTER 2
+#define MDIR_SCAN_TILE_ROWS 256
+int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
+                       int mode, int sample_stride, int n_sample,
+                       float* dense_out, int64_t dense_ld,
+                       const uint64_t* tau, uint32_t idx_base,
+                       uint64_t* cand, uint32_t* cand_count, int cap, void* stream);
+
+/* key helpers exposed for tests: key = (~orderable(score) << 32) | index        */
+uint64_t mdir_make_key(float score, uint32_t index);
+float    mdir_key_score(uint64_t key);
+
+/* For each query: tau[q] = the kth-smallest key among scores[q*ld + i], i < n
+ * (index part of the key = pos_to_idx(i): i itself, or for a compact sample
+ * ((i/256)*sample_stride)*256 + i%256, plus idx_base); the kth best items are
+ * also appended to cand[q] (cand_count advanced) when cand != NULL.             */
+int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth,
+                    int sample_stride, uint32_t idx_base,
+                    uint64_t* tau, uint64_t* cand, uint32_t* cand_count, int cap, void* stream);
+
+/* For each query: sort min(count, cap) candidate keys, emit the best k as
+ * (score fp32, index int32) rows of out_*(n_q, k) (padded with -inf / -1), and set
+ * overflow[q] = 1 and tau[q] = kth key of what was kept when count > cap.
+ * Also the shard merge: feed it the all-gathered (n_q, G*k) keys.               */
+int mdir_topk_finalize(const uint64_t* cand, const uint32_t* cand_count, int cap, int n_q, int k,
+                       float* out_scores, int32_t* out_idx, uint64_t* out_keys,
+                       uint64_t* tau, int32_t* overflow, void* stream);
+
+/* Exact fp32 re-scoring of a shortlist: out[q, j] = <db32[idx[q,j]-idx_base], q32[q]>
+ * (idx < 0 or outside this shard -> -inf); then callers re-finalize.             */
+int mdir_rescore_f32(const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int n_q, int D,
+                     const int32_t* idx, int kk, uint64_t* out_keys, void* stream);
+
+/* Full per-query ranking of a score matrix given in the REFERENCE layout
+ * scores (n_db, n_q) fp32 C-order -> ranks (n_db, n_q) int64 C-order, identical to
+ * np.argsort(-scores, axis=0, kind='stable') (cirscore.py:70; ties by ascending
+ * index).  query_major != 0 means scores is already (n_q, n_db).
+ * ws: mdir_rank_workspace_bytes() bytes.                                         */
+size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q);
+int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major,
+                     int64_t* ranks, void* ws, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,99 @@
+// Shared helpers for libmdir_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/mdir_b200.h"
+
+namespace mdir {
+
+void set_error(const std::string& s);
+int fail_arg(const char* what);
+
+#define MDIR_CHECK_ARG(cond)                                              \
+    do {                                                                  \
+        if (!(cond)) return ::mdir::fail_arg(#cond);                      \
+    } while (0)
+
+#define MDIR_CUDA(expr)                                                   \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) {                                          \
+            ::mdir::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+            return (int)_e;                                               \
+        }                                                                 \
+    } while (0)
+
+#define MDIR_LAUNCH_CHECK()                                               \
+    do {                                                                  \
+        cudaError_t _e = cudaGetLastError();                              \
+        if (_e != cudaSuccess) {                                          \
+            ::mdir::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); \
+            return (int)_e;                                               \
+        }                                                                 \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32); red must hold 32 floats.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;   // every warp holds the total
+}
+
+// ---- 64-bit candidate keys: smaller key == better (score desc, index asc) --------
+__host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; return c.u;
+#endif
+}
+__host__ __device__ __forceinline__ float bits_f32(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    union { float f; uint32_t u; } c; c.u = u; return c.f;
+#endif
+}
+// ascending-orderable transform of an fp32, with -0 canonicalised to +0 so that
+// +-0 tie exactly as they do under numpy's comparison sort.
+__host__ __device__ __forceinline__ uint32_t orderable(float f) {
+    uint32_t u = f32_bits(f);
+    if ((u << 1) == 0u) u = 0u;
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
+    return ((uint64_t)(~orderable(score)) << 32) | (uint64_t)idx;
+}
+__host__ __device__ __forceinline__ float key_score(uint64_t key) {
+    uint32_t o = ~(uint32_t)(key >> 32);
+    uint32_t u = o ^ ((o >> 31) ? 0x80000000u : 0xffffffffu);
+    return bits_f32(u);
+}
+
+}  // namespace mdir

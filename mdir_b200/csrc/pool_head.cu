@@ -1,0 +1,311 @@
+// GeM / MAC / SPoC pooling, L2N, multi-scale aggregation and Lw whitening projection.
+// HBM-bound: the feature maps are read exactly once with 128-bit loads, one warp per
+// (map, channel) plane, warp-shuffle reduction.  See DESIGN.md "pool_planes".
+#include "common.cuh"
+
+namespace mdir {
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+template <int KIND, bool P3>
+__device__ __forceinline__ float pool_elem(float x, float p, float eps) {
+    if (KIND == MDIR_POOL_GEM) {
+        float v = fmaxf(x, eps);
+        if (P3) return v * v * v;
+        return exp2f(p * __log2f(v));          // MUFU.LG2 + MUFU.EX2 (v >= eps > 0)
+    }
+    return x;
+}
+template <int KIND>
+__device__ __forceinline__ float pool_comb(float a, float b) {
+    return KIND == MDIR_POOL_MAC ? fmaxf(a, b) : a + b;
+}
+
+// One warp per plane.  Planes of hw floats start at arbitrary 4-byte alignment (hw = 391
+// is common), so each plane is split into a scalar head up to the first 16-byte boundary,
+// an aligned float4 body and a scalar tail.
+template <int KIND, bool P3>
+__global__ void __launch_bounds__(256) pool_planes_kernel(const float* __restrict__ x, const int64_t* __restrict__ off,
+                                                          const int32_t* __restrict__ hws, int n_maps, int C,
+                                                          int hw_uniform, float p, float eps, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_planes = (int64_t)n_maps * C;
+    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t plane = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); plane < n_planes;
+         plane += warps_total) {
+        const int map = (int)(plane / C);
+        const int c = (int)(plane - (int64_t)map * C);
+        int hw;
+        const float* src;
+        if (off) {
+            hw = hws[map];
+            src = x + off[map] + (int64_t)c * hw;
+        } else {
+            hw = hw_uniform;
+            src = x + plane * (int64_t)hw;
+        }
+        float acc = KIND == MDIR_POOL_MAC ? -INFINITY : 0.f;
+        int head = (int)(((16u - ((uint32_t)(uintptr_t)src & 15u)) & 15u) >> 2);
+        head = min(head, hw);
+        if (lane < head) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(src[lane], p, eps));
+        const int nbody = (hw - head) >> 2;
+        const float4* body = reinterpret_cast<const float4*>(src + head);
+        int i = lane;
+        // 4 independent 128-bit loads in flight per lane
+        for (; i + 96 < nbody; i += 128) {
+            float4 a = ldg_stream(body + i), b = ldg_stream(body + i + 32), cc = ldg_stream(body + i + 64),
+                   d = ldg_stream(body + i + 96);
+            float s0 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(a.x, p, eps), pool_elem<KIND, P3>(a.y, p, eps)),
+                                       pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
+            float s1 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(b.x, p, eps), pool_elem<KIND, P3>(b.y, p, eps)),
+                                       pool_comb<KIND>(pool_elem<KIND, P3>(b.z, p, eps), pool_elem<KIND, P3>(b.w, p, eps)));
+            float s2 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(cc.x, p, eps), pool_elem<KIND, P3>(cc.y, p, eps)),
+                                       pool_comb<KIND>(pool_elem<KIND, P3>(cc.z, p, eps), pool_elem<KIND, P3>(cc.w, p, eps)));
+            float s3 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(d.x, p, eps), pool_elem<KIND, P3>(d.y, p, eps)),
+                                       pool_comb<KIND>(pool_elem<KIND, P3>(d.z, p, eps), pool_elem<KIND, P3>(d.w, p, eps)));
+            acc = pool_comb<KIND>(acc, pool_comb<KIND>(pool_comb<KIND>(s0, s1), pool_comb<KIND>(s2, s3)));
+        }
+        for (; i < nbody; i += 32) {
+            float4 a = ldg_stream(body + i);
+            float s0 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(a.x, p, eps), pool_elem<KIND, P3>(a.y, p, eps)),
+                                       pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
+            acc = pool_comb<KIND>(acc, s0);
+        }
+        const int tail0 = head + (nbody << 2);
+        if (tail0 + lane < hw) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(src[tail0 + lane], p, eps));
+        acc = KIND == MDIR_POOL_MAC ? warp_max(acc) : warp_sum(acc);
+        if (lane == 0) {
+            float r = acc;
+            if (KIND != MDIR_POOL_MAC) r = acc / (float)hw;
+            if (KIND == MDIR_POOL_GEM) r = powf(r, 1.0f / p);
+            out[plane] = r;
+        }
+    }
+}
+
+// x (N, C, inner): out = x / (||x||_2 over C + eps).  One CTA per (n, inner-chunk of 32).
+__global__ void l2n_kernel(const float* x, int N, int C, int inner, float eps, float* out) {   // may run in place
+    __shared__ float red[32];
+    if (inner == 1) {
+        const int n = blockIdx.x;
+        const float* src = x + (int64_t)n * C;
+        float s = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { float v = src[c]; s += v * v; }
+        s = block_sum(s, red);
+        const float inv = 1.0f / (sqrtf(s) + eps);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) out[(int64_t)n * C + c] = src[c] * inv;
+        return;
+    }
+    // generic: thread per inner position, loop over C (coalesced across inner)
+    const int chunks = (inner + blockDim.x - 1) / blockDim.x;
+    const int n = blockIdx.x / chunks;
+    const int j = (blockIdx.x % chunks) * blockDim.x + threadIdx.x;
+    if (j >= inner) return;
+    const float* src = x + (int64_t)n * C * inner + j;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) { float v = src[(int64_t)c * inner]; s += v * v; }
+    const float inv = 1.0f / (sqrtf(s) + eps);
+    float* dst = out + (int64_t)n * C * inner + j;
+    for (int c = 0; c < C; ++c) dst[(int64_t)c * inner] = src[(int64_t)c * inner] * inv;
+}
+
+// One CTA per image.  pooled (n_img, S, C) -> out (n_img, C).
+__global__ void __launch_bounds__(256) ms_aggregate_kernel(const float* __restrict__ pooled, int S, int C, float l2n_eps,
+                                                           float msp, const float* __restrict__ m, float* __restrict__ out) {
+    __shared__ float red[32];
+    __shared__ float inv_norm[16];
+    const int img = blockIdx.x;
+    const float* src = pooled + (int64_t)img * S * C;
+    for (int s = 0; s < S; ++s) {
+        float a = 0.f;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) { float v = src[s * C + c]; a += v * v; }
+        a = block_sum(a, red);
+        if (threadIdx.x == 0) inv_norm[s] = l2n_eps < 0.f ? 1.0f : 1.0f / (sqrtf(a) + l2n_eps);
+    }
+    __syncthreads();
+    const bool one = (msp == 1.0f);
+    float nn = 0.f;
+    float* dst = out + (int64_t)img * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = 0.f;
+        for (int s = 0; s < S; ++s) {
+            float o = src[s * C + c] * inv_norm[s];
+            v += one ? o : powf(o, msp);
+        }
+        v = v / (float)S;
+        if (!one) v = powf(v, 1.0f / msp);
+        dst[c] = v;
+        nn += v * v;
+    }
+    nn = block_sum(nn, red);
+    const float inv = 1.0f / sqrtf(nn);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float v = dst[c] * inv;
+        if (m) v -= m[c];
+        dst[c] = v;
+    }
+}
+
+// GEMV-style projection for small batches: one warp per output row j, all n (<= 8) vectors.
+template <int NV>
+__global__ void __launch_bounds__(256) whiten_gemv_kernel(const float* __restrict__ v, const float* __restrict__ m, int D,
+                                                          const float* __restrict__ P, int dims, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= dims) return;
+    const float* row = P + (int64_t)j * D;
+    float acc[NV];
+#pragma unroll
+    for (int n = 0; n < NV; ++n) acc[n] = 0.f;
+    if ((D & 3) == 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        for (int i = lane; i < (D >> 2); i += 32) {
+            float4 pr = ldg_stream(r4 + i);
+            float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m) mm = reinterpret_cast<const float4*>(m)[i];
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                float4 vv = reinterpret_cast<const float4*>(v + (int64_t)n * D)[i];
+                acc[n] += pr.x * (vv.x - mm.x) + pr.y * (vv.y - mm.y) + pr.z * (vv.z - mm.z) + pr.w * (vv.w - mm.w);
+            }
+        }
+    } else {
+        for (int i = lane; i < D; i += 32) {
+            float pr = row[i];
+            const float mm = m ? m[i] : 0.f;
+#pragma unroll
+            for (int n = 0; n < NV; ++n) acc[n] += pr * (v[(int64_t)n * D + i] - mm);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NV; ++n) {
+        float s = warp_sum(acc[n]);
+        if (lane == 0) out[(int64_t)n * dims + j] = s;
+    }
+}
+
+// Batched projection out(n, dims) = V(n, D) * P(dims, D)^T, fp32 CUDA-core tiles
+// (64 x 64 x 16, 4x4 per thread).  P is re-read once per 64 images: negligible next to
+// the feature-map stream that produced V.
+__global__ void __launch_bounds__(256) whiten_sgemm_kernel(const float* __restrict__ V, const float* __restrict__ m, int n, int D,
+                                                           const float* __restrict__ P, int dims, float* __restrict__ out) {
+    __shared__ float sV[16][64 + 4];
+    __shared__ float sP[16][64 + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int n0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < D; k0 += 16) {
+        // each thread loads 4 elements of each tile: row r = tid/4 (0..63), k = (tid%4)*4..+3
+        const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) << 2;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + kk + e;
+            sV[kk + e][r] = (n0 + r < n && k < D) ? V[(int64_t)(n0 + r) * D + k] - (m ? m[k] : 0.f) : 0.f;
+            sP[kk + e][r] = (j0 + r < dims && k < D) ? P[(int64_t)(j0 + r) * D + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sV[k][ty * 4 + i]; b[i] = sP[k][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int nn = n0 + ty * 4 + i, jj = j0 + tx * 4 + j;
+            if (nn < n && jj < dims) out[(int64_t)nn * dims + jj] = acc[i][j];
+        }
+}
+
+}  // namespace mdir
+
+using namespace mdir;
+
+extern "C" int mdir_pool(int kind, const float* x, const int64_t* off, const int32_t* hw, int n_maps, int C,
+                         int hw_uniform, float p, float eps, float* out, void* stream) {
+    MDIR_CHECK_ARG(kind >= 0 && kind <= 2);
+    MDIR_CHECK_ARG(x && out && n_maps >= 0 && C > 0);
+    MDIR_CHECK_ARG((off == nullptr) == (hw == nullptr));
+    MDIR_CHECK_ARG(off != nullptr || hw_uniform > 0);
+    MDIR_CHECK_ARG(((uintptr_t)x & 3) == 0);
+    if (n_maps == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_planes = (int64_t)n_maps * C;
+    const int64_t blocks_needed = (n_planes + 7) / 8;
+    const int grid = (int)(blocks_needed < (int64_t)kNumSMs * 64 ? blocks_needed : (int64_t)kNumSMs * 64);
+    if (kind == MDIR_POOL_GEM) {
+        MDIR_CHECK_ARG(p > 0.f || p < 0.f);
+        if (p == 3.0f)
+            pool_planes_kernel<MDIR_POOL_GEM, true><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+        else
+            pool_planes_kernel<MDIR_POOL_GEM, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+    } else if (kind == MDIR_POOL_MAC) {
+        pool_planes_kernel<MDIR_POOL_MAC, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+    } else {
+        pool_planes_kernel<MDIR_POOL_SPOC, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+    }
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_l2n(const float* x, int N, int C, int inner, float eps, float* out, void* stream) {
+    MDIR_CHECK_ARG(x && out && N >= 0 && C > 0 && inner > 0);
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (inner == 1) {
+        l2n_kernel<<<N, 256, 0, st>>>(x, N, C, inner, eps, out);
+    } else {
+        const int chunks = (inner + 127) / 128;
+        l2n_kernel<<<N * chunks, 128, 0, st>>>(x, N, C, inner, eps, out);
+    }
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_ms_aggregate(const float* pooled, int n_img, int S, int C, float l2n_eps, float msp, const float* m,
+                                 float* out, void* stream) {
+    MDIR_CHECK_ARG(pooled && out && n_img >= 0 && S >= 1 && S <= 16 && C > 0);
+    if (n_img == 0) return 0;
+    ms_aggregate_kernel<<<n_img, 256, 0, (cudaStream_t)stream>>>(pooled, S, C, l2n_eps, msp, m, out);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_whiten_project(const float* v, const float* m, int n, int D, const float* P, int dims, float renorm_eps,
+                                   float* out, void* stream) {
+    MDIR_CHECK_ARG(v && P && out && n >= 0 && D > 0 && dims > 0);
+    MDIR_CHECK_ARG(((uintptr_t)v & 15) == 0 && ((uintptr_t)P & 15) == 0 && ((uintptr_t)m & 15) == 0);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 4) {
+        const int grid = (dims + 7) / 8;
+        switch (n) {
+            case 1: whiten_gemv_kernel<1><<<grid, 256, 0, st>>>(v, m, D, P, dims, out); break;
+            case 2: whiten_gemv_kernel<2><<<grid, 256, 0, st>>>(v, m, D, P, dims, out); break;
+            case 3: whiten_gemv_kernel<3><<<grid, 256, 0, st>>>(v, m, D, P, dims, out); break;
+            default: whiten_gemv_kernel<4><<<grid, 256, 0, st>>>(v, m, D, P, dims, out); break;
+        }
+    } else {
+        dim3 grid((dims + 63) / 64, (n + 63) / 64);
+        whiten_sgemm_kernel<<<grid, 256, 0, st>>>(v, m, n, D, P, dims, out);
+    }
+    MDIR_LAUNCH_CHECK();
+    if (renorm_eps >= 0.f) {
+        l2n_kernel<<<n, 256, 0, st>>>(out, n, dims, 1, renorm_eps, out);
+        MDIR_LAUNCH_CHECK();
+    }
+    return 0;
+}

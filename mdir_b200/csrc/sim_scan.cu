@@ -1,0 +1,390 @@
+// Query x database similarity as a dense contraction on tcgen05 / TMEM tiles fed by TMA.
+// Replaces np.dot(vecs.T, qvecs) (mdir/components/optim/score/cirscore.py:69) and fuses the
+// selection half of np.argsort (cirscore.py:70) into the epilogue so that the n_db-wide
+// score rows never land in HBM in FILTER mode.
+//
+// One persistent CTA per SM, 192 threads, warp-specialised:
+//   warp 0      TMA producer: per k-block one 256x64 bf16 box of the database (A operand,
+//               32 KB, SWIZZLE_128B) + one N x 64 box of the queries (B operand, L2-resident)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: two M=128 accumulators
+//               (db rows 0-127 / 128-255 of the tile) x N query columns, fp32, double-buffered
+//               in TMEM (4 x 128 columns = all 512)
+//   warps 2-5   epilogue: tcgen05.ld 32x32b (lane = db row, column = query); DENSE/SAMPLE
+//               modes store scores query-major (coalesced: 32 lanes = 32 consecutive rows),
+//               FILTER mode compares against the per-query threshold key and appends the rare
+//               survivors (expected k*n_tiles/n_sample per query) to the candidate lists.
+// Orientation: database rows sit on the UMMA M axis so that no MMA rows are wasted on the
+// 70 -> 80 padded queries (hard part 1).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace mdir {
+
+constexpr int kBlockM = MDIR_SCAN_TILE_ROWS;   // 256 db rows per tile = two UMMA M=128 halves
+constexpr int kBlockK = 64;                    // bf16 elements = one 128-byte swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 32768
+constexpr int kMaxN = 128;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+constexpr uint32_t kTmemCols = 512;
+
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version 1 [46,48) | layout 2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+
+struct ScanParams {
+    int64_t n_db;
+    int n_q, n_pad, num_k_blocks, n_tiles;
+    int mode, sample_stride, n_sample, n_work, num_stages;
+    float* dense_out;
+    int64_t dense_ld;
+    const uint64_t* tau;
+    uint32_t idx_base;
+    uint64_t* cand;
+    uint32_t* cand_count;
+    int cap;
+    uint64_t db_hint;
+};
+
+__device__ __forceinline__ int tile_of_work(const ScanParams& p, int j) {
+    if (p.mode == MDIR_SCAN_DENSE) return j;
+    if (p.mode == MDIR_SCAN_SAMPLE) return j * p.sample_stride;
+    // FILTER: every tile that is not a sample tile
+    if (p.n_sample == 0) return j;
+    const int per = p.sample_stride - 1;
+    const int in_groups = p.n_sample * per;
+    if (j < in_groups) {
+        const int g = j / per;
+        return g * p.sample_stride + 1 + (j - g * per);
+    }
+    return p.n_sample * p.sample_stride + (j - in_groups);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_constant__ CUtensorMap tmap_db,
+                                                                const __grid_constant__ CUtensorMap tmap_q, const ScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint64_t tau_s[kMaxN];
+    __shared__ float tau_f[kMaxN];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
+    const uint32_t stage_bytes = (uint32_t)kABytes + b_bytes;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_db) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_q) : "memory");
+        for (int s = 0; s < p.num_stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(smem_u32(&tmem_full_bar[b]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[b]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (p.mode == MDIR_SCAN_FILTER) {
+        for (int c = threadIdx.x; c < kMaxN; c += kThreads) {
+            uint64_t t = c < p.n_q ? p.tau[c] : 0ull;
+            tau_s[c] = t;
+            tau_f[c] = ((uint32_t)(t >> 32) == 0xffffffffu) ? -INFINITY : key_score(t);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int j = blockIdx.x; j < p.n_work; j += gridDim.x) {
+                const int row0 = tile_of_work(p, j) * kBlockM;
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+                    const uint32_t fb = smem_u32(&full_bar[stage]);
+                    const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
+                    mbar_expect_tx(fb, stage_bytes);
+                    tma_load_2d(a_dst, &tmap_db, fb, kb * kBlockK, row0, p.db_hint);
+                    tma_load_2d(a_dst + kABytes, &tmap_q, fb, kb * kBlockK, 0, kEvictLast);
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
+                const int b = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(smem_u32(&tmem_empty_bar[b]), acc_phase ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                    mbar_wait(smem_u32(&full_bar[stage]), phase);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_base + (uint32_t)stage * stage_bytes;
+                    const uint32_t b_base = a_base + kABytes;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 + h) * 128u;
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)h * (128u * 128u) + (uint32_t)k * 32u);
+                            const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)k * 32u);
+                            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(smem_u32(&empty_bar[stage]));     // frees the smem slot when these MMAs retire
+                    if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(smem_u32(&tmem_full_bar[b]));         // accumulators of this tile are complete
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+        int it = 0;
+        for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
+            const int b = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int tile = tile_of_work(p, j);
+            mbar_wait(smem_u32(&tmem_full_bar[b]), acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int r_in_tile = h * 128 + quarter * 32 + lane;
+                const int64_t row = (int64_t)tile * kBlockM + r_in_tile;
+                const bool row_ok = row < p.n_db;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * 128u;
+                const int64_t out_row = (p.mode == MDIR_SCAN_SAMPLE ? (int64_t)j * kBlockM : (int64_t)tile * kBlockM) + r_in_tile;
+                const uint32_t gidx = p.idx_base + (uint32_t)row;
+#pragma unroll 1
+                for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(taddr + (uint32_t)c0, v);
+                    tmem_ld_wait();
+                    if (p.mode != MDIR_SCAN_FILTER) {
+                        // rows past the end of the database only exist in the compact SAMPLE buffer: mark them -inf
+                        if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.n_q)
+                                    p.dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
+                        }
+                    } else if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float s = __uint_as_float(v[i]);
+                            if (s >= tau_f[c0 + i] && c0 + i < p.n_q) {
+                                const uint64_t key = make_key(s, gidx);
+                                if (key <= tau_s[c0 + i]) {
+                                    const uint32_t pos = atomicAdd(&p.cand_count[c0 + i], 1u);
+                                    if (pos < (uint32_t)p.cap) p.cand[(int64_t)(c0 + i) * p.cap + pos] = key;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[b]));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return MDIR_E_DRIVER;
+    }
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+        return MDIR_E_DRIVER;
+    }
+    return 0;
+}
+
+}  // namespace mdir
+
+using namespace mdir;
+
+extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode, int sample_stride,
+                                  int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
+                                  uint64_t* cand, uint32_t* cand_count, int cap, void* stream) {
+    MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 8 && (D % 8) == 0);
+    MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
+    MDIR_CHECK_ARG(mode >= 0 && mode <= 2);
+    MDIR_CHECK_ARG(n_db + (int64_t)idx_base <= ((int64_t)1 << 32));
+    ScanParams p;
+    p.n_db = n_db;
+    p.n_q = n_q;
+    p.n_pad = (n_q + 15) & ~15;
+    p.num_k_blocks = (D + kBlockK - 1) / kBlockK;
+    const int64_t n_tiles64 = (n_db + kBlockM - 1) / kBlockM;
+    MDIR_CHECK_ARG(n_tiles64 < ((int64_t)1 << 23));
+    p.n_tiles = (int)n_tiles64;
+    p.mode = mode;
+    p.sample_stride = sample_stride;
+    p.n_sample = n_sample;
+    if (mode == MDIR_SCAN_DENSE) {
+        MDIR_CHECK_ARG(dense_out && dense_ld >= n_db);
+        p.n_work = p.n_tiles;
+    } else if (mode == MDIR_SCAN_SAMPLE) {
+        MDIR_CHECK_ARG(dense_out && n_sample >= 1 && sample_stride >= 1);
+        MDIR_CHECK_ARG((int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
+        MDIR_CHECK_ARG(dense_ld >= (int64_t)n_sample * kBlockM);
+        p.n_work = n_sample;
+    } else {
+        MDIR_CHECK_ARG(tau && cand && cand_count && cap >= 1);
+        MDIR_CHECK_ARG(n_sample >= 0 && (n_sample == 0 || sample_stride >= 2));
+        MDIR_CHECK_ARG(n_sample == 0 || (int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
+        p.n_work = p.n_tiles - n_sample;
+    }
+    p.dense_out = dense_out;
+    p.dense_ld = dense_ld;
+    p.tau = tau;
+    p.idx_base = idx_base;
+    p.cand = cand;
+    p.cand_count = cand_count;
+    p.cap = cap;
+    // a database that fits L2 (126 MB) is worth keeping there across query blocks / passes
+    p.db_hint = ((int64_t)n_db * D * 2 > (int64_t)96 * 1024 * 1024) ? kEvictFirst : kEvictNormal;
+    if (p.n_work <= 0) return 0;
+
+    const int stage_bytes = kABytes + p.n_pad * 128;
+    int stages = (232448 - 1024 - 4096) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    MDIR_CHECK_ARG(stages >= 2);
+    p.num_stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+
+    CUtensorMap tmap_db, tmap_q;
+    int rc = make_tmap_bf16(&tmap_db, db, (uint64_t)n_db, (uint64_t)D, kBlockM);
+    if (rc) return rc;
+    rc = make_tmap_bf16(&tmap_q, q, (uint64_t)n_q, (uint64_t)D, (uint32_t)p.n_pad);
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+        attr_set = true;
+    }
+    const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
+    sim_scan_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
