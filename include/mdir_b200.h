@@ -31,6 +31,8 @@ int         mdir_abi_version(void);
 const char* mdir_last_error(void);
 /* 0 when the current device is compute capability 10.x with >= 148 SMs usable. */
 int         mdir_device_check(void);
+/* number of kernels this library has launched in this process (for bench accounting) */
+uint64_t    mdir_launch_count(void);
 
 /* ---------------------------------------------------------------- pooling ---
  * kind: 0 = GeM, 1 = MAC, 2 = SPoC.
@@ -143,14 +145,23 @@ int mdir_topk_finalize(const uint64_t* cand, const uint32_t* cand_count, int cap
 int mdir_rescore_f32(const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int n_q, int D,
                      const int32_t* idx, int kk, uint64_t* out_keys, void* stream);
 
+/* alpha query expansion / database-side augmentation.  NOT in the reference (SURVEY.md
+ * App. E; parity unpinned): acc[q, :] = sum_j max(scores[q,j], 0)^alpha * db32[idx[q,j] -
+ * idx_base, :] over the shortlist entries this shard owns (others contribute 0, so shards
+ * combine with an all-reduce);  mdir_add_l2n: out = (a + b) / ||a + b||, b may be NULL.   */
+int mdir_qe_accumulate(const float* db32, int64_t n_db, uint32_t idx_base, int D, const int32_t* idx,
+                       const float* scores, int n_q, int n_qe, float alpha, float* acc, void* stream);
+int mdir_add_l2n(const float* a, const float* b, int n, int D, float* out, void* stream);
+
 /* Full per-query ranking of a score matrix given in the REFERENCE layout
  * scores (n_db, n_q) fp32 C-order -> ranks (n_db, n_q) int64 C-order, identical to
  * np.argsort(-scores, axis=0, kind='stable') (cirscore.py:70; ties by ascending
- * index).  query_major != 0 means scores is already (n_q, n_db).
+ * index).  query_major != 0 means scores is already (n_q, n_db).  ranks_ld >= n_q is
+ * the row pitch of ranks in elements (lets callers fill a column block of a wider array).
  * ws: mdir_rank_workspace_bytes() bytes.                                         */
 size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q);
 int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major,
-                     int64_t* ranks, void* ws, void* stream);
+                     int64_t* ranks, int64_t ranks_ld, void* ws, void* stream);
 
 #ifdef __cplusplus
 }

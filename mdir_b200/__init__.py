@@ -1,0 +1,20 @@
+"""mdir_b200 -- B200-native (sm_100a) implementation of jenicek/mdir's post-backbone retrieval
+hot path behind the reference's own plug-in surface.
+
+    layers    GeM / MAC / SPoC / L2N modules + POOLING registry     (cirtorch/layers)
+    wrappers  CirMultiscaleAggregation, CirtorchWhiten, whitenapply, RetrievalHead
+    clahe     clahe_u8, ChannelClahe / ImageClahe / ApplyClahe ...  (mdir transforms)
+    search    rank(), Index, ShardedIndex, ranks_from_scores, topk_from_scores
+    qe        alpha-QE / DBA (not in the reference; parity unpinned)
+    score     CirDatasetAp replacement + install()
+
+All arithmetic runs in hand-written CUDA kernels (mdir_b200/csrc) reached through the C ABI in
+include/mdir_b200.h; there is no CPU or PyTorch fallback -- a missing library raises."""
+from ._lib import MdirError, lib  # noqa: F401
+from .layers import GeM, MAC, SPoC, L2N, POOLING, gem, mac, spoc, l2n  # noqa: F401
+from .wrappers import CirMultiscaleAggregation, CirtorchWhiten, RetrievalHead, whitenapply  # noqa: F401
+from .clahe import clahe_u8, ChannelClahe, ImageClahe, ApplyClahe, AddClaheFromRgb, CreateClahedImage  # noqa: F401
+from .search import Index, ShardedIndex, rank, ranks_from_scores, topk_from_scores  # noqa: F401
+from .score import install  # noqa: F401
+
+__version__ = "0.1.0"

@@ -23,6 +23,7 @@ PROTOTYPES = {
     "mdir_abi_version": (_i, []),
     "mdir_last_error": (C.c_char_p, []),
     "mdir_device_check": (_i, []),
+    "mdir_launch_count": (_u64, []),
     "mdir_pool": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "mdir_l2n": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "mdir_ms_aggregate": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
@@ -36,8 +37,10 @@ PROTOTYPES = {
     "mdir_select_kth": (_i, [_vp, _i64, _i64, _i, _i, _i, _u32, _vp, _vp, _vp, _i, _vp]),
     "mdir_topk_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdir_rescore_f32": (_i, [_vp, _i64, _u32, _vp, _i, _i, _vp, _i, _vp, _vp]),
+    "mdir_qe_accumulate": (_i, [_vp, _i64, _u32, _i, _vp, _vp, _i, _i, _f, _vp, _vp]),
+    "mdir_add_l2n": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "mdir_rank_workspace_bytes": (_sz, [_i64, _i]),
-    "mdir_rank_scores": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "mdir_rank_scores": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
 }
 
 

@@ -3,6 +3,7 @@
 
 namespace mdir {
 static thread_local std::string g_err;
+unsigned long long g_launches = 0;
 void set_error(const std::string& s) { g_err = s; }
 int fail_arg(const char* what) {
     g_err = std::string("invalid argument: ") + what;
@@ -12,6 +13,8 @@ int fail_arg(const char* what) {
 
 extern "C" int mdir_abi_version(void) { return MDIR_ABI_VERSION; }
 extern "C" const char* mdir_last_error(void) { return mdir::g_err.c_str(); }
+
+extern "C" uint64_t mdir_launch_count(void) { return mdir::g_launches; }
 
 extern "C" int mdir_device_check(void) {
     int dev = 0;

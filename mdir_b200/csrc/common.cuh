@@ -26,8 +26,11 @@ int fail_arg(const char* what);
         }                                                                 \
     } while (0)
 
+extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+
 #define MDIR_LAUNCH_CHECK()                                               \
     do {                                                                  \
+        ++::mdir::g_launches;                                             \
         cudaError_t _e = cudaGetLastError();                              \
         if (_e != cudaSuccess) {                                          \
             ::mdir::set_error(std::string("kernel launch: ") + cudaGetErrorString(_e)); \

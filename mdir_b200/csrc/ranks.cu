@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint32_t* __re
 
 // vals (n_q, n_db) u32 -> ranks (n_db, n_q) int64
 __global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __restrict__ vals, int64_t n_db, int n_q,
-                                                              int64_t* __restrict__ ranks) {
+                                                              int64_t* __restrict__ ranks, int64_t ranks_ld) {
     __shared__ uint32_t tile[32][33];
     const int64_t r0 = (int64_t)blockIdx.x * 32;
     const int q0 = blockIdx.y * 32;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __
     for (int r = ty; r < 32; r += 8) {
         const int64_t row = r0 + r;
         const int q = q0 + tx;
-        if (row < n_db && q < n_q) ranks[row * n_q + q] = (int64_t)tile[tx][r];
+        if (row < n_db && q < n_q) ranks[row * ranks_ld + q] = (int64_t)tile[tx][r];
     }
 }
 
@@ -186,9 +186,9 @@ extern "C" size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q) {
     return 4 * arr + align256((size_t)n_q * 256 * n_chunks * 4);
 }
 
-extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, void* ws,
-                                void* stream) {
-    MDIR_CHECK_ARG(scores && ranks && ws && n_db >= 1 && n_q >= 1);
+extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, int64_t ranks_ld,
+                                void* ws, void* stream) {
+    MDIR_CHECK_ARG(scores && ranks && ws && n_db >= 1 && n_q >= 1 && ranks_ld >= n_q);
     MDIR_CHECK_ARG(n_db < ((int64_t)1 << 32) && n_q <= 65535);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t arr = align256((size_t)n_db * n_q * 4);
@@ -220,7 +220,7 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         vin = vout;
         vout = (vout == vA) ? vB : vA;
     }
-    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vin, n_db, n_q, ranks);
+    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vin, n_db, n_q, ranks, ranks_ld);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

@@ -173,6 +173,45 @@ __global__ void __launch_bounds__(256) pack_bf16_transpose_kernel(const float* _
     }
 }
 
+// alpha-QE / DBA accumulation (NOT in the reference).  One CTA per query:
+// acc[q, :] = sum_j max(s_j, 0)^alpha * db32[idx_j - idx_base, :] over the entries this shard owns.
+__global__ void __launch_bounds__(256) qe_accumulate_kernel(const float* __restrict__ db32, int64_t n_db, uint32_t idx_base, int D,
+                                                            const int32_t* __restrict__ idx, const float* __restrict__ scores,
+                                                            int n_qe, float alpha, float* __restrict__ acc) {
+    __shared__ float w_s[256];
+    __shared__ int64_t row_s[256];
+    const int q = blockIdx.x;
+    for (int j = threadIdx.x; j < n_qe; j += blockDim.x) {
+        const int32_t gi = idx[(int64_t)q * n_qe + j];
+        const int64_t row = (int64_t)(uint32_t)gi - (int64_t)idx_base;
+        const bool own = gi >= 0 && row >= 0 && row < n_db;
+        row_s[j] = own ? row : -1;
+        w_s[j] = own ? powf(fmaxf(scores[(int64_t)q * n_qe + j], 0.f), alpha) : 0.f;
+    }
+    __syncthreads();
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float a = 0.f;
+        for (int j = 0; j < n_qe; ++j)
+            if (row_s[j] >= 0) a = fmaf(w_s[j], db32[row_s[j] * D + d], a);
+        acc[(int64_t)q * D + d] = a;
+    }
+}
+
+// out[n, :] = (a[n, :] + b[n, :]) / ||a[n, :] + b[n, :]||   (b may be NULL)
+__global__ void __launch_bounds__(256) add_l2n_kernel(const float* a, const float* b, int D, float* out) {
+    __shared__ float red[32];
+    const int n = blockIdx.x;
+    float s = 0.f;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float v = a[(int64_t)n * D + d] + (b ? b[(int64_t)n * D + d] : 0.f);
+        s += v * v;
+    }
+    s = block_sum(s, red);
+    const float inv = 1.0f / sqrtf(s);
+    for (int d = threadIdx.x; d < D; d += blockDim.x)
+        out[(int64_t)n * D + d] = (a[(int64_t)n * D + d] + (b ? b[(int64_t)n * D + d] : 0.f)) * inv;
+}
+
 }  // namespace mdir
 
 using namespace mdir;
@@ -235,6 +274,23 @@ extern "C" int mdir_pack_bf16(const float* src, int64_t n, int D, int src_is_Dxn
         MDIR_CHECK_ARG(grid.y <= 65535);
         pack_bf16_transpose_kernel<<<grid, 256, 0, st>>>(src, n, D, (__nv_bfloat16*)dst);
     }
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_qe_accumulate(const float* db32, int64_t n_db, uint32_t idx_base, int D, const int32_t* idx, const float* scores,
+                                  int n_q, int n_qe, float alpha, float* acc, void* stream) {
+    MDIR_CHECK_ARG(db32 && idx && scores && acc && n_db >= 0 && D > 0 && n_q >= 0 && n_qe >= 1 && n_qe <= 256);
+    if (n_q == 0) return 0;
+    qe_accumulate_kernel<<<n_q, 256, 0, (cudaStream_t)stream>>>(db32, n_db, idx_base, D, idx, scores, n_qe, alpha, acc);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_add_l2n(const float* a, const float* b, int n, int D, float* out, void* stream) {
+    MDIR_CHECK_ARG(a && out && n >= 0 && D > 0);
+    if (n == 0) return 0;
+    add_l2n_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(a, b, D, out);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

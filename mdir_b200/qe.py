@@ -1,0 +1,60 @@
+"""alpha query expansion and database-side augmentation on top of the fused scan + top-k.
+
+NOT in the reference (parity unpinned): these follow the published
+definitions restated in oracle/oracle.py:alpha_qe / dba.  Builder-chosen defaults:
+alpha = 3, n_qe = 10, k_dba = 10, negative similarities clamped to 0, self included in DBA."""
+import torch
+
+from . import _lib
+from .search import Index, ShardedIndex, MAX_Q
+
+
+def _accumulate(index, idx, scores, alpha):
+    n_q, n_qe = idx.shape
+    acc = torch.empty((n_q, index.D), dtype=torch.float32, device=index.device)
+    with torch.cuda.device(index.device):
+        _lib.check(_lib.lib().mdir_qe_accumulate(_lib.ptr(index.db32), index.n, index.idx_base, index.D, _lib.ptr(idx.contiguous()),
+                                                 _lib.ptr(scores.contiguous()), n_q, n_qe, float(alpha), _lib.ptr(acc), _lib.stream()),
+                   "mdir_qe_accumulate")
+    return acc
+
+
+def _add_l2n(a, b):
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.lib().mdir_add_l2n(_lib.ptr(a), _lib.ptr(b), a.shape[0], a.shape[1], _lib.ptr(out), _lib.stream()), "mdir_add_l2n")
+    return out
+
+
+def expand_queries(index, q, alpha=3.0, n_qe=10):
+    """q' = normalise(q + sum_{i<=n_qe} max(s_i,0)^alpha x_i).  index: Index or ShardedIndex
+    (shards contribute the rows they own; one all-reduce of N_q x D fp32 combines them)."""
+    local = index.local if isinstance(index, ShardedIndex) else index
+    if local.db32 is None:
+        raise _lib.MdirError("query expansion needs the fp32 master copy (keep_fp32=True)")
+    from .search import _as_dev_f32
+    q32 = _as_dev_f32(q, local.device)
+    s, i = index.search(q32, n_qe, precision="fp32")
+    acc = _accumulate(local, i, s, alpha)
+    if isinstance(index, ShardedIndex) and index.world > 1:
+        index.dist.all_reduce(acc, group=index.group)
+    return _add_l2n(q32, acc)
+
+
+def search_qe(index, q, k, alpha=3.0, n_qe=10, precision="fp32"):
+    """alpha-QE search: two similarity + top-k passes."""
+    return index.search(expand_queries(index, q, alpha, n_qe), k, precision=precision)
+
+
+def dba(index, alpha=3.0, k_dba=10):
+    """Database-side augmentation of a single-GPU Index: every row replaced by the normalised
+    alpha-weighted sum of its own top-k_dba neighbours (self included).  Returns a new Index.
+    Each block of 128 rows is one streaming pass of the database (HBM-bound form)."""
+    if index.db32 is None:
+        raise _lib.MdirError("DBA needs the fp32 master copy (keep_fp32=True)")
+    out = torch.empty_like(index.db32)
+    for r0 in range(0, index.n, MAX_Q):
+        r1 = min(r0 + MAX_Q, index.n)
+        s, i = index.search(index.db32[r0:r1], k_dba, precision="fp32")
+        out[r0:r1] = _add_l2n(_accumulate(index, i, s, alpha), None)
+    return Index(out, device=index.device, keep_fp32=True, idx_base=index.idx_base)

@@ -1,0 +1,83 @@
+"""Drop-in for mdir's evaluation criterion ``CirDatasetAp``
+(mdir/components/optim/score/cirscore.py:16-80) and ``install()``, which patches the
+reference's registries in place so that ``mdir.stages.validate.validate(scenario, ())`` runs
+unchanged with the similarity + ranking (and pooling / whitening / CLAHE) on the B200 kernels.
+
+Nothing here imports the reference at module import time: ``install()`` needs an importable
+``mdir`` package (the user's checkout) and raises otherwise."""
+import numpy as np
+
+from . import layers, wrappers, clahe, search
+
+
+def rank_and_evaluate(dataset, vecs, qvecs, gnd, compute_map_and_print, device="cuda"):
+    """cirscore.py:65-71 with the dot product and argsort replaced by search.rank."""
+    if hasattr(vecs, "numpy"):
+        vecs = vecs.numpy()
+    if hasattr(qvecs, "numpy"):
+        qvecs = qvecs.numpy()
+    ranks = search.rank(vecs, qvecs, device=device)
+    return compute_map_and_print(dataset, ranks, gnd)
+
+
+def make_cirdatasetap(base_cls, extract_vectors, compute_map_and_print, stopwatch_cls):
+    """Build the replacement class against the reference's own base (dataset parsing, logging and
+    mAP stay the reference's; only cirscore.py:69-70 changes)."""
+
+    class CirDatasetAp(base_cls):
+        def __call__(self, network, device, logger):
+            stopwatch = stopwatch_cls()
+            print('>> {}: database images...'.format(self.dataset))
+            vecs = extract_vectors(network, self.images, self.image_size, self.transforms, device=device)
+            print('>> {}: query images...'.format(self.dataset))
+            if self.images == self.qimages and set(self.bbxs) == {None}:
+                qvecs = vecs.clone()
+            else:
+                qvecs = extract_vectors(network, self.qimages, self.image_size, self.transforms, device=device, bbxs=self.bbxs)
+            stopwatch.lap("extract_descriptors")
+            print('>> {}: Evaluating...'.format(self.dataset))
+            averages, scores = rank_and_evaluate(self.dataset, vecs, qvecs, self.gnd, compute_map_and_print, device=device)
+            stopwatch.lap("compute_score")
+            first_score = scores[list(scores.keys())[0]]
+            logger(None, len(first_score), "dataset", stopwatch.reset(), "scalar/time")
+            logger(None, len(first_score), "score_avg", averages, "scalar/score")
+            assert len({len(x) for x in scores.values()}) == 1
+            for i, _ in enumerate(first_score):
+                logger(i, len(first_score), "score", {x: scores[x][i] for x in scores}, "scalar/score")
+
+    return CirDatasetAp
+
+
+def install():
+    """Patch POOLING, WRAPPERS_LABELS, TRANSFORMS and SCORES of an importable ``mdir`` in place
+    (SURVEY.md 8b).  Returns the dict of patched registry entries."""
+    try:
+        import mdir  # noqa: F401
+        import cirtorch.networks.imageretrievalnet as irn
+        import mdir.components.data.wrapper as mwrap
+        import mdir.components.data.transform as mtrans
+        import mdir.components.optim.score as mscore
+        import mdir.components.optim.score.cirscore as cirscore
+        from mdir.tools.stats import StopWatch
+    except ImportError as exc:
+        raise RuntimeError("mdir_b200.install() needs the reference package `mdir` importable "
+                           "(put the jenicek/mdir checkout on sys.path): %s" % exc)
+    patched = {}
+    for key, cls in layers.POOLING.items():
+        irn.POOLING[key] = cls
+        patched["POOLING[%s]" % key] = cls
+    irn.L2N = layers.L2N
+    patched["L2N"] = layers.L2N
+    mwrap.WRAPPERS_LABELS["cirwhiten"] = wrappers.CirtorchWhiten
+    mwrap.WRAPPERS_LABELS["cirmultiscale"] = wrappers.CirMultiscaleAggregation
+    patched["WRAPPERS_LABELS[cirwhiten]"] = wrappers.CirtorchWhiten
+    patched["WRAPPERS_LABELS[cirmultiscale]"] = wrappers.CirMultiscaleAggregation
+    for key, cls in (("apply_clahe", clahe.ApplyClahe), ("add_clahe_fromrgb", clahe.AddClaheFromRgb),
+                     ("create_clahed", clahe.CreateClahedImage)):
+        if key in mtrans.TRANSFORMS:
+            mtrans.TRANSFORMS[key] = cls
+            patched["TRANSFORMS[%s]" % key] = cls
+    new_cls = make_cirdatasetap(cirscore.CirDatasetAp, cirscore.extract_vectors, cirscore.compute_map_and_print, StopWatch)
+    mscore.SCORES["cirdatasetap"] = new_cls
+    patched["SCORES[cirdatasetap]"] = new_cls
+    return patched

@@ -1,0 +1,392 @@
+"""Query x database similarity, top-k and full ranks.
+
+Replaces, for mdir's evaluation (mdir/components/optim/score/cirscore.py:65-70):
+
+    scores = np.dot(vecs.T, qvecs)          # (N_db, N_q)
+    ranks  = np.argsort(-scores, axis=0)    # (N_db, N_q) int64
+
+* ``rank(vecs, qvecs)``      -- the drop-in: host (D,N) matrices in, (N_db,N_q) int64 ranks out.
+* ``Index``                  -- a database resident in HBM as row-major bf16 (+ optional fp32
+                                master for exact re-scoring); ``search`` = tcgen05 scan with the
+                                top-k selection fused into the epilogue, ``scores`` / ``ranks``
+                                = the dense path.
+* ``ShardedIndex``           -- rows sharded contiguously over the ranks of a torch.distributed
+                                group; local top-k + one all-gather of N_q*k keys + merge.
+* ``ranks_from_scores`` / ``topk_from_scores`` -- the sort/selection kernels fed an existing
+                                (N_db, N_q) score matrix (bit-exact vs the stable argsort).
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+TILE = 256            # MDIR_SCAN_TILE_ROWS
+MAX_Q = 128           # queries resident per scan pass
+CAND_CAP = 8192       # per-query candidate list capacity (keys)
+MAX_SAMPLE_TILES = 128
+
+
+def _as_dev_f32(x, device):
+    if isinstance(x, np.ndarray):
+        x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+    if x.dtype != torch.float32:
+        x = x.float()
+    if x.device != device:
+        x = x.pin_memory().to(device, non_blocking=True) if x.device.type == "cpu" else x.to(device)
+    return x.contiguous()
+
+
+def pack_bf16(x, dxn=False):
+    """x fp32 cuda: (n, D) rows, or with dxn=True the reference's (D, n) -> (n, D) bf16 rows."""
+    _lib.require_cuda(x, "descriptors")
+    x = x.contiguous()
+    if dxn:
+        D, n = x.shape
+    else:
+        n, D = x.shape
+    if D % 8:
+        raise _lib.MdirError("descriptor dimension must be a multiple of 8 (got %d)" % D)
+    out = torch.empty((n, D), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().mdir_pack_bf16(_lib.ptr(x), n, D, 1 if dxn else 0, _lib.ptr(out), _lib.stream()), "mdir_pack_bf16")
+    return out
+
+
+class Index:
+    """A (shard of a) descriptor database on one GPU."""
+
+    def __init__(self, vecs, dxn=False, device="cuda", keep_fp32=True, idx_base=0):
+        """vecs: (n, D) fp32 rows (torch/numpy, host or device), or (D, n) with dxn=True
+        (the layout extract_vectors returns, cirtorch/networks/imageretrievalnet.py:291)."""
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.MdirError("Index needs a CUDA device (no CPU path)")
+        v = _as_dev_f32(vecs, self.device)
+        self.db16 = pack_bf16(v, dxn=dxn)
+        self.n, self.D = self.db16.shape
+        self.idx_base = int(idx_base)
+        self.db32 = None
+        if keep_fp32:
+            self.db32 = v.t().contiguous() if dxn else v
+        self._ws = {}
+
+    @classmethod
+    def from_packed(cls, db16, db32=None, idx_base=0):
+        self = cls.__new__(cls)
+        self.device = db16.device
+        self.db16 = db16
+        self.n, self.D = db16.shape
+        self.db32 = db32
+        self.idx_base = int(idx_base)
+        self._ws = {}
+        return self
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, name, shape, dtype):
+        key = (name, tuple(shape), dtype)
+        b = self._ws.get(key)
+        if b is None:
+            b = torch.empty(shape, dtype=dtype, device=self.device)
+            self._ws[key] = b
+        return b
+
+    def _plan(self, kth):
+        """Sampling plan for the threshold pass: (n_sample, stride) or None for the dense route."""
+        n_tiles = (self.n + TILE - 1) // TILE
+        if n_tiles < 64:
+            return None
+        n_sample = min(MAX_SAMPLE_TILES, n_tiles // 8)
+        stride = n_tiles // n_sample
+        # every sampled tile must be full so the sample holds n_sample*256 valid scores
+        if (n_sample - 1) * stride == n_tiles - 1 and self.n % TILE:
+            n_sample -= 1
+        if n_sample * TILE < 2 * kth or stride < 2:
+            return None
+        return n_sample, stride
+
+    def _scan(self, q16, mode, stride, n_sample, dense, dense_ld, tau, cand, cnt):
+        _lib.check(_lib.lib().mdir_sim_scan_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16), q16.shape[0], self.D, mode, stride,
+                                                 n_sample, _lib.ptr(dense), dense_ld, _lib.ptr(tau), self.idx_base, _lib.ptr(cand),
+                                                 _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_sim_scan_bf16")
+
+    def _topk_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
+        """Exact top-kth of one block of <= 128 queries by bf16-input/fp32-accumulate scores."""
+        lib = _lib.lib()
+        nq = q16.shape[0]
+        tau = self._buf("tau", (MAX_Q,), torch.int64)
+        cand = self._buf("cand", (MAX_Q, CAND_CAP), torch.int64)
+        cnt = self._buf("cnt", (MAX_Q,), torch.int32)
+        cnt.zero_()
+        plan = self._plan(kth)
+        if plan is None:
+            dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
+            self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
+            _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
+                                           _lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_select_kth")
+        else:
+            n_sample, stride = plan
+            rows = n_sample * TILE
+            sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
+            ld = MAX_SAMPLE_TILES * TILE
+            self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
+            _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
+                                           _lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_select_kth")
+            prof = getattr(self, "prof", None)
+            if prof is not None:      # bench.py: CUDA events around the dominant kernel, on its own stream
+                prof.begin()
+            self._scan(q16, 2, stride, n_sample, None, 0, tau, cand, cnt)
+            if prof is not None:
+                prof.end((self.n - rows) * self.D * 2)
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, nq, kth, _lib.ptr(out_scores), _lib.ptr(out_idx),
+                                          _lib.ptr(out_keys), _lib.ptr(tau), _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+
+    def _refilter_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
+        """Overflow recovery: tau was tightened by finalize; re-scan every tile against it."""
+        lib = _lib.lib()
+        nq = q16.shape[0]
+        tau = self._buf("tau", (MAX_Q,), torch.int64)
+        cand = self._buf("cand", (MAX_Q, CAND_CAP), torch.int64)
+        cnt = self._buf("cnt", (MAX_Q,), torch.int32)
+        cnt.zero_()
+        self._scan(q16, 2, 0, 0, None, 0, tau, cand, cnt)
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, nq, kth, _lib.ptr(out_scores), _lib.ptr(out_idx),
+                                          _lib.ptr(out_keys), _lib.ptr(tau), _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+
+    # ------------------------------------------------------------------ public
+    def search(self, q, k, precision="fp32", shortlist=None, check=True, return_keys=False):
+        """q: (N_q, D) fp32 (host or device).  Returns (scores (N_q,k) fp32, idx (N_q,k) int32) on
+        the device, ordered by (score desc, index asc); idx = idx_base + local row, -1 padding.
+
+        precision="bf16": exact top-k of the bf16-input / fp32-accumulate scores.
+        precision="fp32": bf16 shortlist of `shortlist` (default 4k) per query, re-scored exactly in
+                          fp32 against the fp32 master copy, then top-k of those.
+        check=False skips the (synchronising) candidate-overflow check; call check_overflow() later."""
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            q32 = _as_dev_f32(q, self.device)
+            nq_all = q32.shape[0]
+            if q32.shape[1] != self.D:
+                raise _lib.MdirError("query dimension %d != database dimension %d" % (q32.shape[1], self.D))
+            k = int(k)
+            k_eff = min(k, self.n)
+            if precision == "fp32":
+                if self.db32 is None:
+                    raise _lib.MdirError("precision='fp32' needs keep_fp32=True")
+                kth = min(self.n, int(shortlist or 4 * k))
+            elif precision == "bf16":
+                kth = k_eff
+            else:
+                raise ValueError("precision must be 'fp32' or 'bf16'")
+            if kth > CAND_CAP // 2:
+                raise _lib.MdirError("k/shortlist %d too large for the fused path (max %d); use ranks()" % (kth, CAND_CAP // 2))
+            q16 = pack_bf16(q32)
+            out_s = torch.empty((nq_all, k), dtype=torch.float32, device=self.device)
+            out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
+            out_k = torch.empty((nq_all, k), dtype=torch.int64, device=self.device) if return_keys else None
+            self._ovf = self._buf("ovf", (max(nq_all, 1),), torch.int32)
+            for q0 in range(0, nq_all, MAX_Q):
+                q1 = min(q0 + MAX_Q, nq_all)
+                nq = q1 - q0
+                ovf = self._ovf[q0:q1]
+                if precision == "bf16":
+                    bs, bi = out_s[q0:q1], out_i[q0:q1]
+                    bk = out_k[q0:q1] if return_keys else None
+                    if k_eff < k:      # pad columns beyond the database size
+                        bs.fill_(float("-inf")); bi.fill_(-1)
+                        if bk is not None:
+                            bk.fill_(-1)
+                        tmp_s = torch.empty((nq, k_eff), dtype=torch.float32, device=self.device)
+                        tmp_i = torch.empty((nq, k_eff), dtype=torch.int32, device=self.device)
+                        tmp_k = torch.empty((nq, k_eff), dtype=torch.int64, device=self.device)
+                        self._run_block(q16[q0:q1], k_eff, tmp_s, tmp_i, tmp_k, ovf, check)
+                        bs[:, :k_eff] = tmp_s; bi[:, :k_eff] = tmp_i
+                        if bk is not None:
+                            bk[:, :k_eff] = tmp_k
+                    else:
+                        self._run_block(q16[q0:q1], k, bs, bi, bk, ovf, check)
+                else:
+                    sl_i = self._buf("sl_i", (MAX_Q, kth), torch.int32)[:nq]
+                    self._run_block(q16[q0:q1], kth, None, sl_i, None, ovf, check)
+                    keys = self._buf("sl_k", (MAX_Q, kth), torch.int64)[:nq]
+                    _lib.check(lib.mdir_rescore_f32(_lib.ptr(self.db32), self.n, self.idx_base, _lib.ptr(q32[q0:q1]), nq, self.D,
+                                                    _lib.ptr(sl_i), kth, _lib.ptr(keys), _lib.stream()), "mdir_rescore_f32")
+                    cnt = self._buf("sl_cnt", (MAX_Q,), torch.int32)
+                    cnt.fill_(kth)
+                    _lib.check(lib.mdir_topk_finalize(_lib.ptr(keys), _lib.ptr(cnt), kth, nq, k, _lib.ptr(out_s[q0:q1]),
+                                                      _lib.ptr(out_i[q0:q1]), _lib.ptr(out_k[q0:q1]) if return_keys else None,
+                                                      None, None, _lib.stream()), "mdir_topk_finalize")
+            if return_keys:
+                return out_s, out_i, out_k
+            return out_s, out_i
+
+    def _run_block(self, q16, kth, out_s, out_i, out_k, ovf, check):
+        self._topk_block(q16, kth, out_s, out_i, out_k, ovf)
+        if check:
+            guard = 0
+            while bool(ovf.any().item()):
+                guard += 1
+                if guard > 8:
+                    raise _lib.MdirError("candidate overflow did not converge")
+                self._refilter_block(q16, kth, out_s, out_i, out_k, ovf)
+
+    def check_overflow(self):
+        """True if the last search(check=False) overflowed a candidate list (results then invalid)."""
+        return bool(self._ovf.any().item())
+
+    def scores(self, q, out=None):
+        """Dense scores, QUERY-major: (N_q, N_db) fp32 on the device (bf16 inputs, fp32 accumulate)."""
+        with torch.cuda.device(self.device):
+            q32 = _as_dev_f32(q, self.device)
+            nq_all = q32.shape[0]
+            q16 = pack_bf16(q32)
+            if out is None:
+                out = torch.empty((nq_all, self.n), dtype=torch.float32, device=self.device)
+            for q0 in range(0, nq_all, MAX_Q):
+                q1 = min(q0 + MAX_Q, nq_all)
+                self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], self.n, None, None, None)
+            return out
+
+    def ranks(self, q, max_pairs=1 << 28):
+        """Full ranking: (N_db, N_q) int64 C-order on the device (== np.argsort(-scores, axis=0,
+        kind='stable') of this index's scores).  Queries are processed in chunks of at most
+        max_pairs // N_db to bound the radix-sort workspace (16 B per pair)."""
+        lib = _lib.lib()
+        with torch.cuda.device(self.device):
+            q32 = _as_dev_f32(q, self.device)
+            nq_all = q32.shape[0]
+            out = torch.empty((self.n, nq_all), dtype=torch.int64, device=self.device)
+            chunk = max(1, min(nq_all, max_pairs // max(self.n, 1)))
+            chunk = max(1, min(chunk, 65535))
+            ws = torch.empty(lib.mdir_rank_workspace_bytes(self.n, chunk), dtype=torch.uint8, device=self.device)
+            sc = torch.empty((chunk, self.n), dtype=torch.float32, device=self.device)
+            for q0 in range(0, nq_all, chunk):
+                q1 = min(q0 + chunk, nq_all)
+                self.scores(q32[q0:q1], out=sc[:q1 - q0])
+                _lib.check(lib.mdir_rank_scores(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
+                                                _lib.stream()), "mdir_rank_scores")
+            return out
+
+
+def ranks_from_scores(scores, device="cuda"):
+    """scores (N_db, N_q) fp32 in the reference layout (host or device) -> ranks (N_db, N_q) int64
+    on the device, bit-identical to np.argsort(-scores, axis=0, kind='stable')."""
+    lib = _lib.lib()
+    dev = torch.device(device)
+    s = _as_dev_f32(scores, dev)
+    n_db, n_q = s.shape
+    with torch.cuda.device(dev):
+        out = torch.empty((n_db, n_q), dtype=torch.int64, device=dev)
+        ws = torch.empty(lib.mdir_rank_workspace_bytes(n_db, n_q), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mdir_rank_scores(_lib.ptr(s), n_db, n_q, 0, _lib.ptr(out), n_q, _lib.ptr(ws), _lib.stream()), "mdir_rank_scores")
+    return out
+
+
+def topk_from_scores(scores, k, device="cuda"):
+    """scores (N_db, N_q) fp32 -> (idx (k, N_q) int64, val (k, N_q) fp32) on the device: the first
+    k rows of ranks_from_scores without sorting the rest."""
+    lib = _lib.lib()
+    dev = torch.device(device)
+    s = _as_dev_f32(scores, dev)
+    n_db, n_q = s.shape
+    k = int(k)
+    if k > min(n_db, 16384):
+        raise _lib.MdirError("k too large for the selection path; use ranks_from_scores")
+    with torch.cuda.device(dev):
+        st = s.t().contiguous()                       # query-major for coalesced selection
+        tau = torch.empty((n_q,), dtype=torch.int64, device=dev)
+        cand = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+        cnt = torch.zeros((n_q,), dtype=torch.int32, device=dev)
+        out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+        out_i = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), _lib.ptr(cnt), k,
+                                       _lib.stream()), "mdir_select_kth")
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), k, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None, None,
+                                          _lib.stream()), "mdir_topk_finalize")
+    return out_i.t().contiguous().long(), out_s.t().contiguous()
+
+
+def rank(vecs, qvecs, device="cuda"):
+    """The drop-in for cirscore.py:69-70.  vecs (D, N_db), qvecs (D, N_q): fp32 numpy/torch host
+    matrices as extract_vectors returns them.  -> ranks (N_db, N_q) int64 numpy, C-order."""
+    dev = torch.device(device)
+    index = Index(vecs, dxn=True, device=dev, keep_fp32=False)
+    q = _as_dev_f32(qvecs, dev).t().contiguous()
+    return index.ranks(q).cpu().numpy()
+
+
+class ShardedIndex:
+    """Database rows sharded contiguously over a torch.distributed group (one process per GPU):
+    shard g = rows [g*ceil(N/G), ...).  search() = local fused top-k, ONE all-gather of
+    N_q*k 64-bit keys per rank (NCCL over NVLink), merge by (score desc, index asc): identical to
+    the single-GPU answer by construction.  There is no other collective on the data path."""
+
+    def __init__(self, local_vecs, idx_base, group=None, device="cuda", keep_fp32=True, dxn=False):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = Index(local_vecs, dxn=dxn, device=device, keep_fp32=keep_fp32, idx_base=idx_base)
+        self.device = self.local.device
+
+    @staticmethod
+    def shard_bounds(n_total, world, rank):
+        per = (n_total + world - 1) // world
+        lo = min(rank * per, n_total)
+        return lo, min(lo + per, n_total)
+
+    def search(self, q, k, precision="fp32", shortlist=None, check=True):
+        s, i, keys = self.local.search(q, k, precision=precision, shortlist=shortlist, check=check, return_keys=True)
+        if self.world == 1:
+            return s, i
+        return merge_keys(keys, self.world, self.group, k)
+
+
+def merge_keys(local_keys, world, group, k):
+    """All-gather (N_q, k) int64 keys from every rank and merge to the global top-k.
+    Works on NCCL (device tensors) and gloo (host tensors; CPU tests of the sharding logic use
+    merge_keys_host below instead of the CUDA merge)."""
+    import torch.distributed as dist
+    lib = _lib.lib()
+    nq = local_keys.shape[0]
+    gathered = torch.empty((world * nq, k), dtype=torch.int64, device=local_keys.device)
+    dist.all_gather_into_tensor(gathered, local_keys.contiguous(), group=group)
+    allk = gathered.view(world, nq, k).permute(1, 0, 2).contiguous().view(nq, world * k)
+    cnt = torch.full((nq,), world * k, dtype=torch.int32, device=local_keys.device)
+    out_s = torch.empty((nq, k), dtype=torch.float32, device=local_keys.device)
+    out_i = torch.empty((nq, k), dtype=torch.int32, device=local_keys.device)
+    with torch.cuda.device(local_keys.device):
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(allk), _lib.ptr(cnt), world * k, nq, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None,
+                                          None, _lib.stream()), "mdir_topk_finalize")
+    return out_s, out_i
+
+
+# ---- host-side key helpers (pure integer logic; used by the gloo sharding tests) ------------
+
+def make_keys_host(scores, idx):
+    """numpy restatement of common.cuh:make_key for (score, index) arrays -> uint64 keys."""
+    s = np.ascontiguousarray(scores, dtype=np.float32).copy()
+    s[s == 0] = 0.0                                     # canonical +0
+    u = s.view(np.uint32)
+    o = np.where(u >> 31 != 0, ~u, u | np.uint32(0x80000000)).astype(np.uint32)
+    return ((~o).astype(np.uint64) << np.uint64(32)) | np.asarray(idx).astype(np.uint32).astype(np.uint64)
+
+
+def keys_to_host(keys):
+    """uint64 keys -> (scores fp32, idx int64); the all-ones key is padding (-inf, -1)."""
+    keys = np.asarray(keys).astype(np.uint64)
+    o = (~(keys >> np.uint64(32))).astype(np.uint32)
+    u = np.where(o >> 31 != 0, o & np.uint32(0x7fffffff), ~o).astype(np.uint32)
+    sc = u.view(np.float32).copy()
+    idx = (keys & np.uint64(0xffffffff)).astype(np.int64)
+    pad = keys == np.uint64(0xffffffffffffffff)
+    sc[pad] = -np.inf
+    idx[pad] = -1
+    return sc, idx
+
+
+def merge_keys_host(gathered, k):
+    """gathered: (world, N_q, k) uint64 -> merged (N_q, k) uint64 (ascending key = best first)."""
+    g = np.asarray(gathered).astype(np.uint64)
+    world, nq, kk = g.shape
+    allk = np.transpose(g, (1, 0, 2)).reshape(nq, world * kk)
+    return np.sort(allk, axis=1)[:, :k]

@@ -1,0 +1,143 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol that
+include/mdir_b200.h declares; host-side key/merge/shard logic; loud failure without CUDA;
+registry patching by install() (only where the reference checkout is present)."""
+import os
+import re
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, synth, ref_import
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    from mdir_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mdir_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mdir_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(libpath):
+    names = declared_symbols()
+    assert len(names) >= 18
+    l = ctypes.CDLL(libpath)
+    for n in names:
+        assert hasattr(l, n), "missing export " + n
+    from mdir_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
+    assert _lib.lib().mdir_abi_version() == 1
+
+
+def test_key_helpers_match_c(libpath):
+    from mdir_b200 import _lib
+    from mdir_b200.search import make_keys_host, keys_to_host
+    l = _lib.lib()
+    rs = np.random.RandomState(0)
+    s = np.concatenate([rs.randn(200).astype(np.float32), np.array([0.0, -0.0, 1e-40, -1e-40, np.inf, -np.inf], np.float32)])
+    i = rs.randint(0, 2 ** 32 - 1, size=s.shape[0], dtype=np.int64)
+    k = make_keys_host(s, i)
+    for a, b, kk in zip(s, i, k):
+        assert l.mdir_make_key(float(a), int(b)) == int(kk)
+    sc, idx = keys_to_host(k)
+    assert np.array_equal(sc, np.where(s == 0, np.float32(0), s)) and np.array_equal(idx, i)
+    # key order == (score desc, index asc) == stable argsort of -scores
+    sc2 = np.round(rs.randn(500) * 3).astype(np.float32) / 3
+    keys = make_keys_host(sc2, np.arange(500))
+    assert np.array_equal(np.argsort(keys, kind="stable"), oracle.ranks_from_scores(sc2[:, None])[:, 0])
+
+
+def test_merge_keys_host_equals_global_topk():
+    from mdir_b200.search import make_keys_host, keys_to_host, merge_keys_host, ShardedIndex
+    db = synth.descriptors(1000, 32, 5, clusters=10)
+    q, _ = synth.planted_queries(db, 9, 6)
+    sc = oracle.scores(db.T, q.T)                      # (N, Nq)
+    sc = np.round(sc * 50).astype(np.float32) / 50      # ties across shards
+    k = 20
+    for world in (1, 2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = ShardedIndex.shard_bounds(1000, world, r)
+            idx, val = oracle.topk_from_scores(sc[lo:hi], min(k, hi - lo))
+            keys = make_keys_host(val.T, idx.T + lo)
+            pad = np.full((9, k), np.uint64(0xffffffffffffffff))
+            pad[:, :keys.shape[1]] = keys
+            parts.append(pad)
+        merged = merge_keys_host(np.stack(parts), k)
+        msc, midx = keys_to_host(merged)
+        gidx, gval = oracle.topk_from_scores(sc, k)
+        assert np.array_equal(midx, gidx.T) and np.array_equal(msc, gval.T), world
+
+
+def test_shard_bounds_cover():
+    from mdir_b200.search import ShardedIndex
+    for n in (0, 1, 7, 1001001):
+        for w in (1, 2, 4, 8):
+            b = [ShardedIndex.shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+
+
+def test_module_surface_matches_reference_names():
+    import mdir_b200
+    g = mdir_b200.GeM(p=2.9137)
+    assert repr(g) == "GeM(p=2.9137, eps=1e-06)"
+    assert list(g.state_dict().keys()) == ["p"] and g.p.shape == (1,)
+    assert repr(mdir_b200.MAC()) == "MAC()" and repr(mdir_b200.SPoC()) == "SPoC()"
+    assert repr(mdir_b200.L2N()) == "L2N(eps=1e-06)"
+    assert set(mdir_b200.POOLING) == {"gem", "mac", "spoc"}
+    ms = mdir_b200.CirMultiscaleAggregation("True", "cpu")
+    assert np.allclose(ms.scales, [1, 1 / np.sqrt(2), 0.5])
+    assert mdir_b200.CirMultiscaleAggregation(False, "cpu").scales == [1]
+    t, was = ms.preprocess(torch.zeros(1, 3, 64, 48), None)
+    assert [tuple(x.shape[-2:]) for x in t] == [(64, 48), (45, 33), (32, 24)] and was is False
+
+
+def test_no_cpu_fallback():
+    import mdir_b200
+    with pytest.raises(mdir_b200.MdirError):
+        mdir_b200.gem(torch.zeros(1, 4, 3, 3))
+    with pytest.raises(mdir_b200.MdirError):
+        mdir_b200.l2n(torch.zeros(1, 4, 1, 1))
+    with pytest.raises(mdir_b200.MdirError):
+        mdir_b200.clahe_u8(torch.zeros(8, 8, dtype=torch.uint8))
+    with pytest.raises(mdir_b200.MdirError):
+        mdir_b200.Index(np.zeros((4, 8), np.float32), device="cpu")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mdir_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference checkout not present (GPU box)")
+def test_install_patches_registries():
+    ref_import.import_reference()
+    import mdir_b200
+    patched = mdir_b200.install()
+    import cirtorch.networks.imageretrievalnet as irn
+    import mdir.components.data.wrapper as mwrap
+    import mdir.components.data.transform as mtrans
+    import mdir.components.optim.score as mscore
+    assert irn.POOLING["gem"] is mdir_b200.GeM and irn.POOLING["mac"] is mdir_b200.MAC
+    assert "rmac" in irn.POOLING                                   # untouched (out of scope)
+    assert mwrap.WRAPPERS_LABELS["cirwhiten"] is mdir_b200.CirtorchWhiten
+    assert mwrap.WRAPPERS_LABELS["cirmultiscale"] is mdir_b200.CirMultiscaleAggregation
+    assert mtrans.TRANSFORMS["apply_clahe"] is mdir_b200.ApplyClahe
+    assert mscore.SCORES["cirdatasetap"].__name__ == "CirDatasetAp"
+    assert len(patched) >= 9
+    # the yaml-driven wrapper factory builds ours (wrapper.py:209-220)
+    comp = mwrap.initialize_wrappers({"1_cirmultiscale": {"scales": True}}, torch.device("cpu"))
+    assert isinstance(comp.wrappers[0], mdir_b200.CirMultiscaleAggregation)

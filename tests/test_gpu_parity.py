@@ -1,0 +1,379 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against oracle/ and the committed
+golden vectors (outputs of the reference itself), on the same seeded inputs.
+
+Bars (BASELINE.json north_star): CLAHE and sort/top-k indexing bit-exact; pooled / whitened
+descriptors within 1e-5 relative; similarity scores within 2e-3 absolute on the bf16 path;
+mAP within 0.01."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+REL = 1e-5
+
+
+def close(a, b, rtol=REL, atol=0.0):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().numpy()
+    np.testing.assert_allclose(np.asarray(a, np.float64), np.asarray(b, np.float64), rtol=rtol, atol=atol)
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mdir_b200
+    from mdir_b200 import _lib
+    _lib.check(_lib.lib().mdir_device_check(), "device check")
+    return mdir_b200
+
+
+# ------------------------------------------------------------------ pooling / L2N
+@pytest.mark.parametrize("si", range(len(synth.POOL_SHAPES)))
+@pytest.mark.parametrize("kind", ["relu", "signed", "zeros"])
+def test_pooling_vs_oracle_and_golden(m, golden, si, kind):
+    g = golden("pooling")
+    x = synth.fmap(synth.POOL_SHAPES[si], 100 + si, kind)
+    xd = dev(x)
+    tag = "s%d_%s" % (si, kind)
+    assert np.array_equal(m.MAC()(xd).cpu().numpy(), g[tag + "_mac"])              # max is exact
+    close(m.SPoC()(xd), g[tag + "_spoc"], atol=1e-7)
+    close(m.SPoC()(xd), oracle.spoc(x), atol=1e-7)
+    close(m.L2N()(m.MAC()(xd)), g[tag + "_l2n_mac"], atol=1e-7)
+    for p in synth.POOL_PS:
+        out = m.GeM(p=p).to(DEV)(xd)
+        assert out.shape == (x.shape[0], x.shape[1], 1, 1)
+        close(out, oracle.gem(x, p))
+        close(out, g[tag + "_gem_p%g" % p])
+        close(m.L2N()(out), g[tag + "_l2n_gem_p%g" % p], atol=1e-8)
+
+
+def test_gem_zero_and_learned_p(m):
+    z = torch.zeros(1, 8, 5, 5, device=DEV)
+    close(m.gem(z, 3.0), np.full((1, 8, 1, 1), 9.99999656e-07), rtol=1e-6)
+    gm = m.GeM(p=3).to(DEV)
+    gm.p.data.fill_(2.5)                       # learnable parameter is honoured
+    x = synth.fmap((1, 16, 9, 7), 5)
+    close(gm(dev(x)), oracle.gem(x, 2.5))
+    assert "p=2.5000" in repr(gm)
+
+
+def test_l2n_inner(m):
+    x = synth.fmap((3, 37, 5, 4), 9, "signed")
+    close(m.l2n(dev(x)), oracle.l2n(x), atol=1e-8)
+
+
+def test_pool_full_size_properties(m):
+    # C1/C2 shapes: (B,2048,32,24) maps; size-independent properties instead of a CPU oracle
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn((24, 2048, 32, 24), device=DEV, generator=g).clamp_(min=0)
+    p = 2.9137
+    y = m.gem(x, p)
+    mx, mean = m.mac(x), m.spoc(x)
+    assert torch.all(y <= mx * (1 + 1e-5) + 1e-6) and torch.all(y + 1e-6 >= mean * (1 - 1e-5))     # power-mean inequality
+    close(m.gem(x * 2.0, p), (y * 2.0).cpu().numpy(), rtol=2e-5)                               # homogeneity
+    sub = x[5:6, 100:164].contiguous()
+    close(m.gem(sub, p), oracle.gem(sub.cpu().numpy(), p))
+    close(y[5:6, 100:164], oracle.gem(sub.cpu().numpy(), p))
+
+
+# ------------------------------------------------------------------ head
+def _fake_model(pooling, p):
+    return types.SimpleNamespace(meta={"pooling": pooling, "regional": False, "whitening": False, "out_channels": 128},
+                                 pool=types.SimpleNamespace(p=torch.tensor([p])))
+
+
+def test_head_vs_golden(m, golden):
+    g = golden("head")
+    C = 128
+    hw = [(32, 24), (23, 17), (16, 12)]
+    lw = {"m": g["lw_m"], "P": g["lw_P"]}
+    for pooling, ps in (("gem", (3.0, 2.9137)), ("mac", (3.0,)), ("spoc", (3.0,))):
+        for p in ps:
+            pool = {"gem": lambda: m.GeM(p=p), "mac": m.MAC, "spoc": m.SPoC}[pooling]().to(DEV)
+            model = _fake_model(pooling, p)
+            ms = m.CirMultiscaleAggregation(True, DEV)
+            for img in range(3):
+                fm = [synth.fmap((1, C, h, w), 200 + 10 * img + s, "relu") for s, (h, w) in enumerate(hw)]
+                # the reference's per-scale tail: norm(pool(o)).squeeze().permute  (imageretrievalnet.py:107-115)
+                outs = []
+                for s in range(3):
+                    o = m.L2N()(pool(dev(fm[s]))).squeeze(-1).squeeze(-1).permute(1, 0)
+                    close(o, g["tail_%s_p%g_i%d_s%d" % (pooling, p, img, s)], atol=1e-8)
+                    outs.append(o)
+                v = ms.postprocess([o.clone() for o in outs], model, False)
+                close(v, g["agg_%s_p%g_i%d" % (pooling, p, img)], atol=1e-8)
+                v1 = m.CirMultiscaleAggregation([1], DEV).postprocess([outs[0].clone()], model, False)
+                close(v1, g["agg1_%s_p%g_i%d" % (pooling, p, img)], atol=1e-8)
+                for dims in (None, 64, 32):
+                    wh = m.CirtorchWhiten(lw, dims, DEV)
+                    w = wh.postprocess(v.clone(), model, None)
+                    assert w.shape == (dims or C,)
+                    close(w, g["wh_%s_p%g_i%d_d%s" % (pooling, p, img, dims)], rtol=2e-5, atol=3e-7)
+    out = m.whitenapply(g["whitenapply_X"], g["lw_m"], g["lw_P"])
+    assert out.dtype == np.float64 and out.shape == (128, 40)
+    close(out, g["whitenapply_full"], rtol=2e-5, atol=3e-7)
+    close(m.whitenapply(g["whitenapply_X"], g["lw_m"], g["lw_P"], 48), g["whitenapply_d48"], rtol=2e-5, atol=3e-7)
+
+
+def test_batched_head_vs_oracle(m, golden):
+    g = golden("head")
+    C = 128
+    lw = {"m": g["lw_m"], "P": g["lw_P"]}
+    hws = [[(32, 24), (23, 17), (16, 12)], [(24, 32), (17, 23), (12, 16)], [(31, 21), (22, 15), (16, 11)], [(8, 8), (6, 6), (4, 4)]]
+    fmaps, flat = [], []
+    for i, hw in enumerate(hws * 3):                      # 12 ragged images (> 4: exercises the SGEMM projection)
+        per = [synth.fmap((1, C, h, w), 900 + 7 * i + s, "relu") for s, (h, w) in enumerate(hw)]
+        fmaps.append(per)
+        flat += [dev(f) for f in per]
+    for dims in (None, 64):
+        head = m.RetrievalHead("gem", p=2.9137, whitening=lw, dimensions=dims, nscales=3, device=DEV)
+        out = head(flat).cpu().numpy()
+        for i, per in enumerate(fmaps):
+            ref = oracle.gem_head(per, 2.9137, 1e-6, lw["m"], lw["P"], dims)
+            close(out[i], ref, rtol=2e-5, atol=3e-7)
+    # single-scale, no whitening, packed NCHW input (C1 shape family)
+    x = synth.fmap((5, C, 32, 24), 77)
+    head = m.RetrievalHead("gem", p=3.0, nscales=1, device=DEV)
+    out = head(dev(x)).cpu().numpy()
+    for i in range(5):
+        close(out[i], oracle.gem_head([x[i:i + 1]], 3.0, 1e-6), atol=1e-8)
+
+
+# ------------------------------------------------------------------ CLAHE
+def test_clahe_bit_exact_all_cases(m, golden):
+    g = golden("clahe")
+    cases = synth.clahe_cases()
+    for clip in (4, 2, 40):
+        sel = [c for c in cases if c[3] == clip]
+        imgs = [synth.image_u8(hw, dist, seed) for (_, hw, dist, _, seed) in sel]
+        outs = m.clahe_u8([dev(i) for i in imgs], clip, (8, 8))               # one ragged batch per clip limit
+        for (key, hw, dist, _, seed), img, out in zip(sel, imgs, outs):
+            o = out.cpu().numpy()
+            assert synth.sha(img) == str(g["in_sha_" + key])
+            assert synth.sha(o) == str(g["out_sha_" + key]), key
+            if hw in synth.CLAHE_SMALL:
+                assert np.array_equal(o, g["out_" + key]), key
+            if hw in synth.CLAHE_SMALL or dist == "gamma":
+                assert np.array_equal(o, oracle.clahe_u8(img, clip, 8, 8)), key
+
+
+def test_clahe_grid_pitch_and_wrappers(m, golden):
+    g = golden("clahe")
+    img = synth.image_u8((127, 93), "gamma", 77)
+    assert np.array_equal(m.clahe_u8(dev(img), 3, (4, 6)).cpu().numpy(), g["grid4x6_127x93"])
+    # strided (pitch != width) view and a (B,H,W) batch
+    big = dev(synth.image_u8((127, 200), "uniform", 3))
+    view = big[:, 50:143]
+    assert np.array_equal(m.clahe_u8(view, 4, (8, 8)).cpu().numpy(), oracle.clahe_u8(view.cpu().numpy(), 4, 8, 8))
+    batch = np.stack([synth.image_u8((96, 128), d, 40 + i) for i, d in enumerate(synth.CLAHE_DISTS)])
+    out = m.clahe_u8(dev(batch), 4, (8, 8)).cpu().numpy()
+    for i in range(batch.shape[0]):
+        assert np.array_equal(out[i], oracle.clahe_u8(batch[i], 4, 8, 8))
+    chan = (synth.image_u8((200, 150), "gamma", 78).astype(np.float32) + np.float32(0.37)) / np.float32(255.3)
+    assert np.array_equal(m.ChannelClahe(4, 8).apply(chan), g["channelclahe_200x150"])
+    assert np.array_equal(m.ChannelClahe("4", "8").apply(chan), g["channelclahe_200x150"])      # string args from the mini-language
+    cv2 = pytest.importorskip("cv2")
+    for hw, grid, clip in (((3, 5), (8, 8), 4), ((50, 70), (5, 3), 4), ((64, 48), (8, 8), 0), ((2, 3), (8, 8), 4), ((2048, 33), (8, 8), 4)):
+        im = synth.image_u8(hw, "bimodal", 600 + hw[0])
+        ref = cv2.createCLAHE(clipLimit=clip, tileGridSize=grid).apply(im)
+        assert np.array_equal(m.clahe_u8(dev(im), clip, grid).cpu().numpy(), ref), (hw, grid, clip)
+
+
+def test_apply_clahe_transform(m):
+    cv2 = pytest.importorskip("cv2")
+    rs = np.random.RandomState(3)
+    pic = (rs.rand(120, 160, 3) ** 3).astype(np.float32)
+    out = m.ApplyClahe("4", "lab", "8")(pic)
+    assert isinstance(out, list) and out[0].shape == pic.shape
+    # reference arithmetic restated with cv2 for the colour conversion + the oracle CLAHE
+    spc = (cv2.cvtColor(pic, cv2.COLOR_RGB2LAB) + np.array([0, 128, 128], np.float32)) / np.array([100.0, 255.0, 255.0], np.float32)
+    spc[:, :, 0] = oracle.channel_clahe(spc[:, :, 0], 4, 8)
+    ref = cv2.cvtColor(spc * np.array([100.0, 255.0, 255.0], np.float32) - np.array([0, 128, 128], np.float32), cv2.COLOR_LAB2RGB)
+    assert np.array_equal(out[0], ref)
+    two = m.CreateClahedImage()(pic)
+    assert len(two) == 2 and np.array_equal(two[1], ref)
+    four = m.AddClaheFromRgb()(pic)[0]
+    assert four.shape == (120, 160, 4)
+
+
+# ------------------------------------------------------------------ ranks / top-k on the reference's scores
+def test_ranks_from_reference_scores_bit_exact(m, golden):
+    g = golden("search")
+    assert np.array_equal(m.ranks_from_scores(g["scores"]).cpu().numpy(), g["ranks_stable"])
+    assert np.array_equal(m.ranks_from_scores(g["scores_ties"]).cpu().numpy(), g["ranks_ties_stable"])
+    for k in (1, 17, 100, 500):
+        idx, val = m.topk_from_scores(g["scores_ties"], k)
+        assert np.array_equal(idx.cpu().numpy(), g["ranks_ties_stable"][:k])
+        assert np.array_equal(val.cpu().numpy(), np.take_along_axis(g["scores_ties"], g["ranks_ties_stable"][:k], 0))
+
+
+def test_ranks_edge_cases(m):
+    rs = np.random.RandomState(8)
+    for n_db, n_q in ((1, 1), (2, 3), (4096, 2), (4097, 5), (12345, 33), (70000, 3)):
+        sc = rs.randn(n_db, n_q).astype(np.float32)
+        sc[rs.rand(n_db, n_q) < 0.3] = 0.5                        # heavy ties
+        sc[0, 0] = -0.0
+        if n_db > 1:
+            sc[1, 0] = 0.0
+        if n_db > 3:
+            sc[2, 0] = np.inf
+            sc[3, 0] = -np.inf
+        assert np.array_equal(m.ranks_from_scores(sc).cpu().numpy(), oracle.ranks_from_scores(sc)), (n_db, n_q)
+
+
+# ------------------------------------------------------------------ similarity + search
+def test_scores_and_drop_in_rank(m, golden):
+    g = golden("search")
+    db = synth.descriptors(500, 64, 11, clusters=20)
+    q, _ = synth.planted_queries(db, 12, 12)
+    index = m.Index(db, device=DEV)
+    sc = index.scores(q).cpu().numpy()                            # (N_q, N_db)
+    np.testing.assert_allclose(sc.T, g["scores"], rtol=0, atol=2e-3)
+    # fp32 search == reference top-k wherever the reference's own gap exceeds fp32 noise
+    s, i = index.search(q, 50, precision="fp32", shortlist=200)
+    ref_i, ref_v = oracle.topk_from_scores(g["scores"], 50)
+    np.testing.assert_allclose(s.cpu().numpy().T, ref_v, rtol=0, atol=2e-6)
+    _assert_same_order(i.cpu().numpy().T, ref_i, ref_v, 2e-6)
+    # the drop-in: (D,N) host matrices -> (N_db,N_q) int64 ranks -> the reference's compute_map
+    ranks = m.rank(np.ascontiguousarray(db.T), np.ascontiguousarray(q.T))
+    assert ranks.dtype == np.int64 and ranks.shape == (500, 12) and ranks.flags["C_CONTIGUOUS"]
+    assert np.array_equal(np.sort(ranks, axis=0), np.tile(np.arange(500)[:, None], (1, 12)))     # each column a permutation
+    gnd = synth.gnd_okjunk(500, 12, 13, empty_every=5)
+    mp, aps, _, _ = oracle.compute_map(ranks, gnd, [1, 5, 10])
+    assert abs(mp - float(g["okjunk_map"])) < 0.01
+    avg, _, _ = oracle.compute_map_emh(ranks, synth.gnd_emh(500, 12, 14))
+    for k_ in avg:
+        assert abs(avg[k_] - float(g["emh_" + k_])) < 0.01
+
+
+def _assert_same_order(got, ref_i, ref_v, tol):
+    """Indices must agree except where the reference scores are within tol (summation-order noise)."""
+    k, nq = ref_i.shape
+    for j in range(nq):
+        for r in range(k):
+            if got[r, j] != ref_i[r, j]:
+                near = np.abs(ref_v[:, j] - ref_v[r, j]) <= tol
+                assert got[r, j] in ref_i[near, j] or r == k - 1, (r, j)
+
+
+@pytest.mark.parametrize("n_db,n_q,D,k", [(300, 5, 64, 10), (20000, 70, 256, 100), (16389, 128, 136, 64), (70000, 200, 64, 100), (50, 3, 8, 100)])
+def test_search_bf16_equals_topk_of_own_scores(m, n_db, n_q, D, k):
+    db = synth.descriptors(n_db, D, 100 + n_q, clusters=50)
+    q, src = synth.planted_queries(db, n_q, 7)
+    index = m.Index(db, device=DEV, idx_base=1000)
+    sc = index.scores(q).cpu().numpy().T                          # (N_db, N_q) of the same bf16 path
+    s, i = index.search(q, k, precision="bf16")
+    ref_i, ref_v = oracle.topk_from_scores(sc, min(k, n_db))
+    kk = min(k, n_db)
+    assert np.array_equal(i.cpu().numpy().T[:kk], ref_i + 1000)
+    assert np.array_equal(s.cpu().numpy().T[:kk], ref_v)
+    if k > n_db:
+        assert np.all(i.cpu().numpy()[:, n_db:] == -1) and np.all(np.isneginf(s.cpu().numpy()[:, n_db:]))
+    assert np.all(i.cpu().numpy()[:, 0] == src + 1000)            # planted neighbour found first
+
+
+def test_search_fp32_matches_reference_topk(m):
+    db = synth.descriptors(30000, 128, 41, clusters=200)
+    q, _ = synth.planted_queries(db, 70, 42)
+    index = m.Index(db, device=DEV)
+    s, i = index.search(q, 100, precision="fp32")
+    sc = oracle.scores(db.T, q.T)
+    ref_i, ref_v = oracle.topk_from_scores(sc, 100)
+    np.testing.assert_allclose(s.cpu().numpy().T, ref_v, rtol=0, atol=3e-6)
+    _assert_same_order(i.cpu().numpy().T, ref_i, ref_v, 3e-6)
+
+
+def test_search_overflow_recovery(m):
+    # adversarial order: scores increase with the row index, so every tile beats the sample
+    # threshold and the candidate lists overflow; the re-threshold loop must still be exact
+    n_db, D = 40000, 64
+    rs = np.random.RandomState(5)
+    base = rs.randn(D).astype(np.float32)
+    base /= np.linalg.norm(base)
+    noise = rs.randn(n_db, D).astype(np.float32) * 0.01
+    db = (np.linspace(0.1, 1.0, n_db, dtype=np.float32)[:, None] * base[None, :] + noise).astype(np.float32)
+    q = np.stack([base, -base, base + 0.1 * rs.randn(D).astype(np.float32)]).astype(np.float32)
+    index = m.Index(db, device=DEV)
+    sc = index.scores(q).cpu().numpy().T
+    s, i = index.search(q, 100, precision="bf16")
+    ref_i, ref_v = oracle.topk_from_scores(sc, 100)
+    assert np.array_equal(i.cpu().numpy().T, ref_i) and np.array_equal(s.cpu().numpy().T, ref_v)
+    # duplicates: identical rows tie on score and must come back in index order
+    dup = np.repeat(synth.descriptors(50, 64, 3), 400, axis=0)
+    index = m.Index(dup, device=DEV)
+    s, i = index.search(dup[:2], 500, precision="bf16")
+    ref_i, _ = oracle.topk_from_scores(index.scores(dup[:2]).cpu().numpy().T, 500)
+    assert np.array_equal(i.cpu().numpy().T, ref_i)
+
+
+def test_sharded_merge_equals_single(m):
+    from mdir_b200 import _lib
+    db = synth.descriptors(50000, 64, 61, clusters=100)
+    q, _ = synth.planted_queries(db, 70, 62)
+    k = 100
+    single = m.Index(db, device=DEV)
+    s1, i1 = single.search(q, k, precision="bf16")
+    for world in (2, 4, 8):
+        keys = []
+        for r in range(world):
+            lo, hi = m.ShardedIndex.shard_bounds(db.shape[0], world, r)
+            shard = m.Index(db[lo:hi], device=DEV, idx_base=lo)
+            keys.append(shard.search(q, k, precision="bf16", return_keys=True)[2])
+        allk = torch.stack(keys).permute(1, 0, 2).contiguous().view(70, world * k)
+        cnt = torch.full((70,), world * k, dtype=torch.int32, device=DEV)
+        out_s = torch.empty((70, k), dtype=torch.float32, device=DEV)
+        out_i = torch.empty((70, k), dtype=torch.int32, device=DEV)
+        _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(allk), _lib.ptr(cnt), world * k, 70, k, _lib.ptr(out_s), _lib.ptr(out_i),
+                                                 None, None, None, _lib.stream()))
+        assert torch.equal(out_i, i1) and torch.equal(out_s, s1), world
+
+
+def test_r1m_full_size_properties(m):
+    # BASELINE config 4 at full size: 70 q x 1,001,001 x 2048.  Size-independent checks:
+    # planted neighbours come back first; the fused top-100 equals the top-100 selected from a
+    # dense scan of the same index; fp32 re-scoring returns exactly-recomputed scores.
+    n_db, D, n_q, k = 1001001, 2048, 70, 100
+    g = torch.Generator(device=DEV).manual_seed(4)
+    db = torch.empty((n_db, D), dtype=torch.float32, device=DEV)
+    for r0 in range(0, n_db, 65536):
+        blk = torch.randn((min(65536, n_db - r0), D), device=DEV, generator=g)
+        db[r0:r0 + blk.shape[0]] = blk / blk.norm(dim=1, keepdim=True)
+    src = torch.randint(0, n_db, (n_q,), device=DEV, generator=g)
+    q = db[src] + 0.5 * torch.randn((n_q, D), device=DEV, generator=g) / D ** 0.5
+    q = q / q.norm(dim=1, keepdim=True)
+    index = m.Index.from_packed(m.search.pack_bf16(db), db32=db)
+    s, i = index.search(q, k, precision="bf16")
+    assert torch.equal(i[:, 0].long(), src)
+    dense = index.scores(q)                                       # (70, 1001001)
+    idx2, val2 = m.topk_from_scores(dense.t().contiguous(), k)
+    assert torch.equal(idx2.t().int(), i) and torch.equal(val2.t(), s)
+    s32, i32 = index.search(q, k, precision="fp32")
+    exact = (db[i32.long().view(-1)].view(n_q, k, D) * q[:, None, :]).sum(-1)
+    assert torch.allclose(s32, exact, rtol=0, atol=2e-6)
+    assert torch.all(s32[:, :-1] >= s32[:, 1:]) and torch.equal(i32[:, 0].long(), src)
+    assert (s32 - s).abs().max().item() < 2e-3                   # bf16 scores within the stated tolerance
+
+
+# ------------------------------------------------------------------ alpha-QE / DBA (parity unpinned: vs the restated definitions)
+def test_qe_and_dba(m):
+    from mdir_b200 import qe
+    db = synth.descriptors(5000, 64, 21, clusters=40)
+    q, _ = synth.planted_queries(db, 9, 22)
+    index = m.Index(db, device=DEV)
+    q2 = qe.expand_queries(index, q, alpha=3.0, n_qe=10).cpu().numpy()
+    close(q2, oracle.alpha_qe(db, q, 3.0, 10), rtol=1e-4, atol=2e-6)
+    s, i = qe.search_qe(index, q, 20)
+    ref_i, ref_v = oracle.topk_from_scores(db @ oracle.alpha_qe(db, q, 3.0, 10).T, 20)
+    np.testing.assert_allclose(s.cpu().numpy().T, ref_v, rtol=0, atol=1e-5)
+    small = synth.descriptors(600, 64, 23, clusters=10)
+    aug = qe.dba(m.Index(small, device=DEV), alpha=3.0, k_dba=5)
+    close(aug.db32, oracle.dba(small, 3.0, 5), rtol=1e-4, atol=2e-6)

@@ -175,7 +175,7 @@ static void test_ranks(int64_t n_db, int n_q, bool ties) {
     CK(cudaMalloc(&d_sc, sc.size() * 4)); CK(cudaMalloc(&d_r, sc.size() * 8));
     CK(cudaMalloc(&ws, mdir_rank_workspace_bytes(n_db, n_q)));
     CK(cudaMemcpy(d_sc, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
-    MD(mdir_rank_scores(d_sc, n_db, n_q, 0, d_r, ws, 0));
+    MD(mdir_rank_scores(d_sc, n_db, n_q, 0, d_r, n_q, ws, 0));
     CK(cudaDeviceSynchronize());
     std::vector<int64_t> r(sc.size());
     CK(cudaMemcpy(r.data(), d_r, r.size() * 8, cudaMemcpyDeviceToHost));
