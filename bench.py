@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on its own configuration:
+
+    queries/s against a 1,001,001 x 2048 database (R1M shape, config 4), 70 queries per step,
+    top-100 per query identical to the fp32 reference ranking (bf16 tcgen05 scan + fused
+    threshold filter + exact fp32 re-scoring of a 200-entry shortlist),
+    on N B200s of one node (database rows sharded, local top-k, one NCCL all-gather of keys).
+
+A "step" = one batch of 70 queries ranked against the whole database.
+  value  : device-resident queries, CUDA-event timed, max over ranks
+  e2e    : the same through the public API with HOST buffers: pinned-host queries -> H2D ->
+           search -> D2H of the (scores, idx) result, every step.  The database is the resident
+           index (state, like weights), not a per-step input; `e2e_cold_db_ms` reports the
+           one-off upload + bf16 packing of the database separately.
+  --impl reference : the reference's CPU path (np.dot + np.argsort, cirscore.py:69-70, restated
+           in oracle/oracle.py) on the host cores, on a bounded row sample of the same workload.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun
+(python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DB, DIM, N_Q, TOPK = 1001001, 2048, 70, 100
+METRIC = "queries/s vs 1M x 2048 db (70-query batches, top-100, fp32-faithful ranking)"
+UNIT = "queries/s"
+WORKLOAD = "R1M: 70 q x 1,001,001 x 2048-D db, top-100 (BASELINE.json configs[3]; 4.1 GB bf16 + 8.2 GB fp32 master)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the head / CLAHE side measurements")
+    ap.add_argument("--cpu-rows", type=int, default=100000, help="database row sample for the CPU baseline")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ CPU reference arm
+def cpu_reference(rows, reps):
+    """The reference's own arithmetic (cirscore.py:69-70) through the oracle port, all host
+    threads numpy/BLAS will use, on `rows` database rows x 70 queries; queries/s extrapolated
+    linearly in N_db (argsort is n log n, so this flatters the CPU slightly)."""
+    import numpy as np
+    from oracle import oracle
+    rs = np.random.RandomState(4)
+    vecs = rs.standard_normal((DIM, rows)).astype(np.float32)        # (D, N_db) as extract_vectors returns
+    vecs /= np.linalg.norm(vecs, axis=0, keepdims=True)
+    qvecs = rs.standard_normal((DIM, N_Q)).astype(np.float32)
+    qvecs /= np.linalg.norm(qvecs, axis=0, keepdims=True)
+    oracle.ranks(vecs[:, :1000], qvecs)                               # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        sc = oracle.scores(vecs, qvecs)
+        rk = np.argsort(-sc, axis=0)                                   # the reference's exact call (default kind)
+        ts.append(time.perf_counter() - t0)
+        assert rk.shape == (rows, N_Q)
+    t = float(np.median(ts))
+    scale = N_DB / float(rows)
+    return {"value": N_Q / (t * scale), "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
+            "sample": "np.dot + np.argsort(axis=0) on %d of %d db rows x 70 queries x 2048-D, median of %d, time scaled x%.2f"
+                      % (rows, N_DB, reps, scale),
+            "ms_per_step_extrapolated": t * scale * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, min(args.steps, 5))
+    cb = cpu_reference(args.cpu_rows, reps)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
+            "warmup": 1, "ms_per_step": cb["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, torch_device_index):
+        super().__init__(daemon=True)
+        self.samples = []
+        self.stop_flag = False
+        self.active = False
+        self.ok = False
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
+
+    def run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((self.active, mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def summary(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
+        import statistics
+        act = [s for s in self.samples if s[0]] or self.samples
+        names = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+                 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+        bits = 0
+        for _, _, r in act:
+            bits |= r
+        return {"sm_mhz": statistics.median([s[1] for s in act]) if act else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(n for b, n in names.items() if bits & b and n != "gpu_idle"), "samples": len(act)}
+
+
+class KernelProf:
+    """CUDA events around the dominant kernel on the stream it is launched on."""
+
+    def __init__(self, torch):
+        self.torch = torch
+        self.pairs = []
+        self.bytes = 0
+        self.on = False
+
+    def begin(self):
+        if self.on:
+            self._e0 = self.torch.cuda.Event(enable_timing=True)
+            self._e0.record()
+
+    def end(self, nbytes):
+        if self.on:
+            e1 = self.torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.pairs.append((self._e0, e1))
+            self.bytes = nbytes
+
+    def mean_ms(self):
+        return sum(a.elapsed_time(b) for a, b in self.pairs) / max(len(self.pairs), 1)
+
+
+# ------------------------------------------------------------------ our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import mdir_b200
+    from mdir_b200 import _lib
+    from mdir_b200.search import Index, ShardedIndex, merge_keys, pack_bf16
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (python -m torch.distributed.run --nproc-per-node %d bench.py ...)" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.lib().mdir_device_check(), "device check")
+    lib = _lib.lib()
+
+    # ---- synthetic database shard (rows [lo, hi) of the 1,001,001), built on the device -------
+    lo, hi = ShardedIndex.shard_bounds(N_DB, world, rank)
+    t_build0 = time.perf_counter()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    db32 = torch.empty((hi - lo, DIM), dtype=torch.float32, device=dev)
+    for r0 in range(0, hi - lo, 65536):
+        blk = torch.randn((min(65536, hi - lo - r0), DIM), device=dev, generator=g)
+        db32[r0:r0 + blk.shape[0]] = blk / blk.norm(dim=1, keepdim=True)
+    gq = torch.Generator(device="cpu").manual_seed(99)
+    q_host = torch.randn((N_Q, DIM), generator=gq)
+    q_host = (q_host / q_host.norm(dim=1, keepdim=True)).pin_memory()
+    torch.cuda.synchronize()
+    # cold path of the index build (packing only; the fp32 rows are already resident)
+    t0 = time.perf_counter()
+    index = Index.from_packed(pack_bf16(db32), db32=db32, idx_base=lo)
+    torch.cuda.synchronize()
+    pack_ms = (time.perf_counter() - t0) * 1e3
+    prof = KernelProf(torch)
+    index.prof = prof
+    q_dev = q_host.to(dev)
+
+    def step_device():
+        s, i, keys = index.search(q_dev, TOPK, precision="fp32", check=False, return_keys=True)
+        if world > 1:
+            s, i = merge_keys(keys, world, None, TOPK)
+        return s, i
+
+    out_host = torch.empty((N_Q, TOPK * 2), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        qd = q_host.to(dev, non_blocking=True)
+        s, i, keys = index.search(qd, TOPK, precision="fp32", check=False, return_keys=True)
+        if world > 1:
+            s, i = merge_keys(keys, world, None, TOPK)
+        out_host[:, :TOPK].copy_(s, non_blocking=True)
+        out_host[:, TOPK:].view(torch.int32).copy_(i, non_blocking=True)
+        torch.cuda.synchronize()
+        return out_host
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        s_chk, i_chk = step_device()
+    torch.cuda.synchronize()
+    assert not index.check_overflow(), "candidate overflow on the benchmark data"
+    for _ in range(3):
+        step_e2e()
+
+    # ---- timed region: `value` ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if sampler.ok:
+        sampler.start()
+    launches0 = lib.mdir_launch_count()
+    prof.on = True
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    sampler.active = True
+    ev[0].record()
+    for _ in range(args.steps):
+        step_device()
+    ev[1].record()
+    barrier()
+    sampler.active = False
+    prof.on = False
+    launches = lib.mdir_launch_count() - launches0
+    assert not index.check_overflow()
+    ms_total = ev[0].elapsed_time(ev[1])
+    scan_ms = prof.mean_ms()
+
+    # ---- timed region: e2e (host buffers in, host result out, every step) --------------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+
+    # bf16-only mode (no fp32 re-scoring), for the record
+    for _ in range(3):
+        index.search(q_dev, TOPK, precision="bf16", check=False)
+    e2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    e2[0].record()
+    n_b = max(10, args.steps // 4)
+    for _ in range(n_b):
+        index.search(q_dev, TOPK, precision="bf16", check=False)
+    e2[1].record()
+    torch.cuda.synchronize()
+    bf16_ms = e2[0].elapsed_time(e2[1]) / n_b
+
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_s, scan_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, scan_ms = [float(x) for x in t.tolist()]
+
+    # ---- sanity: planted result is self-consistent with an exact recomputation -------------------
+    s_chk, i_chk = step_device()
+    own = (i_chk >= lo) & (i_chk < hi)
+    rows = (i_chk.long() - lo).clamp_(0, hi - lo - 1)
+    exact = (db32[rows.view(-1)].view(N_Q, TOPK, DIM) * q_dev[:, None, :]).sum(-1)
+    assert torch.all(((exact - s_chk).abs() < 2e-6) | ~own), "fp32 re-scored values disagree with an exact recomputation"
+    assert torch.all(s_chk[:, :-1] >= s_chk[:, 1:])
+
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        extras = side_measurements(torch, mdir_b200, dev)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    achieved = prof.bytes / 1e9 / (scan_ms * 1e-3) if scan_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sim_scan_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
+    ms_step = ms_total / args.steps
+    line = {
+        "metric": METRIC, "value": N_Q * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": 2 * TOPK, "db_rows_per_gpu": hi - lo,
+                   "sharding": "db rows contiguous over %d GPU(s); all-gather of %d B of keys per rank" % (world, N_Q * TOPK * 8),
+                   "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": N_Q * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N_Q * DIM * 4, "d2h_bytes_per_step": N_Q * TOPK * 8,
+                "ms_per_step": e2e_s / args.steps * 1e3, "timing": "wall clock around %d steps, barrier + synchronize both sides" % args.steps},
+        "e2e_cold_db_ms": {"pack_fp32_to_bf16_ms": pack_ms,
+                           "note": "one-off index build for this shard; host->device upload of the fp32 rows would add %.1f GB over PCIe" % ((hi - lo) * DIM * 4 / 1e9)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "sim_scan_kernel (FILTER pass)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "algorithmic_bytes_per_launch": prof.bytes, "avg_launch_ms": scan_ms, "share_of_step": scan_ms / ms_step},
+        "bf16_only_ms_per_step": bf16_ms,
+    }
+    if world == 1:
+        cb = cpu_reference(args.cpu_rows, 3)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line.update(extras)
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_measurements(torch, mdir_b200, dev):
+    """The second half of BASELINE.json's metric: GeM + whiten descriptors/s (C2 head shape) and
+    CLAHE images/s, each with its HBM-roofline fraction.  Outside the timed region of `value`."""
+    from mdir_b200 import _lib
+    peak, _ = measured_peaks()
+    out = {}
+    # head: 192 images x 3 scales of 2048 x {32x24, 23x17, 16x12}; P 2048x2048
+    B, C = 192, 2048
+    hws = [(32, 24), (23, 17), (16, 12)]
+    g = torch.Generator(device=dev).manual_seed(7)
+    fm = []
+    for _ in range(B):
+        for (h, w) in hws:
+            fm.append(torch.randn((1, C, h, w), device=dev, generator=g).clamp_(min=0))
+    P = torch.randn((C, C), device=dev, generator=g) / C ** 0.5
+    m = torch.randn((C, 1), device=dev, generator=g) * 0.01
+    head = mdir_b200.RetrievalHead("gem", p=2.9137, whitening={"P": P.cpu().numpy(), "m": m.cpu().numpy()}, nscales=3, device=dev)
+    for _ in range(3):
+        head(fm)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    reps = 10
+    for _ in range(reps):
+        head(fm)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    bytes_img = 4 * C * sum(h * w for h, w in hws)
+    out["head"] = {"metric": "GeM+L2N+multiscale+Lw descriptors/s (C2 head: 3 scales, 2048-D)", "value": B / (ms * 1e-3), "unit": "descriptors/s",
+                   "batch": B, "ms_per_batch": ms, "algorithmic_bytes_per_descriptor": bytes_img,
+                   "hbm_frac_of_measured": B * bytes_img / 1e9 / (ms * 1e-3) / peak}
+    del fm
+    # CLAHE: 256 images of 768 x 1024 u8 (night-like gamma distribution)
+    n_img = 256
+    imgs = (torch.rand((n_img, 768, 1024), device=dev, generator=g) ** 4 * 255).to(torch.uint8)
+    for _ in range(3):
+        mdir_b200.clahe_u8(imgs, 4, (8, 8))
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(reps):
+        mdir_b200.clahe_u8(imgs, 4, (8, 8))
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / reps
+    out["clahe"] = {"metric": "CLAHE u8 images/s (768x1024, clip 4, 8x8 tiles)", "value": n_img / (ms * 1e-3), "unit": "images/s",
+                    "batch": n_img, "ms_per_batch": ms, "algorithmic_bytes_per_image": 2 * 768 * 1024,
+                    "hbm_frac_of_measured": n_img * 2 * 768 * 1024 / 1e9 / (ms * 1e-3) / peak}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

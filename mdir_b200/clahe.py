@@ -22,6 +22,7 @@ def clahe_u8(images, clip_limit=4.0, grid=(8, 8), out=None):
     different sizes.  Returns the same structure.  grid = (tiles_x, tiles_y) like cv2."""
     lib = _lib.lib()
     single = False
+    batched_out = None
     if isinstance(images, torch.Tensor):
         _lib.require_cuda(images, "images")
         if images.dtype != torch.uint8:
@@ -31,6 +32,9 @@ def clahe_u8(images, clip_limit=4.0, grid=(8, 8), out=None):
             planes = [images]
         elif images.dim() == 3:
             planes = list(images)
+            if out is None and images.is_contiguous():
+                batched_out = torch.empty_like(images)
+                out = list(batched_out)
         else:
             raise _lib.MdirError("expected (H,W) or (B,H,W)")
     else:
@@ -61,6 +65,8 @@ def clahe_u8(images, clip_limit=4.0, grid=(8, 8), out=None):
                                      tiles_x, tiles_y, _lib.ptr(ws), _lib.stream()), "mdir_clahe_u8")
     if single:
         return outs[0]
+    if batched_out is not None:
+        return batched_out
     if isinstance(images, torch.Tensor):
         return torch.stack(outs)
     return outs

@@ -14,88 +14,200 @@ __device__ __forceinline__ uint32_t sample_pos_to_idx(int64_t i, int sample_stri
     return idx_base + (uint32_t)(j * sample_stride * MDIR_SCAN_TILE_ROWS + r);
 }
 
-// One CTA (1024 threads) per query: MSB-first 8-bit radix select over 64-bit keys.
+// Warp 0 helper: given hist[256] and the remaining rank k (1-based), find the bin where the
+// running count reaches k.  Returns the bin; *before = items in earlier bins.
+__device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, uint32_t* before) {
+    const int lane = threadIdx.x & 31;
+    uint32_t loc[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - sum;
+    const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
+    const int src = hit ? (__ffs(hit) - 1) : 31;
+    int bin = 0;
+    uint32_t acc = excl;
+    if (lane == src) {
+        int j = 0;
+        for (; j < 7; ++j) {
+            if (acc + loc[j] >= k) break;
+            acc += loc[j];
+        }
+        bin = lane * 8 + j;
+    }
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    acc = __shfl_sync(0xffffffffu, acc, src);
+    *before = acc;
+    return bin;
+}
+
+// One CTA (1024 threads) per query.  MSB-first 8-bit radix select on the 32-bit score key
+// (4 passes over the L2-resident score row, warp-aggregated shared-memory histogram updates).
+// tau = (kth-best score key << 32) | 0xffffffff, i.e. every item whose score ties the kth best
+// passes; those items (>= kth of them) are appended to cand.
 __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restrict__ scores, int64_t ld, int64_t n, int kth,
                                                           int sample_stride, uint32_t idx_base, uint64_t* __restrict__ tau,
                                                           uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count, int cap) {
     __shared__ uint32_t hist[256];
-    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_prefix;
     __shared__ uint32_t s_k;
     const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31;
     const float* sc = scores + (int64_t)q * ld;
-    uint64_t result;
+    uint32_t result;
+    const int64_t n_round = (n + 1023) & ~(int64_t)1023;
     if ((int64_t)kth > n) {
-        result = ~0ull;
+        result = 0xffffffffu;
     } else {
-        if (threadIdx.x == 0) { s_prefix = 0ull; s_k = (uint32_t)kth; }
+        if (threadIdx.x == 0) { s_prefix = 0u; s_k = (uint32_t)kth; }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            for (int64_t i = threadIdx.x; i < n_round; i += 1024) {
+                const bool valid = i < n;
+                const uint32_t key = valid ? ~orderable(sc[i]) : 0u;
+                const bool hit = valid && ((key & himask) == prefix);
+                if (__any_sync(0xffffffffu, hit)) {
+                    const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t before;
+                const int b = find_bin_warp0(hist, s_k, &before);
+                if (lane == 0) {
+                    s_k -= before;
+                    s_prefix = prefix | ((uint32_t)b << shift);
+                }
+            }
+            __syncthreads();
+        }
+        result = s_prefix;
+    }
+    if (threadIdx.x == 0) tau[q] = ((uint64_t)result << 32) | 0xffffffffull;
+    if (cand) {
+        for (int64_t i = threadIdx.x; i < n; i += 1024) {
+            const float v = sc[i];
+            if (~orderable(v) <= result) {
+                const uint32_t pos = atomicAdd(&cand_count[q], 1u);
+                if (pos < (uint32_t)cap) cand[(int64_t)q * cap + pos] = make_key(v, sample_pos_to_idx(i, sample_stride, idx_base));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
+    for (int kk = 2; kk <= n; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = a[i], y = a[ixj];
+                    const bool asc = (i & kk) == 0;
+                    if ((x > y) == asc) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA (1024 threads) per query.  Candidates are staged in shared memory; when there are many
+// more than k, the k best are first isolated by an in-smem MSB radix select (keys are unique) and
+// only those are sorted.  dynamic smem = (cap_pow2 + kpow2) * 8 bytes.
+__global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_count,
+                                                             int cap, int k, int cap_pow2, float* __restrict__ out_scores,
+                                                             int32_t* __restrict__ out_idx, uint64_t* __restrict__ out_keys,
+                                                             uint64_t* __restrict__ tau, int32_t* __restrict__ overflow) {
+    extern __shared__ uint64_t skeys[];
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_k, s_done, s_out;
+    uint64_t* sorted = skeys + cap_pow2;          // kpow2 entries
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t count = cand_count[q];
+    const int cnt = (int)min(count, (uint32_t)cap);
+    const uint64_t* src = cand + (int64_t)q * cap;
+    int kpow2 = 32;
+    while (kpow2 < k) kpow2 <<= 1;
+    const uint64_t* res;       // ascending keys, at least min(k, cnt) valid
+    int nres;
+    if (cnt <= 2 * kpow2 || cnt <= 1024) {
+        int n = 32;
+        while (n < cnt) n <<= 1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = i < cnt ? src[i] : ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(skeys, n);
+        res = skeys;
+        nres = cnt;
+    } else {
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) skeys[i] = src[i];
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_k = (uint32_t)k; s_done = 0u; s_out = 0u; }
+        __syncthreads();
+        const int cnt_round = (cnt + 1023) & ~1023;
+        uint64_t thresh = ~0ull;
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
             if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
             __syncthreads();
             const uint64_t prefix = s_prefix;
             const uint64_t himask = pass == 0 ? 0ull : (~0ull << (shift + 8));
-            for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint64_t key = make_key(sc[i], sample_pos_to_idx(i, sample_stride, idx_base));
-                if ((key & himask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xffu], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                uint32_t k = s_k, acc = 0;
-                int b = 0;
-                for (; b < 256; ++b) {
-                    if (acc + hist[b] >= k) break;
-                    acc += hist[b];
-                }
-                s_k = k - acc;
-                s_prefix = prefix | ((uint64_t)b << shift);
-            }
-            __syncthreads();
-        }
-        result = s_prefix;
-    }
-    if (threadIdx.x == 0) tau[q] = result;
-    if (cand) {
-        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint64_t key = make_key(sc[i], sample_pos_to_idx(i, sample_stride, idx_base));
-            if (key <= result) {
-                const uint32_t pos = atomicAdd(&cand_count[q], 1u);
-                if (pos < (uint32_t)cap) cand[(int64_t)q * cap + pos] = key;
-            }
-        }
-    }
-}
-
-// One CTA (1024 threads) per query; dynamic smem = npow2 * 8 bytes.
-__global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_count,
-                                                             int cap, int k, int npow2_max, float* __restrict__ out_scores,
-                                                             int32_t* __restrict__ out_idx, uint64_t* __restrict__ out_keys,
-                                                             uint64_t* __restrict__ tau, int32_t* __restrict__ overflow) {
-    extern __shared__ uint64_t skeys[];
-    const int q = blockIdx.x;
-    const uint32_t count = cand_count[q];
-    const int cnt = (int)min(count, (uint32_t)cap);
-    int n = 32;
-    while (n < cnt) n <<= 1;
-    n = min(n, npow2_max);
-    const uint64_t* src = cand + (int64_t)q * cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = i < cnt ? src[i] : ~0ull;
-    __syncthreads();
-    for (int kk = 2; kk <= n; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t a = skeys[i], b = skeys[ixj];
-                    const bool asc = (i & kk) == 0;
-                    if ((a > b) == asc) { skeys[i] = b; skeys[ixj] = a; }
+            for (int i = threadIdx.x; i < cnt_round; i += 1024) {
+                const bool valid = i < cnt;
+                const uint64_t key = valid ? skeys[i] : 0ull;
+                const bool hit = valid && ((key & himask) == prefix);
+                if (__any_sync(0xffffffffu, hit)) {
+                    const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                 }
             }
             __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t before;
+                const int b = find_bin_warp0(hist, s_k, &before);
+                if (lane == 0) {
+                    const uint32_t need = s_k - before;
+                    s_k = need;
+                    s_prefix = prefix | ((uint64_t)b << shift);
+                    // the whole bin is wanted: everything with this prefix is in the top k
+                    if (need == hist[b] || shift == 0) s_done = 1u;
+                }
+            }
+            __syncthreads();
+            if (s_done) {
+                thresh = s_prefix | (shift ? ((1ull << shift) - 1ull) : 0ull);
+                break;
+            }
         }
+        for (int i = threadIdx.x; i < kpow2; i += blockDim.x) sorted[i] = ~0ull;
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint64_t key = skeys[i];
+            if (key <= thresh) {
+                const uint32_t pos = atomicAdd(&s_out, 1u);
+                if (pos < (uint32_t)kpow2) sorted[pos] = key;
+            }
+        }
+        __syncthreads();
+        bitonic_sort_smem(sorted, kpow2);
+        res = sorted;
+        nres = min(cnt, k);
     }
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint64_t key = j < cnt ? skeys[j] : ~0ull;
-        const bool ok = j < cnt && key != ~0ull;
+        const uint64_t key = j < nres ? res[j] : ~0ull;
+        const bool ok = j < nres && key != ~0ull;
         if (out_scores) out_scores[(int64_t)q * k + j] = ok ? key_score(key) : -INFINITY;
         if (out_idx) out_idx[(int64_t)q * k + j] = ok ? (int32_t)(uint32_t)key : -1;
         if (out_keys) out_keys[(int64_t)q * k + j] = ok ? key : ~0ull;
@@ -103,7 +215,7 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     if (threadIdx.x == 0 && overflow) {
         const bool ovf = count > (uint32_t)cap;
         overflow[q] = ovf ? 1 : 0;
-        if (ovf && tau) tau[q] = skeys[min(k, cnt) - 1];
+        if (ovf && tau) tau[q] = res[min(k, nres) - 1];
     }
 }
 
@@ -232,17 +344,18 @@ extern "C" int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n
 
 extern "C" int mdir_topk_finalize(const uint64_t* cand, const uint32_t* cand_count, int cap, int n_q, int k, float* out_scores,
                                   int32_t* out_idx, uint64_t* out_keys, uint64_t* tau, int32_t* overflow, void* stream) {
-    MDIR_CHECK_ARG(cand && cand_count && cap >= 1 && cap <= 16384 && n_q >= 0 && k >= 1);
+    MDIR_CHECK_ARG(cand && cand_count && cap >= 1 && cap <= 16384 && n_q >= 0 && k >= 1 && k <= 4096);
     if (n_q == 0) return 0;
-    int npow2 = 32;
-    while (npow2 < cap) npow2 <<= 1;
-    const size_t smem = (size_t)npow2 * 8;
+    int cap_pow2 = 32, kpow2 = 32;
+    while (cap_pow2 < cap) cap_pow2 <<= 1;
+    while (kpow2 < k) kpow2 <<= 1;
+    const size_t smem = (size_t)(cap_pow2 + kpow2) * 8;
     static bool attr_set = false;
     if (!attr_set) {
-        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 4096) * 8));
         attr_set = true;
     }
-    topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_count, cap, k, npow2, out_scores, out_idx,
+    topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_count, cap, k, cap_pow2, out_scores, out_idx,
                                                                      out_keys, tau, overflow);
     MDIR_LAUNCH_CHECK();
     return 0;

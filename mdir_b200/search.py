@@ -23,7 +23,8 @@ from . import _lib
 TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries resident per scan pass
 CAND_CAP = 8192       # per-query candidate list capacity (keys)
-MAX_SAMPLE_TILES = 128
+MAX_SAMPLE_TILES = 512
+TARGET_CAND = 3000    # expected candidates per query the sampling plan aims for (kth * n_tiles / n_sample)
 
 
 def _as_dev_f32(x, device):
@@ -91,15 +92,17 @@ class Index:
         return b
 
     def _plan(self, kth):
-        """Sampling plan for the threshold pass: (n_sample, stride) or None for the dense route."""
+        """Sampling plan for the threshold pass: (n_sample, stride) or None for the dense route.
+        The threshold is the kth best of n_sample*256 sampled rows, so about kth * n_tiles / n_sample
+        rows survive the filter pass; n_sample is sized to keep that near TARGET_CAND."""
         n_tiles = (self.n + TILE - 1) // TILE
         if n_tiles < 64:
             return None
-        n_sample = min(MAX_SAMPLE_TILES, n_tiles // 8)
+        want = -(-kth * n_tiles // TARGET_CAND)                     # ceil
+        if want > 148:                                              # whole waves of the 148 persistent CTAs
+            want = -(-want // 148) * 148
+        n_sample = max(32, min(MAX_SAMPLE_TILES, n_tiles // 4, want))
         stride = n_tiles // n_sample
-        # every sampled tile must be full so the sample holds n_sample*256 valid scores
-        if (n_sample - 1) * stride == n_tiles - 1 and self.n % TILE:
-            n_sample -= 1
         if n_sample * TILE < 2 * kth or stride < 2:
             return None
         return n_sample, stride
@@ -158,7 +161,7 @@ class Index:
         the device, ordered by (score desc, index asc); idx = idx_base + local row, -1 padding.
 
         precision="bf16": exact top-k of the bf16-input / fp32-accumulate scores.
-        precision="fp32": bf16 shortlist of `shortlist` (default 4k) per query, re-scored exactly in
+        precision="fp32": bf16 shortlist of `shortlist` (default 2k) per query, re-scored exactly in
                           fp32 against the fp32 master copy, then top-k of those.
         check=False skips the (synchronising) candidate-overflow check; call check_overflow() later."""
         lib = _lib.lib()
@@ -172,7 +175,7 @@ class Index:
             if precision == "fp32":
                 if self.db32 is None:
                     raise _lib.MdirError("precision='fp32' needs keep_fp32=True")
-                kth = min(self.n, int(shortlist or 4 * k))
+                kth = min(self.n, int(shortlist or 2 * k))
             elif precision == "bf16":
                 kth = k_eff
             else:
@@ -283,25 +286,32 @@ def ranks_from_scores(scores, device="cuda"):
 
 def topk_from_scores(scores, k, device="cuda"):
     """scores (N_db, N_q) fp32 -> (idx (k, N_q) int64, val (k, N_q) fp32) on the device: the first
-    k rows of ranks_from_scores without sorting the rest."""
+    k rows of ranks_from_scores without sorting the rest (radix-select the kth score, gather
+    everything that ties or beats it, sort those).  Falls back to the full sort when more rows tie
+    with the kth score than the candidate buffer holds."""
     lib = _lib.lib()
     dev = torch.device(device)
     s = _as_dev_f32(scores, dev)
     n_db, n_q = s.shape
     k = int(k)
-    if k > min(n_db, 16384):
-        raise _lib.MdirError("k too large for the selection path; use ranks_from_scores")
+    if k > min(n_db, 4096):
+        r = ranks_from_scores(s, device=dev)[:k]
+        return r, torch.gather(s, 0, r)
+    cap = int(min(16384, max(4 * k, 1024)))
     with torch.cuda.device(dev):
         st = s.t().contiguous()                       # query-major for coalesced selection
         tau = torch.empty((n_q,), dtype=torch.int64, device=dev)
-        cand = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+        cand = torch.empty((n_q, cap), dtype=torch.int64, device=dev)
         cnt = torch.zeros((n_q,), dtype=torch.int32, device=dev)
         out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n_q, k), dtype=torch.int32, device=dev)
-        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), _lib.ptr(cnt), k,
+        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), _lib.ptr(cnt), cap,
                                        _lib.stream()), "mdir_select_kth")
-        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), k, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None, None,
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), cap, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None, None,
                                           _lib.stream()), "mdir_topk_finalize")
+        if int(cnt.max().item()) > cap:               # too many exact ties at the kth score
+            r = ranks_from_scores(s, device=dev)[:k]
+            return r, torch.gather(s, 0, r)
     return out_i.t().contiguous().long(), out_s.t().contiguous()
 
 
