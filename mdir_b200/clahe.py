@@ -17,58 +17,58 @@ import torch
 from . import _lib
 
 
-def clahe_u8(images, clip_limit=4.0, grid=(8, 8), out=None):
-    """images: one (H,W) / (B,H,W) uint8 cuda tensor, or a list of (H,W) uint8 cuda tensors of
-    different sizes.  Returns the same structure.  grid = (tiles_x, tiles_y) like cv2."""
+_DESC_DTYPE = np.dtype([("src_off", np.int64), ("dst_off", np.int64), ("H", np.int32), ("W", np.int32),
+                        ("src_pitch", np.int32), ("dst_pitch", np.int32)])
+
+
+def _launch(sbase, dbase, descs_np, dev, max_h, max_w, clip_limit, grid):
     lib = _lib.lib()
-    single = False
-    batched_out = None
+    n = descs_np.shape[0]
+    descs_d = torch.from_numpy(descs_np.view(np.uint8).reshape(-1)).to(dev)
+    tiles_x, tiles_y = int(grid[0]), int(grid[1])
+    ws = torch.empty(lib.mdir_clahe_workspace_bytes(n, tiles_x, tiles_y), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdir_clahe_u8(ctypes.c_void_p(sbase), ctypes.c_void_p(dbase), _lib.ptr(descs_d), n, int(max_h), int(max_w),
+                                     float(clip_limit), tiles_x, tiles_y, _lib.ptr(ws), _lib.stream()), "mdir_clahe_u8")
+
+
+def clahe_u8(images, clip_limit=4.0, grid=(8, 8)):
+    """images: one (H,W) / (B,H,W) uint8 cuda tensor, or a list of (H,W) uint8 cuda tensors of
+    different sizes (one launch for the whole ragged batch).  Returns the same structure.
+    grid = (tiles_x, tiles_y) like cv2's tileGridSize."""
     if isinstance(images, torch.Tensor):
         _lib.require_cuda(images, "images")
-        if images.dtype != torch.uint8:
-            raise _lib.MdirError("clahe_u8 expects uint8")
-        if images.dim() == 2:
-            single = True
-            planes = [images]
-        elif images.dim() == 3:
-            planes = list(images)
-            if out is None and images.is_contiguous():
-                batched_out = torch.empty_like(images)
-                out = list(batched_out)
-        else:
-            raise _lib.MdirError("expected (H,W) or (B,H,W)")
-    else:
-        planes = list(images)
-        for p in planes:
-            _lib.require_cuda(p, "image")
-            if p.dtype != torch.uint8 or p.dim() != 2:
-                raise _lib.MdirError("clahe_u8 expects a list of (H,W) uint8 tensors")
+        if images.dtype != torch.uint8 or images.dim() not in (2, 3):
+            raise _lib.MdirError("clahe_u8 expects a uint8 (H,W) or (B,H,W) tensor")
+        x = images if images.dim() == 3 else images.unsqueeze(0)
+        if x.stride(2) != 1 or x.numel() == 0:
+            if x.numel() == 0:
+                raise _lib.MdirError("empty image")
+            x = x.contiguous()
+        B, H, W = x.shape
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+        descs = np.empty(B, dtype=_DESC_DTYPE)
+        descs["src_off"] = np.arange(B, dtype=np.int64) * x.stride(0)
+        descs["dst_off"] = np.arange(B, dtype=np.int64) * (H * W)
+        descs["H"], descs["W"], descs["src_pitch"], descs["dst_pitch"] = H, W, x.stride(1), W
+        _launch(x.data_ptr(), out.data_ptr(), descs, x.device, H, W, clip_limit, grid)
+        return out if images.dim() == 3 else out[0]
+    planes = list(images)
     if not planes:
         return []
+    for p in planes:
+        _lib.require_cuda(p, "image")
+        if p.dtype != torch.uint8 or p.dim() != 2 or p.numel() == 0:
+            raise _lib.MdirError("clahe_u8 expects a list of non-empty (H,W) uint8 tensors")
     planes = [p if p.stride(1) == 1 else p.contiguous() for p in planes]
     dev = planes[0].device
-    outs = [torch.empty((p.shape[0], p.shape[1]), dtype=torch.uint8, device=dev) for p in planes] if out is None else out
+    outs = [torch.empty((p.shape[0], p.shape[1]), dtype=torch.uint8, device=dev) for p in planes]
     sbase = min(p.data_ptr() for p in planes)
     dbase = min(o.data_ptr() for o in outs)
-    descs = (_lib.ImageDesc * len(planes))()
+    descs = np.empty(len(planes), dtype=_DESC_DTYPE)
     for i, (p, o) in enumerate(zip(planes, outs)):
-        if p.shape[0] < 1 or p.shape[1] < 1:
-            raise _lib.MdirError("empty image")
-        descs[i] = _lib.ImageDesc(p.data_ptr() - sbase, o.data_ptr() - dbase, p.shape[0], p.shape[1], p.stride(0), o.stride(0))
-    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
-    descs_d = raw.to(dev, non_blocking=False)
-    tiles_x, tiles_y = int(grid[0]), int(grid[1])
-    ws = torch.empty(lib.mdir_clahe_workspace_bytes(len(planes), tiles_x, tiles_y), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(lib.mdir_clahe_u8(ctypes.c_void_p(sbase), ctypes.c_void_p(dbase), _lib.ptr(descs_d), len(planes),
-                                     max(p.shape[0] for p in planes), max(p.shape[1] for p in planes), float(clip_limit),
-                                     tiles_x, tiles_y, _lib.ptr(ws), _lib.stream()), "mdir_clahe_u8")
-    if single:
-        return outs[0]
-    if batched_out is not None:
-        return batched_out
-    if isinstance(images, torch.Tensor):
-        return torch.stack(outs)
+        descs[i] = (p.data_ptr() - sbase, o.data_ptr() - dbase, p.shape[0], p.shape[1], p.stride(0), o.stride(0))
+    _launch(sbase, dbase, descs, dev, max(p.shape[0] for p in planes), max(p.shape[1] for p in planes), clip_limit, grid)
     return outs
 
 

@@ -1,14 +1,17 @@
 // CLAHE on batches of ragged 8UC1 images, bit-exact against cv2.createCLAHE(...).apply
 // (algorithm: SURVEY.md App. A; oracle/oracle.py:clahe_u8).
 //
-//  kernel 1  clahe_lut_kernel    one CTA per (tile, image): per-warp private uint32
-//            histograms in shared memory filled with warp-aggregated (match.any) updates,
-//            clip-limit redistribution, block scan, LUT = sat_u8(rint(cdf * 255/area)).
+//  kernel 1  clahe_lut_kernel    one CTA per (tile, image): the tile is read as aligned 16-byte
+//            chunks (4 in flight per thread), per-warp private uint32 histograms in shared memory
+//            updated with run-length-aggregated atomics, clip-limit redistribution, block scan,
+//            LUT = sat_u8(rint(cdf * 255/area)).
 //  kernel 2  clahe_interp_kernel one CTA per interpolation cell (the rectangle between four
 //            tile centres, where the four contributing LUTs are fixed): the four LUTs are
 //            interleaved into one uint32[256] table in shared memory so each pixel costs a
 //            single LDS; the bilinear blend uses individually rounded fp32 mul/add in
-//            OpenCV's association (no FMA contraction) and round-half-even.
+//            OpenCV's association (no FMA contraction) and round-half-even; a thread owns 8
+//            consecutive pixels (64-bit loads/stores, 4 rows in flight).
+//  The batch is processed in chunks of <= 48 MB of pixels so that pass 2 re-reads from L2.
 #include "common.cuh"
 
 namespace mdir {
@@ -38,6 +41,26 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+// run-length aggregated histogram update of the bytes [jlo, jhi) of a 16-byte chunk
+__device__ __forceinline__ void hist_chunk(uint32_t* h, const uint32_t (&w)[4], int jlo, int jhi) {
+    int prev = -1;
+    uint32_t run = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (j >= jlo && j < jhi) {
+            const int v = (int)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+            if (v == prev) {
+                ++run;
+            } else {
+                if (run) atomicAdd(&h[prev], run);
+                prev = v;
+                run = 1;
+            }
+        }
+    }
+    if (run) atomicAdd(&h[prev], run);
+}
+
 __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, const mdir_image_desc* __restrict__ descs,
                                                         double clip, int tiles_x, int tiles_y, uint8_t* __restrict__ luts) {
     __shared__ uint32_t whist[8][256];
@@ -55,17 +78,55 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     const uint8_t* base = src + d.src_off;
     const int x0 = tx * g.tw, y0 = ty * g.th;
     uint32_t* myh = whist[w];
-    for (int r = w; r < g.th; r += 8) {
-        const int sy = reflect101(y0 + r, d.H);
-        const uint8_t* row = base + (int64_t)sy * d.src_pitch;
-        for (int c0 = 0; c0 < g.tw; c0 += 32) {
-            const int c = c0 + lane;
-            const bool valid = c < g.tw;
-            int v = 256 + lane;                       // unique sentinel: never groups with a pixel value
-            if (valid) v = row[reflect101(x0 + c, d.W)];
-            const unsigned peers = __match_any_sync(0xffffffffu, v);
-            if (valid && lane == (__ffs(peers) - 1)) myh[v] += __popc(peers);   // leaders hold distinct bins
-            __syncwarp();
+    // columns [x0, x0 + vw) of the tile lie inside the image; the rest (right border tiles of
+    // images whose width is not a multiple of tiles_x) are BORDER_REFLECT_101 copies
+    const int vw = max(0, min(g.tw, d.W - x0));
+    if (vw > 0) {
+        // 16-byte chunks: cpr per tile row (rows start at arbitrary alignment), 4 loads in flight per thread
+        const int cpr = (vw + 15) / 16 + 1;
+        const int total = g.th * cpr;
+        for (int c0 = threadIdx.x; c0 < total; c0 += 4 * 256) {
+            uint32_t wv[4][4];
+            int jlo[4], jhi[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ci = c0 + u * 256;
+                jlo[u] = 0; jhi[u] = 0;
+                if (ci < total) {
+                    const int r = ci / cpr, c = ci - r * cpr;
+                    const uint8_t* rowp = base + (int64_t)reflect101(y0 + r, d.H) * d.src_pitch;
+                    const uint8_t* seg_lo = rowp + x0;
+                    const uint8_t* seg_hi = seg_lo + vw;
+                    const uint8_t* chunk = (const uint8_t*)((uintptr_t)seg_lo & ~(uintptr_t)15) + 16 * c;
+                    const uint8_t* lo = chunk > seg_lo ? chunk : seg_lo;
+                    const uint8_t* hi = chunk + 16 < seg_hi ? chunk + 16 : seg_hi;
+                    if (lo < hi) {
+                        jlo[u] = (int)(lo - chunk);
+                        jhi[u] = (int)(hi - chunk);
+                        if (chunk >= rowp && chunk + 16 <= rowp + d.W) {          // whole chunk inside this image row
+                            const uint4 q = *reinterpret_cast<const uint4*>(chunk);
+                            wv[u][0] = q.x; wv[u][1] = q.y; wv[u][2] = q.z; wv[u][3] = q.w;
+                        } else {
+                            wv[u][0] = wv[u][1] = wv[u][2] = wv[u][3] = 0u;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)          // compile-time indices keep wv in registers
+                                if (j >= jlo[u] && j < jhi[u]) wv[u][j >> 2] |= (uint32_t)chunk[j] << (8 * (j & 3));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (jlo[u] < jhi[u]) hist_chunk(myh, wv[u], jlo[u], jhi[u]);
+        }
+    }
+    const int rw = g.tw - vw;
+    if (rw > 0) {
+        const int total = g.th * rw;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int r = i / rw, c = vw + (i - r * rw);
+            const uint8_t* rowp = base + (int64_t)reflect101(y0 + r, d.H) * d.src_pitch;
+            atomicAdd(&myh[rowp[reflect101(x0 + c, d.W)]], 1u);
         }
     }
     __syncthreads();
@@ -131,8 +192,9 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     const int cy = cell / (tiles_x + 1), cx = cell - cy * (tiles_x + 1);
     const mdir_image_desc d = descs[img];
     const ClaheGeom g = clahe_geom(d.H, d.W, tiles_x, tiles_y);
-    // nominal pixel ranges of this cell: raw tile index floor(x/tw - 0.5) == cx - 1
-    const int margin = 2 + (max(g.tw, g.th) >> 8);
+    // nominal pixel ranges of this cell: raw tile index floor(x/tw - 0.5) == cx - 1.  The exact fp32
+    // boundary can differ from the nominal one by a pixel, hence the margin + the per-pixel ownership test.
+    const int margin = 1 + (max(g.tw, g.th) >> 9);
     int xs = (cx == 0) ? 0 : (((2 * cx - 1) * g.tw + 1) >> 1) - margin;
     int xe = (((2 * cx + 1) * g.tw + 1) >> 1) + margin;
     int ys = (cy == 0) ? 0 : (((2 * cy - 1) * g.th + 1) >> 1) - margin;
@@ -155,65 +217,85 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     const float inv_th = __fdiv_rn(1.0f, (float)g.th);
     const uint8_t* sbase = src + d.src_off;
     uint8_t* dbase = dst + d.dst_off;
-    const bool vec_ok = (((uintptr_t)sbase | (uintptr_t)dbase | (uintptr_t)d.src_pitch | (uintptr_t)d.dst_pitch) & 3) == 0;
+    const bool vec_ok = (((uintptr_t)sbase | (uintptr_t)dbase | (uintptr_t)d.src_pitch | (uintptr_t)d.dst_pitch) & 7) == 0;
 
-    const int gx = threadIdx.x & 31, gy = threadIdx.x >> 5;   // 32 x-groups of 4 pixels, 8 rows per pass
-    const int xs4 = xs & ~3;
-    for (int x4 = xs4 + gx * 4; x4 < xe; x4 += 128) {
-        // per-column weights for the 4 pixels of this group (reused over all rows)
-        float xa[4], xa1[4];
-        bool mine_x[4];
-        bool any_x = false, all_x = true;
+    // thread -> (group of 8 consecutive pixels, row slot); a thread keeps its x-group for all rows so the
+    // 8 column weights live in registers.  Groups are aligned to 8 in image coordinates.
+    const int xs8 = xs & ~7;
+    const int n_groups = (xe - xs8 + 7) >> 3;
+    const int gpp = min(n_groups, 256);                 // groups per pass
+    const int rows_pp = 256 / gpp;                      // rows per pass
+    const int gslot = threadIdx.x % gpp, rslot = threadIdx.x / gpp;
+    if (rslot >= rows_pp) return;
+    for (int g0 = gslot; g0 < n_groups; g0 += gpp) {
+        const int x8 = xs8 + g0 * 8;
+        float xa[8], xa1[8];
+        uint32_t mine = 0;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int x = x4 + e;
+        for (int e = 0; e < 8; ++e) {
+            const int x = x8 + e;
             const float txf = __fsub_rn(__fmul_rn((float)x, inv_tw), 0.5f);
             const float fl = floorf(txf);
             xa[e] = __fsub_rn(txf, fl);
             xa1[e] = __fsub_rn(1.0f, xa[e]);
-            mine_x[e] = (x >= xs) && (x < xe) && ((int)fl == cx - 1);
-            any_x |= mine_x[e];
-            all_x &= mine_x[e];
+            if (x >= xs && x < xe && (int)fl == cx - 1) mine |= 1u << e;
         }
-        if (!any_x) continue;
-        for (int y = ys + gy; y < ye; y += 8) {
-            const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-            const float fly = floorf(tyf);
-            if ((int)fly != cy - 1) continue;
-            const float ya = __fsub_rn(tyf, fly);
-            const float ya1 = __fsub_rn(1.0f, ya);
-            const uint8_t* srow = sbase + (int64_t)y * d.src_pitch;
-            uint8_t* drow = dbase + (int64_t)y * d.dst_pitch;
-            uint32_t pix;
-            const bool full = all_x && (x4 + 3 < d.W);
-            if (vec_ok && x4 + 3 < d.W) {
-                pix = *reinterpret_cast<const uint32_t*>(srow + x4);
-            } else {
-                pix = 0;
+        if (!mine) continue;
+        const bool in_row = x8 + 7 < d.W;
+        const bool full = (mine == 0xffu) && in_row;
+        for (int yb = ys + rslot; yb < ye; yb += 4 * rows_pp) {
+            uint2 pix[4];
+            // 4 row loads in flight
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (x4 + e < d.W) pix |= (uint32_t)srow[x4 + e] << (8 * e);
+            for (int u = 0; u < 4; ++u) {
+                const int y = yb + u * rows_pp;
+                pix[u] = make_uint2(0u, 0u);
+                if (y < ye) {
+                    const uint8_t* srow = sbase + (int64_t)y * d.src_pitch;
+                    if (vec_ok && in_row) {
+                        pix[u] = *reinterpret_cast<const uint2*>(srow + x8);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (x8 + e < d.W) {
+                                const uint32_t b = (uint32_t)srow[x8 + e] << (8 * (e & 3));
+                                if (e < 4) pix[u].x |= b; else pix[u].y |= b;
+                            }
+                    }
+                }
             }
-            uint32_t outw = 0;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const uint32_t l = lut4[(pix >> (8 * e)) & 0xffu];
-                const float l11 = u8_to_f32(l & 0xffu), l12 = u8_to_f32((l >> 8) & 0xffu);
-                const float l21 = u8_to_f32((l >> 16) & 0xffu), l22 = u8_to_f32(l >> 24);
-                const float top = __fadd_rn(__fmul_rn(l11, xa1[e]), __fmul_rn(l12, xa[e]));
-                const float bot = __fadd_rn(__fmul_rn(l21, xa1[e]), __fmul_rn(l22, xa[e]));
-                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-                // round-half-even via the 1.5*2^23 magic constant (0 <= res < 2^22)
-                int q = (int)(__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x3ffu);
-                q = min(q, 255);
-                outw |= (uint32_t)q << (8 * e);
-            }
-            if (vec_ok && full) {
-                *reinterpret_cast<uint32_t*>(drow + x4) = outw;
-            } else {
+            for (int u = 0; u < 4; ++u) {
+                const int y = yb + u * rows_pp;
+                if (y >= ye) continue;
+                const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+                const float fly = floorf(tyf);
+                if ((int)fly != cy - 1) continue;
+                const float ya = __fsub_rn(tyf, fly);
+                const float ya1 = __fsub_rn(1.0f, ya);
+                uint32_t outw[2] = {0u, 0u};
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (mine_x[e]) drow[x4 + e] = (uint8_t)(outw >> (8 * e));
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t pw = e < 4 ? pix[u].x : pix[u].y;
+                    const uint32_t l = lut4[(pw >> (8 * (e & 3))) & 0xffu];
+                    const float l11 = u8_to_f32(l & 0xffu), l12 = u8_to_f32((l >> 8) & 0xffu);
+                    const float l21 = u8_to_f32((l >> 16) & 0xffu), l22 = u8_to_f32(l >> 24);
+                    const float top = __fadd_rn(__fmul_rn(l11, xa1[e]), __fmul_rn(l12, xa[e]));
+                    const float bot = __fadd_rn(__fmul_rn(l21, xa1[e]), __fmul_rn(l22, xa[e]));
+                    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                    // round-half-even via the 1.5*2^23 magic constant (0 <= res < 2^22)
+                    int q = (int)(__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x3ffu);
+                    q = min(q, 255);
+                    outw[e >> 2] |= (uint32_t)q << (8 * (e & 3));
+                }
+                uint8_t* drow = dbase + (int64_t)y * d.dst_pitch;
+                if (vec_ok && full) {
+                    *reinterpret_cast<uint2*>(drow + x8) = make_uint2(outw[0], outw[1]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (mine & (1u << e)) drow[x8 + e] = (uint8_t)(outw[e >> 2] >> (8 * (e & 3)));
+                }
             }
         }
     }
@@ -234,13 +316,21 @@ extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_
     MDIR_CHECK_ARG(n_img >= 0 && n_img <= 65535);
     MDIR_CHECK_ARG(tiles_x >= 1 && tiles_y >= 1 && tiles_x * tiles_y <= 4096);
     MDIR_CHECK_ARG(max_H >= 1 && max_W >= 1);
-    (void)max_H; (void)max_W;
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* luts = (uint8_t*)ws;
-    clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n_img), 256, 0, st>>>(src, descs, clip, tiles_x, tiles_y, luts);
-    MDIR_LAUNCH_CHECK();
-    clahe_interp_kernel<<<dim3((tiles_x + 1) * (tiles_y + 1), n_img), 256, 0, st>>>(src, dst, descs, tiles_x, tiles_y, luts);
-    MDIR_LAUNCH_CHECK();
+    // Both passes read the source; processing the batch in chunks of <= ~48 MB of pixels lets the
+    // interpolation pass of a chunk hit L2 (126 MB) for the pixels its LUT pass just streamed.
+    const int64_t px = (int64_t)max_H * max_W;
+    int chunk = (int)((int64_t)48 * 1024 * 1024 / (px > 0 ? px : 1));
+    if (chunk < 1) chunk = 1;
+    for (int i0 = 0; i0 < n_img; i0 += chunk) {
+        const int n = (n_img - i0) < chunk ? (n_img - i0) : chunk;
+        uint8_t* l = luts + (size_t)i0 * tiles_x * tiles_y * 256;
+        clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n), 256, 0, st>>>(src, descs + i0, clip, tiles_x, tiles_y, l);
+        MDIR_LAUNCH_CHECK();
+        clahe_interp_kernel<<<dim3((tiles_x + 1) * (tiles_y + 1), n), 256, 0, st>>>(src, dst, descs + i0, tiles_x, tiles_y, l);
+        MDIR_LAUNCH_CHECK();
+    }
     return 0;
 }

@@ -12,12 +12,23 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     return r;
 }
 
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int KIND, bool P3>
 __device__ __forceinline__ float pool_elem(float x, float p, float eps) {
     if (KIND == MDIR_POOL_GEM) {
         float v = fmaxf(x, eps);
         if (P3) return v * v * v;
-        return exp2f(p * __log2f(v));          // MUFU.LG2 + MUFU.EX2 (v >= eps > 0)
+        return ex2_ftz(p * lg2_ftz(v));        // MUFU.LG2 + MUFU.EX2; v >= eps > 0 so no denormal handling needed
     }
     return x;
 }
@@ -25,59 +36,62 @@ template <int KIND>
 __device__ __forceinline__ float pool_comb(float a, float b) {
     return KIND == MDIR_POOL_MAC ? fmaxf(a, b) : a + b;
 }
+template <int KIND, bool P3>
+__device__ __forceinline__ float pool_elem4(float4 a, float p, float eps) {
+    return pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(a.x, p, eps), pool_elem<KIND, P3>(a.y, p, eps)),
+                           pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
+}
 
-// One warp per plane.  Planes of hw floats start at arbitrary 4-byte alignment (hw = 391
-// is common), so each plane is split into a scalar head up to the first 16-byte boundary,
-// an aligned float4 body and a scalar tail.
+// One warp per plane.  Planes of hw floats start at arbitrary 4-byte alignment (hw = 391 is
+// common), so each plane is split into a scalar head up to the first 16-byte boundary, an
+// aligned float4 body and a scalar tail.  All loads of a plane (head, tail and up to 8
+// predicated 128-bit body loads per lane = 1024 floats) are issued before any is consumed, so
+// a warp keeps up to 4 KB in flight and the pass is bandwidth- rather than latency-bound.
 template <int KIND, bool P3>
 __global__ void __launch_bounds__(256) pool_planes_kernel(const float* __restrict__ x, const int64_t* __restrict__ off,
                                                           const int32_t* __restrict__ hws, int n_maps, int C,
                                                           int hw_uniform, float p, float eps, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const int64_t n_planes = (int64_t)n_maps * C;
-    const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t plane = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); plane < n_planes;
-         plane += warps_total) {
-        const int map = (int)(plane / C);
-        const int c = (int)(plane - (int64_t)map * C);
+    const uint32_t n_planes = (uint32_t)n_maps * (uint32_t)C;
+    const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
+    const float ident = KIND == MDIR_POOL_MAC ? -INFINITY : 0.f;
+    for (uint32_t plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); plane < n_planes; plane += warps_total) {
         int hw;
         const float* src;
         if (off) {
-            hw = hws[map];
-            src = x + off[map] + (int64_t)c * hw;
+            const uint32_t map = plane / (uint32_t)C;
+            const uint32_t c = plane - map * (uint32_t)C;
+            hw = __ldg(hws + map);
+            src = x + __ldg(off + map) + (int64_t)c * hw;
         } else {
             hw = hw_uniform;
-            src = x + plane * (int64_t)hw;
+            src = x + (int64_t)plane * hw;
         }
-        float acc = KIND == MDIR_POOL_MAC ? -INFINITY : 0.f;
         int head = (int)(((16u - ((uint32_t)(uintptr_t)src & 15u)) & 15u) >> 2);
         head = min(head, hw);
-        if (lane < head) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(src[lane], p, eps));
         const int nbody = (hw - head) >> 2;
-        const float4* body = reinterpret_cast<const float4*>(src + head);
-        int i = lane;
-        // 4 independent 128-bit loads in flight per lane
-        for (; i + 96 < nbody; i += 128) {
-            float4 a = ldg_stream(body + i), b = ldg_stream(body + i + 32), cc = ldg_stream(body + i + 64),
-                   d = ldg_stream(body + i + 96);
-            float s0 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(a.x, p, eps), pool_elem<KIND, P3>(a.y, p, eps)),
-                                       pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
-            float s1 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(b.x, p, eps), pool_elem<KIND, P3>(b.y, p, eps)),
-                                       pool_comb<KIND>(pool_elem<KIND, P3>(b.z, p, eps), pool_elem<KIND, P3>(b.w, p, eps)));
-            float s2 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(cc.x, p, eps), pool_elem<KIND, P3>(cc.y, p, eps)),
-                                       pool_comb<KIND>(pool_elem<KIND, P3>(cc.z, p, eps), pool_elem<KIND, P3>(cc.w, p, eps)));
-            float s3 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(d.x, p, eps), pool_elem<KIND, P3>(d.y, p, eps)),
-                                       pool_comb<KIND>(pool_elem<KIND, P3>(d.z, p, eps), pool_elem<KIND, P3>(d.w, p, eps)));
-            acc = pool_comb<KIND>(acc, pool_comb<KIND>(pool_comb<KIND>(s0, s1), pool_comb<KIND>(s2, s3)));
-        }
-        for (; i < nbody; i += 32) {
-            float4 a = ldg_stream(body + i);
-            float s0 = pool_comb<KIND>(pool_comb<KIND>(pool_elem<KIND, P3>(a.x, p, eps), pool_elem<KIND, P3>(a.y, p, eps)),
-                                       pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
-            acc = pool_comb<KIND>(acc, s0);
-        }
         const int tail0 = head + (nbody << 2);
-        if (tail0 + lane < hw) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(src[tail0 + lane], p, eps));
+        const float4* body = reinterpret_cast<const float4*>(src + head);
+        const bool has_head = lane < head, has_tail = tail0 + lane < hw;
+        float hv = 0.f, tv = 0.f;
+        if (has_head) hv = __ldg(src + lane);
+        if (has_tail) tv = __ldg(src + tail0 + lane);
+        float acc = ident;
+        for (int j0 = 0; j0 < nbody; j0 += 256) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = j0 + u * 32 + lane;
+                if (i < nbody) v[u] = ldg_stream(body + i);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = j0 + u * 32 + lane;
+                if (i < nbody) acc = pool_comb<KIND>(acc, pool_elem4<KIND, P3>(v[u], p, eps));
+            }
+        }
+        if (has_head) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(hv, p, eps));
+        if (has_tail) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(tv, p, eps));
         acc = KIND == MDIR_POOL_MAC ? warp_max(acc) : warp_sum(acc);
         if (lane == 0) {
             float r = acc;
@@ -189,35 +203,63 @@ __global__ void __launch_bounds__(256) whiten_gemv_kernel(const float* __restric
     }
 }
 
-// Batched projection out(n, dims) = V(n, D) * P(dims, D)^T, fp32 CUDA-core tiles
-// (64 x 64 x 16, 4x4 per thread).  P is re-read once per 64 images: negligible next to
-// the feature-map stream that produced V.
-__global__ void __launch_bounds__(256) whiten_sgemm_kernel(const float* __restrict__ V, const float* __restrict__ m, int n, int D,
-                                                           const float* __restrict__ P, int dims, float* __restrict__ out) {
-    __shared__ float sV[16][64 + 4];
-    __shared__ float sP[16][64 + 4];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int n0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+// Batched projection out(n, dims) = (V(n, D) - m) * P(dims, D)^T, fp32 CUDA-core tiles:
+// BM (images) x 64 (output dims) x 16 (k) per CTA, 4x4 outputs per thread, 128-bit global and
+// shared-memory accesses.  BM = 32 for small batches so the grid still covers the 148 SMs.
+// P is re-read once per BM images: negligible next to the feature-map stream that produced V.
+template <int BM>
+__global__ void __launch_bounds__(BM * 4) whiten_sgemm_kernel(const float* __restrict__ V, const float* __restrict__ m, int n, int D,
+                                                              const float* __restrict__ P, int dims, float* __restrict__ out) {
+    __shared__ __align__(16) float sV[16][BM + 4];
+    __shared__ __align__(16) float sP[16][64 + 4];
+    constexpr int kThreads = BM * 4;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // tx -> 4 output dims, ty -> 4 images
+    const int n0 = blockIdx.y * BM, j0 = blockIdx.x * 64;
+    const bool vec = (D & 3) == 0;
     float acc[4][4] = {};
     for (int k0 = 0; k0 < D; k0 += 16) {
-        // each thread loads 4 elements of each tile: row r = tid/4 (0..63), k = (tid%4)*4..+3
-        const int r = threadIdx.x >> 2, kk = (threadIdx.x & 3) << 2;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int k = k0 + kk + e;
-            sV[kk + e][r] = (n0 + r < n && k < D) ? V[(int64_t)(n0 + r) * D + k] - (m ? m[k] : 0.f) : 0.f;
-            sP[kk + e][r] = (j0 + r < dims && k < D) ? P[(int64_t)(j0 + r) * D + k] : 0.f;
+        // tile loads: one float4 along k per (row, k-quad); BM*4 quads for V, 256 quads for P
+        for (int t = threadIdx.x; t < BM * 4; t += kThreads) {
+            const int r = t >> 2, kk = (t & 3) << 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + r < n) {
+                const float* src = V + (int64_t)(n0 + r) * D + k0 + kk;
+                if (vec && k0 + kk + 3 < D) {
+                    v = *reinterpret_cast<const float4*>(src);
+                    if (m) { const float4 mm = *reinterpret_cast<const float4*>(m + k0 + kk); v.x -= mm.x; v.y -= mm.y; v.z -= mm.z; v.w -= mm.w; }
+                } else {
+                    float* pv = &v.x;
+                    for (int e = 0; e < 4; ++e)
+                        if (k0 + kk + e < D) pv[e] = src[e] - (m ? m[k0 + kk + e] : 0.f);
+                }
+            }
+            sV[kk + 0][r] = v.x; sV[kk + 1][r] = v.y; sV[kk + 2][r] = v.z; sV[kk + 3][r] = v.w;
+        }
+        for (int t = threadIdx.x; t < 64 * 4; t += kThreads) {
+            const int r = t >> 2, kk = (t & 3) << 2;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + r < dims) {
+                const float* src = P + (int64_t)(j0 + r) * D + k0 + kk;
+                if (vec && k0 + kk + 3 < D) {
+                    v = ldg_stream(reinterpret_cast<const float4*>(src));
+                } else {
+                    float* pv = &v.x;
+                    for (int e = 0; e < 4; ++e)
+                        if (k0 + kk + e < D) pv[e] = src[e];
+                }
+            }
+            sP[kk + 0][r] = v.x; sP[kk + 1][r] = v.y; sP[kk + 2][r] = v.z; sP[kk + 3][r] = v.w;
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-            float a[4], b[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sV[k][ty * 4 + i]; b[i] = sP[k][tx * 4 + i]; }
+            const float4 a = *reinterpret_cast<const float4*>(&sV[k][ty * 4]);
+            const float4 b = *reinterpret_cast<const float4*>(&sP[k][tx * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
         }
         __syncthreads();
     }
@@ -241,11 +283,12 @@ extern "C" int mdir_pool(int kind, const float* x, const int64_t* off, const int
     MDIR_CHECK_ARG((off == nullptr) == (hw == nullptr));
     MDIR_CHECK_ARG(off != nullptr || hw_uniform > 0);
     MDIR_CHECK_ARG(((uintptr_t)x & 3) == 0);
+    MDIR_CHECK_ARG((int64_t)n_maps * C < ((int64_t)1 << 31));
     if (n_maps == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_planes = (int64_t)n_maps * C;
     const int64_t blocks_needed = (n_planes + 7) / 8;
-    const int grid = (int)(blocks_needed < (int64_t)kNumSMs * 64 ? blocks_needed : (int64_t)kNumSMs * 64);
+    const int grid = (int)(blocks_needed < (int64_t)kNumSMs * 32 ? blocks_needed : (int64_t)kNumSMs * 32);
     if (kind == MDIR_POOL_GEM) {
         MDIR_CHECK_ARG(p > 0.f || p < 0.f);
         if (p == 3.0f)
@@ -299,8 +342,12 @@ extern "C" int mdir_whiten_project(const float* v, const float* m, int n, int D,
             default: whiten_gemv_kernel<4><<<grid, 256, 0, st>>>(v, m, D, P, dims, out); break;
         }
     } else {
-        dim3 grid((dims + 63) / 64, (n + 63) / 64);
-        whiten_sgemm_kernel<<<grid, 256, 0, st>>>(v, m, n, D, P, dims, out);
+        const int jt = (dims + 63) / 64;
+        if ((int64_t)jt * ((n + 63) / 64) >= 2 * kNumSMs) {
+            whiten_sgemm_kernel<64><<<dim3(jt, (n + 63) / 64), 256, 0, st>>>(v, m, n, D, P, dims, out);
+        } else {
+            whiten_sgemm_kernel<32><<<dim3(jt, (n + 31) / 32), 128, 0, st>>>(v, m, n, D, P, dims, out);
+        }
     }
     MDIR_LAUNCH_CHECK();
     if (renorm_eps >= 0.f) {

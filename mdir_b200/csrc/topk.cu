@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
     const int lane = threadIdx.x & 31;
     const float* sc = scores + (int64_t)q * ld;
     uint32_t result;
-    const int64_t n_round = (n + 1023) & ~(int64_t)1023;
+    const int64_t n_round = (n + 8191) & ~(int64_t)8191;
     if ((int64_t)kth > n) {
         result = 0xffffffffu;
     } else {
@@ -71,14 +71,25 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
             __syncthreads();
             const uint32_t prefix = s_prefix;
             const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-            for (int64_t i = threadIdx.x; i < n_round; i += 1024) {
-                const bool valid = i < n;
-                const uint32_t key = valid ? ~orderable(sc[i]) : 0u;
-                const bool hit = valid && ((key & himask) == prefix);
-                if (__any_sync(0xffffffffu, hit)) {
-                    const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
-                    const unsigned peers = __match_any_sync(0xffffffffu, d);
-                    if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+            // 8 independent loads in flight per thread (the row is L2-resident; latency-bound otherwise)
+            for (int64_t base = 0; base < n_round; base += 8 * 1024) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t i = base + u * 1024 + threadIdx.x;
+                    v[u] = i < n ? __ldg(sc + i) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t i = base + u * 1024 + threadIdx.x;
+                    const bool valid = i < n;
+                    const uint32_t key = ~orderable(v[u]);
+                    const bool hit = valid && ((key & himask) == prefix);
+                    if (__any_sync(0xffffffffu, hit)) {
+                        const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
+                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+                    }
                 }
             }
             __syncthreads();
@@ -96,11 +107,20 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
     }
     if (threadIdx.x == 0) tau[q] = ((uint64_t)result << 32) | 0xffffffffull;
     if (cand) {
-        for (int64_t i = threadIdx.x; i < n; i += 1024) {
-            const float v = sc[i];
-            if (~orderable(v) <= result) {
-                const uint32_t pos = atomicAdd(&cand_count[q], 1u);
-                if (pos < (uint32_t)cap) cand[(int64_t)q * cap + pos] = make_key(v, sample_pos_to_idx(i, sample_stride, idx_base));
+        for (int64_t base = 0; base < n_round; base += 8 * 1024) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = base + u * 1024 + threadIdx.x;
+                v[u] = i < n ? __ldg(sc + i) : -INFINITY;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t i = base + u * 1024 + threadIdx.x;
+                if (i < n && ~orderable(v[u]) <= result) {
+                    const uint32_t pos = atomicAdd(&cand_count[q], 1u);
+                    if (pos < (uint32_t)cap) cand[(int64_t)q * cap + pos] = make_key(v[u], sample_pos_to_idx(i, sample_stride, idx_base));
+                }
             }
         }
     }

@@ -24,7 +24,7 @@ TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries resident per scan pass
 CAND_CAP = 8192       # per-query candidate list capacity (keys)
 MAX_SAMPLE_TILES = 512
-TARGET_CAND = 3000    # expected candidates per query the sampling plan aims for (kth * n_tiles / n_sample)
+TARGET_CAND = 5500    # expected candidates per query the sampling plan aims for (kth * n_tiles / n_sample)
 
 
 def _as_dev_f32(x, device):
@@ -338,6 +338,18 @@ class ShardedIndex:
         self.local = Index(local_vecs, dxn=dxn, device=device, keep_fp32=keep_fp32, idx_base=idx_base)
         self.device = self.local.device
 
+    @classmethod
+    def from_local(cls, local_index, group=None):
+        """Wrap an already-built local shard (its idx_base = first global row it owns)."""
+        import torch.distributed as dist
+        self = cls.__new__(cls)
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = local_index
+        self.device = local_index.device
+        return self
+
     @staticmethod
     def shard_bounds(n_total, world, rank):
         per = (n_total + world - 1) // world
@@ -400,3 +412,50 @@ def merge_keys_host(gathered, k):
     world, nq, kk = g.shape
     allk = np.transpose(g, (1, 0, 2)).reshape(nq, world * kk)
     return np.sort(allk, axis=1)[:, :k]
+
+
+class GraphedSearch:
+    """One search step captured in a CUDA graph (CUDA streams and graphs instead of per-call
+    launches): static query buffer in, static (scores, idx) out.  Works for an Index or a
+    ShardedIndex (the NCCL all-gather of keys is captured too).  Every replay re-runs the whole
+    chain: bf16 packing of the queries, sample scan, threshold select, filter scan, finalize,
+    [fp32 re-scoring, finalize], [all-gather, merge].
+
+        gs = GraphedSearch(index, n_q=70, k=100)
+        scores, idx = gs(q)            # q: (70, D) fp32, host (pinned) or device
+        gs.check_overflow()            # after a sync: True -> rerun through index.search()
+    """
+
+    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None):
+        self.index = index
+        self.local = index.local if isinstance(index, ShardedIndex) else index
+        dev = self.local.device
+        self.k, self.precision, self.shortlist = int(k), precision, shortlist
+        self.q = torch.zeros((n_q, self.local.D), dtype=torch.float32, device=dev)
+        self.local.prof = None
+
+        def step():
+            return index.search(self.q, self.k, precision=self.precision, shortlist=self.shortlist, check=False)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(3):                      # warm-up: workspaces, function attributes, NCCL channels
+                    step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.local.prof = prof
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = step()
+            self.local.prof = None
+
+    def __call__(self, q=None):
+        if q is not None:
+            self.q.copy_(q, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+    def check_overflow(self):
+        return self.local.check_overflow()

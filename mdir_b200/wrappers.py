@@ -138,6 +138,14 @@ def whitenapply(X, m, P, dimensions=None, device="cuda"):
     return np.ascontiguousarray(out.cpu().numpy().T).astype(np.asarray(X).dtype, copy=False)
 
 
+class PackedMaps:
+    """Device-side description of a ragged batch of feature maps (see RetrievalHead.pack)."""
+
+    def __init__(self, base, off, hw, n_maps, C, device, keepalive=None):
+        self.base, self.off, self.hw, self.n_maps, self.C, self.device = base, off, hw, n_maps, C, device
+        self._keepalive = keepalive
+
+
 class RetrievalHead:
     """Batched post-backbone head for B images x S scales:
     pool (GeM/MAC/SPoC) -> L2N -> multi-scale aggregation (msp rule) -> [Lw centre + project +
@@ -161,18 +169,11 @@ class RetrievalHead:
             self.m = torch.tensor(lw['m'], dtype=torch.float32, device=self.device).reshape(-1).contiguous()
             self.dimensions = dimensions or self.P.shape[0]
 
-    def pool_maps(self, fmaps):
-        """fmaps: flat list of (1,C,h,w)/(C,h,w) fp32 cuda tensors (image-major, scale-minor),
-        or one packed (n_maps, C, h, w) tensor.  -> (n_maps, C)."""
-        lib = _lib.lib()
-        if isinstance(fmaps, torch.Tensor):
-            x = _lib.require_cuda(fmaps, "fmaps").contiguous()
-            n_maps, Cc = x.shape[0], x.shape[1]
-            out = torch.empty((n_maps, Cc), dtype=torch.float32, device=x.device)
-            with torch.cuda.device(x.device):
-                _lib.check(lib.mdir_pool(self.kind, _lib.ptr(x), None, None, n_maps, Cc, x.shape[2] * x.shape[3], self.p, self.eps,
-                                         _lib.ptr(out), _lib.stream()), "mdir_pool")
-            return out
+    def pack(self, fmaps):
+        """Describe a ragged set of feature maps once: flat list of (1,C,h,w)/(C,h,w) fp32 cuda
+        tensors (image-major, scale-minor) -> PackedMaps (device offset / size tables).  The maps
+        are NOT copied; the table stays valid as long as the tensors keep their storage (e.g. a
+        pre-allocated arena the backbone writes into)."""
         maps = []
         for f in fmaps:
             _lib.require_cuda(f, "fmap")
@@ -185,12 +186,25 @@ class RetrievalHead:
         off = torch.tensor([(f.data_ptr() - base) // 4 for f in maps], dtype=torch.int64)
         hw = torch.tensor([f.shape[1] * f.shape[2] for f in maps], dtype=torch.int32)
         dev = maps[0].device
-        off_d = off.to(dev, non_blocking=True)
-        hw_d = hw.to(dev, non_blocking=True)
-        out = torch.empty((len(maps), Cc), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        return PackedMaps(base, off.to(dev), hw.to(dev), len(maps), Cc, dev, maps)
+
+    def pool_maps(self, fmaps):
+        """fmaps: PackedMaps, a flat list of tensors (packed on the fly), or one uniform
+        (n_maps, C, h, w) tensor.  -> (n_maps, C) pooled (not yet normalised)."""
+        lib = _lib.lib()
+        if isinstance(fmaps, torch.Tensor):
+            x = _lib.require_cuda(fmaps, "fmaps").contiguous()
+            n_maps, Cc = x.shape[0], x.shape[1]
+            out = torch.empty((n_maps, Cc), dtype=torch.float32, device=x.device)
+            with torch.cuda.device(x.device):
+                _lib.check(lib.mdir_pool(self.kind, _lib.ptr(x), None, None, n_maps, Cc, x.shape[2] * x.shape[3], self.p, self.eps,
+                                         _lib.ptr(out), _lib.stream()), "mdir_pool")
+            return out
+        pm = fmaps if isinstance(fmaps, PackedMaps) else self.pack(fmaps)
+        out = torch.empty((pm.n_maps, pm.C), dtype=torch.float32, device=pm.device)
+        with torch.cuda.device(pm.device):
             import ctypes
-            _lib.check(lib.mdir_pool(self.kind, ctypes.c_void_p(base), _lib.ptr(off_d), _lib.ptr(hw_d), len(maps), Cc, 0, self.p,
+            _lib.check(lib.mdir_pool(self.kind, ctypes.c_void_p(pm.base), _lib.ptr(pm.off), _lib.ptr(pm.hw), pm.n_maps, pm.C, 0, self.p,
                                      self.eps, _lib.ptr(out), _lib.stream()), "mdir_pool")
         return out
 

@@ -363,6 +363,21 @@ def test_r1m_full_size_properties(m):
     assert (s32 - s).abs().max().item() < 2e-3                   # bf16 scores within the stated tolerance
 
 
+def test_graphed_search_replays(m):
+    from mdir_b200.search import GraphedSearch
+    db = synth.descriptors(40000, 128, 71, clusters=100)
+    index = m.Index(db, device=DEV)
+    gs = GraphedSearch(index, n_q=70, k=100)
+    for seed in (1, 2, 3):
+        q, src = synth.planted_queries(db, 70, seed)
+        s, i = gs(torch.from_numpy(q).pin_memory())
+        torch.cuda.synchronize()
+        assert not gs.check_overflow()
+        s2, i2 = index.search(q, 100)
+        assert torch.equal(i, i2) and torch.equal(s, s2)
+        assert np.array_equal(i.cpu().numpy()[:, 0], src)
+
+
 # ------------------------------------------------------------------ alpha-QE / DBA (parity unpinned: vs the restated definitions)
 def test_qe_and_dba(m):
     from mdir_b200 import qe

@@ -196,7 +196,7 @@ static void test_ranks(int64_t n_db, int n_q, bool ties) {
 static void bench_big() {
     const int64_t n_db = 1001001; const int n_q = 70, D = 2048, k = 200, cap = 8192;
     const int n_tiles = (int)((n_db + 255) / 256);
-    const int n_sample = 296, stride = n_tiles / n_sample;
+    const int n_sample = 143, stride = n_tiles / n_sample;
     __nv_bfloat16 *d_db, *d_q;
     CK(cudaMalloc(&d_db, (size_t)n_db * D * 2)); CK(cudaMalloc(&d_q, (size_t)n_q * D * 2));
     fill_bf16<<<(unsigned)(((int64_t)n_db * D + 255) / 256), 256>>>(d_db, (int64_t)n_db * D, 1u);
