@@ -301,10 +301,13 @@ def run_ours(args):
     torch.cuda.synchronize()
     bf16_ms = e2[0].elapsed_time(e2[1]) / n_b
 
+    per_rank = None
     if world > 1:
-        t = torch.tensor([ms_total, e2e_s, scan_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, scan_ms = [float(x) for x in t.tolist()]
+        mine = torch.tensor([ms_total, e2e_s, scan_ms], dtype=torch.float64, device=dev)
+        allr = torch.empty((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr.view(-1), mine)
+        per_rank = {"ms_total": allr[:, 0].tolist(), "e2e_s": allr[:, 1].tolist(), "scan_ms": allr[:, 2].tolist()}
+        ms_total, e2e_s, scan_ms = [float(x) for x in allr.max(dim=0).values.tolist()]
 
     # ---- sanity: planted result is self-consistent with an exact recomputation -------------------
     s_chk, i_chk = step_device()
@@ -319,9 +322,7 @@ def run_ours(args):
         extras = side_measurements(torch, mdir_b200, dev)
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        finish(dist, world)
         return
 
     peak, peak_src = measured_peaks()
@@ -354,11 +355,25 @@ def run_ours(args):
     if world == 1:
         cb = cpu_reference(args.cpu_rows, 3)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if per_rank is not None:
+        line["per_rank"] = per_rank
     line.update(extras)
     print(json.dumps(line))
+    sys.stdout.flush()
+    finish(dist, world)
+
+
+def finish(dist, world):
+    """Multi-rank exit: barrier, then leave without tearing NCCL down (communicators referenced by
+    captured CUDA graphs make destroy_process_group() block)."""
     if world > 1:
+        import torch
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def side_measurements(torch, mdir_b200, dev):

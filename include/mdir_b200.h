@@ -105,38 +105,48 @@ int mdir_pack_bf16(const float* src, int64_t n, int D, int src_is_Dxn, uint16_t*
  *   mode MDIR_SCAN_SAMPLE  : only tiles t = j*sample_stride (j < n_sample), written
  *                            compactly: out[q * dense_ld + j*256 + r]
  *   mode MDIR_SCAN_FILTER  : all tiles EXCEPT the sample tiles (n_sample may be 0);
- *                            a score is appended to cand[q] iff its 64-bit key
- *                            (mdir key order: score desc, index asc) <= tau[q].
- * cand: (n_q, cap) u64 keys, cand_count: (n_q) u32 (caller zeroes it; counts may
- * exceed cap -- entries beyond cap are dropped and the caller must re-threshold).
+ *                            a score is appended to the query's candidates iff its 64-bit
+ *                            key (mdir key order: score desc, index asc) <= tau[q].
+ * Candidate storage (no global atomics: every producer owns a segment):
+ *   cand       (n_q, cap_s + 148*cap_l) u64 keys; per query, segment 0 = [0, cap_s) belongs
+ *              to mdir_select_kth, segment 1+c = [cap_s + c*cap_l, +cap_l) to scan CTA c
+ *   seg_counts (n_q, MDIR_CAND_SEGS) u32: how many keys each producer appended (may exceed
+ *              the segment capacity: the surplus was dropped, mdir_topk_finalize reports
+ *              overflow and a tightened tau, and the caller re-scans).  Caller zeroes it.
  * Keys carry idx_base + row so shards emit global indices.                      */
 #define MDIR_SCAN_DENSE  0
 #define MDIR_SCAN_SAMPLE 1
 #define MDIR_SCAN_FILTER 2
 #define MDIR_SCAN_TILE_ROWS 256
+#define MDIR_CAND_SEGS 149
 int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
                        int mode, int sample_stride, int n_sample,
                        float* dense_out, int64_t dense_ld,
                        const uint64_t* tau, uint32_t idx_base,
-                       uint64_t* cand, uint32_t* cand_count, int cap, void* stream);
+                       uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream);
 
 /* key helpers exposed for tests: key = (~orderable(score) << 32) | index        */
 uint64_t mdir_make_key(float score, uint32_t index);
 float    mdir_key_score(uint64_t key);
 
-/* For each query: tau[q] = the kth-smallest key among scores[q*ld + i], i < n
- * (index part of the key = pos_to_idx(i): i itself, or for a compact sample
- * ((i/256)*sample_stride)*256 + i%256, plus idx_base); the kth best items are
- * also appended to cand[q] (cand_count advanced) when cand != NULL.             */
+/* For each query: radix-select the kth best (score desc, index asc) key among
+ * scores[q*ld + i], i < n, and set tau[q] to it (exactly kth rows have key <= tau).
+ * The index part of a key = pos_to_idx(i): i itself, or for a compact sample
+ * ((i/256)*sample_stride)*256 + i%256, plus idx_base.  When cand != NULL the kth items
+ * with key <= tau are written to segment 0 of the query's cand row (row pitch cand_row
+ * keys, capacity cap) and seg_counts[q*n_seg + 0] is set to their number.        */
 int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth,
                     int sample_stride, uint32_t idx_base,
-                    uint64_t* tau, uint64_t* cand, uint32_t* cand_count, int cap, void* stream);
+                    uint64_t* tau, uint64_t* cand, int64_t cand_row, uint32_t* seg_counts, int n_seg,
+                    int cap, void* stream);
 
-/* For each query: sort min(count, cap) candidate keys, emit the best k as
- * (score fp32, index int32) rows of out_*(n_q, k) (padded with -inf / -1), and set
- * overflow[q] = 1 and tau[q] = kth key of what was kept when count > cap.
- * Also the shard merge: feed it the all-gathered (n_q, G*k) keys.               */
-int mdir_topk_finalize(const uint64_t* cand, const uint32_t* cand_count, int cap, int n_q, int k,
+/* For each query: gather the candidate keys of its n_seg segments (segment 0 holds up to
+ * cap0 keys, the others cap_l each), emit the best k as (score fp32, index int32) rows of
+ * out_*(n_q, k) (padded with -inf / -1), and set overflow[q] = 1 and tau[q] = kth key of
+ * what was kept when a segment (or the 16384-key staging area) overflowed.
+ * Also the shard merge and the post-rescoring sort: n_seg = 1, cap0 = keys per query.  */
+int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg,
+                       int cap0, int cap_l, int n_q, int k,
                        float* out_scores, int32_t* out_idx, uint64_t* out_keys,
                        uint64_t* tau, int32_t* overflow, void* stream);
 

@@ -3,12 +3,13 @@
 //
 //  kernel 1  clahe_lut_kernel    one CTA per (tile, image): the tile is read as aligned 16-byte
 //            chunks (4 in flight per thread), per-warp private uint32 histograms in shared memory
-//            updated with run-length-aggregated atomics, clip-limit redistribution, block scan,
+//            updated with run-length-aggregated atomics (per-lane byte counters were tried and
+//            lost to their own zero/flush traffic), clip-limit redistribution, block scan,
 //            LUT = sat_u8(rint(cdf * 255/area)).
 //  kernel 2  clahe_interp_kernel one CTA per interpolation cell (the rectangle between four
 //            tile centres, where the four contributing LUTs are fixed): the four LUTs are
-//            interleaved into one uint32[256] table in shared memory so each pixel costs a
-//            single LDS; the bilinear blend uses individually rounded fp32 mul/add in
+//            interleaved into one float4[256] table in shared memory so each pixel costs a
+//            single LDS.128; the bilinear blend uses individually rounded fp32 mul/add in
 //            OpenCV's association (no FMA contraction) and round-half-even; a thread owns 8
 //            consecutive pixels (64-bit loads/stores, 4 rows in flight).
 //  The batch is processed in chunks of <= 48 MB of pixels so that pass 2 re-reads from L2.
@@ -179,14 +180,10 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     luts[(((int64_t)img * tiles_y + ty) * tiles_x + tx) * 256 + i] = (uint8_t)q;
 }
 
-__device__ __forceinline__ float u8_to_f32(uint32_t b) {   // exact, avoids the quarter-rate I2F
-    return __fadd_rn(__uint_as_float(0x4B000000u | b), -8388608.0f);
-}
-
 __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                            const mdir_image_desc* __restrict__ descs, int tiles_x, int tiles_y,
                                                            const uint8_t* __restrict__ luts) {
-    __shared__ uint32_t lut4[256];
+    __shared__ float4 lutf[256];          // the four contributing LUTs, pre-converted: one LDS.128 per pixel
     const int img = blockIdx.y;
     const int cell = blockIdx.x;
     const int cy = cell / (tiles_x + 1), cx = cell - cy * (tiles_x + 1);
@@ -208,8 +205,8 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
         const int tx1 = max(cx - 1, 0), tx2 = min(cx, tiles_x - 1);
         const uint8_t* L = luts + (int64_t)img * tiles_y * tiles_x * 256;
         const int v = threadIdx.x;
-        lut4[v] = (uint32_t)L[(ty1 * tiles_x + tx1) * 256 + v] | ((uint32_t)L[(ty1 * tiles_x + tx2) * 256 + v] << 8) |
-                  ((uint32_t)L[(ty2 * tiles_x + tx1) * 256 + v] << 16) | ((uint32_t)L[(ty2 * tiles_x + tx2) * 256 + v] << 24);
+        lutf[v] = make_float4((float)L[(ty1 * tiles_x + tx1) * 256 + v], (float)L[(ty1 * tiles_x + tx2) * 256 + v],
+                              (float)L[(ty2 * tiles_x + tx1) * 256 + v], (float)L[(ty2 * tiles_x + tx2) * 256 + v]);
     }
     __syncthreads();
 
@@ -277,15 +274,12 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const uint32_t pw = e < 4 ? pix[u].x : pix[u].y;
-                    const uint32_t l = lut4[(pw >> (8 * (e & 3))) & 0xffu];
-                    const float l11 = u8_to_f32(l & 0xffu), l12 = u8_to_f32((l >> 8) & 0xffu);
-                    const float l21 = u8_to_f32((l >> 16) & 0xffu), l22 = u8_to_f32(l >> 24);
-                    const float top = __fadd_rn(__fmul_rn(l11, xa1[e]), __fmul_rn(l12, xa[e]));
-                    const float bot = __fadd_rn(__fmul_rn(l21, xa1[e]), __fmul_rn(l22, xa[e]));
+                    const float4 l = lutf[(pw >> (8 * (e & 3))) & 0xffu];
+                    const float top = __fadd_rn(__fmul_rn(l.x, xa1[e]), __fmul_rn(l.y, xa[e]));
+                    const float bot = __fadd_rn(__fmul_rn(l.z, xa1[e]), __fmul_rn(l.w, xa[e]));
                     const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-                    // round-half-even via the 1.5*2^23 magic constant (0 <= res < 2^22)
-                    int q = (int)(__float_as_uint(__fadd_rn(res, 12582912.0f)) & 0x3ffu);
-                    q = min(q, 255);
+                    // round-half-even via the 1.5*2^23 magic constant; 0 <= res < 255.5 so the byte cannot wrap
+                    const uint32_t q = __float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu;
                     outw[e >> 2] |= (uint32_t)q << (8 * (e & 3));
                 }
                 uint8_t* drow = dbase + (int64_t)y * d.dst_pitch;
@@ -319,6 +313,7 @@ extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* luts = (uint8_t*)ws;
+
     // Both passes read the source; processing the batch in chunks of <= ~48 MB of pixels lets the
     // interpolation pass of a chunk hit L2 (126 MB) for the pixels its LUT pass just streamed.
     const int64_t px = (int64_t)max_H * max_W;

@@ -42,41 +42,62 @@ __device__ __forceinline__ float pool_elem4(float4 a, float p, float eps) {
                            pool_comb<KIND>(pool_elem<KIND, P3>(a.z, p, eps), pool_elem<KIND, P3>(a.w, p, eps)));
 }
 
-// One warp per plane.  Planes of hw floats start at arbitrary 4-byte alignment (hw = 391 is
-// common), so each plane is split into a scalar head up to the first 16-byte boundary, an
-// aligned float4 body and a scalar tail.  All loads of a plane (head, tail and up to 8
-// predicated 128-bit body loads per lane = 1024 floats) are issued before any is consumed, so
-// a warp keeps up to 4 KB in flight and the pass is bandwidth- rather than latency-bound.
-template <int KIND, bool P3>
+// One warp per UNIT of G consecutive planes of one map (G = 4 when C % 4 == 0, else 1).  The G
+// planes are contiguous in memory, so the warp streams them as ONE run of G*hw floats: a scalar
+// head up to the first 16-byte boundary, aligned float4 chunks (up to 8 per lane in flight = 4 KB
+// per warp), a scalar tail.  A chunk almost always lies inside a single plane (its plane id costs
+// three compares); the <= 3 chunks per unit that straddle a plane boundary take a per-element path.
+// Per-plane fixed costs (address math, reduction, final pow) are shared by the G planes, which is
+// what keeps the instruction stream below the HBM time for small planes (16x12 = 192 floats).
+template <int KIND, int G>
+__device__ __forceinline__ void acc_add(float (&acc)[G], int pid, float v) {
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+        if (G == 1 || pid == g) acc[g] = pool_comb<KIND>(acc[g], v);
+}
+
+template <int KIND, bool P3, int G>
 __global__ void __launch_bounds__(256) pool_planes_kernel(const float* __restrict__ x, const int64_t* __restrict__ off,
                                                           const int32_t* __restrict__ hws, int n_maps, int C,
                                                           int hw_uniform, float p, float eps, float* __restrict__ out) {
     const int lane = threadIdx.x & 31;
-    const uint32_t n_planes = (uint32_t)n_maps * (uint32_t)C;
+    const uint32_t units_per_map = (uint32_t)C / G;
+    const uint32_t n_units = (uint32_t)n_maps * units_per_map;
     const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
     const float ident = KIND == MDIR_POOL_MAC ? -INFINITY : 0.f;
-    for (uint32_t plane = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); plane < n_planes; plane += warps_total) {
+    const float inv_p = 1.0f / p;
+    for (uint32_t unit = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); unit < n_units; unit += warps_total) {
         int hw;
         const float* src;
         if (off) {
-            const uint32_t map = plane / (uint32_t)C;
-            const uint32_t c = plane - map * (uint32_t)C;
+            const uint32_t map = unit / units_per_map;
+            const uint32_t c0 = (unit - map * units_per_map) * G;
             hw = __ldg(hws + map);
-            src = x + __ldg(off + map) + (int64_t)c * hw;
+            src = x + __ldg(off + map) + (int64_t)c0 * hw;
         } else {
             hw = hw_uniform;
-            src = x + (int64_t)plane * hw;
+            src = x + (int64_t)unit * G * hw;
         }
+        const int T = G * hw;                                   // floats in this unit
+        const int b1 = hw, b2 = 2 * hw, b3 = 3 * hw;            // plane boundaries (element offsets)
         int head = (int)(((16u - ((uint32_t)(uintptr_t)src & 15u)) & 15u) >> 2);
-        head = min(head, hw);
-        const int nbody = (hw - head) >> 2;
+        head = min(head, T);
+        const int nbody = (T - head) >> 2;
         const int tail0 = head + (nbody << 2);
         const float4* body = reinterpret_cast<const float4*>(src + head);
-        const bool has_head = lane < head, has_tail = tail0 + lane < hw;
-        float hv = 0.f, tv = 0.f;
-        if (has_head) hv = __ldg(src + lane);
-        if (has_tail) tv = __ldg(src + tail0 + lane);
-        float acc = ident;
+        float acc[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = ident;
+        // scalar head / tail elements (each < 4)
+        {
+            const int e = lane < head ? lane : tail0 + (lane - head);
+            if (lane < head || e < T) {
+                if (e < T) {
+                    const int pid = G == 1 ? 0 : (e >= b1) + (e >= b2) + (e >= b3);
+                    acc_add<KIND, G>(acc, pid, pool_elem<KIND, P3>(__ldg(src + e), p, eps));
+                }
+            }
+        }
         for (int j0 = 0; j0 < nbody; j0 += 256) {
             float4 v[8];
 #pragma unroll
@@ -87,17 +108,47 @@ __global__ void __launch_bounds__(256) pool_planes_kernel(const float* __restric
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = j0 + u * 32 + lane;
-                if (i < nbody) acc = pool_comb<KIND>(acc, pool_elem4<KIND, P3>(v[u], p, eps));
+                if (i < nbody) {
+                    const int e = head + 4 * i;
+                    const int pid = G == 1 ? 0 : (e >= b1) + (e >= b2) + (e >= b3);
+                    const int pid3 = G == 1 ? 0 : (e + 3 >= b1) + (e + 3 >= b2) + (e + 3 >= b3);
+                    if (pid == pid3) {
+                        acc_add<KIND, G>(acc, pid, pool_elem4<KIND, P3>(v[u], p, eps));
+                    } else {                                     // chunk straddles a plane boundary (rare)
+                        const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int pe = (e + t >= b1) + (e + t >= b2) + (e + t >= b3);
+                            acc_add<KIND, G>(acc, pe, pool_elem<KIND, P3>(vv[t], p, eps));
+                        }
+                    }
+                }
             }
         }
-        if (has_head) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(hv, p, eps));
-        if (has_tail) acc = pool_comb<KIND>(acc, pool_elem<KIND, P3>(tv, p, eps));
-        acc = KIND == MDIR_POOL_MAC ? warp_max(acc) : warp_sum(acc);
-        if (lane == 0) {
-            float r = acc;
-            if (KIND != MDIR_POOL_MAC) r = acc / (float)hw;
-            if (KIND == MDIR_POOL_GEM) r = powf(r, 1.0f / p);
-            out[plane] = r;
+        // reduce: G == 4 uses a butterfly that leaves plane (lane >> 3)'s total in lanes with (lane & 7) == 0
+        float r;
+        if (G == 4) {
+            const bool h = (lane & 16) != 0;
+            float k0 = h ? acc[2 % G] : acc[0], k1 = h ? acc[3 % G] : acc[1 % G];
+            const float s0 = h ? acc[0] : acc[2 % G], s1 = h ? acc[1 % G] : acc[3 % G];
+            k0 = pool_comb<KIND>(k0, __shfl_xor_sync(0xffffffffu, s0, 16));
+            k1 = pool_comb<KIND>(k1, __shfl_xor_sync(0xffffffffu, s1, 16));
+            const bool q = (lane & 8) != 0;
+            r = q ? k1 : k0;
+            const float snd = q ? k0 : k1;
+            r = pool_comb<KIND>(r, __shfl_xor_sync(0xffffffffu, snd, 8));
+            r = pool_comb<KIND>(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            r = pool_comb<KIND>(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = pool_comb<KIND>(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        } else {
+            r = KIND == MDIR_POOL_MAC ? warp_max(acc[0]) : warp_sum(acc[0]);
+        }
+        if (KIND != MDIR_POOL_MAC) r = r / (float)hw;
+        if (KIND == MDIR_POOL_GEM) r = powf(r, inv_p);           // all lanes: uniform, no divergence
+        if (G == 4) {
+            if ((lane & 7) == 0) out[(int64_t)unit * 4 + (lane >> 3)] = r;
+        } else {
+            if (lane == 0) out[unit] = r;
         }
     }
 }
@@ -286,20 +337,25 @@ extern "C" int mdir_pool(int kind, const float* x, const int64_t* off, const int
     MDIR_CHECK_ARG((int64_t)n_maps * C < ((int64_t)1 << 31));
     if (n_maps == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t n_planes = (int64_t)n_maps * C;
-    const int64_t blocks_needed = (n_planes + 7) / 8;
+    const bool quad = (C % 4) == 0;
+    const int64_t n_units = (int64_t)n_maps * (quad ? C / 4 : C);
+    const int64_t blocks_needed = (n_units + 7) / 8;
     const int grid = (int)(blocks_needed < (int64_t)kNumSMs * 32 ? blocks_needed : (int64_t)kNumSMs * 32);
+#define MDIR_POOL_LAUNCH(KIND, P3)                                                                                          \
+    do {                                                                                                                    \
+        if (quad) pool_planes_kernel<KIND, P3, 4><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);   \
+        else pool_planes_kernel<KIND, P3, 1><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);        \
+    } while (0)
     if (kind == MDIR_POOL_GEM) {
         MDIR_CHECK_ARG(p > 0.f || p < 0.f);
-        if (p == 3.0f)
-            pool_planes_kernel<MDIR_POOL_GEM, true><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
-        else
-            pool_planes_kernel<MDIR_POOL_GEM, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+        if (p == 3.0f) MDIR_POOL_LAUNCH(MDIR_POOL_GEM, true);
+        else MDIR_POOL_LAUNCH(MDIR_POOL_GEM, false);
     } else if (kind == MDIR_POOL_MAC) {
-        pool_planes_kernel<MDIR_POOL_MAC, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+        MDIR_POOL_LAUNCH(MDIR_POOL_MAC, false);
     } else {
-        pool_planes_kernel<MDIR_POOL_SPOC, false><<<grid, 256, 0, st>>>(x, off, hw, n_maps, C, hw_uniform, p, eps, out);
+        MDIR_POOL_LAUNCH(MDIR_POOL_SPOC, false);
     }
+#undef MDIR_POOL_LAUNCH
     MDIR_LAUNCH_CHECK();
     return 0;
 }

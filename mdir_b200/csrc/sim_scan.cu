@@ -102,9 +102,9 @@ struct ScanParams {
     int64_t dense_ld;
     const uint64_t* tau;
     uint32_t idx_base;
-    uint64_t* cand;
-    uint32_t* cand_count;
-    int cap;
+    uint64_t* cand;          // (n_q, cap_s + 148 * cap_l): segment 0 = select kernel, segment 1 + cta = this CTA
+    uint32_t* seg_counts;    // (n_q, MDIR_CAND_SEGS)
+    int cap_s, cap_l;
     uint64_t db_hint;
 };
 
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     __shared__ uint32_t tmem_base_s;
     __shared__ uint64_t tau_s[kMaxN];
     __shared__ float tau_f[kMaxN];
+    __shared__ uint32_t cand_n[kMaxN];     // candidates this CTA has appended per query (CTA-private list: no global atomics)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             uint64_t t = c < p.n_q ? p.tau[c] : 0ull;
             tau_s[c] = t;
             tau_f[c] = ((uint32_t)(t >> 32) == 0xffffffffu) ? -INFINITY : key_score(t);
+            cand_n[c] = 0u;
         }
     }
     tc_fence_before();
@@ -223,6 +225,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     } else {
         // ------------------------------------------------------------ epilogue (warps 2..5)
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
+        const int64_t cand_row = (int64_t)p.cap_s + (int64_t)kNumSMs * p.cap_l;
+        const int64_t cand_seg_off = (int64_t)p.cap_s + (int64_t)blockIdx.x * p.cap_l;
         int it = 0;
         for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
             const int b = it & 1;
@@ -258,8 +262,9 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                             if (s >= tau_f[c0 + i] && c0 + i < p.n_q) {
                                 const uint64_t key = make_key(s, gidx);
                                 if (key <= tau_s[c0 + i]) {
-                                    const uint32_t pos = atomicAdd(&p.cand_count[c0 + i], 1u);
-                                    if (pos < (uint32_t)p.cap) p.cand[(int64_t)(c0 + i) * p.cap + pos] = key;
+                                    const uint32_t pos = atomicAdd(&cand_n[c0 + i], 1u);      // shared memory, rare
+                                    if (pos < (uint32_t)p.cap_l)
+                                        p.cand[(int64_t)(c0 + i) * cand_row + cand_seg_off + pos] = key;
                                 }
                             }
                         }
@@ -269,6 +274,11 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[b]));
+        }
+        if (p.mode == MDIR_SCAN_FILTER) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
+            const int t = threadIdx.x - 64;
+            if (t < p.n_q) p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + 1 + blockIdx.x] = cand_n[t];
         }
     }
 
@@ -324,7 +334,7 @@ using namespace mdir;
 
 extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode, int sample_stride,
                                   int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
-                                  uint64_t* cand, uint32_t* cand_count, int cap, void* stream) {
+                                  uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
     MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 8 && (D % 8) == 0);
     MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
     MDIR_CHECK_ARG(mode >= 0 && mode <= 2);
@@ -349,7 +359,7 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
         MDIR_CHECK_ARG(dense_ld >= (int64_t)n_sample * kBlockM);
         p.n_work = n_sample;
     } else {
-        MDIR_CHECK_ARG(tau && cand && cand_count && cap >= 1);
+        MDIR_CHECK_ARG(tau && cand && seg_counts && cap_s >= 0 && cap_l >= 1);
         MDIR_CHECK_ARG(n_sample >= 0 && (n_sample == 0 || sample_stride >= 2));
         MDIR_CHECK_ARG(n_sample == 0 || (int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
         p.n_work = p.n_tiles - n_sample;
@@ -359,8 +369,9 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
     p.tau = tau;
     p.idx_base = idx_base;
     p.cand = cand;
-    p.cand_count = cand_count;
-    p.cap = cap;
+    p.seg_counts = seg_counts;
+    p.cap_s = cap_s;
+    p.cap_l = cap_l;
     // a database that fits L2 (126 MB) is worth keeping there across query blocks / passes
     p.db_hint = ((int64_t)n_db * D * 2 > (int64_t)96 * 1024 * 1024) ? kEvictFirst : kEvictNormal;
     if (p.n_work <= 0) return 0;

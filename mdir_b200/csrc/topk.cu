@@ -48,18 +48,23 @@ __device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, 
 
 // One CTA (1024 threads) per query.  MSB-first 8-bit radix select on the 32-bit score key
 // (4 passes over the L2-resident score row, warp-aggregated shared-memory histogram updates).
-// tau = (kth-best score key << 32) | 0xffffffff, i.e. every item whose score ties the kth best
-// passes; those items (>= kth of them) are appended to cand.
+// tau = (kth-best score key << 32) | index limit: normally 0xffffffff (the rows tying the kth
+// score are all wanted); when more rows tie than are wanted, 4 more passes select the lowest
+// indices among them, so exactly kth rows have key <= tau.  Those rows are appended to cand.
 __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restrict__ scores, int64_t ld, int64_t n, int kth,
                                                           int sample_stride, uint32_t idx_base, uint64_t* __restrict__ tau,
-                                                          uint64_t* __restrict__ cand, uint32_t* __restrict__ cand_count, int cap) {
+                                                          uint64_t* __restrict__ cand, int64_t cand_row, uint32_t* __restrict__ seg_counts,
+                                                          int n_seg, int cap) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ uint32_t s_k;
+    __shared__ uint32_t s_n;
+    __shared__ uint32_t s_ties;
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31;
     const float* sc = scores + (int64_t)q * ld;
     uint32_t result;
+    uint32_t idx_limit = 0xffffffffu;      // index part of tau (all ties pass unless narrowed below)
     const int64_t n_round = (n + 8191) & ~(int64_t)8191;
     if ((int64_t)kth > n) {
         result = 0xffffffffu;
@@ -99,14 +104,53 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                 if (lane == 0) {
                     s_k -= before;
                     s_prefix = prefix | ((uint32_t)b << shift);
+                    s_ties = hist[b];
                 }
             }
             __syncthreads();
         }
         result = s_prefix;
+        // s_k of the s_ties rows that tie the kth score are wanted.  When not all of them are, the
+        // lowest indices win (stable-argsort order): radix-select the s_k-th smallest index among them.
+        if (s_k < s_ties) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_prefix = 0u;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+                __syncthreads();
+                const uint32_t prefix = s_prefix;
+                const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+                for (int64_t base = 0; base < n_round; base += 1024) {
+                    const int64_t i = base + threadIdx.x;
+                    const bool valid = i < n;
+                    const float v = valid ? __ldg(sc + i) : 0.f;
+                    const uint32_t idx = sample_pos_to_idx(valid ? i : 0, sample_stride, idx_base);
+                    const bool hit = valid && (~orderable(v) == result) && ((idx & himask) == prefix);
+                    if (__any_sync(0xffffffffu, hit)) {
+                        const int d = hit ? (int)((idx >> shift) & 0xffu) : 256 + lane;
+                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    uint32_t before;
+                    const int b = find_bin_warp0(hist, s_k, &before);
+                    if (lane == 0) {
+                        s_k -= before;
+                        s_prefix = prefix | ((uint32_t)b << shift);
+                    }
+                }
+                __syncthreads();
+            }
+            idx_limit = s_prefix;
+        }
     }
-    if (threadIdx.x == 0) tau[q] = ((uint64_t)result << 32) | 0xffffffffull;
+    const uint64_t tau_key = ((uint64_t)result << 32) | (uint64_t)idx_limit;
+    if (threadIdx.x == 0) { tau[q] = tau_key; s_n = 0u; }
     if (cand) {
+        __syncthreads();
         for (int64_t base = 0; base < n_round; base += 8 * 1024) {
             float v[8];
 #pragma unroll
@@ -118,11 +162,16 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
             for (int u = 0; u < 8; ++u) {
                 const int64_t i = base + u * 1024 + threadIdx.x;
                 if (i < n && ~orderable(v[u]) <= result) {
-                    const uint32_t pos = atomicAdd(&cand_count[q], 1u);
-                    if (pos < (uint32_t)cap) cand[(int64_t)q * cap + pos] = make_key(v[u], sample_pos_to_idx(i, sample_stride, idx_base));
+                    const uint64_t key = make_key(v[u], sample_pos_to_idx(i, sample_stride, idx_base));
+                    if (key <= tau_key) {
+                        const uint32_t pos = atomicAdd(&s_n, 1u);
+                        if (pos < (uint32_t)cap) cand[(int64_t)q * cand_row + pos] = key;
+                    }
                 }
             }
         }
+        __syncthreads();
+        if (threadIdx.x == 0) seg_counts[(int64_t)q * n_seg] = s_n;      // segment 0 of this query
     }
 }
 
@@ -142,23 +191,63 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
     }
 }
 
-// One CTA (1024 threads) per query.  Candidates are staged in shared memory; when there are many
-// more than k, the k best are first isolated by an in-smem MSB radix select (keys are unique) and
-// only those are sorted.  dynamic smem = (cap_pow2 + kpow2) * 8 bytes.
-__global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cand_count,
-                                                             int cap, int k, int cap_pow2, float* __restrict__ out_scores,
+// One CTA (1024 threads) per query.  The candidates of a query live in n_seg segments of its
+// cand row (segment 0: cap0 slots, the others cap_l slots each; seg_counts holds how many each
+// producer appended).  They are compacted into shared memory; when there are many more than k,
+// the k best are first isolated by an in-smem MSB radix select (keys are unique) and only those
+// are sorted.  dynamic smem = (smem_cap + kpow2) * 8 bytes.
+__global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, int64_t cand_row,
+                                                             const uint32_t* __restrict__ seg_counts, int n_seg, int cap0, int cap_l,
+                                                             int k, int smem_cap, float* __restrict__ out_scores,
                                                              int32_t* __restrict__ out_idx, uint64_t* __restrict__ out_keys,
                                                              uint64_t* __restrict__ tau, int32_t* __restrict__ overflow) {
     extern __shared__ uint64_t skeys[];
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_k, s_done, s_out;
-    uint64_t* sorted = skeys + cap_pow2;          // kpow2 entries
+    __shared__ int s_off[MDIR_CAND_SEGS + 1];
+    __shared__ int s_ovf;
+    uint64_t* sorted = skeys + smem_cap;          // kpow2 entries
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31;
-    const uint32_t count = cand_count[q];
-    const int cnt = (int)min(count, (uint32_t)cap);
-    const uint64_t* src = cand + (int64_t)q * cap;
+    // segment offsets (exclusive scan of the clamped counts) by warp 0
+    if (threadIdx.x < 32) {
+        int run = 0, ovf = 0;
+        for (int s0 = 0; s0 < n_seg; s0 += 32) {
+            const int sg = s0 + lane;
+            int c = 0;
+            if (sg < n_seg) {
+                const uint32_t raw = seg_counts[(int64_t)q * n_seg + sg];
+                const uint32_t cp = (uint32_t)(sg == 0 ? cap0 : cap_l);
+                if (raw > cp) ovf = 1;
+                c = (int)min(raw, cp);
+            }
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (sg < n_seg) s_off[sg] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        ovf = __any_sync(0xffffffffu, ovf);
+        if (lane == 0) { s_off[n_seg] = run; s_ovf = ovf; }
+    }
+    __syncthreads();
+    const int total = s_off[n_seg];
+    const int cnt = min(total, smem_cap);
+    const bool ovf_any = s_ovf || total > smem_cap;
+    {   // compaction: warp w copies segments w, w+32, ...
+        const uint64_t* row = cand + (int64_t)q * cand_row;
+        for (int sg = threadIdx.x >> 5; sg < n_seg; sg += 32) {
+            const int o = s_off[sg], c = s_off[sg + 1] - o;
+            const uint64_t* src = row + (sg == 0 ? 0 : (int64_t)cap0 + (int64_t)(sg - 1) * cap_l);
+            for (int i = lane; i < c; i += 32)
+                if (o + i < smem_cap) skeys[o + i] = src[i];
+        }
+    }
+    __syncthreads();
     int kpow2 = 32;
     while (kpow2 < k) kpow2 <<= 1;
     const uint64_t* res;       // ascending keys, at least min(k, cnt) valid
@@ -166,13 +255,12 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     if (cnt <= 2 * kpow2 || cnt <= 1024) {
         int n = 32;
         while (n < cnt) n <<= 1;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) skeys[i] = i < cnt ? src[i] : ~0ull;
+        for (int i = cnt + threadIdx.x; i < n; i += blockDim.x) skeys[i] = ~0ull;
         __syncthreads();
         bitonic_sort_smem(skeys, n);
         res = skeys;
         nres = cnt;
     } else {
-        for (int i = threadIdx.x; i < cnt; i += blockDim.x) skeys[i] = src[i];
         if (threadIdx.x == 0) { s_prefix = 0ull; s_k = (uint32_t)k; s_done = 0u; s_out = 0u; }
         __syncthreads();
         const int cnt_round = (cnt + 1023) & ~1023;
@@ -233,9 +321,8 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         if (out_keys) out_keys[(int64_t)q * k + j] = ok ? key : ~0ull;
     }
     if (threadIdx.x == 0 && overflow) {
-        const bool ovf = count > (uint32_t)cap;
-        overflow[q] = ovf ? 1 : 0;
-        if (ovf && tau) tau[q] = res[min(k, nres) - 1];
+        overflow[q] = ovf_any ? 1 : 0;
+        if (ovf_any && tau && nres > 0) tau[q] = res[min(k, nres) - 1];
     }
 }
 
@@ -352,31 +439,39 @@ extern "C" uint64_t mdir_make_key(float score, uint32_t index) { return make_key
 extern "C" float mdir_key_score(uint64_t key) { return key_score(key); }
 
 extern "C" int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth, int sample_stride,
-                               uint32_t idx_base, uint64_t* tau, uint64_t* cand, uint32_t* cand_count, int cap, void* stream) {
+                               uint32_t idx_base, uint64_t* tau, uint64_t* cand, int64_t cand_row, uint32_t* seg_counts, int n_seg,
+                               int cap, void* stream) {
     MDIR_CHECK_ARG(scores && tau && n >= 0 && n_q >= 0 && kth >= 1 && ld >= n);
-    MDIR_CHECK_ARG(cand == nullptr || (cand_count != nullptr && cap >= 1));
+    MDIR_CHECK_ARG(cand == nullptr || (seg_counts != nullptr && cap >= 1 && n_seg >= 1 && cand_row >= cap));
     if (n_q == 0) return 0;
-    select_kth_kernel<<<n_q, 1024, 0, (cudaStream_t)stream>>>(scores, ld, n, kth, sample_stride, idx_base, tau, cand,
-                                                              cand_count, cap);
+    select_kth_kernel<<<n_q, 1024, 0, (cudaStream_t)stream>>>(scores, ld, n, kth, sample_stride, idx_base, tau, cand, cand_row,
+                                                              seg_counts, n_seg, cap);
     MDIR_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int mdir_topk_finalize(const uint64_t* cand, const uint32_t* cand_count, int cap, int n_q, int k, float* out_scores,
-                                  int32_t* out_idx, uint64_t* out_keys, uint64_t* tau, int32_t* overflow, void* stream) {
-    MDIR_CHECK_ARG(cand && cand_count && cap >= 1 && cap <= 16384 && n_q >= 0 && k >= 1 && k <= 4096);
+extern "C" int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0, int cap_l,
+                                  int n_q, int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau,
+                                  int32_t* overflow, void* stream) {
+    MDIR_CHECK_ARG(cand && seg_counts && n_seg >= 1 && n_seg <= MDIR_CAND_SEGS && cap0 >= 0 && n_q >= 0 && k >= 1 && k <= 4096);
+    MDIR_CHECK_ARG(n_seg == 1 || cap_l >= 1);
+    MDIR_CHECK_ARG(cand_row >= (int64_t)cap0 + (int64_t)(n_seg - 1) * cap_l);
     if (n_q == 0) return 0;
-    int cap_pow2 = 32, kpow2 = 32;
-    while (cap_pow2 < cap) cap_pow2 <<= 1;
+    int kpow2 = 32;
     while (kpow2 < k) kpow2 <<= 1;
-    const size_t smem = (size_t)(cap_pow2 + kpow2) * 8;
+    // shared-memory staging capacity: everything the segments can hold, at most 16384 keys
+    int64_t want = (int64_t)cap0 + (int64_t)(n_seg - 1) * cap_l;
+    int smem_cap = 1024;
+    while (smem_cap < want && smem_cap < 16384) smem_cap <<= 1;
+    if (smem_cap < 2 * kpow2) smem_cap = 2 * kpow2;
+    const size_t smem = (size_t)(smem_cap + kpow2) * 8;
     static bool attr_set = false;
     if (!attr_set) {
         MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 4096) * 8));
         attr_set = true;
     }
-    topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_count, cap, k, cap_pow2, out_scores, out_idx,
-                                                                     out_keys, tau, overflow);
+    topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap,
+                                                                     out_scores, out_idx, out_keys, tau, overflow);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

@@ -22,9 +22,13 @@ from . import _lib
 
 TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries resident per scan pass
-CAND_CAP = 8192       # per-query candidate list capacity (keys)
+N_SEGS = 149          # MDIR_CAND_SEGS: segment 0 = select kernel, 1 + c = scan CTA c
+CAP_S = 8192          # capacity of segment 0 (the >= kth sample rows that pass, incl. ties)
+CAP_L = 96            # capacity of each scan CTA's private segment
+CAND_ROW = CAP_S + 148 * CAP_L
+STAGE_CAP = 16384     # keys mdir_topk_finalize can stage in shared memory
 MAX_SAMPLE_TILES = 512
-TARGET_CAND = 5500    # expected candidates per query the sampling plan aims for (kth * n_tiles / n_sample)
+TARGET_CAND = 4500    # candidates per query the sampling plan aims for (kth * n_tiles / n_sample), ~30 per CTA segment
 
 
 def _as_dev_f32(x, device):
@@ -110,50 +114,54 @@ class Index:
     def _scan(self, q16, mode, stride, n_sample, dense, dense_ld, tau, cand, cnt):
         _lib.check(_lib.lib().mdir_sim_scan_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16), q16.shape[0], self.D, mode, stride,
                                                  n_sample, _lib.ptr(dense), dense_ld, _lib.ptr(tau), self.idx_base, _lib.ptr(cand),
-                                                 _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_sim_scan_bf16")
+                                                 _lib.ptr(cnt), CAP_S, CAP_L, _lib.stream()), "mdir_sim_scan_bf16")
+
+    def _cand_bufs(self):
+        return (self._buf("tau", (MAX_Q,), torch.int64), self._buf("cand", (MAX_Q, CAND_ROW), torch.int64),
+                self._buf("segcnt", (MAX_Q, N_SEGS), torch.int32))
+
+    def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf):
+        _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth,
+                                                 _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
+                                                 _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+
+    def _dense_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
+        """All scores of the block -> exact kth-key select -> sort.  The route for small databases
+        and the guaranteed-terminating recovery when a candidate segment overflowed (the select
+        emits exactly kth keys, so nothing can overflow here)."""
+        lib = _lib.lib()
+        nq = q16.shape[0]
+        tau, cand, cnt = self._cand_bufs()
+        cnt.zero_()
+        dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
+        self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
+        _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
+                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, _lib.stream()), "mdir_select_kth")
+        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf)
 
     def _topk_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
         """Exact top-kth of one block of <= 128 queries by bf16-input/fp32-accumulate scores."""
         lib = _lib.lib()
         nq = q16.shape[0]
-        tau = self._buf("tau", (MAX_Q,), torch.int64)
-        cand = self._buf("cand", (MAX_Q, CAND_CAP), torch.int64)
-        cnt = self._buf("cnt", (MAX_Q,), torch.int32)
-        cnt.zero_()
         plan = self._plan(kth)
         if plan is None:
-            dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
-            self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
-            _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
-                                           _lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_select_kth")
-        else:
-            n_sample, stride = plan
-            rows = n_sample * TILE
-            sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
-            ld = MAX_SAMPLE_TILES * TILE
-            self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
-            _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
-                                           _lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, _lib.stream()), "mdir_select_kth")
-            prof = getattr(self, "prof", None)
-            if prof is not None:      # bench.py: CUDA events around the dominant kernel, on its own stream
-                prof.begin()
-            self._scan(q16, 2, stride, n_sample, None, 0, tau, cand, cnt)
-            if prof is not None:
-                prof.end((self.n - rows) * self.D * 2)
-        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, nq, kth, _lib.ptr(out_scores), _lib.ptr(out_idx),
-                                          _lib.ptr(out_keys), _lib.ptr(tau), _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
-
-    def _refilter_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
-        """Overflow recovery: tau was tightened by finalize; re-scan every tile against it."""
-        lib = _lib.lib()
-        nq = q16.shape[0]
-        tau = self._buf("tau", (MAX_Q,), torch.int64)
-        cand = self._buf("cand", (MAX_Q, CAND_CAP), torch.int64)
-        cnt = self._buf("cnt", (MAX_Q,), torch.int32)
+            return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf)
+        tau, cand, cnt = self._cand_bufs()
         cnt.zero_()
-        self._scan(q16, 2, 0, 0, None, 0, tau, cand, cnt)
-        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), CAND_CAP, nq, kth, _lib.ptr(out_scores), _lib.ptr(out_idx),
-                                          _lib.ptr(out_keys), _lib.ptr(tau), _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+        n_sample, stride = plan
+        rows = n_sample * TILE
+        sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
+        ld = MAX_SAMPLE_TILES * TILE
+        self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
+        _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
+                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, _lib.stream()), "mdir_select_kth")
+        prof = getattr(self, "prof", None)
+        if prof is not None:      # bench.py: CUDA events around the dominant kernel, on its own stream
+            prof.begin()
+        self._scan(q16, 2, stride, n_sample, None, 0, tau, cand, cnt)
+        if prof is not None:
+            prof.end((self.n - rows) * self.D * 2)
+        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf)
 
     # ------------------------------------------------------------------ public
     def search(self, q, k, precision="fp32", shortlist=None, check=True, return_keys=False):
@@ -180,8 +188,8 @@ class Index:
                 kth = k_eff
             else:
                 raise ValueError("precision must be 'fp32' or 'bf16'")
-            if kth > CAND_CAP // 2:
-                raise _lib.MdirError("k/shortlist %d too large for the fused path (max %d); use ranks()" % (kth, CAND_CAP // 2))
+            if kth > 4096:
+                raise _lib.MdirError("k/shortlist %d too large for the fused path (max 4096); use ranks()" % kth)
             q16 = pack_bf16(q32)
             out_s = torch.empty((nq_all, k), dtype=torch.float32, device=self.device)
             out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
@@ -215,7 +223,7 @@ class Index:
                                                     _lib.ptr(sl_i), kth, _lib.ptr(keys), _lib.stream()), "mdir_rescore_f32")
                     cnt = self._buf("sl_cnt", (MAX_Q,), torch.int32)
                     cnt.fill_(kth)
-                    _lib.check(lib.mdir_topk_finalize(_lib.ptr(keys), _lib.ptr(cnt), kth, nq, k, _lib.ptr(out_s[q0:q1]),
+                    _lib.check(lib.mdir_topk_finalize(_lib.ptr(keys), kth, _lib.ptr(cnt), 1, kth, 0, nq, k, _lib.ptr(out_s[q0:q1]),
                                                       _lib.ptr(out_i[q0:q1]), _lib.ptr(out_k[q0:q1]) if return_keys else None,
                                                       None, None, _lib.stream()), "mdir_topk_finalize")
             if return_keys:
@@ -224,13 +232,11 @@ class Index:
 
     def _run_block(self, q16, kth, out_s, out_i, out_k, ovf, check):
         self._topk_block(q16, kth, out_s, out_i, out_k, ovf)
-        if check:
-            guard = 0
-            while bool(ovf.any().item()):
-                guard += 1
-                if guard > 8:
-                    raise _lib.MdirError("candidate overflow did not converge")
-                self._refilter_block(q16, kth, out_s, out_i, out_k, ovf)
+        if check and bool(ovf.any().item()):
+            # a candidate segment overflowed (adversarial row order / massive ties): exact dense route
+            self._dense_block(q16, kth, out_s, out_i, out_k, ovf)
+            if bool(ovf.any().item()):
+                raise _lib.MdirError("dense recovery overflowed (internal error)")
 
     def check_overflow(self):
         """True if the last search(check=False) overflowed a candidate list (results then invalid)."""
@@ -297,7 +303,7 @@ def topk_from_scores(scores, k, device="cuda"):
     if k > min(n_db, 4096):
         r = ranks_from_scores(s, device=dev)[:k]
         return r, torch.gather(s, 0, r)
-    cap = int(min(16384, max(4 * k, 1024)))
+    cap = int(min(STAGE_CAP, max(4 * k, 1024)))
     with torch.cuda.device(dev):
         st = s.t().contiguous()                       # query-major for coalesced selection
         tau = torch.empty((n_q,), dtype=torch.int64, device=dev)
@@ -305,10 +311,10 @@ def topk_from_scores(scores, k, device="cuda"):
         cnt = torch.zeros((n_q,), dtype=torch.int32, device=dev)
         out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n_q, k), dtype=torch.int32, device=dev)
-        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), _lib.ptr(cnt), cap,
+        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), cap, _lib.ptr(cnt), 1, cap,
                                        _lib.stream()), "mdir_select_kth")
-        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), _lib.ptr(cnt), cap, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None, None,
-                                          _lib.stream()), "mdir_topk_finalize")
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), cap, _lib.ptr(cnt), 1, cap, 0, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None,
+                                          None, None, _lib.stream()), "mdir_topk_finalize")
         if int(cnt.max().item()) > cap:               # too many exact ties at the kth score
             r = ranks_from_scores(s, device=dev)[:k]
             return r, torch.gather(s, 0, r)
@@ -377,8 +383,8 @@ def merge_keys(local_keys, world, group, k):
     out_s = torch.empty((nq, k), dtype=torch.float32, device=local_keys.device)
     out_i = torch.empty((nq, k), dtype=torch.int32, device=local_keys.device)
     with torch.cuda.device(local_keys.device):
-        _lib.check(lib.mdir_topk_finalize(_lib.ptr(allk), _lib.ptr(cnt), world * k, nq, k, _lib.ptr(out_s), _lib.ptr(out_i), None, None,
-                                          None, _lib.stream()), "mdir_topk_finalize")
+        _lib.check(lib.mdir_topk_finalize(_lib.ptr(allk), world * k, _lib.ptr(cnt), 1, world * k, 0, nq, k, _lib.ptr(out_s), _lib.ptr(out_i),
+                                          None, None, None, _lib.stream()), "mdir_topk_finalize")
     return out_s, out_i
 
 

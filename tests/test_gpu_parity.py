@@ -332,8 +332,8 @@ def test_sharded_merge_equals_single(m):
         cnt = torch.full((70,), world * k, dtype=torch.int32, device=DEV)
         out_s = torch.empty((70, k), dtype=torch.float32, device=DEV)
         out_i = torch.empty((70, k), dtype=torch.int32, device=DEV)
-        _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(allk), _lib.ptr(cnt), world * k, 70, k, _lib.ptr(out_s), _lib.ptr(out_i),
-                                                 None, None, None, _lib.stream()))
+        _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(allk), world * k, _lib.ptr(cnt), 1, world * k, 0, 70, k, _lib.ptr(out_s),
+                                                 _lib.ptr(out_i), None, None, None, _lib.stream()))
         assert torch.equal(out_i, i1) and torch.equal(out_s, s1), world
 
 

@@ -100,7 +100,7 @@ static void test_dense(int64_t n_db, int n_q, int D) {
     CK(cudaMalloc(&d_out, (size_t)n_q * n_db * 4));
     CK(cudaMemset(d_out, 0xff, (size_t)n_q * n_db * 4));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_DENSE, 0, 0, d_out, n_db, nullptr, 0, nullptr,
-                          nullptr, 0, 0));
+                          nullptr, 0, 0, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> out((size_t)n_q * n_db);
     CK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -120,7 +120,8 @@ static void test_dense(int64_t n_db, int n_q, int D) {
 }
 
 // sample -> select -> filter -> finalize, compared with an exact sort of the GPU's own dense scores
-static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sample, int cap) {
+static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sample, int cap_s) {
+    const int cap_l = 96; const int64_t cap = cap_s + 148 * (int64_t)cap_l; const int NS = MDIR_CAND_SEGS;
     Scan s = make_scan(n_db, n_q, D);
     float *d_dense, *d_sample, *d_os; int32_t* d_oi; uint64_t *d_tau, *d_cand; uint32_t* d_cnt; int32_t* d_ovf;
     const int64_t n_samp_rows = (int64_t)n_sample * MDIR_SCAN_TILE_ROWS;
@@ -128,25 +129,26 @@ static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sam
     CK(cudaMalloc(&d_sample, (size_t)n_q * n_samp_rows * 4));
     CK(cudaMalloc(&d_os, (size_t)n_q * k * 4)); CK(cudaMalloc(&d_oi, (size_t)n_q * k * 4));
     CK(cudaMalloc(&d_tau, n_q * 8)); CK(cudaMalloc(&d_cand, (size_t)n_q * cap * 8));
-    CK(cudaMalloc(&d_cnt, n_q * 4)); CK(cudaMalloc(&d_ovf, n_q * 4));
+    CK(cudaMalloc(&d_cnt, n_q * NS * 4)); CK(cudaMalloc(&d_ovf, n_q * 4));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_DENSE, 0, 0, d_dense, n_db, nullptr, 0, nullptr,
-                          nullptr, 0, 0));
-    CK(cudaMemset(d_cnt, 0, n_q * 4));
+                          nullptr, 0, 0, 0));
+    CK(cudaMemset(d_cnt, 0, n_q * NS * 4));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_SAMPLE, stride, n_sample, d_sample, n_samp_rows,
-                          nullptr, 0, nullptr, nullptr, 0, 0));
-    MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, d_cnt, cap, 0));
+                          nullptr, 0, nullptr, nullptr, 0, 0, 0));
+    MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 0));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_FILTER, stride, n_sample, nullptr, 0, d_tau, 0,
-                          d_cand, d_cnt, cap, 0));
-    MD(mdir_topk_finalize(d_cand, d_cnt, cap, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
+                          d_cand, d_cnt, cap_s, cap_l, 0));
+    MD(mdir_topk_finalize(d_cand, cap, d_cnt, NS, cap_s, cap_l, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> dense((size_t)n_q * n_db), os((size_t)n_q * k);
     std::vector<int32_t> oi((size_t)n_q * k), ovf(n_q);
-    std::vector<uint32_t> cnt(n_q);
+    std::vector<uint32_t> cnt_all((size_t)n_q * NS), cnt(n_q);
     CK(cudaMemcpy(dense.data(), d_dense, dense.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(os.data(), d_os, os.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(oi.data(), d_oi, oi.size() * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(ovf.data(), d_ovf, n_q * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(cnt.data(), d_cnt, n_q * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt_all.data(), d_cnt, (size_t)n_q * NS * 4, cudaMemcpyDeviceToHost));
+    for (int qi = 0; qi < n_q; ++qi) { cnt[qi] = 0; for (int sg = 0; sg < NS; ++sg) cnt[qi] += cnt_all[(size_t)qi * NS + sg]; }
     int64_t bad = 0; uint32_t maxcnt = 0; int novf = 0;
     for (int qi = 0; qi < n_q; ++qi) {
         maxcnt = std::max(maxcnt, cnt[qi]); novf += ovf[qi];
@@ -193,10 +195,11 @@ static void test_ranks(int64_t n_db, int n_q, bool ties) {
     cudaFree(d_sc); cudaFree(d_r); cudaFree(ws);
 }
 
-static void bench_big() {
-    const int64_t n_db = 1001001; const int n_q = 70, D = 2048, k = 200, cap = 8192;
+static void bench_big(int64_t n_db, int n_q, int n_sample) {
+    const int D = 2048, k = 200, cap_s = 8192, cap_l = 96, NS = MDIR_CAND_SEGS; const int64_t cap = cap_s + 148 * (int64_t)cap_l;
     const int n_tiles = (int)((n_db + 255) / 256);
-    const int n_sample = 143, stride = n_tiles / n_sample;
+    const int stride = n_tiles / n_sample;
+    printf("bench_big n_db=%lld n_q=%d n_sample=%d stride=%d\n", (long long)n_db, n_q, n_sample, stride);
     __nv_bfloat16 *d_db, *d_q;
     CK(cudaMalloc(&d_db, (size_t)n_db * D * 2)); CK(cudaMalloc(&d_q, (size_t)n_q * D * 2));
     fill_bf16<<<(unsigned)(((int64_t)n_db * D + 255) / 256), 256>>>(d_db, (int64_t)n_db * D, 1u);
@@ -207,32 +210,37 @@ static void bench_big() {
     CK(cudaMalloc(&d_sample, (size_t)n_q * n_samp_rows * 4));
     CK(cudaMalloc(&d_os, (size_t)n_q * k * 4)); CK(cudaMalloc(&d_oi, (size_t)n_q * k * 4));
     CK(cudaMalloc(&d_tau, n_q * 8)); CK(cudaMalloc(&d_cand, (size_t)n_q * cap * 8));
-    CK(cudaMalloc(&d_cnt, n_q * 4)); CK(cudaMalloc(&d_ovf, n_q * 4));
+    CK(cudaMalloc(&d_cnt, n_q * NS * 4)); CK(cudaMalloc(&d_ovf, n_q * 4));
     cudaEvent_t e[6];
     for (auto& ev : e) CK(cudaEventCreate(&ev));
-    for (int rep = 0; rep < 6; ++rep) {
-        CK(cudaMemsetAsync(d_cnt, 0, n_q * 4));
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaMemsetAsync(d_cnt, 0, n_q * NS * 4));
         CK(cudaEventRecord(e[0]));
         MD(mdir_sim_scan_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, MDIR_SCAN_SAMPLE, stride, n_sample, d_sample, n_samp_rows,
-                              nullptr, 0, nullptr, nullptr, 0, 0));
+                              nullptr, 0, nullptr, nullptr, 0, 0, 0));
         CK(cudaEventRecord(e[1]));
-        MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, d_cnt, cap, 0));
+        MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 0));
         CK(cudaEventRecord(e[2]));
         MD(mdir_sim_scan_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, MDIR_SCAN_FILTER, stride, n_sample, nullptr, 0, d_tau, 0,
-                              d_cand, d_cnt, cap, 0));
+                              d_cand, d_cnt, cap_s, cap_l, 0));
         CK(cudaEventRecord(e[3]));
-        MD(mdir_topk_finalize(d_cand, d_cnt, cap, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
+        MD(mdir_topk_finalize(d_cand, cap, d_cnt, NS, cap_s, cap_l, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
         CK(cudaEventRecord(e[4]));
         CK(cudaDeviceSynchronize());
         float t[4];
         for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&t[i], e[i], e[i + 1]));
-        std::vector<uint32_t> cnt(n_q);
-        CK(cudaMemcpy(cnt.data(), d_cnt, n_q * 4, cudaMemcpyDeviceToHost));
-        uint32_t mx = 0; for (auto c : cnt) mx = std::max(mx, c);
+        std::vector<uint32_t> cnt((size_t)n_q * NS);
+        CK(cudaMemcpy(cnt.data(), d_cnt, (size_t)n_q * NS * 4, cudaMemcpyDeviceToHost));
+        uint32_t mx = 0, mxseg = 0;
+        for (int qi = 0; qi < n_q; ++qi) { uint32_t tot = 0; for (int sg = 0; sg < NS; ++sg) { tot += cnt[(size_t)qi * NS + sg]; if (sg) mxseg = std::max(mxseg, cnt[(size_t)qi * NS + sg]); } mx = std::max(mx, tot); }
+        std::vector<int32_t> ovf(n_q); CK(cudaMemcpy(ovf.data(), d_ovf, n_q * 4, cudaMemcpyDeviceToHost));
+        int novf = 0; for (auto o : ovf) novf += o;
+        if (rep == 1) printf("   max segment fill %u of %d, overflow flags %d\n", mxseg, cap_l, novf);
         const double gb = (double)(n_db - n_samp_rows) * D * 2 / 1e9;
-        printf("rep %d: sample %.3f ms  select %.3f ms  filter %.3f ms (%.0f GB/s)  finalize %.3f ms  total %.3f ms  maxcand %u\n", rep,
+        if (rep) printf("rep %d: sample %.3f ms  select %.3f ms  filter %.3f ms (%.0f GB/s)  finalize %.3f ms  total %.3f ms  maxcand %u\n", rep,
                t[0], t[1], t[2], gb / (t[2] * 1e-3), t[3], t[0] + t[1] + t[2] + t[3], mx);
     }
+    cudaFree(d_db); cudaFree(d_q); cudaFree(d_sample); cudaFree(d_os); cudaFree(d_oi); cudaFree(d_tau); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_ovf);
 }
 
 int main(int argc, char** argv) {
@@ -245,10 +253,18 @@ int main(int argc, char** argv) {
     test_dense(777, 128, 512);
     test_topk(20000, 70, 256, 100, 8, 8, 8192);
     test_topk(5000, 5, 64, 10, 2, 3, 1024);
+    test_topk(100000, 128, 128, 200, 12, 32, 8192);
     test_ranks(5000, 7, false);
     test_ranks(4993, 70, true);
     test_ranks(100, 3, true);
-    if (argc > 1 && !strcmp(argv[1], "big")) bench_big();
+    if (argc > 1 && !strcmp(argv[1], "big")) {
+        bench_big(1001001, 70, 176);
+        bench_big(500501, 70, 87);
+        bench_big(250251, 70, 44);
+        bench_big(125126, 70, 32);
+        bench_big(1001001, 128, 176);
+        bench_big(1001001, 16, 176);
+    }
     printf("%s (%d failures)\n", failures ? "SELFTEST FAILED" : "SELFTEST PASSED", failures);
     return failures ? 1 : 0;
 }
