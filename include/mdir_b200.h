@@ -125,6 +125,18 @@ int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int 
                        const uint64_t* tau, uint32_t idx_base,
                        uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream);
 
+/* The same scan with fp32 operands consumed as TF32 (tcgen05 kind::tf32, fp32 accumulate):
+ * db (n_db, D) and q (n_q, D) row-major fp32, D % 4 == 0.  Used directly it is the TF32
+ * similarity variant; fed the (n, 3D) matrices written by mdir_split_tf32x3 (role 0 for the
+ * database side, role 1 for the query side) it computes hi*hi + hi*lo + lo*hi = an
+ * fp32-faithful ("3xTF32") dot product.                                              */
+int mdir_sim_scan_tf32(const float* db, int64_t n_db, const float* q, int n_q, int D,
+                       int mode, int sample_stride, int n_sample,
+                       float* dense_out, int64_t dense_ld,
+                       const uint64_t* tau, uint32_t idx_base,
+                       uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream);
+int mdir_split_tf32x3(const float* src, int64_t n, int D, int role, float* dst, void* stream);
+
 /* key helpers exposed for tests: key = (~orderable(score) << 32) | index        */
 uint64_t mdir_make_key(float score, uint32_t index);
 float    mdir_key_score(uint64_t key);

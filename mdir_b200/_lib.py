@@ -32,6 +32,8 @@ PROTOTYPES = {
     "mdir_clahe_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp]),
     "mdir_pack_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "mdir_sim_scan_bf16": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),
+    "mdir_sim_scan_tf32": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),
+    "mdir_split_tf32x3": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "mdir_make_key": (_u64, [_f, _u32]),
     "mdir_key_score": (_f, [_u64]),
     "mdir_select_kth": (_i, [_vp, _i64, _i64, _i, _i, _i, _u32, _vp, _vp, _i64, _vp, _i, _i, _vp]),

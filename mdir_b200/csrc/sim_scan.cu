@@ -22,9 +22,10 @@
 namespace mdir {
 
 constexpr int kBlockM = MDIR_SCAN_TILE_ROWS;   // 256 db rows per tile = two UMMA M=128 halves
-constexpr int kBlockK = 64;                    // bf16 elements = one 128-byte swizzle row
-constexpr int kUmmaK = 16;
-constexpr int kABytes = kBlockM * kBlockK * 2;  // 32768
+constexpr int kBlockKBytes = 128;               // one 128-byte swizzle row per operand row and k-block:
+                                                //   64 bf16 (UMMA_K = 16) or 32 fp32/tf32 (UMMA_K = 8): 4 MMAs of 32 bytes either way
+constexpr int kKSteps = 4;
+constexpr int kABytes = kBlockM * kBlockKBytes;  // 32768
 constexpr int kMaxN = 128;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
@@ -68,14 +69,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -122,6 +134,7 @@ __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j) {
     return p.n_sample * p.sample_stride + (j - in_groups);
 }
 
+template <bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_constant__ CUtensorMap tmap_db,
                                                                 const __grid_constant__ CUtensorMap tmap_q, const ScanParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -182,8 +195,9 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
                     mbar_expect_tx(fb, stage_bytes);
-                    tma_load_2d(a_dst, &tmap_db, fb, kb * kBlockK, row0, p.db_hint);
-                    tma_load_2d(a_dst + kABytes, &tmap_q, fb, kb * kBlockK, 0, kEvictLast);
+                    constexpr int kElemsPerBlock = TF32 ? 32 : 64;
+                    tma_load_2d(a_dst, &tmap_db, fb, kb * kElemsPerBlock, row0, p.db_hint);
+                    tma_load_2d(a_dst + kABytes, &tmap_q, fb, kb * kElemsPerBlock, 0, kEvictLast);
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -191,8 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, K-major A/B, N>>3 [17,23), M>>4 [24,29)
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: D=f32 [4,6)=1, A/B format [7,10)/[10,13) = 1 (bf16) or 2 (tf32), K-major A/B,
+            // N>>3 [17,23), M>>4 [24,29)
+            constexpr uint32_t fmt = TF32 ? 2u : 1u;
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -210,10 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     for (int h = 0; h < 2; ++h) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 + h) * 128u;
 #pragma unroll
-                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        for (int k = 0; k < kKSteps; ++k) {
                             const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)h * (128u * 128u) + (uint32_t)k * 32u);
                             const uint64_t bd = umma_desc_sw128(b_base + (uint32_t)k * 32u);
-                            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_ss<TF32>(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
                     umma_commit(smem_u32(&empty_bar[stage]));     // frees the smem slot when these MMAs retire
@@ -308,17 +324,17 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-static int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int make_tmap(CUtensorMap* map, bool tf32, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return MDIR_E_DRIVER;
     }
     cuuint64_t gdim[2] = {cols, rows};
-    cuuint64_t gstride[1] = {cols * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+    cuuint64_t gstride[1] = {cols * (tf32 ? 4u : 2u)};
+    cuuint32_t box[2] = {(cuuint32_t)(tf32 ? 32 : 64), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+    CUresult r = fn(map, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -332,10 +348,11 @@ static int make_tmap_bf16(CUtensorMap* map, const void* ptr, uint64_t rows, uint
 
 using namespace mdir;
 
-extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode, int sample_stride,
-                                  int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
-                                  uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
-    MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 8 && (D % 8) == 0);
+static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, int n_q, int D, int mode, int sample_stride, int n_sample,
+                       float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base, uint64_t* cand,
+                       uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
+    const int esz = tf32 ? 4 : 2;
+    MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 16 / esz && (D % (16 / esz)) == 0);
     MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
     MDIR_CHECK_ARG(mode >= 0 && mode <= 2);
     MDIR_CHECK_ARG(n_db + (int64_t)idx_base <= ((int64_t)1 << 32));
@@ -343,7 +360,8 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
     p.n_db = n_db;
     p.n_q = n_q;
     p.n_pad = (n_q + 15) & ~15;
-    p.num_k_blocks = (D + kBlockK - 1) / kBlockK;
+    const int elems_per_block = kBlockKBytes / esz;
+    p.num_k_blocks = (D + elems_per_block - 1) / elems_per_block;
     const int64_t n_tiles64 = (n_db + kBlockM - 1) / kBlockM;
     MDIR_CHECK_ARG(n_tiles64 < ((int64_t)1 << 23));
     p.n_tiles = (int)n_tiles64;
@@ -373,7 +391,7 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
     p.cap_s = cap_s;
     p.cap_l = cap_l;
     // a database that fits L2 (126 MB) is worth keeping there across query blocks / passes
-    p.db_hint = ((int64_t)n_db * D * 2 > (int64_t)96 * 1024 * 1024) ? kEvictFirst : kEvictNormal;
+    p.db_hint = ((int64_t)n_db * D * esz > (int64_t)96 * 1024 * 1024) ? kEvictFirst : kEvictNormal;
     if (p.n_work <= 0) return 0;
 
     const int stage_bytes = kABytes + p.n_pad * 128;
@@ -384,18 +402,60 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
     const size_t smem = (size_t)stages * stage_bytes + 1024;
 
     CUtensorMap tmap_db, tmap_q;
-    int rc = make_tmap_bf16(&tmap_db, db, (uint64_t)n_db, (uint64_t)D, kBlockM);
+    int rc = make_tmap(&tmap_db, tf32, db, (uint64_t)n_db, (uint64_t)D, kBlockM);
     if (rc) return rc;
-    rc = make_tmap_bf16(&tmap_q, q, (uint64_t)n_q, (uint64_t)D, (uint32_t)p.n_pad);
+    rc = make_tmap(&tmap_q, tf32, q, (uint64_t)n_q, (uint64_t)D, (uint32_t)p.n_pad);
     if (rc) return rc;
 
     static bool attr_set = false;
     if (!attr_set) {
-        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
         attr_set = true;
     }
     const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
-    sim_scan_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
+    if (tf32) sim_scan_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
+    else sim_scan_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode, int sample_stride,
+                                  int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
+                                  uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
+    return launch_scan(false, db, n_db, q, n_q, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts,
+                       cap_s, cap_l, stream);
+}
+
+extern "C" int mdir_sim_scan_tf32(const float* db, int64_t n_db, const float* q, int n_q, int D, int mode, int sample_stride,
+                                  int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
+                                  uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
+    return launch_scan(true, db, n_db, q, n_q, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts,
+                       cap_s, cap_l, stream);
+}
+
+// fp32 -> [hi | hi | lo] (role 0, database side) or [hi | lo | hi] (role 1, query side) with hi = x truncated to
+// tf32 (10 explicit mantissa bits) and lo = x - hi (exact): scanning the two (n, 3D) matrices against each other
+// with kind::tf32 accumulates hi*hi + hi*lo + lo*hi in fp32, i.e. an fp32-faithful dot product (3xTF32).
+__global__ void __launch_bounds__(256) split_tf32x3_kernel(const float* __restrict__ src, int64_t n, int D, int role, float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * D) return;
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    const float x = src[i];
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const float lo = x - hi;
+    float* o = dst + r * 3 * (int64_t)D;
+    o[d] = hi;
+    o[D + d] = role == 0 ? hi : lo;
+    o[2 * D + d] = role == 0 ? lo : hi;
+}
+
+extern "C" int mdir_split_tf32x3(const float* src, int64_t n, int D, int role, float* dst, void* stream) {
+    MDIR_CHECK_ARG(src && dst && n >= 0 && D > 0 && (role == 0 || role == 1));
+    if (n == 0) return 0;
+    const int64_t total = n * D;
+    split_tf32x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, D, role, dst);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

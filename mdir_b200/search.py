@@ -242,22 +242,50 @@ class Index:
         """True if the last search(check=False) overflowed a candidate list (results then invalid)."""
         return bool(self._ovf.any().item())
 
-    def scores(self, q, out=None):
-        """Dense scores, QUERY-major: (N_q, N_db) fp32 on the device (bf16 inputs, fp32 accumulate)."""
+    def _split3(self, x, role):
+        """(n, D) fp32 -> (n, 3D) fp32 [hi|hi|lo] (role 0) / [hi|lo|hi] (role 1) for the 3xTF32 scan."""
+        n, D = x.shape
+        out = torch.empty((n, 3 * D), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib().mdir_split_tf32x3(_lib.ptr(x), n, D, role, _lib.ptr(out), _lib.stream()), "mdir_split_tf32x3")
+        return out
+
+    def scores(self, q, out=None, precision="bf16"):
+        """Dense scores, QUERY-major: (N_q, N_db) fp32 on the device.
+        precision "bf16": bf16 operands, fp32 accumulate (|err| <~ 1e-3 on unit vectors);
+                  "tf32": fp32 operands consumed as TF32 by the tensor cores;
+                  "fp32": 3xTF32 split (hi*hi + hi*lo + lo*hi) = fp32-faithful (|err| ~ 1e-6);
+        tf32 / fp32 need the fp32 master copy (keep_fp32=True); fp32 caches a 3x-wide split of it."""
+        lib = _lib.lib()
         with torch.cuda.device(self.device):
             q32 = _as_dev_f32(q, self.device)
             nq_all = q32.shape[0]
-            q16 = pack_bf16(q32)
             if out is None:
                 out = torch.empty((nq_all, self.n), dtype=torch.float32, device=self.device)
+            if precision == "bf16":
+                q16 = pack_bf16(q32)
+                for q0 in range(0, nq_all, MAX_Q):
+                    q1 = min(q0 + MAX_Q, nq_all)
+                    self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], self.n, None, None, None)
+                return out
+            if precision not in ("tf32", "fp32"):
+                raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")
+            if self.db32 is None:
+                raise _lib.MdirError("precision=%r needs keep_fp32=True" % precision)
+            if precision == "tf32":
+                dbx, qx, D = self.db32, q32, self.D
+            else:
+                if getattr(self, "_db_x3", None) is None:
+                    self._db_x3 = self._split3(self.db32, 0)
+                dbx, qx, D = self._db_x3, self._split3(q32, 1), 3 * self.D
             for q0 in range(0, nq_all, MAX_Q):
                 q1 = min(q0 + MAX_Q, nq_all)
-                self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], self.n, None, None, None)
+                _lib.check(lib.mdir_sim_scan_tf32(_lib.ptr(dbx), self.n, _lib.ptr(qx[q0:q1]), q1 - q0, D, 0, 0, 0, _lib.ptr(out[q0:q1]),
+                                                  self.n, None, self.idx_base, None, None, 0, 0, _lib.stream()), "mdir_sim_scan_tf32")
             return out
 
-    def ranks(self, q, max_pairs=1 << 28):
+    def ranks(self, q, max_pairs=1 << 28, precision="bf16"):
         """Full ranking: (N_db, N_q) int64 C-order on the device (== np.argsort(-scores, axis=0,
-        kind='stable') of this index's scores).  Queries are processed in chunks of at most
+        kind='stable') of this index's scores at the given precision, see scores()).  Queries are processed in chunks of at most
         max_pairs // N_db to bound the radix-sort workspace (16 B per pair)."""
         lib = _lib.lib()
         with torch.cuda.device(self.device):
@@ -270,7 +298,7 @@ class Index:
             sc = torch.empty((chunk, self.n), dtype=torch.float32, device=self.device)
             for q0 in range(0, nq_all, chunk):
                 q1 = min(q0 + chunk, nq_all)
-                self.scores(q32[q0:q1], out=sc[:q1 - q0])
+                self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
                 _lib.check(lib.mdir_rank_scores(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
                                                 _lib.stream()), "mdir_rank_scores")
             return out
@@ -321,13 +349,16 @@ def topk_from_scores(scores, k, device="cuda"):
     return out_i.t().contiguous().long(), out_s.t().contiguous()
 
 
-def rank(vecs, qvecs, device="cuda"):
+def rank(vecs, qvecs, device="cuda", precision="fp32"):
     """The drop-in for cirscore.py:69-70.  vecs (D, N_db), qvecs (D, N_q): fp32 numpy/torch host
-    matrices as extract_vectors returns them.  -> ranks (N_db, N_q) int64 numpy, C-order."""
+    matrices as extract_vectors returns them.  -> ranks (N_db, N_q) int64 numpy, C-order.
+    The default precision "fp32" (3xTF32 on the tensor cores) reproduces the reference's fp32
+    scores to ~1e-6, so the ranks differ from it only inside fp32 summation noise; "bf16" is the
+    fast path (ranks may swap where scores are within ~1e-3)."""
     dev = torch.device(device)
-    index = Index(vecs, dxn=True, device=dev, keep_fp32=False)
+    index = Index(vecs, dxn=True, device=dev, keep_fp32=(precision != "bf16"))
     q = _as_dev_f32(qvecs, dev).t().contiguous()
-    return index.ranks(q).cpu().numpy()
+    return index.ranks(q, precision=precision).cpu().numpy()
 
 
 class ShardedIndex:

@@ -255,6 +255,26 @@ def test_scores_and_drop_in_rank(m, golden):
         assert abs(avg[k_] - float(g["emh_" + k_])) < 0.01
 
 
+def test_tf32_and_fp32_faithful_scores(m, golden):
+    g = golden("search")
+    db = synth.descriptors(500, 64, 11, clusters=20)
+    q, _ = synth.planted_queries(db, 12, 12)
+    index = m.Index(db, device=DEV)
+    np.testing.assert_allclose(index.scores(q, precision="tf32").cpu().numpy().T, g["scores"], rtol=0, atol=2e-3)
+    s32 = index.scores(q, precision="fp32").cpu().numpy().T
+    np.testing.assert_allclose(s32, g["scores"], rtol=0, atol=2e-6)                    # fp32-faithful (3xTF32)
+    ranks = index.ranks(q, precision="fp32").cpu().numpy()
+    _assert_same_order(ranks, g["ranks_stable"], np.take_along_axis(g["scores"], g["ranks_stable"], 0), 4e-6)
+    # larger, non-multiple-of-32 dimension, several query blocks
+    db2 = synth.descriptors(3000, 136, 31)
+    q2 = synth.descriptors(150, 136, 32)
+    idx2 = m.Index(db2, device=DEV)
+    ref = oracle.scores(db2.T, q2.T)
+    np.testing.assert_allclose(idx2.scores(q2, precision="fp32").cpu().numpy().T, ref, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(idx2.scores(q2, precision="tf32").cpu().numpy().T, ref, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(idx2.scores(q2, precision="bf16").cpu().numpy().T, ref, rtol=0, atol=2e-3)
+
+
 def _assert_same_order(got, ref_i, ref_v, tol):
     """Indices must agree except where the reference scores are within tol (summation-order noise)."""
     k, nq = ref_i.shape
