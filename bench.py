@@ -329,7 +329,7 @@ def run_ours(args):
     achieved = prof.bytes / 1e9 / (scan_ms * 1e-3) if scan_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sim_scan_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and world == 1:      # the ncu capture is of the 1-GPU launch
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
     ms_step = ms_total / args.steps
@@ -422,9 +422,33 @@ def side_measurements(torch, mdir_b200, dev):
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / reps
+    del imgs
     out["clahe"] = {"metric": "CLAHE u8 images/s (768x1024, clip 4, 8x8 tiles)", "value": n_img / (ms * 1e-3), "unit": "images/s",
                     "batch": n_img, "ms_per_batch": ms, "algorithmic_bytes_per_image": 2 * 768 * 1024,
                     "hbm_frac_of_measured": n_img * 2 * 768 * 1024 / 1e9 / (ms * 1e-3) / peak}
+    # full (N_db, N_q) ranks: C1 shape (70 q x 4,993 x 2048, fp32-faithful scores) and a C3-shaped slice
+    # (1,024 of the 10,000 queries x 100,000 x 512, bf16 scores); device-resident in and out
+    from mdir_b200.search import Index
+    for tag, n_db, D, nq, prec in (("ranks_c1", 4993, 2048, 70, "fp32"), ("ranks_c3_slice", 100000, 512, 1024, "bf16")):
+        db = torch.randn((n_db, D), device=dev, generator=g)
+        db = db / db.norm(dim=1, keepdim=True)
+        q = torch.randn((nq, D), device=dev, generator=g)
+        q = q / q.norm(dim=1, keepdim=True)
+        idx = Index(db, device=dev, keep_fp32=(prec != "bf16"))
+        for _ in range(2):
+            r = idx.ranks(q, precision=prec)
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(5):
+            r = idx.ranks(q, precision=prec)
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 5
+        pairs = n_db * nq
+        out[tag] = {"metric": "full per-query ranks (scores + segmented radix sort + int64 (N_db,N_q) write)", "shape": "%d q x %d db x %d-D, %s scores" % (nq, n_db, D, prec),
+                    "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "hbm_floor_frac": pairs * 12 / 1e9 / (ms * 1e-3) / peak,
+                    "note": "floor = 12 B/pair (4 B score + 8 B int64 rank) at the measured HBM peak"}
+        del idx, db, r
     return out
 
 

@@ -72,6 +72,13 @@ int mdir_ms_aggregate(const float* pooled, int n_img, int S, int C, float l2n_ep
 int mdir_whiten_project(const float* v, const float* m, int n, int D, const float* P, int dims,
                         float renorm_eps, float* out, void* stream);
 
+/* The same projection on the tensor cores (3xTF32 = fp32-faithful) for batches: Px3 is
+ * mdir_split_tf32x3(P[:dims_total], role 0) = (dims_total, 3D) fp32, built once per Lw.
+ * ws: mdir_whiten_tc_workspace_bytes(n, D, dims) bytes.  D % 4 == 0.                 */
+size_t mdir_whiten_tc_workspace_bytes(int n, int D, int dims);
+int mdir_whiten_project_tc(const float* v, const float* m, int n, int D, const float* Px3, int dims,
+                           float renorm_eps, float* out, void* ws, void* stream);
+
 /* ------------------------------------------------------------------ CLAHE ---
  * Bit-exact cv2.createCLAHE(clipLimit=clip, tileGridSize=(tiles_x,tiles_y)).apply
  * on a batch of ragged 8UC1 images.  Replaces ChannelClahe.apply's cv2 call

@@ -28,6 +28,8 @@ PROTOTYPES = {
     "mdir_l2n": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "mdir_ms_aggregate": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),
     "mdir_whiten_project": (_i, [_vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp]),
+    "mdir_whiten_tc_workspace_bytes": (_sz, [_i, _i, _i]),
+    "mdir_whiten_project_tc": (_i, [_vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "mdir_clahe_workspace_bytes": (_sz, [_i, _i, _i]),
     "mdir_clahe_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp]),
     "mdir_pack_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp]),

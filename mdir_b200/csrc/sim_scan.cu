@@ -118,7 +118,33 @@ struct ScanParams {
     uint32_t* seg_counts;    // (n_q, MDIR_CAND_SEGS)
     int cap_s, cap_l;
     uint64_t db_hint;
+    // DENSE mode only: the k-blocks are split over k_split CTAs per tile; split ks writes its partial sums to
+    // dense_out + ks * split_stride (the caller adds the k_split partial planes in a fixed order)
+    int k_split, kb_per_split;
+    int64_t split_stride;
 };
+
+struct WorkItem {
+    int tile, ks, kb0, nkb;
+};
+
+__device__ __forceinline__ int tile_of_work(const ScanParams& p, int j);
+
+__device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
+    WorkItem w;
+    if (p.mode == MDIR_SCAN_DENSE && p.k_split > 1) {
+        w.tile = j / p.k_split;
+        w.ks = j - w.tile * p.k_split;
+        w.kb0 = w.ks * p.kb_per_split;
+        w.nkb = min(p.kb_per_split, p.num_k_blocks - w.kb0);
+    } else {
+        w.tile = tile_of_work(p, j);
+        w.ks = 0;
+        w.kb0 = 0;
+        w.nkb = p.num_k_blocks;
+    }
+    return w;
+}
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j) {
     if (p.mode == MDIR_SCAN_DENSE) return j;
@@ -189,8 +215,9 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             int stage = 0;
             uint32_t phase = 0;
             for (int j = blockIdx.x; j < p.n_work; j += gridDim.x) {
-                const int row0 = tile_of_work(p, j) * kBlockM;
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const WorkItem w = decode_work(p, j);
+                const int row0 = w.tile * kBlockM;
+                for (int kb = w.kb0; kb < w.kb0 + w.nkb; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
                     const uint32_t fb = smem_u32(&full_bar[stage]);
                     const uint32_t a_dst = smem_base + (uint32_t)stage * stage_bytes;
@@ -217,7 +244,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(smem_u32(&tmem_empty_bar[b]), acc_phase ^ 1u);
                 tc_fence_after();
-                for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+                const int nkb = decode_work(p, j).nkb;
+                for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
                     const uint32_t a_base = smem_base + (uint32_t)stage * stage_bytes;
@@ -247,7 +275,9 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const int tile = tile_of_work(p, j);
+            const WorkItem w = decode_work(p, j);
+            const int tile = w.tile;
+            float* dense_out = p.dense_out + (int64_t)w.ks * p.split_stride;
             mbar_wait(smem_u32(&tmem_full_bar[b]), acc_phase);
             tc_fence_after();
 #pragma unroll 1
@@ -269,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
                                 if (c0 + i < p.n_q)
-                                    p.dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
+                                    dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
                         }
                     } else if (row_ok) {
 #pragma unroll
@@ -350,7 +380,7 @@ using namespace mdir;
 
 static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, int n_q, int D, int mode, int sample_stride, int n_sample,
                        float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base, uint64_t* cand,
-                       uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
+                       uint32_t* seg_counts, int cap_s, int cap_l, void* stream, int k_split = 1, int64_t split_stride = 0) {
     const int esz = tf32 ? 4 : 2;
     MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 16 / esz && (D % (16 / esz)) == 0);
     MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
@@ -368,9 +398,16 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.mode = mode;
     p.sample_stride = sample_stride;
     p.n_sample = n_sample;
+    p.k_split = 1;
+    p.kb_per_split = p.num_k_blocks;
+    p.split_stride = split_stride;
     if (mode == MDIR_SCAN_DENSE) {
         MDIR_CHECK_ARG(dense_out && dense_ld >= n_db);
-        p.n_work = p.n_tiles;
+        if (k_split > 1) {
+            p.kb_per_split = (p.num_k_blocks + k_split - 1) / k_split;
+            p.k_split = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // every split gets >= 1 k-block
+        }
+        p.n_work = p.n_tiles * p.k_split;
     } else if (mode == MDIR_SCAN_SAMPLE) {
         MDIR_CHECK_ARG(dense_out && n_sample >= 1 && sample_stride >= 1);
         MDIR_CHECK_ARG((int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
@@ -457,5 +494,92 @@ extern "C" int mdir_split_tf32x3(const float* src, int64_t n, int D, int role, f
     const int64_t total = n * D;
     split_tf32x3_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, n, D, role, dst);
     MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- Lw projection on the tensor cores: out = normalise(P[:dims] (v - m)) with 3xTF32 (fp32-faithful) -------------
+namespace mdir {
+
+// (v - m) -> [hi | lo | hi] (query-side role of the 3xTF32 split), rows [r0, r0 + nb)
+__global__ void __launch_bounds__(256) center_split_kernel(const float* __restrict__ v, const float* __restrict__ m, int nb, int D,
+                                                           float* __restrict__ dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nb * D) return;
+    const int64_t r = i / D;
+    const int d = (int)(i - r * D);
+    const float x = v[i] - (m ? m[d] : 0.f);
+    const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    float* o = dst + r * 3 * (int64_t)D;
+    o[d] = hi;
+    o[D + d] = x - hi;
+    o[2 * D + d] = hi;
+}
+
+// out[r, :] = sum_ks partial[ks, r, :], then / (||.|| + eps) when eps >= 0.  One CTA per row.
+__global__ void __launch_bounds__(256) sum_partials_l2n_kernel(const float* __restrict__ partial, int k_split, int64_t split_stride,
+                                                               int64_t ld, int dims, float eps, float* __restrict__ out, int64_t out_ld) {
+    __shared__ float red[32];
+    const int r = blockIdx.x;
+    float nn = 0.f;
+    for (int j = threadIdx.x; j < dims; j += blockDim.x) {
+        float a = 0.f;
+        for (int ks = 0; ks < k_split; ++ks) a += partial[(int64_t)ks * split_stride + (int64_t)r * ld + j];
+        out[(int64_t)r * out_ld + j] = a;
+        nn += a * a;
+    }
+    if (eps < 0.f) return;
+    nn = block_sum(nn, red);
+    const float inv = 1.0f / (sqrtf(nn) + eps);
+    for (int j = threadIdx.x; j < dims; j += blockDim.x) out[(int64_t)r * out_ld + j] *= inv;
+}
+
+static int whiten_plan(int D, int dims, int* k_split) {
+    const int tiles = (dims + kBlockM - 1) / kBlockM;
+    const int nkb = (3 * D + 31) / 32;
+    int ks = kNumSMs / tiles;
+    if (ks < 1) ks = 1;
+    if (ks > nkb) ks = nkb;
+    const int per = (nkb + ks - 1) / ks;
+    *k_split = (nkb + per - 1) / per;
+    return 0;
+}
+
+}  // namespace mdir
+
+extern "C" size_t mdir_whiten_tc_workspace_bytes(int n, int D, int dims) {
+    if (n <= 0 || D <= 0 || dims <= 0) return 0;
+    int ks;
+    whiten_plan(D, dims, &ks);
+    const size_t nb = n < kMaxN ? n : kMaxN;
+    return nb * 3 * (size_t)D * 4 + (size_t)ks * nb * dims * 4 + 512;
+}
+
+extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int D, const float* Px3, int dims, float renorm_eps,
+                                      float* out, void* ws, void* stream) {
+    MDIR_CHECK_ARG(v && Px3 && out && ws && n >= 0 && D > 0 && (D % 4) == 0 && dims > 0);
+    MDIR_CHECK_ARG((((uintptr_t)Px3 | (uintptr_t)ws) & 15) == 0);
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int ks;
+    whiten_plan(D, dims, &ks);
+    const int nb_max = n < kMaxN ? n : kMaxN;
+    float* vx3 = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    float* partial = vx3 + (size_t)nb_max * 3 * D;
+    for (int r0 = 0; r0 < n; r0 += kMaxN) {
+        const int nb = (n - r0) < kMaxN ? (n - r0) : kMaxN;
+        const int64_t total = (int64_t)nb * D;
+        center_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v + (size_t)r0 * D, m, nb, D, vx3);
+        MDIR_LAUNCH_CHECK();
+        const int64_t split_stride = (int64_t)nb * dims;
+        int rc = launch_scan(true, Px3, dims, vx3, nb, 3 * D, MDIR_SCAN_DENSE, 0, 0, partial, dims, nullptr, 0, nullptr, nullptr, 0, 0,
+                             stream, ks, split_stride);
+        if (rc) return rc;
+        // launch_scan may have reduced the split count; recompute it the same way
+        const int nkb = (3 * D + 31) / 32;
+        const int per = (nkb + ks - 1) / ks;
+        const int ks_eff = ks > 1 ? (nkb + per - 1) / per : 1;
+        sum_partials_l2n_kernel<<<nb, 256, 0, st>>>(partial, ks_eff, split_stride, dims, dims, renorm_eps, out + (size_t)r0 * dims, dims);
+        MDIR_LAUNCH_CHECK();
+    }
     return 0;
 }

@@ -42,12 +42,29 @@ def ms_aggregate(vectors, nscales, msp, m=None, normalized=True, l2n_eps=1e-6):
     return out
 
 
-def whiten_project(v, m, P, dims, renorm_eps=1e-6):
-    """v (n, D) fp32 cuda, m (D,) or None, P (>=dims, D) -> (n, dims)"""
+def split_lw(P):
+    """P (dims, D) fp32 cuda -> (dims, 3D) [hi|hi|lo] for the tensor-core (3xTF32) projection."""
+    P = P.contiguous()
+    out = torch.empty((P.shape[0], 3 * P.shape[1]), dtype=torch.float32, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.lib().mdir_split_tf32x3(_lib.ptr(P), P.shape[0], P.shape[1], 0, _lib.ptr(out), _lib.stream()), "mdir_split_tf32x3")
+    return out
+
+
+def whiten_project(v, m, P, dims, renorm_eps=1e-6, Px3=None):
+    """v (n, D) fp32 cuda, m (D,) or None, P (>=dims, D) -> (n, dims).  Batches of more than 4
+    vectors go to the tensor cores when the pre-split Px3 = split_lw(P) is supplied."""
     _lib.require_cuda(v, "v")
     v = v.contiguous()
     n, D = v.shape
     out = torch.empty((n, dims), dtype=torch.float32, device=v.device)
+    if Px3 is not None and n > 4 and D % 4 == 0:
+        lib = _lib.lib()
+        with torch.cuda.device(v.device):
+            ws = torch.empty(lib.mdir_whiten_tc_workspace_bytes(n, D, int(dims)), dtype=torch.uint8, device=v.device)
+            _lib.check(lib.mdir_whiten_project_tc(_lib.ptr(v), _lib.ptr(m), n, D, _lib.ptr(Px3), int(dims), float(renorm_eps),
+                                                  _lib.ptr(out), _lib.ptr(ws), _lib.stream()), "mdir_whiten_project_tc")
+        return out
     with torch.cuda.device(v.device):
         _lib.check(_lib.lib().mdir_whiten_project(_lib.ptr(v), _lib.ptr(m), n, D, _lib.ptr(P), int(dims), float(renorm_eps),
                                                   _lib.ptr(out), _lib.stream()), "mdir_whiten_project")
@@ -134,7 +151,7 @@ def whitenapply(X, m, P, dimensions=None, device="cuda"):
     Xt = torch.as_tensor(np.ascontiguousarray(np.asarray(X).T), dtype=torch.float32).to(device)
     mt = torch.as_tensor(np.asarray(m).reshape(-1), dtype=torch.float32).to(device)
     Pt = torch.as_tensor(np.ascontiguousarray(np.asarray(P)[:dimensions]), dtype=torch.float32).to(device)
-    out = whiten_project(Xt, mt, Pt, dimensions)
+    out = whiten_project(Xt, mt, Pt, dimensions, Px3=split_lw(Pt) if Pt.shape[1] % 4 == 0 else None)
     return np.ascontiguousarray(out.cpu().numpy().T).astype(np.asarray(X).dtype, copy=False)
 
 
@@ -168,6 +185,7 @@ class RetrievalHead:
             self.P = torch.tensor(lw['P'], dtype=torch.float32, device=self.device).contiguous()
             self.m = torch.tensor(lw['m'], dtype=torch.float32, device=self.device).reshape(-1).contiguous()
             self.dimensions = dimensions or self.P.shape[0]
+            self.Px3 = split_lw(self.P) if self.P.shape[1] % 4 == 0 else None
 
     def pack(self, fmaps):
         """Describe a ragged set of feature maps once: flat list of (1,C,h,w)/(C,h,w) fp32 cuda
@@ -214,5 +232,5 @@ class RetrievalHead:
         assert n_maps % self.nscales == 0
         v = ms_aggregate(pooled.view(n_maps // self.nscales, self.nscales, Cc), self.nscales, self.msp, normalized=False)
         if self.P is not None:
-            v = whiten_project(v, self.m, self.P, self.dimensions)
+            v = whiten_project(v, self.m, self.P, self.dimensions, Px3=self.Px3)
         return v
