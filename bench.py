@@ -3,7 +3,7 @@
 
     queries/s against a 1,001,001 x 2048 database (R1M shape, config 4), 70 queries per step,
     top-100 per query identical to the fp32 reference ranking (bf16 tcgen05 scan + fused
-    threshold filter + exact fp32 re-scoring of a 200-entry shortlist),
+    threshold filter + exact fp32 re-scoring of a 132-entry shortlist),
     on N B200s of one node (database rows sharded, local top-k, one NCCL all-gather of keys).
 
 A "step" = one batch of 70 queries ranked against the whole database.
@@ -185,7 +185,7 @@ def run_ours(args):
     import torch
     import mdir_b200
     from mdir_b200 import _lib
-    from mdir_b200.search import Index, ShardedIndex, GraphedSearch, pack_bf16
+    from mdir_b200.search import Index, ShardedIndex, GraphedSearch, pack_bf16, default_shortlist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -337,7 +337,7 @@ def run_ours(args):
         "metric": METRIC, "value": N_Q * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": 2 * TOPK, "db_rows_per_gpu": hi - lo,
+        "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK), "db_rows_per_gpu": hi - lo,
                    "sharding": "db rows contiguous over %d GPU(s); all-gather of %d B of keys per rank" % (world, N_Q * TOPK * 8),
                    "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
         "clocks": sampler.summary(),

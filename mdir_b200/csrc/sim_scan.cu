@@ -515,22 +515,45 @@ __global__ void __launch_bounds__(256) center_split_kernel(const float* __restri
     o[2 * D + d] = hi;
 }
 
-// out[r, :] = sum_ks partial[ks, r, :], then / (||.|| + eps) when eps >= 0.  One CTA per row.
-__global__ void __launch_bounds__(256) sum_partials_l2n_kernel(const float* __restrict__ partial, int k_split, int64_t split_stride,
-                                                               int64_t ld, int dims, float eps, float* __restrict__ out, int64_t out_ld) {
-    __shared__ float red[32];
-    const int r = blockIdx.x;
-    float nn = 0.f;
-    for (int j = threadIdx.x; j < dims; j += blockDim.x) {
-        float a = 0.f;
-        for (int ks = 0; ks < k_split; ++ks) a += partial[(int64_t)ks * split_stride + (int64_t)r * ld + j];
-        out[(int64_t)r * out_ld + j] = a;
-        nn += a * a;
+// out[i] = sum_ks partial[ks * split_stride + i] in a fixed order (deterministic), 4 elements per thread
+__global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ partial, int k_split, int64_t split_stride,
+                                                           int64_t total, float* __restrict__ out) {
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= total) return;
+    if (i + 3 < total && (split_stride & 3) == 0) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ks = 0;
+        for (; ks + 3 < k_split; ks += 4) {                       // 4 independent 128-bit loads in flight
+            const float4 v0 = *reinterpret_cast<const float4*>(partial + (int64_t)ks * split_stride + i);
+            const float4 v1 = *reinterpret_cast<const float4*>(partial + (int64_t)(ks + 1) * split_stride + i);
+            const float4 v2 = *reinterpret_cast<const float4*>(partial + (int64_t)(ks + 2) * split_stride + i);
+            const float4 v3 = *reinterpret_cast<const float4*>(partial + (int64_t)(ks + 3) * split_stride + i);
+            a.x = (((a.x + v0.x) + v1.x) + v2.x) + v3.x; a.y = (((a.y + v0.y) + v1.y) + v2.y) + v3.y;
+            a.z = (((a.z + v0.z) + v1.z) + v2.z) + v3.z; a.w = (((a.w + v0.w) + v1.w) + v2.w) + v3.w;
+        }
+        for (; ks < k_split; ++ks) {
+            const float4 v = *reinterpret_cast<const float4*>(partial + (int64_t)ks * split_stride + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(out + i) = a;
+    } else {
+        for (int64_t e = i; e < total && e < i + 4; ++e) {
+            float a = 0.f;
+            for (int ks = 0; ks < k_split; ++ks) a += partial[(int64_t)ks * split_stride + e];
+            out[e] = a;
+        }
     }
-    if (eps < 0.f) return;
-    nn = block_sum(nn, red);
-    const float inv = 1.0f / (sqrtf(nn) + eps);
-    for (int j = threadIdx.x; j < dims; j += blockDim.x) out[(int64_t)r * out_ld + j] *= inv;
+}
+
+// x / (||x||_2 + eps) per row, in place (rows of `dims` floats)
+__global__ void __launch_bounds__(256) row_l2n_kernel(float* x, int dims, float eps) {
+    __shared__ float red[32];
+    float* row = x + (int64_t)blockIdx.x * dims;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < dims; j += blockDim.x) { const float v = row[j]; s += v * v; }
+    s = block_sum(s, red);
+    const float inv = 1.0f / (sqrtf(s) + eps);
+    for (int j = threadIdx.x; j < dims; j += blockDim.x) row[j] *= inv;
 }
 
 static int whiten_plan(int D, int dims, int* k_split) {
@@ -578,8 +601,13 @@ extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int
         const int nkb = (3 * D + 31) / 32;
         const int per = (nkb + ks - 1) / ks;
         const int ks_eff = ks > 1 ? (nkb + per - 1) / per : 1;
-        sum_partials_l2n_kernel<<<nb, 256, 0, st>>>(partial, ks_eff, split_stride, dims, dims, renorm_eps, out + (size_t)r0 * dims, dims);
+        float* o = out + (size_t)r0 * dims;
+        sum_partials_kernel<<<(unsigned)((split_stride / 4 + 256) / 256), 256, 0, st>>>(partial, ks_eff, split_stride, split_stride, o);
         MDIR_LAUNCH_CHECK();
+        if (renorm_eps >= 0.f) {
+            row_l2n_kernel<<<nb, 256, 0, st>>>(o, dims, renorm_eps);
+            MDIR_LAUNCH_CHECK();
+        }
     }
     return 0;
 }

@@ -31,6 +31,13 @@ MAX_SAMPLE_TILES = 512
 TARGET_CAND = 4500    # candidates per query the sampling plan aims for (kth * n_tiles / n_sample), ~30 per CTA segment
 
 
+def default_shortlist(k):
+    """bf16 shortlist size for an exact fp32 top-k: bf16 score noise (~3e-5 at D=2048 on unit vectors)
+    is ~40x smaller than the score gap between rank k and rank k+32 of a 1M-row database, so the true
+    fp32 top-k lies inside the bf16 top-(k+32)."""
+    return max(int(k) + 32, -(-5 * int(k) // 4))
+
+
 def _as_dev_f32(x, device):
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
@@ -169,7 +176,7 @@ class Index:
         the device, ordered by (score desc, index asc); idx = idx_base + local row, -1 padding.
 
         precision="bf16": exact top-k of the bf16-input / fp32-accumulate scores.
-        precision="fp32": bf16 shortlist of `shortlist` (default 2k) per query, re-scored exactly in
+        precision="fp32": bf16 shortlist of `shortlist` (default max(k+32, 1.25k)) per query, re-scored exactly in
                           fp32 against the fp32 master copy, then top-k of those.
         check=False skips the (synchronising) candidate-overflow check; call check_overflow() later."""
         lib = _lib.lib()
@@ -183,7 +190,7 @@ class Index:
             if precision == "fp32":
                 if self.db32 is None:
                     raise _lib.MdirError("precision='fp32' needs keep_fp32=True")
-                kth = min(self.n, int(shortlist or 2 * k))
+                kth = min(self.n, int(shortlist or default_shortlist(k)))
             elif precision == "bf16":
                 kth = k_eff
             else:
