@@ -169,6 +169,15 @@ int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* s
                        float* out_scores, int32_t* out_idx, uint64_t* out_keys,
                        uint64_t* tau, int32_t* overflow, void* stream);
 
+/* mdir_topk_finalize + exact fp32 re-scoring fused: selects the `shortlist` best keys (bf16
+ * scores), recomputes their dot products in fp32 from db32 (rows idx - idx_base of this shard)
+ * against q32[q], re-sorts and emits the best k_out (out_* are (n_q, k_out)).           */
+int mdir_topk_finalize_rescore(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg,
+                               int cap0, int cap_l, int n_q, int shortlist, int k_out,
+                               const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int D,
+                               float* out_scores, int32_t* out_idx, uint64_t* out_keys,
+                               uint64_t* tau, int32_t* overflow, void* stream);
+
 /* Exact fp32 re-scoring of a shortlist: out[q, j] = <db32[idx[q,j]-idx_base], q32[q]>
  * (idx < 0 or outside this shard -> -inf); then callers re-finalize.             */
 int mdir_rescore_f32(const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int n_q, int D,

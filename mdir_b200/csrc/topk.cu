@@ -46,6 +46,43 @@ __device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, 
     return bin;
 }
 
+// kth smallest (1-based) of ONE 32-bit value per thread of a 1024-thread block (4 radix passes of
+// one element each).  Used to bound the selection: the kth smallest of the per-thread minima is an
+// upper bound B of the kth smallest key overall, so only the few keys <= B take part in the real
+// selection passes (the warp-aggregated histogram update is the expensive part of a pass).
+__device__ __forceinline__ uint32_t block_kth_of_thread_values(uint32_t val, uint32_t kth, uint32_t* hist, uint32_t* s_prefix,
+                                                               uint32_t* s_k) {
+    const int lane = threadIdx.x & 31;
+    __syncthreads();
+    if (threadIdx.x == 0) { *s_prefix = 0u; *s_k = kth; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t prefix = *s_prefix;
+        const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        const bool hit = (val & himask) == prefix;
+        if (__any_sync(0xffffffffu, hit)) {
+            const int d = hit ? (int)((val >> shift) & 0xffu) : 256 + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t before;
+            const int b = find_bin_warp0(hist, *s_k, &before);
+            if (lane == 0) {
+                *s_k -= before;
+                *s_prefix = prefix | ((uint32_t)b << shift);
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t r = *s_prefix;
+    __syncthreads();
+    return r;
+}
+
 // One CTA (1024 threads) per query.  MSB-first 8-bit radix select on the 32-bit score key
 // (4 passes over the L2-resident score row, warp-aggregated shared-memory histogram updates).
 // tau = (kth-best score key << 32) | index limit: normally 0xffffffff (the rows tying the kth
@@ -69,6 +106,22 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
     if ((int64_t)kth > n) {
         result = 0xffffffffu;
     } else {
+        uint32_t bound = 0xffffffffu;
+        if (kth <= 1024) {                 // see block_kth_of_thread_values: one extra streaming pass for the bound
+            uint32_t mymin = 0xffffffffu;
+            for (int64_t base = 0; base < n_round; base += 8 * 1024) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int64_t i = base + u * 1024 + threadIdx.x;
+                    v[u] = i < n ? __ldg(sc + i) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (base + u * 1024 + threadIdx.x < n) mymin = min(mymin, ~orderable(v[u]));
+            }
+            bound = block_kth_of_thread_values(mymin, (uint32_t)kth, hist, &s_prefix, &s_k);
+        }
         if (threadIdx.x == 0) { s_prefix = 0u; s_k = (uint32_t)kth; }
         for (int pass = 0; pass < 4; ++pass) {
             const int shift = 24 - 8 * pass;
@@ -89,7 +142,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                     const int64_t i = base + u * 1024 + threadIdx.x;
                     const bool valid = i < n;
                     const uint32_t key = ~orderable(v[u]);
-                    const bool hit = valid && ((key & himask) == prefix);
+                    const bool hit = valid && key <= bound && ((key & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
                         const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
                         const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -175,6 +228,118 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
     }
 }
 
+// Register-resident variant for n <= 32 * 1024 rows (the usual sample size): every thread keeps its
+// 32 score keys in registers, so the 4 (+4) radix passes and the append pass never re-read the row.
+__global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __restrict__ scores, int64_t ld, int n, int kth,
+                                                                 int sample_stride, uint32_t idx_base, uint64_t* __restrict__ tau,
+                                                                 uint64_t* __restrict__ cand, int64_t cand_row,
+                                                                 uint32_t* __restrict__ seg_counts, int n_seg, int cap) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_k, s_n, s_ties;
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const float* sc = scores + (int64_t)q * ld;
+    uint32_t key[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) {
+        const int i = u * 1024 + threadIdx.x;
+        key[u] = i < n ? ~orderable(__ldg(sc + i)) : 0xffffffffu;     // padding sorts last (and is never valid)
+    }
+    uint32_t result = 0xffffffffu, idx_limit = 0xffffffffu;
+    if (kth <= n) {
+        uint32_t bound = 0xffffffffu;
+        if (kth <= 1024) {
+            uint32_t mymin = 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < 32; ++u)
+                if (u * 1024 + (int)threadIdx.x < n) mymin = min(mymin, key[u]);
+            bound = block_kth_of_thread_values(mymin, (uint32_t)kth, hist, &s_prefix, &s_k);
+        }
+        if (threadIdx.x == 0) { s_prefix = 0u; s_k = (uint32_t)kth; }
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+                const bool valid = u * 1024 + (int)threadIdx.x < n;
+                const bool hit = valid && key[u] <= bound && ((key[u] & himask) == prefix);
+                if (__any_sync(0xffffffffu, hit)) {
+                    const int d = hit ? (int)((key[u] >> shift) & 0xffu) : 256 + lane;
+                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                uint32_t before;
+                const int b = find_bin_warp0(hist, s_k, &before);
+                if (lane == 0) {
+                    s_k -= before;
+                    s_prefix = prefix | ((uint32_t)b << shift);
+                    s_ties = hist[b];
+                }
+            }
+            __syncthreads();
+        }
+        result = s_prefix;
+        if (s_k < s_ties) {            // more rows tie the kth score than are wanted: lowest indices win
+            __syncthreads();
+            if (threadIdx.x == 0) s_prefix = 0u;
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
+                __syncthreads();
+                const uint32_t prefix = s_prefix;
+                const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+                for (int u = 0; u < 32; ++u) {
+                    const int i = u * 1024 + threadIdx.x;
+                    const uint32_t idx = sample_pos_to_idx(i, sample_stride, idx_base);
+                    const bool hit = i < n && key[u] == result && ((idx & himask) == prefix);
+                    if (__any_sync(0xffffffffu, hit)) {
+                        const int d = hit ? (int)((idx >> shift) & 0xffu) : 256 + lane;
+                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    uint32_t before;
+                    const int b = find_bin_warp0(hist, s_k, &before);
+                    if (lane == 0) {
+                        s_k -= before;
+                        s_prefix = prefix | ((uint32_t)b << shift);
+                    }
+                }
+                __syncthreads();
+            }
+            idx_limit = s_prefix;
+        }
+    }
+    const uint64_t tau_key = ((uint64_t)result << 32) | (uint64_t)idx_limit;
+    if (threadIdx.x == 0) { tau[q] = tau_key; s_n = 0u; }
+    if (cand) {
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            const int i = u * 1024 + threadIdx.x;
+            if (i < n && key[u] <= result) {
+                // key = (~orderable(score) << 32) | idx: the upper half is exactly the register key
+                const uint64_t k64 = ((uint64_t)key[u] << 32) | (uint64_t)sample_pos_to_idx(i, sample_stride, idx_base);
+                if (k64 <= tau_key) {
+                    const uint32_t pos = atomicAdd(&s_n, 1u);
+                    if (pos < (uint32_t)cap) cand[(int64_t)q * cand_row + pos] = k64;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) seg_counts[(int64_t)q * n_seg] = s_n;
+    }
+}
+
 __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
     for (int kk = 2; kk <= n; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
@@ -200,7 +365,9 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
                                                              const uint32_t* __restrict__ seg_counts, int n_seg, int cap0, int cap_l,
                                                              int k, int smem_cap, float* __restrict__ out_scores,
                                                              int32_t* __restrict__ out_idx, uint64_t* __restrict__ out_keys,
-                                                             uint64_t* __restrict__ tau, int32_t* __restrict__ overflow) {
+                                                             uint64_t* __restrict__ tau, int32_t* __restrict__ overflow,
+                                                             const float* __restrict__ db32, int64_t n_db, uint32_t idx_base,
+                                                             const float* __restrict__ q32, int D, int k_out) {
     extern __shared__ uint64_t skeys[];
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix;
@@ -313,16 +480,68 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         res = sorted;
         nres = min(cnt, k);
     }
-    for (int j = threadIdx.x; j < k; j += blockDim.x) {
-        const uint64_t key = j < nres ? res[j] : ~0ull;
-        const bool ok = j < nres && key != ~0ull;
-        if (out_scores) out_scores[(int64_t)q * k + j] = ok ? key_score(key) : -INFINITY;
-        if (out_idx) out_idx[(int64_t)q * k + j] = ok ? (int32_t)(uint32_t)key : -1;
-        if (out_keys) out_keys[(int64_t)q * k + j] = ok ? key : ~0ull;
-    }
     if (threadIdx.x == 0 && overflow) {
         overflow[q] = ovf_any ? 1 : 0;
         if (ovf_any && tau && nres > 0) tau[q] = res[min(k, nres) - 1];
+    }
+    int k_emit = k;
+    if (db32) {
+        // fused exact re-scoring: the k best keys by bf16 score are a shortlist; recompute their dot
+        // products in fp32 from the master copy (one warp per row, the query staged in shared memory),
+        // re-sort, and emit the best k_out.
+        uint64_t* rk = const_cast<uint64_t*>(res);
+        float* qs = reinterpret_cast<float*>(sorted + kpow2);
+        for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = q32[(int64_t)q * D + i];
+        const int nk = min(k, nres);
+        __syncthreads();
+        for (int j = threadIdx.x >> 5; j < nk; j += 32) {
+            const uint64_t key = rk[j];
+            const uint32_t gi = (uint32_t)key;
+            const int64_t row = (int64_t)gi - (int64_t)idx_base;
+            uint64_t nkey = ~0ull;
+            if (key != ~0ull && row >= 0 && row < n_db) {
+                const float* a = db32 + row * D;
+                float acc = 0.f;
+                if ((D & 3) == 0) {
+                    const float4* a4 = reinterpret_cast<const float4*>(a);
+                    const float4* b4 = reinterpret_cast<const float4*>(qs);
+                    const int n4 = D >> 2;
+                    float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+                    int i = lane;
+                    for (; i + 96 < n4; i += 128) {            // 4 independent 128-bit loads in flight per lane
+                        const float4 x0 = __ldg(a4 + i), x1 = __ldg(a4 + i + 32), x2 = __ldg(a4 + i + 64), x3 = __ldg(a4 + i + 96);
+                        const float4 y0 = b4[i], y1 = b4[i + 32], y2 = b4[i + 64], y3 = b4[i + 96];
+                        acc = fmaf(x0.x, y0.x, acc); acc = fmaf(x0.y, y0.y, acc); acc = fmaf(x0.z, y0.z, acc); acc = fmaf(x0.w, y0.w, acc);
+                        acc1 = fmaf(x1.x, y1.x, acc1); acc1 = fmaf(x1.y, y1.y, acc1); acc1 = fmaf(x1.z, y1.z, acc1); acc1 = fmaf(x1.w, y1.w, acc1);
+                        acc2 = fmaf(x2.x, y2.x, acc2); acc2 = fmaf(x2.y, y2.y, acc2); acc2 = fmaf(x2.z, y2.z, acc2); acc2 = fmaf(x2.w, y2.w, acc2);
+                        acc3 = fmaf(x3.x, y3.x, acc3); acc3 = fmaf(x3.y, y3.y, acc3); acc3 = fmaf(x3.z, y3.z, acc3); acc3 = fmaf(x3.w, y3.w, acc3);
+                    }
+                    for (; i < n4; i += 32) {
+                        const float4 x = __ldg(a4 + i), y = b4[i];
+                        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+                    }
+                    acc = (acc + acc1) + (acc2 + acc3);
+                } else {
+                    for (int i = lane; i < D; i += 32) acc = fmaf(a[i], qs[i], acc);
+                }
+                acc = warp_sum(acc);
+                nkey = make_key(acc, gi);
+            }
+            __syncwarp();
+            if (lane == 0) rk[j] = nkey;
+        }
+        for (int j = nk + threadIdx.x; j < kpow2; j += blockDim.x) rk[j] = ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(rk, kpow2);
+        nres = nk;
+        k_emit = k_out;
+    }
+    for (int j = threadIdx.x; j < k_emit; j += blockDim.x) {
+        const uint64_t key = j < nres ? res[j] : ~0ull;
+        const bool ok = j < nres && key != ~0ull;
+        if (out_scores) out_scores[(int64_t)q * k_emit + j] = ok ? key_score(key) : -INFINITY;
+        if (out_idx) out_idx[(int64_t)q * k_emit + j] = ok ? (int32_t)(uint32_t)key : -1;
+        if (out_keys) out_keys[(int64_t)q * k_emit + j] = ok ? key : ~0ull;
     }
 }
 
@@ -444,15 +663,21 @@ extern "C" int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n
     MDIR_CHECK_ARG(scores && tau && n >= 0 && n_q >= 0 && kth >= 1 && ld >= n);
     MDIR_CHECK_ARG(cand == nullptr || (seg_counts != nullptr && cap >= 1 && n_seg >= 1 && cand_row >= cap));
     if (n_q == 0) return 0;
+    if (n <= 32 * 1024) {
+        select_kth_reg_kernel<<<n_q, 1024, 0, (cudaStream_t)stream>>>(scores, ld, (int)n, kth, sample_stride, idx_base, tau, cand,
+                                                                      cand_row, seg_counts, n_seg, cap);
+        MDIR_LAUNCH_CHECK();
+        return 0;
+    }
     select_kth_kernel<<<n_q, 1024, 0, (cudaStream_t)stream>>>(scores, ld, n, kth, sample_stride, idx_base, tau, cand, cand_row,
                                                               seg_counts, n_seg, cap);
     MDIR_LAUNCH_CHECK();
     return 0;
 }
 
-extern "C" int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0, int cap_l,
-                                  int n_q, int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau,
-                                  int32_t* overflow, void* stream) {
+static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0, int cap_l, int n_q,
+                           int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau, int32_t* overflow,
+                           const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int D, int k_out, void* stream) {
     MDIR_CHECK_ARG(cand && seg_counts && n_seg >= 1 && n_seg <= MDIR_CAND_SEGS && cap0 >= 0 && n_q >= 0 && k >= 1 && k <= 4096);
     MDIR_CHECK_ARG(n_seg == 1 || cap_l >= 1);
     MDIR_CHECK_ARG(cand_row >= (int64_t)cap0 + (int64_t)(n_seg - 1) * cap_l);
@@ -464,16 +689,38 @@ extern "C" int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const 
     int smem_cap = 1024;
     while (smem_cap < want && smem_cap < 16384) smem_cap <<= 1;
     if (smem_cap < 2 * kpow2) smem_cap = 2 * kpow2;
-    const size_t smem = (size_t)(smem_cap + kpow2) * 8;
+    size_t smem = (size_t)(smem_cap + kpow2) * 8;
+    if (db32) {
+        MDIR_CHECK_ARG(q32 && D > 0 && D <= 8192 && k_out >= 1 && k_out <= k && n_db >= 0);
+        MDIR_CHECK_ARG((((uintptr_t)db32 | (uintptr_t)q32) & 15) == 0);
+        smem += (size_t)D * 4;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 4096) * 8));
+        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 4096) * 8 + 8192 * 4));
         attr_set = true;
     }
     topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap,
-                                                                     out_scores, out_idx, out_keys, tau, overflow);
+                                                                     out_scores, out_idx, out_keys, tau, overflow, db32, n_db, idx_base,
+                                                                     q32, D, k_out);
     MDIR_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0, int cap_l,
+                                  int n_q, int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau,
+                                  int32_t* overflow, void* stream) {
+    return launch_finalize(cand, cand_row, seg_counts, n_seg, cap0, cap_l, n_q, k, out_scores, out_idx, out_keys, tau, overflow, nullptr, 0,
+                           0, nullptr, 0, 0, stream);
+}
+
+extern "C" int mdir_topk_finalize_rescore(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0,
+                                          int cap_l, int n_q, int shortlist, int k_out, const float* db32, int64_t n_db,
+                                          uint32_t idx_base, const float* q32, int D, float* out_scores, int32_t* out_idx,
+                                          uint64_t* out_keys, uint64_t* tau, int32_t* overflow, void* stream) {
+    MDIR_CHECK_ARG(db32 != nullptr);
+    return launch_finalize(cand, cand_row, seg_counts, n_seg, cap0, cap_l, n_q, shortlist, out_scores, out_idx, out_keys, tau, overflow,
+                           db32, n_db, idx_base, q32, D, k_out, stream);
 }
 
 extern "C" int mdir_rescore_f32(const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int n_q, int D,

@@ -127,12 +127,20 @@ class Index:
         return (self._buf("tau", (MAX_Q,), torch.int64), self._buf("cand", (MAX_Q, CAND_ROW), torch.int64),
                 self._buf("segcnt", (MAX_Q, N_SEGS), torch.int32))
 
-    def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf):
-        _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth,
-                                                 _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
-                                                 _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+    def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore=None):
+        """rescore = (q32_block, k_out): fused exact fp32 re-scoring of the kth-long bf16 shortlist."""
+        if rescore is None:
+            _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth,
+                                                     _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
+                                                     _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
+        else:
+            q32, k_out = rescore
+            _lib.check(_lib.lib().mdir_topk_finalize_rescore(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth, k_out,
+                                                             _lib.ptr(self.db32), self.n, self.idx_base, _lib.ptr(q32), self.D,
+                                                             _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
+                                                             _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize_rescore")
 
-    def _dense_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
+    def _dense_block(self, q16, kth, out_scores, out_idx, out_keys, ovf, rescore=None):
         """All scores of the block -> exact kth-key select -> sort.  The route for small databases
         and the guaranteed-terminating recovery when a candidate segment overflowed (the select
         emits exactly kth keys, so nothing can overflow here)."""
@@ -144,15 +152,15 @@ class Index:
         self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
                                        _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, _lib.stream()), "mdir_select_kth")
-        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf)
+        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore)
 
-    def _topk_block(self, q16, kth, out_scores, out_idx, out_keys, ovf):
+    def _topk_block(self, q16, kth, out_scores, out_idx, out_keys, ovf, rescore=None):
         """Exact top-kth of one block of <= 128 queries by bf16-input/fp32-accumulate scores."""
         lib = _lib.lib()
         nq = q16.shape[0]
         plan = self._plan(kth)
         if plan is None:
-            return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf)
+            return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf, rescore)
         tau, cand, cnt = self._cand_bufs()
         cnt.zero_()
         n_sample, stride = plan
@@ -168,7 +176,7 @@ class Index:
         self._scan(q16, 2, stride, n_sample, None, 0, tau, cand, cnt)
         if prof is not None:
             prof.end((self.n - rows) * self.D * 2)
-        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf)
+        self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore)
 
     # ------------------------------------------------------------------ public
     def search(self, q, k, precision="fp32", shortlist=None, check=True, return_keys=False):
@@ -190,7 +198,7 @@ class Index:
             if precision == "fp32":
                 if self.db32 is None:
                     raise _lib.MdirError("precision='fp32' needs keep_fp32=True")
-                kth = min(self.n, int(shortlist or default_shortlist(k)))
+                kth = max(k_eff, min(self.n, int(shortlist or default_shortlist(k))))
             elif precision == "bf16":
                 kth = k_eff
             else:
@@ -206,42 +214,32 @@ class Index:
                 q1 = min(q0 + MAX_Q, nq_all)
                 nq = q1 - q0
                 ovf = self._ovf[q0:q1]
-                if precision == "bf16":
-                    bs, bi = out_s[q0:q1], out_i[q0:q1]
-                    bk = out_k[q0:q1] if return_keys else None
-                    if k_eff < k:      # pad columns beyond the database size
-                        bs.fill_(float("-inf")); bi.fill_(-1)
-                        if bk is not None:
-                            bk.fill_(-1)
-                        tmp_s = torch.empty((nq, k_eff), dtype=torch.float32, device=self.device)
-                        tmp_i = torch.empty((nq, k_eff), dtype=torch.int32, device=self.device)
-                        tmp_k = torch.empty((nq, k_eff), dtype=torch.int64, device=self.device)
-                        self._run_block(q16[q0:q1], k_eff, tmp_s, tmp_i, tmp_k, ovf, check)
-                        bs[:, :k_eff] = tmp_s; bi[:, :k_eff] = tmp_i
-                        if bk is not None:
-                            bk[:, :k_eff] = tmp_k
-                    else:
-                        self._run_block(q16[q0:q1], k, bs, bi, bk, ovf, check)
+                bs, bi = out_s[q0:q1], out_i[q0:q1]
+                bk = out_k[q0:q1] if return_keys else None
+                rescore = (q32[q0:q1], k_eff) if precision == "fp32" else None
+                kk = kth if precision == "fp32" else k_eff
+                if k_eff < k:          # database smaller than k: pad the columns beyond it
+                    bs.fill_(float("-inf")); bi.fill_(-1)
+                    if bk is not None:
+                        bk.fill_(-1)
+                    tmp_s = torch.empty((nq, k_eff), dtype=torch.float32, device=self.device)
+                    tmp_i = torch.empty((nq, k_eff), dtype=torch.int32, device=self.device)
+                    tmp_k = torch.empty((nq, k_eff), dtype=torch.int64, device=self.device)
+                    self._run_block(q16[q0:q1], kk, tmp_s, tmp_i, tmp_k, ovf, check, rescore=rescore)
+                    bs[:, :k_eff] = tmp_s; bi[:, :k_eff] = tmp_i
+                    if bk is not None:
+                        bk[:, :k_eff] = tmp_k
                 else:
-                    sl_i = self._buf("sl_i", (MAX_Q, kth), torch.int32)[:nq]
-                    self._run_block(q16[q0:q1], kth, None, sl_i, None, ovf, check)
-                    keys = self._buf("sl_k", (MAX_Q, kth), torch.int64)[:nq]
-                    _lib.check(lib.mdir_rescore_f32(_lib.ptr(self.db32), self.n, self.idx_base, _lib.ptr(q32[q0:q1]), nq, self.D,
-                                                    _lib.ptr(sl_i), kth, _lib.ptr(keys), _lib.stream()), "mdir_rescore_f32")
-                    cnt = self._buf("sl_cnt", (MAX_Q,), torch.int32)
-                    cnt.fill_(kth)
-                    _lib.check(lib.mdir_topk_finalize(_lib.ptr(keys), kth, _lib.ptr(cnt), 1, kth, 0, nq, k, _lib.ptr(out_s[q0:q1]),
-                                                      _lib.ptr(out_i[q0:q1]), _lib.ptr(out_k[q0:q1]) if return_keys else None,
-                                                      None, None, _lib.stream()), "mdir_topk_finalize")
+                    self._run_block(q16[q0:q1], kk, bs, bi, bk, ovf, check, rescore=rescore)
             if return_keys:
                 return out_s, out_i, out_k
             return out_s, out_i
 
-    def _run_block(self, q16, kth, out_s, out_i, out_k, ovf, check):
-        self._topk_block(q16, kth, out_s, out_i, out_k, ovf)
+    def _run_block(self, q16, kth, out_s, out_i, out_k, ovf, check, rescore=None):
+        self._topk_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
         if check and bool(ovf.any().item()):
             # a candidate segment overflowed (adversarial row order / massive ties): exact dense route
-            self._dense_block(q16, kth, out_s, out_i, out_k, ovf)
+            self._dense_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
             if bool(ovf.any().item()):
                 raise _lib.MdirError("dense recovery overflowed (internal error)")
 
