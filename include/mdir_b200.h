@@ -201,6 +201,18 @@ size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q);
 int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major,
                      int64_t* ranks, int64_t ranks_ld, void* ws, void* stream);
 
+/* ------------------------------------------------------------------- mAP ---
+ * Average precision and precision@kappa per query from the ranks array, on the device.
+ * Replaces compute_ap / compute_map (mdir/external/cirtorch/utils/evaluate.py:3-111).
+ * ranks: (n_db, n_q) int64 C-order.  The ground truth arrives flattened: items[i] is a db index
+ * that is positive (item_class 0, "ok") or junk (item_class 1) for query item_query[i];
+ * n_pos[q] = len(gnd[q]['ok']) (0 -> AP = NaN, excluded by the caller as in evaluate.py:68-72).
+ * aps: (n_q) fp64; prs: (n_q, n_kappa) fp64 (n_kappa <= 16).  ws: mdir_map_workspace_bytes().   */
+size_t mdir_map_workspace_bytes(int64_t n_db, int n_q);
+int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* items, const int32_t* item_query,
+                    const int32_t* item_class, int64_t n_items, const int32_t* n_pos, const int32_t* kappas,
+                    int n_kappa, double* aps, double* prs, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@ hot path behind the reference's own plug-in surface.
     clahe     clahe_u8, ChannelClahe / ImageClahe / ApplyClahe ...  (mdir transforms)
     search    rank(), Index, ShardedIndex, ranks_from_scores, topk_from_scores
     qe        alpha-QE / DBA (not in the reference; parity unpinned)
+    evaluate  compute_map / compute_map_and_print on the device      (cirtorch/utils/evaluate.py)
     score     CirDatasetAp replacement + install()
 
 All arithmetic runs in hand-written CUDA kernels (mdir_b200/csrc) reached through the C ABI in
@@ -15,6 +16,7 @@ from .layers import GeM, MAC, SPoC, L2N, POOLING, gem, mac, spoc, l2n  # noqa: F
 from .wrappers import CirMultiscaleAggregation, CirtorchWhiten, RetrievalHead, whitenapply  # noqa: F401
 from .clahe import clahe_u8, ChannelClahe, ImageClahe, ApplyClahe, AddClaheFromRgb, CreateClahedImage  # noqa: F401
 from .search import Index, ShardedIndex, rank, ranks_from_scores, topk_from_scores  # noqa: F401
+from .evaluate import compute_map, compute_map_and_print  # noqa: F401
 from .score import install  # noqa: F401
 
 __version__ = "0.1.0"

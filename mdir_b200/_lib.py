@@ -44,6 +44,8 @@ PROTOTYPES = {
     "mdir_rescore_f32": (_i, [_vp, _i64, _u32, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "mdir_qe_accumulate": (_i, [_vp, _i64, _u32, _i, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "mdir_add_l2n": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    "mdir_map_workspace_bytes": (_sz, [_i64, _i]),
+    "mdir_compute_ap": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mdir_rank_workspace_bytes": (_sz, [_i64, _i]),
     "mdir_rank_scores": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
 }

@@ -7,17 +7,21 @@ Nothing here imports the reference at module import time: ``install()`` needs an
 ``mdir`` package (the user's checkout) and raises otherwise."""
 import numpy as np
 
-from . import layers, wrappers, clahe, search
+from . import layers, wrappers, clahe, search, evaluate
 
 
-def rank_and_evaluate(dataset, vecs, qvecs, gnd, compute_map_and_print, device="cuda"):
-    """cirscore.py:65-71 with the dot product and argsort replaced by search.rank."""
-    if hasattr(vecs, "numpy"):
-        vecs = vecs.numpy()
-    if hasattr(qvecs, "numpy"):
-        qvecs = qvecs.numpy()
-    ranks = search.rank(vecs, qvecs, device=device)
-    return compute_map_and_print(dataset, ranks, gnd)
+def rank_and_evaluate(dataset, vecs, qvecs, gnd, compute_map_and_print=None, device="cuda"):
+    """cirscore.py:65-71 on the device: similarity (3xTF32, fp32-faithful) -> full ranks -> mAP.
+    The (N_db, N_q) ranks never leave the GPU; pass the reference's compute_map_and_print to
+    evaluate on the host instead (it receives the same int64 C-order array)."""
+    import torch
+    dev = torch.device(device if str(device) != "cpu" else "cuda")
+    index = search.Index(vecs, dxn=True, device=dev, keep_fp32=True)
+    q = search._as_dev_f32(qvecs, dev).t().contiguous()
+    ranks = index.ranks(q, precision="fp32")
+    if compute_map_and_print is not None:
+        return compute_map_and_print(dataset, ranks.cpu().numpy(), gnd)
+    return evaluate.compute_map_and_print(dataset, ranks, gnd, device=dev)
 
 
 def make_cirdatasetap(base_cls, extract_vectors, compute_map_and_print, stopwatch_cls):
@@ -36,7 +40,7 @@ def make_cirdatasetap(base_cls, extract_vectors, compute_map_and_print, stopwatc
                 qvecs = extract_vectors(network, self.qimages, self.image_size, self.transforms, device=device, bbxs=self.bbxs)
             stopwatch.lap("extract_descriptors")
             print('>> {}: Evaluating...'.format(self.dataset))
-            averages, scores = rank_and_evaluate(self.dataset, vecs, qvecs, self.gnd, compute_map_and_print, device=device)
+            averages, scores = rank_and_evaluate(self.dataset, vecs, qvecs, self.gnd, device=device)
             stopwatch.lap("compute_score")
             first_score = scores[list(scores.keys())[0]]
             logger(None, len(first_score), "dataset", stopwatch.reset(), "scalar/time")

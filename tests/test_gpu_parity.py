@@ -398,6 +398,44 @@ def test_graphed_search_replays(m):
         assert np.array_equal(i.cpu().numpy()[:, 0], src)
 
 
+# ------------------------------------------------------------------ mAP on the device (section 8f, f3)
+def test_compute_map_device(m, golden):
+    g = golden("search")
+    ru = g["ranks_ref_unstable"]
+    gnd = synth.gnd_okjunk(500, 12, 13, empty_every=5)
+    mp, aps, pr, prs = m.compute_map(ru, gnd, [1, 5, 10])
+    close(mp, g["okjunk_map"], rtol=1e-12)
+    np.testing.assert_array_equal(np.isnan(aps), np.isnan(g["okjunk_aps"]))
+    close(np.nan_to_num(aps), np.nan_to_num(g["okjunk_aps"]), rtol=1e-12)
+    close(pr, g["okjunk_pr"], rtol=1e-12)
+    close(np.nan_to_num(prs), np.nan_to_num(g["okjunk_prs"]), rtol=1e-12)
+    avg, per = m.compute_map_and_print("roxford5k", dev(ru), synth.gnd_emh(500, 12, 14))
+    for k_ in avg:
+        close(avg[k_], g["emh_" + k_], rtol=1e-12)
+    for k_ in per:
+        close(np.nan_to_num(per[k_]), np.nan_to_num(g["emh_" + k_]), rtol=1e-12)
+    # the CirDatasetAp replacement path: descriptors -> ranks -> mAP, all on the device
+    from mdir_b200.score import rank_and_evaluate
+    db = synth.descriptors(500, 64, 11, clusters=20)
+    q, _ = synth.planted_queries(db, 12, 12)
+    import io, contextlib
+    with contextlib.redirect_stdout(io.StringIO()):
+        avg2, _ = rank_and_evaluate("synth", torch.from_numpy(np.ascontiguousarray(db.T)), torch.from_numpy(np.ascontiguousarray(q.T)), gnd)
+    assert abs(avg2["map"] - float(g["okjunk_map"])) < 0.01
+    # larger than one 1024-row chunk, many positives / junk, vs the oracle
+    rs = np.random.RandomState(3)
+    n_db, n_q = 30011, 9
+    ranks = np.stack([rs.permutation(n_db) for _ in range(n_q)], axis=1)
+    gnd2 = synth.gnd_okjunk(n_db, n_q, 5, n_ok=300, n_junk=500)
+    gnd2[4]["ok"] = []                                     # no positives -> NaN, excluded
+    ref = oracle.compute_map(ranks, gnd2, [1, 5, 10, 100])
+    got = m.compute_map(ranks, gnd2, [1, 5, 10, 100])
+    close(got[0], ref[0], rtol=1e-12)
+    close(np.nan_to_num(got[1]), np.nan_to_num(ref[1]), rtol=1e-12)
+    close(got[2], ref[2], rtol=1e-12)
+    close(np.nan_to_num(got[3]), np.nan_to_num(ref[3]), rtol=1e-12)
+
+
 # ------------------------------------------------------------------ alpha-QE / DBA (parity unpinned: vs the restated definitions)
 def test_qe_and_dba(m):
     from mdir_b200 import qe
