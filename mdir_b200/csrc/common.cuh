@@ -90,8 +90,13 @@ __host__ __device__ __forceinline__ uint32_t orderable(float f) {
     if ((u << 1) == 0u) u = 0u;
     return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
 }
+// descending-score key: smaller == better.  NaN scores (the reference produces NaN rows for missing
+// images) rank last, in index order, exactly as np.argsort(-scores) places them.
+__host__ __device__ __forceinline__ uint32_t desc_key(float score) {
+    return (score != score) ? 0xffffffffu : ~orderable(score);
+}
 __host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t idx) {
-    return ((uint64_t)(~orderable(score)) << 32) | (uint64_t)idx;
+    return ((uint64_t)desc_key(score) << 32) | (uint64_t)idx;
 }
 __host__ __device__ __forceinline__ float key_score(uint64_t key) {
     uint32_t o = ~(uint32_t)(key >> 32);

@@ -12,7 +12,7 @@ namespace mdir {
 constexpr int kChunk = 4096;          // keys per CTA
 constexpr int kItems = 16;            // keys per thread (256 threads)
 
-__device__ __forceinline__ uint32_t rank_key(float s) { return ~orderable(s); }   // ascending key == descending score
+__device__ __forceinline__ uint32_t rank_key(float s) { return desc_key(s); }   // ascending key == descending score, NaN last
 
 // scores (n_db, n_q) -> keys (n_q, n_db)
 __global__ void __launch_bounds__(256) keys_transpose_kernel(const float* __restrict__ scores, int64_t n_db, int n_q,

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    if (base + u * 1024 + threadIdx.x < n) mymin = min(mymin, ~orderable(v[u]));
+                    if (base + u * 1024 + threadIdx.x < n) mymin = min(mymin, desc_key(v[u]));
             }
             bound = block_kth_of_thread_values(mymin, (uint32_t)kth, hist, &s_prefix, &s_k);
         }
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                 for (int u = 0; u < 8; ++u) {
                     const int64_t i = base + u * 1024 + threadIdx.x;
                     const bool valid = i < n;
-                    const uint32_t key = ~orderable(v[u]);
+                    const uint32_t key = desc_key(v[u]);
                     const bool hit = valid && key <= bound && ((key & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
                         const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                     const bool valid = i < n;
                     const float v = valid ? __ldg(sc + i) : 0.f;
                     const uint32_t idx = sample_pos_to_idx(valid ? i : 0, sample_stride, idx_base);
-                    const bool hit = valid && (~orderable(v) == result) && ((idx & himask) == prefix);
+                    const bool hit = valid && (desc_key(v) == result) && ((idx & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
                         const int d = hit ? (int)((idx >> shift) & 0xffu) : 256 + lane;
                         const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int64_t i = base + u * 1024 + threadIdx.x;
-                if (i < n && ~orderable(v[u]) <= result) {
+                if (i < n && desc_key(v[u]) <= result) {
                     const uint64_t key = make_key(v[u], sample_pos_to_idx(i, sample_stride, idx_base));
                     if (key <= tau_key) {
                         const uint32_t pos = atomicAdd(&s_n, 1u);
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
 #pragma unroll
     for (int u = 0; u < 32; ++u) {
         const int i = u * 1024 + threadIdx.x;
-        key[u] = i < n ? ~orderable(__ldg(sc + i)) : 0xffffffffu;     // padding sorts last (and is never valid)
+        key[u] = i < n ? desc_key(__ldg(sc + i)) : 0xffffffffu;     // padding sorts last (and is never valid)
     }
     uint32_t result = 0xffffffffu, idx_limit = 0xffffffffu;
     if (kth <= n) {
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
         for (int u = 0; u < 32; ++u) {
             const int i = u * 1024 + threadIdx.x;
             if (i < n && key[u] <= result) {
-                // key = (~orderable(score) << 32) | idx: the upper half is exactly the register key
+                // key = (desc_key(score) << 32) | idx: the upper half is exactly the register key
                 const uint64_t k64 = ((uint64_t)key[u] << 32) | (uint64_t)sample_pos_to_idx(i, sample_stride, idx_base);
                 if (k64 <= tau_key) {
                     const uint32_t pos = atomicAdd(&s_n, 1u);

@@ -194,6 +194,9 @@ class Index:
             if q32.shape[1] != self.D:
                 raise _lib.MdirError("query dimension %d != database dimension %d" % (q32.shape[1], self.D))
             k = int(k)
+            if nq_all == 0:
+                empty = (torch.empty((0, k), dtype=torch.float32, device=self.device), torch.empty((0, k), dtype=torch.int32, device=self.device))
+                return empty + (torch.empty((0, k), dtype=torch.int64, device=self.device),) if return_keys else empty
             k_eff = min(k, self.n)
             if precision == "fp32":
                 if self.db32 is None:
@@ -432,7 +435,8 @@ def make_keys_host(scores, idx):
     s[s == 0] = 0.0                                     # canonical +0
     u = s.view(np.uint32)
     o = np.where(u >> 31 != 0, ~u, u | np.uint32(0x80000000)).astype(np.uint32)
-    return ((~o).astype(np.uint64) << np.uint64(32)) | np.asarray(idx).astype(np.uint32).astype(np.uint64)
+    d = np.where(np.isnan(s), np.uint32(0xffffffff), ~o).astype(np.uint32)      # NaN ranks last
+    return (d.astype(np.uint64) << np.uint64(32)) | np.asarray(idx).astype(np.uint32).astype(np.uint64)
 
 
 def keys_to_host(keys):

@@ -216,6 +216,29 @@ def test_ranks_from_reference_scores_bit_exact(m, golden):
         assert np.array_equal(val.cpu().numpy(), np.take_along_axis(g["scores_ties"], g["ranks_ties_stable"][:k], 0))
 
 
+def test_ranks_nan_rows_and_empty(m):
+    # missing images give NaN descriptor rows in the reference: np.argsort(-scores)
+    # ranks them last in index order
+    rs = np.random.RandomState(4)
+    sc = rs.randn(3000, 5).astype(np.float32)
+    sc[[7, 100, 2999], :] = np.nan
+    sc[5, 2] = np.nan
+    ref = oracle.ranks_from_scores(sc)
+    assert np.array_equal(m.ranks_from_scores(sc).cpu().numpy(), ref)
+    idx, val = m.topk_from_scores(sc, 10)
+    assert np.array_equal(idx.cpu().numpy(), ref[:10])
+    # NaN database rows never enter a top-k
+    db = synth.descriptors(20000, 64, 5)
+    db[[3, 77, 19999]] = np.nan
+    q, src = synth.planted_queries(db[100:], 6, 9)
+    index = m.Index(db, device=DEV)
+    s, i = index.search(q, 50, precision="bf16")
+    assert not np.isnan(s.cpu().numpy()).any() and np.array_equal(i.cpu().numpy()[:, 0], src + 100)
+    # empty query batch
+    s0, i0 = index.search(np.zeros((0, 64), np.float32), 10)
+    assert tuple(s0.shape) == (0, 10) and tuple(i0.shape) == (0, 10)
+
+
 def test_ranks_edge_cases(m):
     rs = np.random.RandomState(8)
     for n_db, n_q in ((1, 1), (2, 3), (4096, 2), (4097, 5), (12345, 33), (70000, 3)):
