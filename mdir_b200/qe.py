@@ -58,3 +58,39 @@ def dba(index, alpha=3.0, k_dba=10):
         s, i = index.search(index.db32[r0:r1], k_dba, precision="fp32")
         out[r0:r1] = _add_l2n(_accumulate(index, i, s, alpha), None)
     return Index(out, device=index.device, keep_fp32=True, idx_base=index.idx_base)
+
+
+def dba_sharded(sharded, alpha=3.0, k_dba=10):
+    """DBA for a row-sharded database (one process per GPU): the shards are all-gathered once
+    (bf16 operand + fp32 master: 12 B per element per GPU -- 24.6 GB for 1M x 2048 of the 180 GB),
+    then every rank augments ITS OWN rows against the full database; the result is a new
+    ShardedIndex with the same row ownership.  Tensor-side work per rank = N/G x N x D, no further
+    collective."""
+    dist = sharded.dist
+    local = sharded.local
+    if local.db32 is None:
+        raise _lib.MdirError("DBA needs the fp32 master copy (keep_fp32=True)")
+    world = sharded.world
+    if world == 1:
+        out = dba(local, alpha, k_dba)
+        return ShardedIndex.from_local(out, sharded.group)
+    dev = local.device
+    sizes = torch.zeros((world,), dtype=torch.int64, device=dev)
+    sizes[dist.get_rank(sharded.group)] = local.n
+    dist.all_reduce(sizes, group=sharded.group)
+    sizes = [int(x) for x in sizes.tolist()]
+    n_max, n_tot = max(sizes), sum(sizes)
+    pad = torch.zeros((n_max, local.D), dtype=torch.float32, device=dev)
+    pad[:local.n] = local.db32
+    gathered = torch.empty((world * n_max, local.D), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(gathered, pad, group=sharded.group)
+    full = torch.cat([gathered[r * n_max:r * n_max + sizes[r]] for r in range(world)]) if any(s != n_max for s in sizes) else gathered
+    del pad
+    full_index = Index(full, device=dev, keep_fp32=True, idx_base=0)
+    out = torch.empty_like(local.db32)
+    for r0 in range(0, local.n, MAX_Q):
+        r1 = min(r0 + MAX_Q, local.n)
+        s, i = full_index.search(local.db32[r0:r1], k_dba, precision="fp32")
+        out[r0:r1] = _add_l2n(_accumulate(full_index, i, s, alpha), None)
+    new_local = Index(out, device=dev, keep_fp32=True, idx_base=local.idx_base)
+    return ShardedIndex.from_local(new_local, sharded.group)

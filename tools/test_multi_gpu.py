@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs):
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/test_multi_gpu.py
+
+Every rank holds a row shard; the sharded search / alpha-QE / DBA results must equal the
+single-GPU results on the whole database bit for bit (indices) -- SURVEY.md section 4,
+"distributed" row.  Rank 0 prints one PASS/FAIL line per check and exits non-zero on failure."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from oracle import synth  # noqa: E402
+import mdir_b200  # noqa: E402
+from mdir_b200 import qe  # noqa: E402
+from mdir_b200.search import GraphedSearch, ShardedIndex  # noqa: E402
+
+
+def main():
+    rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    dist.init_process_group("nccl", device_id=dev)
+    ok_all = True
+
+    def check(name, cond):
+        nonlocal ok_all
+        flag = torch.tensor([1 if cond else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        good = bool(flag.item())
+        ok_all &= good
+        if rank == 0:
+            print("[%s] %s" % ("PASS" if good else "FAIL", name), flush=True)
+
+    n, d, nq, k = 60013, 128, 70, 100
+    db = synth.descriptors(n, d, 81, clusters=150)
+    q, src = synth.planted_queries(db, nq, 82)
+    lo, hi = ShardedIndex.shard_bounds(n, world, rank)
+    sharded = ShardedIndex(db[lo:hi], idx_base=lo, device=dev)
+    single = mdir_b200.Index(db, device=dev)
+    for prec in ("bf16", "fp32"):
+        s1, i1 = single.search(q, k, precision=prec)
+        s2, i2 = sharded.search(q, k, precision=prec)
+        check("sharded search == single (%s)" % prec, torch.equal(i1, i2) and torch.equal(s1, s2))
+    gs = GraphedSearch(sharded, nq, k)
+    s3, i3 = gs(torch.from_numpy(q).pin_memory())
+    torch.cuda.synchronize()
+    s1, i1 = single.search(q, k)
+    check("CUDA-graph sharded search == single", torch.equal(i1, i3) and torch.equal(s1, s3) and not gs.check_overflow())
+    check("planted neighbour first", bool(np.array_equal(i3.cpu().numpy()[:, 0], src)))
+    q1 = qe.expand_queries(single, q, 3.0, 10)
+    q2 = qe.expand_queries(sharded, q, 3.0, 10)
+    check("sharded alpha-QE expansion == single (1e-6)", bool(torch.allclose(q1, q2, rtol=0, atol=1e-6)))
+    small_n = 3000
+    dbs = synth.descriptors(small_n, 64, 83, clusters=20)
+    lo2, hi2 = ShardedIndex.shard_bounds(small_n, world, rank)
+    sh2 = ShardedIndex(dbs[lo2:hi2], idx_base=lo2, device=dev)
+    aug_sh = qe.dba_sharded(sh2, 3.0, 5)
+    aug_single = qe.dba(mdir_b200.Index(dbs, device=dev), 3.0, 5)
+    check("sharded DBA rows == single (1e-6)", bool(torch.allclose(aug_sh.local.db32, aug_single.db32[lo2:hi2], rtol=0, atol=1e-6)))
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        print("MULTI-GPU %s" % ("PASSED" if ok_all else "FAILED"), flush=True)
+    sys.stdout.flush()
+    os._exit(0 if ok_all else 1)
+
+
+if __name__ == "__main__":
+    main()
