@@ -153,11 +153,13 @@ float    mdir_key_score(uint64_t key);
  * The index part of a key = pos_to_idx(i): i itself, or for a compact sample
  * ((i/256)*sample_stride)*256 + i%256, plus idx_base.  When cand != NULL the kth items
  * with key <= tau are written to segment 0 of the query's cand row (row pitch cand_row
- * keys, capacity cap) and seg_counts[q*n_seg + 0] is set to their number.        */
+ * keys, capacity cap) and seg_counts[q*n_seg + 0] is set to their number.
+ * approx != 0 relaxes tau to any valid upper bound of the kth key (>= kth rows pass, typically
+ * a few % more): enough for a filter threshold and about half the work.               */
 int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth,
                     int sample_stride, uint32_t idx_base,
                     uint64_t* tau, uint64_t* cand, int64_t cand_row, uint32_t* seg_counts, int n_seg,
-                    int cap, void* stream);
+                    int cap, int approx, void* stream);
 
 /* For each query: gather the candidate keys of its n_seg segments (segment 0 holds up to
  * cap0 keys, the others cap_l each), emit the best k as (score fp32, index int32) rows of

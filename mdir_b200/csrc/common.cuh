@@ -68,6 +68,20 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return r;   // every warp holds the total
 }
 
+// Lanes of the warp whose 8-bit digit equals this lane's, among the lanes with valid == true
+// (9 ballots + logic).  MATCH.ANY computes the same thing but is an order of magnitude slower on this
+// part when the warp holds many distinct values, which is the common case for radix digits.
+__device__ __forceinline__ unsigned match_digit8(int d, bool valid) {
+    unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1;
+        const unsigned bal = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? bal : ~bal;
+    }
+    return peers;
+}
+
 // ---- 64-bit candidate keys: smaller key == better (score desc, index asc) --------
 __host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
 #ifdef __CUDA_ARCH__

@@ -35,8 +35,13 @@ __global__ void __launch_bounds__(256) keys_transpose_kernel(const float* __rest
 }
 
 __global__ void __launch_bounds__(256) keys_direct_kernel(const float* __restrict__ scores, int64_t total, uint32_t* __restrict__ keys) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) keys[i] = rank_key(scores[i]);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < total) {
+        const float4 v = *reinterpret_cast<const float4*>(scores + i);
+        *reinterpret_cast<uint4*>(keys + i) = make_uint4(rank_key(v.x), rank_key(v.y), rank_key(v.z), rank_key(v.w));
+    } else {
+        for (int64_t j = i; j < total; ++j) keys[j] = rank_key(scores[j]);
+    }
 }
 
 // counts[(q * 256 + digit) * n_chunks + chunk]
@@ -118,8 +123,8 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint32_t* __re
     for (int it = 0; it < kItems; ++it) {
         const int64_t i = base + it * 32 + lane;
         const bool valid = i < n_db;
-        const int d = valid ? (int)((key[it] >> shift) & 0xffu) : 256 + lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int d = (int)((key[it] >> shift) & 0xffu);
+        const unsigned peers = match_digit8(d, valid);
         uint32_t r = 0;
         if (valid) {
             r = cnt[w][d] + __popc(peers & lt);
@@ -202,7 +207,8 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
     const unsigned gx = (unsigned)((n_db + 31) / 32), gy = (unsigned)((n_q + 31) / 32);
     if (query_major) {
         const int64_t total = n_db * n_q;
-        keys_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(scores, total, kA);
+        MDIR_CHECK_ARG(((uintptr_t)scores & 15) == 0);
+        keys_direct_kernel<<<(unsigned)((total / 4 + 256) / 256), 256, 0, st>>>(scores, total, kA);
     } else {
         keys_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, kA);
     }

@@ -63,8 +63,8 @@ __device__ __forceinline__ uint32_t block_kth_of_thread_values(uint32_t val, uin
         const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         const bool hit = (val & himask) == prefix;
         if (__any_sync(0xffffffffu, hit)) {
-            const int d = hit ? (int)((val >> shift) & 0xffu) : 256 + lane;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int d = (int)((val >> shift) & 0xffu);
+            const unsigned peers = match_digit8(d, hit);
             if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
         }
         __syncthreads();
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                     const uint32_t key = desc_key(v[u]);
                     const bool hit = valid && key <= bound && ((key & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
-                        const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
-                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        const int d = (int)((key >> shift) & 0xffu);
+                        const unsigned peers = match_digit8(d, hit);
                         if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                     }
                 }
@@ -181,8 +181,8 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
                     const uint32_t idx = sample_pos_to_idx(valid ? i : 0, sample_stride, idx_base);
                     const bool hit = valid && (desc_key(v) == result) && ((idx & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
-                        const int d = hit ? (int)((idx >> shift) & 0xffu) : 256 + lane;
-                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        const int d = (int)((idx >> shift) & 0xffu);
+                        const unsigned peers = match_digit8(d, hit);
                         if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                     }
                 }
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
 __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __restrict__ scores, int64_t ld, int n, int kth,
                                                                  int sample_stride, uint32_t idx_base, uint64_t* __restrict__ tau,
                                                                  uint64_t* __restrict__ cand, int64_t cand_row,
-                                                                 uint32_t* __restrict__ seg_counts, int n_seg, int cap) {
+                                                                 uint32_t* __restrict__ seg_counts, int n_seg, int cap, int approx) {
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_k, s_n, s_ties;
     const int q = blockIdx.x;
@@ -255,8 +255,11 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
                 if (u * 1024 + (int)threadIdx.x < n) mymin = min(mymin, key[u]);
             bound = block_kth_of_thread_values(mymin, (uint32_t)kth, hist, &s_prefix, &s_k);
         }
-        if (threadIdx.x == 0) { s_prefix = 0u; s_k = (uint32_t)kth; }
-        for (int pass = 0; pass < 4; ++pass) {
+        // approx: the bound itself is a valid threshold (>= kth keys are <= it, typically ~7 % more than kth)
+        const bool use_bound = approx && kth <= 1024;
+        if (threadIdx.x == 0) { s_prefix = use_bound ? bound : 0u; s_k = use_bound ? 0u : (uint32_t)kth; s_ties = 0u; }
+        if (use_bound) __syncthreads();
+        for (int pass = 0; pass < (use_bound ? 0 : 4); ++pass) {
             const int shift = 24 - 8 * pass;
             if (threadIdx.x < 256) hist[threadIdx.x] = 0u;
             __syncthreads();
@@ -267,8 +270,8 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
                 const bool valid = u * 1024 + (int)threadIdx.x < n;
                 const bool hit = valid && key[u] <= bound && ((key[u] & himask) == prefix);
                 if (__any_sync(0xffffffffu, hit)) {
-                    const int d = hit ? (int)((key[u] >> shift) & 0xffu) : 256 + lane;
-                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    const int d = (int)((key[u] >> shift) & 0xffu);
+                    const unsigned peers = match_digit8(d, hit);
                     if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                 }
             }
@@ -300,8 +303,8 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
                     const uint32_t idx = sample_pos_to_idx(i, sample_stride, idx_base);
                     const bool hit = i < n && key[u] == result && ((idx & himask) == prefix);
                     if (__any_sync(0xffffffffu, hit)) {
-                        const int d = hit ? (int)((idx >> shift) & 0xffu) : 256 + lane;
-                        const unsigned peers = __match_any_sync(0xffffffffu, d);
+                        const int d = (int)((idx >> shift) & 0xffu);
+                        const unsigned peers = match_digit8(d, hit);
                         if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                     }
                 }
@@ -443,8 +446,8 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
                 const uint64_t key = valid ? skeys[i] : 0ull;
                 const bool hit = valid && ((key & himask) == prefix);
                 if (__any_sync(0xffffffffu, hit)) {
-                    const int d = hit ? (int)((key >> shift) & 0xffu) : 256 + lane;
-                    const unsigned peers = __match_any_sync(0xffffffffu, d);
+                    const int d = (int)((key >> shift) & 0xffu);
+                    const unsigned peers = match_digit8(d, hit);
                     if (hit && lane == (__ffs(peers) - 1)) atomicAdd(&hist[d], (uint32_t)__popc(peers));
                 }
             }
@@ -659,13 +662,13 @@ extern "C" float mdir_key_score(uint64_t key) { return key_score(key); }
 
 extern "C" int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth, int sample_stride,
                                uint32_t idx_base, uint64_t* tau, uint64_t* cand, int64_t cand_row, uint32_t* seg_counts, int n_seg,
-                               int cap, void* stream) {
+                               int cap, int approx, void* stream) {
     MDIR_CHECK_ARG(scores && tau && n >= 0 && n_q >= 0 && kth >= 1 && ld >= n);
     MDIR_CHECK_ARG(cand == nullptr || (seg_counts != nullptr && cap >= 1 && n_seg >= 1 && cand_row >= cap));
     if (n_q == 0) return 0;
     if (n <= 32 * 1024) {
         select_kth_reg_kernel<<<n_q, 1024, 0, (cudaStream_t)stream>>>(scores, ld, (int)n, kth, sample_stride, idx_base, tau, cand,
-                                                                      cand_row, seg_counts, n_seg, cap);
+                                                                      cand_row, seg_counts, n_seg, cap, approx);
         MDIR_LAUNCH_CHECK();
         return 0;
     }

@@ -151,7 +151,7 @@ class Index:
         dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
         self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
-                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, _lib.stream()), "mdir_select_kth")
+                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 0, _lib.stream()), "mdir_select_kth")
         self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore)
 
     def _topk_block(self, q16, kth, out_scores, out_idx, out_keys, ovf, rescore=None):
@@ -169,7 +169,7 @@ class Index:
         ld = MAX_SAMPLE_TILES * TILE
         self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
-                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, _lib.stream()), "mdir_select_kth")
+                                       _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 1, _lib.stream()), "mdir_select_kth")
         prof = getattr(self, "prof", None)
         if prof is not None:      # bench.py: CUDA events around the dominant kernel, on its own stream
             prof.begin()
@@ -347,7 +347,7 @@ def topk_from_scores(scores, k, device="cuda"):
         cnt = torch.zeros((n_q,), dtype=torch.int32, device=dev)
         out_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
         out_i = torch.empty((n_q, k), dtype=torch.int32, device=dev)
-        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), cap, _lib.ptr(cnt), 1, cap,
+        _lib.check(lib.mdir_select_kth(_lib.ptr(st), n_db, n_db, n_q, k, 0, 0, _lib.ptr(tau), _lib.ptr(cand), cap, _lib.ptr(cnt), 1, cap, 0,
                                        _lib.stream()), "mdir_select_kth")
         _lib.check(lib.mdir_topk_finalize(_lib.ptr(cand), cap, _lib.ptr(cnt), 1, cap, 0, n_q, k, _lib.ptr(out_s), _lib.ptr(out_i), None,
                                           None, None, _lib.stream()), "mdir_topk_finalize")

@@ -135,7 +135,7 @@ static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sam
     CK(cudaMemset(d_cnt, 0, n_q * NS * 4));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_SAMPLE, stride, n_sample, d_sample, n_samp_rows,
                           nullptr, 0, nullptr, nullptr, 0, 0, 0));
-    MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 0));
+    MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 1, 0));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_FILTER, stride, n_sample, nullptr, 0, d_tau, 0,
                           d_cand, d_cnt, cap_s, cap_l, 0));
     MD(mdir_topk_finalize(d_cand, cap, d_cnt, NS, cap_s, cap_l, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
@@ -219,7 +219,7 @@ static void bench_big(int64_t n_db, int n_q, int n_sample) {
         MD(mdir_sim_scan_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, MDIR_SCAN_SAMPLE, stride, n_sample, d_sample, n_samp_rows,
                               nullptr, 0, nullptr, nullptr, 0, 0, 0));
         CK(cudaEventRecord(e[1]));
-        MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 0));
+        MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 1, 0));
         CK(cudaEventRecord(e[2]));
         MD(mdir_sim_scan_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, MDIR_SCAN_FILTER, stride, n_sample, nullptr, 0, d_tau, 0,
                               d_cand, d_cnt, cap_s, cap_l, 0));
