@@ -153,7 +153,8 @@ float    mdir_key_score(uint64_t key);
  * The index part of a key = pos_to_idx(i): i itself, or for a compact sample
  * ((i/256)*sample_stride)*256 + i%256, plus idx_base.  When cand != NULL the kth items
  * with key <= tau are written to segment 0 of the query's cand row (row pitch cand_row
- * keys, capacity cap) and seg_counts[q*n_seg + 0] is set to their number.
+ * keys, capacity cap), seg_counts[q*n_seg + 0] is set to their number and the other
+ * n_seg - 1 counters of the query are zeroed (ready for the FILTER scan that follows).
  * approx != 0 relaxes tau to any valid upper bound of the kth key (>= kth rows pass, typically
  * a few % more): enough for a filter threshold and about half the work.               */
 int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n_q, int kth,

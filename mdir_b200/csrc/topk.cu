@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
         }
         __syncthreads();
         if (threadIdx.x == 0) seg_counts[(int64_t)q * n_seg] = s_n;      // segment 0 of this query
+        for (int sg = 1 + threadIdx.x; sg < n_seg; sg += blockDim.x) seg_counts[(int64_t)q * n_seg + sg] = 0u;   // producers of the next pass start from 0
     }
 }
 
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
         }
         __syncthreads();
         if (threadIdx.x == 0) seg_counts[(int64_t)q * n_seg] = s_n;
+        for (int sg = 1 + threadIdx.x; sg < n_seg; sg += blockDim.x) seg_counts[(int64_t)q * n_seg + sg] = 0u;
     }
 }
 

@@ -146,8 +146,7 @@ class Index:
         emits exactly kth keys, so nothing can overflow here)."""
         lib = _lib.lib()
         nq = q16.shape[0]
-        tau, cand, cnt = self._cand_bufs()
-        cnt.zero_()
+        tau, cand, cnt = self._cand_bufs()       # the select kernel (re)initialises every segment counter
         dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
         self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
@@ -161,8 +160,7 @@ class Index:
         plan = self._plan(kth)
         if plan is None:
             return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf, rescore)
-        tau, cand, cnt = self._cand_bufs()
-        cnt.zero_()
+        tau, cand, cnt = self._cand_bufs()       # the select kernel (re)initialises every segment counter
         n_sample, stride = plan
         rows = n_sample * TILE
         sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
