@@ -9,8 +9,8 @@
 
 namespace mdir {
 
-constexpr int kChunk = 4096;          // keys per CTA
-constexpr int kItems = 16;            // keys per thread (256 threads)
+constexpr int kChunk = 2048;          // keys per CTA
+constexpr int kItems = 8;             // keys per thread (256 threads)
 
 __device__ __forceinline__ uint32_t rank_key(float s) { return desc_key(s); }   // ascending key == descending score, NaN last
 
