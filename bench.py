@@ -477,6 +477,37 @@ def side_measurements(torch, mdir_b200, dev):
     out["clahe"] = {"metric": "CLAHE u8 images/s (768x1024, clip 4, 8x8 tiles)", "value": n_img / (ms * 1e-3), "unit": "images/s",
                     "batch": n_img, "ms_per_batch": ms, "algorithmic_bytes_per_image": 2 * 768 * 1024,
                     "hbm_frac_of_measured": n_img * 2 * 768 * 1024 / 1e9 / (ms * 1e-3) / peak}
+    # the whole ImageClahe transform (RGB -> Lab -> CLAHE(L) -> RGB) on 32 images of 768 x 1024 x 3 float32,
+    # against the reference arithmetic (cv2 float Lab conversions + cv2 CLAHE, as ImageClahe.apply) on the host
+    rgbs = torch.rand((32, 768, 1024, 3), device=dev, generator=g) ** 3
+    lst = list(rgbs)
+    for _ in range(2):
+        mdir_b200.image_clahe(lst, 4, (8, 8))
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(5):
+        mdir_b200.image_clahe(lst, 4, (8, 8))
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 5
+    cpu_ms = None
+    try:
+        import cv2
+        import numpy as np
+        host = rgbs[0].cpu().numpy()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            spc = (cv2.cvtColor(host, cv2.COLOR_RGB2LAB) + np.array([0, 128, 128], np.float32)) / np.array([100.0, 255.0, 255.0], np.float32)
+            spc[:, :, 0] = cv2.createCLAHE(clipLimit=4, tileGridSize=(8, 8)).apply((spc[:, :, 0] * 255).astype(np.uint8)).astype(np.float32) / 255.0
+            cv2.cvtColor(spc * np.array([100.0, 255.0, 255.0], np.float32) - np.array([0, 128, 128], np.float32), cv2.COLOR_LAB2RGB)
+        cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    except Exception:  # noqa: BLE001
+        pass
+    out["image_clahe"] = {"metric": "ImageClahe.apply (RGB->Lab->CLAHE->RGB) images/s, 768x1024x3 float32", "value": 32 / (ms * 1e-3), "unit": "images/s",
+                          "ms_per_image": ms / 32, "algorithmic_bytes_per_image": 24 * 768 * 1024,
+                          "hbm_frac_of_measured": 32 * 24 * 768 * 1024 / 1e9 / (ms * 1e-3) / peak,
+                          "cpu_reference_ms_per_image": cpu_ms, "cpu_threads": "cv2 default"}
+    del rgbs, lst
     # full (N_db, N_q) ranks: C1 shape (70 q x 4,993 x 2048, fp32-faithful scores) and a C3-shaped slice
     # (1,024 of the 10,000 queries x 100,000 x 512, bf16 scores); device-resident in and out
     from mdir_b200.search import Index

@@ -97,6 +97,24 @@ int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_desc* descs
                   int n_img, int max_H, int max_W, double clip, int tiles_x, int tiles_y,
                   void* ws, void* stream);
 
+/* RGB <-> Lab around CLAHE on the device, following OpenCV's float code path as the reference
+ * calls it (rgb2normspace / normspace2rgb, mdir/components/data/transform/functional.py:24-48,
+ * ImageClahe.apply :120-129).  Images are contiguous HWC float32 in [0,1]; descs is a DEVICE array.
+ *   lut       (33,33,33,4) int16: OpenCV's RGB2Lab interpolation lattice {L,a,b,0} (LAB_BASE 2^14)
+ *   gamma_tab (1024,4) fp32: cubic-spline coefficients of the sRGB gamma (Lab2RGBfloat)
+ * mdir_rgb_to_l_u8:      L plane as uint8 = trunc((L/100)*255)   -> feed to mdir_clahe_u8
+ * mdir_lab_clahe_to_rgb: (a, b of the original pixel) + CLAHE'd uint8 L -> RGB float32 HWC       */
+typedef struct {
+    int64_t rgb_off;   /* float offset of pixel (0,0) in the rgb buffers (input and output alike) */
+    int64_t l_off;     /* byte offset of the image's L plane in the uint8 L buffers */
+    int32_t H, W;
+} mdir_rgb_desc;
+int mdir_rgb_to_l_u8(const float* rgb, const mdir_rgb_desc* descs, int n_img, int64_t max_pixels,
+                     const int16_t* lut, uint8_t* l_out, void* stream);
+int mdir_lab_clahe_to_rgb(const float* rgb, const mdir_rgb_desc* descs, int n_img, int64_t max_pixels,
+                          const int16_t* lut, const float* gamma_tab, const uint8_t* l_in, float* out,
+                          void* stream);
+
 /* ------------------------------------------------------- similarity search ---
  * Replaces np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0)
  * (mdir/components/optim/score/cirscore.py:69-70).

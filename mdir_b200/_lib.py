@@ -32,6 +32,8 @@ PROTOTYPES = {
     "mdir_whiten_project_tc": (_i, [_vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "mdir_clahe_workspace_bytes": (_sz, [_i, _i, _i]),
     "mdir_clahe_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _d, _i, _i, _vp, _vp]),
+    "mdir_rgb_to_l_u8": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "mdir_lab_clahe_to_rgb": (_i, [_vp, _vp, _i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "mdir_pack_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "mdir_sim_scan_bf16": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),
     "mdir_sim_scan_tf32": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),

@@ -5,11 +5,13 @@
 * ``ChannelClahe`` / ``ImageClahe`` and the transform classes ``ApplyClahe`` /
   ``AddClaheFromRgb`` / ``CreateClahedImage``: same names and arguments as
   mdir/components/data/transform/{functional.py:109-129, photometric_transforms.py:10-43}.
-  The RGB<->Lab conversion around the L channel stays stock OpenCV (SURVEY.md 8f row f1
-  marks it "next"); only the CLAHE itself is replaced.  These transforms touch the GPU, so
-  run the DataLoader with num_workers=0 on this path (threading).
+  ``image_clahe`` runs the whole ImageClahe transform on the device: RGB->Lab follows OpenCV's
+  float code path bit for bit (trilinear interpolation of its 33^3 fixed-point lattice), CLAHE on
+  the uint8 L plane, Lab->RGB within ~1e-5.  These transforms touch the GPU,
+  so run the DataLoader with num_workers=0 on this path (threading).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -17,6 +19,7 @@ import torch
 from . import _lib
 
 
+_RGB_DESC_DTYPE = np.dtype([("rgb_off", np.int64), ("l_off", np.int64), ("H", np.int32), ("W", np.int32)])
 _DESC_DTYPE = np.dtype([("src_off", np.int64), ("dst_off", np.int64), ("H", np.int32), ("W", np.int32),
                         ("src_pitch", np.int32), ("dst_pitch", np.int32)])
 
@@ -72,6 +75,88 @@ def clahe_u8(images, clip_limit=4.0, grid=(8, 8)):
     return outs
 
 
+# ---------------------------------------------------------------- RGB <-> Lab on the device
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LAB_CACHE = {}
+
+
+def _spline_build(fv):
+    """Natural cubic spline through len(fv) unit-spaced points -> (n, 4) coefficients (OpenCV's splineBuild)."""
+    n = len(fv) - 1
+    tab = np.zeros(n * 4)
+    cn = 0.0
+    for i in range(1, n):
+        t = (fv[i + 1] - fv[i] * 2 + fv[i - 1]) * 3
+        l = 1.0 / (4 - tab[(i - 1) * 4])
+        tab[i * 4] = l
+        tab[i * 4 + 1] = (t - tab[(i - 1) * 4 + 1]) * l
+    for i in range(n - 1, -1, -1):
+        c = tab[i * 4 + 1] - tab[i * 4] * cn
+        b = fv[i + 1] - fv[i] - (cn + c * 2) / 3
+        d = (cn - c) / 3
+        tab[i * 4:i * 4 + 4] = (fv[i], b, c, d)
+        cn = c
+    return tab.reshape(n, 4)
+
+
+def lab_tables(device):
+    """(lut (33,33,33,4) int16, gamma_tab (1024,4) fp32) on `device`, cached."""
+    key = str(device)
+    if key not in _LAB_CACHE:
+        lut = np.load(os.path.join(_HERE, "data", "rgb2lab_lut_s16.npy"))
+        lut4 = np.zeros(lut.shape[:3] + (4,), np.int16)
+        lut4[..., :3] = lut
+        x = np.arange(1025) / 1024.0
+        g = np.where(x <= 0.0031308, x * 12.92, 1.055 * np.power(x, 1 / 2.4) - 0.055)       # sRGB gamma (Lab2RGBfloat)
+        tab = _spline_build(g).astype(np.float32)
+        _LAB_CACHE[key] = (torch.from_numpy(lut4).to(device), torch.from_numpy(tab).to(device))
+    return _LAB_CACHE[key]
+
+
+def image_clahe(images, clip_limit=4, grid=(8, 8)):
+    """ImageClahe.apply (transform/functional.py:120-129, colorspace 'lab') entirely on the device:
+    RGB float32 HWC in [0,1] -> Lab (OpenCV's interpolated float path) -> CLAHE on L as uint8 -> RGB.
+    images: one (H,W,3) cuda tensor or a list of them (ragged sizes, one launch per stage)."""
+    lib = _lib.lib()
+    single = isinstance(images, torch.Tensor)
+    imgs = [images] if single else list(images)
+    if not imgs:
+        return []
+    for im in imgs:
+        _lib.require_cuda(im, "image")
+        if im.dtype != torch.float32 or im.dim() != 3 or im.shape[2] != 3 or im.numel() == 0:
+            raise _lib.MdirError("image_clahe expects non-empty (H,W,3) float32 tensors")
+    imgs = [im.contiguous() for im in imgs]
+    dev = imgs[0].device
+    lut, gamma = lab_tables(dev)
+    outs = [torch.empty_like(im) for im in imgs]
+    npx = [im.shape[0] * im.shape[1] for im in imgs]
+    l_off = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in npx])]).astype(np.int64)
+    l_in = torch.empty((int(l_off[-1]),), dtype=torch.uint8, device=dev)
+    sbase = min(im.data_ptr() for im in imgs)
+    # the output images must sit at the same offsets as the inputs: use one arena laid out like the inputs
+    span = max(im.data_ptr() + im.numel() * 4 for im in imgs) - sbase
+    arena = torch.empty((span // 4,), dtype=torch.float32, device=dev)
+    descs = np.zeros(len(imgs), dtype=_RGB_DESC_DTYPE)
+    for i, im in enumerate(imgs):
+        descs[i] = ((im.data_ptr() - sbase) // 4, int(l_off[i]), im.shape[0], im.shape[1])
+    descs_d = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdir_rgb_to_l_u8(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut), _lib.ptr(l_in),
+                                        _lib.stream()), "mdir_rgb_to_l_u8")
+        planes = [l_in[int(l_off[i]):int(l_off[i]) + npx[i]].view(im.shape[0], im.shape[1]) for i, im in enumerate(imgs)]
+        l_planes = clahe_u8(planes, clip_limit, grid)
+        l_out = torch.empty_like(l_in)
+        for i, pl in enumerate(l_planes):
+            l_out[int(l_off[i]):int(l_off[i]) + npx[i]] = pl.reshape(-1)
+        _lib.check(lib.mdir_lab_clahe_to_rgb(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut),
+                                             _lib.ptr(gamma), _lib.ptr(l_out), _lib.ptr(arena), _lib.stream()), "mdir_lab_clahe_to_rgb")
+    for i, im in enumerate(imgs):
+        o = (im.data_ptr() - sbase) // 4
+        outs[i] = arena[o:o + im.numel()].view(im.shape)
+    return outs[0] if single else outs
+
+
 class ChannelClahe:
     """transform/functional.py:109-117"""
 
@@ -117,6 +202,10 @@ class ImageClahe(ChannelClahe):
         self.colorspace = colorspace
 
     def apply(self, img):
+        if self.colorspace.lower() == "lab" and img.dtype == np.float32 and img.ndim == 3 and img.shape[2] == 3:
+            # whole transform on the device: cv2-compatible RGB->Lab, CLAHE on L, Lab->RGB
+            x = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
+            return image_clahe(x, self.clip_limit, self.grid_size).cpu().numpy()
         spc = rgb2normspace(img, self.colorspace)
         spc[:, :, 0] = super().apply(spc[:, :, 0])
         return normspace2rgb(spc, self.colorspace)

@@ -35,7 +35,7 @@ def main():
     from cirtorch.utils.whiten import whitenapply
     from cirtorch.utils.evaluate import compute_map, compute_map_and_print
     from mdir.components.data.wrapper import CirMultiscaleAggregation, CirtorchWhiten
-    from mdir.components.data.transform.functional import ChannelClahe
+    from mdir.components.data.transform.functional import ChannelClahe, ImageClahe
 
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -110,6 +110,11 @@ def main():
     clahe["grid4x6_127x93"] = cv2.createCLAHE(clipLimit=3, tileGridSize=(4, 6)).apply(img)
     chan = (synth.image_u8((200, 150), "gamma", 78).astype(np.float32) + np.float32(0.37)) / np.float32(255.3)
     clahe["channelclahe_200x150"] = ChannelClahe(4, 8).apply(chan)
+    # the whole transform: RGB -> Lab -> CLAHE(L) -> RGB  (ImageClahe.apply, functional.py:120-129)
+    rgb = (np.random.RandomState(79).rand(90, 122, 3) ** 2.2).astype(np.float32)
+    clahe["imageclahe_in_sha"] = np.array(synth.sha(rgb))
+    clahe["imageclahe_90x122"] = ImageClahe(4, 8, "lab").apply(rgb.copy())
+    clahe["rgb2lab_90x122"] = cv2.cvtColor(rgb, cv2.COLOR_RGB2LAB)
     np.savez_compressed(os.path.join(OUT, "clahe.npz"), **clahe)
 
     # ---- 4. similarity / ranks / mAP (cirscore.py:69-71, evaluate.py) ---------------

@@ -257,6 +257,107 @@ def channel_clahe(chan, clip_limit=4, grid_size=8):
     return clahe_u8(q, float(int(clip_limit)), g[0], g[1]).astype(np.float32) / 255.0
 
 
+def cv2_lab_lattice():
+    """The 33^3 table OpenCV's float RGB->Lab interpolates (color_lab.cpp, RGB2Lab_f with
+    useInterpolation; third-party, opencv-python unpinned in requirements.txt:3 -- the installed wheel is
+    the arbiter): feeding cv2 the lattice points returns the entries exactly."""
+    import cv2
+    g = (np.arange(33) / 32.0).astype(np.float32)
+    R, G, B = np.meshgrid(g, g, g, indexing="ij")
+    lab = cv2.cvtColor(np.stack([R, G, B], -1).reshape(-1, 1, 3), cv2.COLOR_RGB2LAB).reshape(33, 33, 33, 3).astype(np.float64)
+    return np.stack([np.rint(lab[..., 0] / 100 * 16384), np.rint((lab[..., 1] + 128) / 256 * 16384),
+                     np.rint((lab[..., 2] + 128) / 256 * 16384)], -1).astype(np.int64)
+
+
+def rgb2lab_cv(img, lattice):
+    """cv2.cvtColor(float32 RGB, COLOR_RGB2LAB) restated (RGB2Lab_f::operator() + trilinearInterpolate):
+    iR = cvRound(clip(R)*2^14); cell = iR >> 9; 4-bit weights (iR & 511) >> 5; CV_DESCALE(sum, 12)."""
+    f32 = np.float32
+    x = np.clip(np.asarray(img, dtype=f32), 0, 1)
+    ii = np.rint(x * f32(16384)).astype(np.int64)
+    t = ii >> 9
+    fr = (ii & 511) >> 5
+    t1 = np.minimum(t + 1, 32)
+    acc = np.zeros(x.shape[:-1] + (3,), np.int64)
+    for dx in (0, 1):
+        wx = fr[..., 0] if dx else 16 - fr[..., 0]
+        tx = t1[..., 0] if dx else t[..., 0]
+        for dy in (0, 1):
+            wy = fr[..., 1] if dy else 16 - fr[..., 1]
+            ty = t1[..., 1] if dy else t[..., 1]
+            for dz in (0, 1):
+                wz = fr[..., 2] if dz else 16 - fr[..., 2]
+                tz = t1[..., 2] if dz else t[..., 2]
+                acc += lattice[tx, ty, tz] * (wx * wy * wz)[..., None]
+    acc = (acc + 2048) >> 12
+    o = acc.astype(f32) / f32(16384)
+    return np.stack([o[..., 0] * f32(100), o[..., 1] * f32(256) - f32(128), o[..., 2] * f32(256) - f32(128)], -1).astype(f32)
+
+
+def _spline_build(fv):
+    n = len(fv) - 1
+    tab = np.zeros(n * 4)
+    cn = 0.0
+    for i in range(1, n):
+        t = (fv[i + 1] - fv[i] * 2 + fv[i - 1]) * 3
+        l = 1.0 / (4 - tab[(i - 1) * 4])
+        tab[i * 4] = l
+        tab[i * 4 + 1] = (t - tab[(i - 1) * 4 + 1]) * l
+    for i in range(n - 1, -1, -1):
+        c = tab[i * 4 + 1] - tab[i * 4] * cn
+        b = fv[i + 1] - fv[i] - (cn + c * 2) / 3
+        d = (cn - c) / 3
+        tab[i * 4:i * 4 + 4] = (fv[i], b, c, d)
+        cn = c
+    return tab.reshape(n, 4)
+
+
+def lab2rgb_cv(lab):
+    """cv2.cvtColor(float32 Lab, COLOR_LAB2RGB) restated (Lab2RGBfloat + splineInterpolate of the sRGB
+    gamma table); agrees with the wheel to ~6e-6 (FMA contraction / table rounding)."""
+    f32 = np.float32
+    lab = np.asarray(lab, dtype=f32)
+    L, a, b = lab[..., 0], lab[..., 1], lab[..., 2]
+    lT = f32(0.008856) * f32(903.3)
+    fT = f32(7.787) * f32(0.008856) + f32(16.0) / f32(116.0)
+    y_lo = (L / f32(903.3)).astype(f32)
+    fy_lo = (f32(7.787) * y_lo + f32(16.0) / f32(116.0)).astype(f32)
+    fy_hi = ((L + f32(16.0)) / f32(116.0)).astype(f32)
+    y_hi = (fy_hi * fy_hi * fy_hi).astype(f32)
+    lo = L <= lT
+    y = np.where(lo, y_lo, y_hi)
+    fy = np.where(lo, fy_lo, fy_hi)
+
+    def inv(f):
+        return np.where(f <= fT, ((f - f32(16.0) / f32(116.0)) / f32(7.787)).astype(f32), (f * f * f).astype(f32))
+
+    X = inv((a / f32(500.0) + fy).astype(f32))
+    Z = inv((fy - b / f32(200.0)).astype(f32))
+    Mi = np.array([[3.240479, -1.53715, -0.498535], [-0.969256, 1.875991, 0.041556], [0.055648, -0.204043, 1.057311]])
+    C = (Mi * np.array([0.950456, 1.0, 1.088754])[None, :]).astype(f32)
+    rgb = np.stack([C[i, 0] * X + C[i, 1] * y + C[i, 2] * Z for i in range(3)], -1).astype(f32)
+    rgb = np.clip(rgb, 0, 1).astype(f32)
+    xg = np.arange(1025) / 1024.0
+    tab = _spline_build(np.where(xg <= 0.0031308, xg * 12.92, 1.055 * np.power(xg, 1 / 2.4) - 0.055)).astype(f32)
+    xs = (rgb * f32(1024)).astype(f32)
+    ix = np.clip(xs.astype(np.int32), 0, 1023)
+    tt = (xs - ix.astype(f32)).astype(f32)
+    c = tab[ix]
+    return (((c[..., 3] * tt + c[..., 2]) * tt + c[..., 1]) * tt + c[..., 0]).astype(f32)
+
+
+def image_clahe(img, clip_limit=4, grid_size=8, lattice=None):
+    """ImageClahe.apply with colorspace 'lab' (transform/functional.py:120-129 over :24-48):
+    spc = (RGB2LAB(img) + [0,128,128]) / [100,255,255]; spc[...,0] = ChannelClahe(spc[...,0]);
+    LAB2RGB(spc * [100,255,255] - [0,128,128])."""
+    f32 = np.float32
+    lattice = cv2_lab_lattice() if lattice is None else lattice
+    lab = rgb2lab_cv(img, lattice)
+    spc = ((lab + np.array([0, 128, 128], f32)) / np.array([100.0, 255.0, 255.0], f32)).astype(f32)
+    spc[..., 0] = channel_clahe(spc[..., 0], clip_limit, grid_size)
+    return lab2rgb_cv((spc * np.array([100.0, 255.0, 255.0], f32) - np.array([0, 128, 128], f32)).astype(f32))
+
+
 # ----------------------------------------------------------------------------
 # similarity / ranks     mdir/components/optim/score/cirscore.py:65-70
 # ----------------------------------------------------------------------------

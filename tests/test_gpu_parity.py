@@ -188,6 +188,27 @@ def test_clahe_grid_pitch_and_wrappers(m, golden):
         assert np.array_equal(m.clahe_u8(dev(im), clip, grid).cpu().numpy(), ref), (hw, grid, clip)
 
 
+def test_image_clahe_on_device(m, golden):
+    cv2 = pytest.importorskip("cv2")
+    g = golden("clahe")
+    rgb = (np.random.RandomState(79).rand(90, 122, 3) ** 2.2).astype(np.float32)
+    out = m.image_clahe(dev(rgb), 4, (8, 8)).cpu().numpy()
+    np.testing.assert_allclose(out, g["imageclahe_90x122"], rtol=0, atol=2e-5)         # the reference's own output
+    lat = oracle.cv2_lab_lattice()
+    np.testing.assert_allclose(out, oracle.image_clahe(rgb, 4, 8, lat), rtol=0, atol=2e-5)
+    # ragged batch, one launch per stage; sizes not divisible by 8
+    rs = np.random.RandomState(80)
+    imgs = [(rs.rand(h, w, 3) ** 3).astype(np.float32) for h, w in ((37, 53), (128, 96), (65, 200))]
+    imgs[1][:8, :8] = 1.0
+    imgs[1][8:16, :8] = 0.0
+    outs = m.image_clahe([dev(i) for i in imgs], 4, (8, 8))
+    for im, o in zip(imgs, outs):
+        spc = (cv2.cvtColor(im, cv2.COLOR_RGB2LAB) + np.array([0, 128, 128], np.float32)) / np.array([100.0, 255.0, 255.0], np.float32)
+        spc[:, :, 0] = oracle.channel_clahe(spc[:, :, 0], 4, 8)
+        ref = cv2.cvtColor(spc * np.array([100.0, 255.0, 255.0], np.float32) - np.array([0, 128, 128], np.float32), cv2.COLOR_LAB2RGB)
+        np.testing.assert_allclose(o.cpu().numpy(), ref, rtol=0, atol=2e-5)
+
+
 def test_apply_clahe_transform(m):
     cv2 = pytest.importorskip("cv2")
     rs = np.random.RandomState(3)
@@ -198,9 +219,9 @@ def test_apply_clahe_transform(m):
     spc = (cv2.cvtColor(pic, cv2.COLOR_RGB2LAB) + np.array([0, 128, 128], np.float32)) / np.array([100.0, 255.0, 255.0], np.float32)
     spc[:, :, 0] = oracle.channel_clahe(spc[:, :, 0], 4, 8)
     ref = cv2.cvtColor(spc * np.array([100.0, 255.0, 255.0], np.float32) - np.array([0, 128, 128], np.float32), cv2.COLOR_LAB2RGB)
-    assert np.array_equal(out[0], ref)
+    np.testing.assert_allclose(out[0], ref, rtol=0, atol=2e-5)          # Lab<->RGB now runs on the device too
     two = m.CreateClahedImage()(pic)
-    assert len(two) == 2 and np.array_equal(two[1], ref)
+    assert len(two) == 2 and np.allclose(two[1], ref, rtol=0, atol=2e-5)
     four = m.AddClaheFromRgb()(pic)[0]
     assert four.shape == (120, 160, 4)
 

@@ -76,6 +76,22 @@ def test_clahe_golden(golden):
     assert np.array_equal(oracle.channel_clahe(chan, 4, 8), g["channelclahe_200x150"])
 
 
+def test_image_clahe_lab_path(golden):
+    cv2 = pytest.importorskip("cv2")
+    g = golden("clahe")
+    rgb = (np.random.RandomState(79).rand(90, 122, 3) ** 2.2).astype(np.float32)
+    assert synth.sha(rgb) == str(g["imageclahe_in_sha"])
+    lat = oracle.cv2_lab_lattice()
+    import os
+    shipped = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mdir_b200", "data", "rgb2lab_lut_s16.npy"))
+    assert np.array_equal(lat, shipped.astype(np.int64)), "shipped Lab lattice differs from the installed cv2"
+    assert np.array_equal(oracle.rgb2lab_cv(rgb, lat), g["rgb2lab_90x122"])                  # bit-exact restatement
+    assert np.array_equal(oracle.rgb2lab_cv(rgb, lat), cv2.cvtColor(rgb, cv2.COLOR_RGB2LAB))
+    lab = g["rgb2lab_90x122"]
+    np.testing.assert_allclose(oracle.lab2rgb_cv(lab), cv2.cvtColor(lab, cv2.COLOR_LAB2RGB), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(oracle.image_clahe(rgb, 4, 8, lat), g["imageclahe_90x122"], rtol=0, atol=1e-5)
+
+
 def test_clahe_vs_installed_cv2():
     cv2 = pytest.importorskip("cv2")
     for i, (hw, dist, clip, grid) in enumerate([((31, 57), "gamma", 4, (8, 8)), ((100, 100), "bimodal", 2, (8, 8)),
