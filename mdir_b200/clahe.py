@@ -35,7 +35,7 @@ def _launch(sbase, dbase, descs_np, dev, max_h, max_w, clip_limit, grid):
                                      float(clip_limit), tiles_x, tiles_y, _lib.ptr(ws), _lib.stream()), "mdir_clahe_u8")
 
 
-def clahe_u8(images, clip_limit=4.0, grid=(8, 8)):
+def clahe_u8(images, clip_limit=4.0, grid=(8, 8), out=None):
     """images: one (H,W) / (B,H,W) uint8 cuda tensor, or a list of (H,W) uint8 cuda tensors of
     different sizes (one launch for the whole ragged batch).  Returns the same structure.
     grid = (tiles_x, tiles_y) like cv2's tileGridSize."""
@@ -65,7 +65,7 @@ def clahe_u8(images, clip_limit=4.0, grid=(8, 8)):
             raise _lib.MdirError("clahe_u8 expects a list of non-empty (H,W) uint8 tensors")
     planes = [p if p.stride(1) == 1 else p.contiguous() for p in planes]
     dev = planes[0].device
-    outs = [torch.empty((p.shape[0], p.shape[1]), dtype=torch.uint8, device=dev) for p in planes]
+    outs = list(out) if out is not None else [torch.empty((p.shape[0], p.shape[1]), dtype=torch.uint8, device=dev) for p in planes]
     sbase = min(p.data_ptr() for p in planes)
     dbase = min(o.data_ptr() for o in outs)
     descs = np.empty(len(planes), dtype=_DESC_DTYPE)
@@ -144,11 +144,10 @@ def image_clahe(images, clip_limit=4, grid=(8, 8)):
     with torch.cuda.device(dev):
         _lib.check(lib.mdir_rgb_to_l_u8(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut), _lib.ptr(l_in),
                                         _lib.stream()), "mdir_rgb_to_l_u8")
-        planes = [l_in[int(l_off[i]):int(l_off[i]) + npx[i]].view(im.shape[0], im.shape[1]) for i, im in enumerate(imgs)]
-        l_planes = clahe_u8(planes, clip_limit, grid)
         l_out = torch.empty_like(l_in)
-        for i, pl in enumerate(l_planes):
-            l_out[int(l_off[i]):int(l_off[i]) + npx[i]] = pl.reshape(-1)
+        planes = [l_in[int(l_off[i]):int(l_off[i]) + npx[i]].view(im.shape[0], im.shape[1]) for i, im in enumerate(imgs)]
+        oplanes = [l_out[int(l_off[i]):int(l_off[i]) + npx[i]].view(im.shape[0], im.shape[1]) for i, im in enumerate(imgs)]
+        clahe_u8(planes, clip_limit, grid, out=oplanes)
         _lib.check(lib.mdir_lab_clahe_to_rgb(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut),
                                              _lib.ptr(gamma), _lib.ptr(l_out), _lib.ptr(arena), _lib.stream()), "mdir_lab_clahe_to_rgb")
     for i, im in enumerate(imgs):
