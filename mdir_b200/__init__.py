@@ -6,6 +6,7 @@ hot path behind the reference's own plug-in surface.
     clahe     clahe_u8, ChannelClahe / ImageClahe / ApplyClahe ...  (mdir transforms)
     search    rank(), Index, ShardedIndex, ranks_from_scores, topk_from_scores
     qe        alpha-QE / DBA (not in the reference; parity unpinned)
+    extract   batched extract_vectors (no per-image sync)            (cirtorch/networks/imageretrievalnet.py)
     evaluate  compute_map / compute_map_and_print on the device      (cirtorch/utils/evaluate.py)
     score     CirDatasetAp replacement + install()
 
@@ -16,6 +17,7 @@ from .layers import GeM, MAC, SPoC, L2N, POOLING, gem, mac, spoc, l2n  # noqa: F
 from .wrappers import CirMultiscaleAggregation, CirtorchWhiten, RetrievalHead, whitenapply  # noqa: F401
 from .clahe import clahe_u8, image_clahe, ChannelClahe, ImageClahe, ApplyClahe, AddClaheFromRgb, CreateClahedImage  # noqa: F401
 from .search import Index, ShardedIndex, rank, ranks_from_scores, topk_from_scores  # noqa: F401
+from .extract import extract_vectors, extract_from_tensors  # noqa: F401
 from .evaluate import compute_map, compute_map_and_print  # noqa: F401
 from .score import install  # noqa: F401
 

@@ -1,0 +1,131 @@
+"""Batched descriptor extraction: drop-in for cirtorch's ``extract_vectors``
+(mdir/external/cirtorch/networks/imageretrievalnet.py:277-324).
+
+The reference runs ``vecs[:, i] = net(input).cpu()`` per image: ~20 tiny ATen launches for the head
+and one blocking device->host copy per image.  Here the backbone (stock torch, untouched) runs per
+image and scale, the feature maps stay on the device, and every ``group`` images the whole head --
+pool, L2N, multi-scale aggregation, Lw whitening -- is ONE pass of the ``RetrievalHead`` kernels;
+nothing is copied to the host until the end (or never, with ``return_device=True``: the (N, D) matrix
+then feeds ``Index`` directly).
+
+Two kinds of ``net`` are understood (duck-typed, nothing of the reference is imported):
+  * cirtorch's ``ImageRetrievalNet``: ``.features``, ``.pool``, ``.meta``  (+ ``ms`` / ``msp`` arguments,
+    the semantics of ``extract_ss`` / ``extract_ms``);
+  * mdir's ``CirNetwork``: ``.model`` (an ImageRetrievalNet) and ``.wrappers['eval']`` holding
+    ``CirMultiscaleAggregation`` and/or ``CirtorchWhiten`` (mdir/learning/network.py:88-89).
+Local whitening, in-model whitening layers and regional pooling are outside the hot path
+ and raise NotImplementedError.
+"""
+import sys
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+from .wrappers import RetrievalHead
+
+
+class _Plan:
+    def __init__(self, net, ms, msp):
+        model = getattr(net, "model", net)
+        self.model = model
+        self.scales = list(ms)
+        self.msp = float(msp)
+        self.lw = None
+        self.dimensions = None
+        self.interp_unit_scale = False
+        wr = getattr(net, "wrappers", None)
+        if wr is not None and hasattr(net, "model"):
+            comp = wr.get("eval") if isinstance(wr, dict) else wr
+            self.scales, self.msp = [1], None
+            for w in getattr(comp, "wrappers", []):
+                name = w.__class__.__name__
+                if name == "CirMultiscaleAggregation":
+                    self.scales = list(w.scales)
+                    self.interp_unit_scale = len(self.scales) > 1          # wrapper.py:96-107 interpolates every scale
+                elif name == "CirtorchWhiten":
+                    self.lw = {"P": w.P.detach().cpu().numpy(), "m": w.m.detach().cpu().numpy()}
+                    self.dimensions = w.dimensions
+                else:
+                    raise NotImplementedError("wrapper %s is outside the batched extraction path" % name)
+        meta = model.meta
+        if getattr(model, "lwhiten", None) is not None or getattr(model, "whiten", None) is not None or meta.get("regional"):
+            raise NotImplementedError("local / in-model whitening and regional pooling are outside the hot path")
+        self.pooling = meta["pooling"]
+        if self.pooling not in ("gem", "mac", "spoc"):
+            raise NotImplementedError("pooling %r is outside the hot path" % self.pooling)
+        self.p = float(model.pool.p.item()) if self.pooling == "gem" else 3.0
+        self.eps = float(getattr(model.pool, "eps", 1e-6))
+        self.out_dim = self.dimensions or meta.get("out_channels", meta.get("outputdim"))
+
+
+def _head(plan, device):
+    head = RetrievalHead(plan.pooling, p=plan.p, eps=plan.eps, whitening=plan.lw, dimensions=plan.dimensions,
+                         nscales=len(plan.scales), regional=False, model_whitening=False, device=device)
+    if plan.msp is not None:                     # explicit msp of extract_ms (the wrapper path uses the msp rule)
+        head.msp = plan.msp if len(plan.scales) > 1 else 1.0
+    return head
+
+
+def extract_from_tensors(net, tensors, ms=(1,), msp=1, device=None, group=32, return_device=False):
+    """tensors: iterable of already transformed images, (1,3,H,W) or (3,H,W) float tensors (any sizes).
+    Returns (D, N) float32 on the host like the reference, or the (N, D) device matrix."""
+    plan = _Plan(net, ms, msp)
+    dev = torch.device(device) if device is not None else next(plan.model.parameters()).device
+    if dev.type != "cuda":
+        raise _lib.MdirError("extract_vectors needs a CUDA device (no CPU path)")
+    head = _head(plan, dev)
+    chunks, pending = [], []
+
+    def flush():
+        if pending:
+            chunks.append(head(pending))
+            pending.clear()
+
+    with torch.no_grad():
+        for n_img, x in enumerate(tensors):
+            if isinstance(x, dict):                  # missing image -> NaN row (genericdataset.py:54-59)
+                flush()
+                chunks.append(torch.full((1, plan.out_dim), float("nan"), device=dev))
+                continue
+            x = x.to(dev, non_blocking=True)
+            if x.dim() == 3:
+                x = x.unsqueeze(0)
+            for s in plan.scales:
+                xs = x if (s == 1 and not plan.interp_unit_scale) else F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+                pending.append(plan.model.features(xs).float().contiguous())
+            if (n_img + 1) % group == 0:
+                flush()
+        flush()
+    out = torch.cat(chunks) if chunks else torch.empty((0, plan.out_dim), device=dev)
+    if return_device:
+        return out
+    return out.t().contiguous().cpu()
+
+
+def extract_vectors(net, images, image_size, transform, bbxs=None, ms=[1], msp=1, print_freq=10, device=None,
+                    num_workers=0, group=32, return_device=False):
+    """Same arguments as cirtorch's extract_vectors.  ``images`` is a list of paths (loaded with the
+    reference's own ``ImagesFromList``, which must be importable) or a list of tensors.
+    num_workers defaults to 0 because mdir_b200's CLAHE transforms use the GPU."""
+    if len(images) and isinstance(images[0], torch.Tensor):
+        return extract_from_tensors(net, images, ms, msp, device, group, return_device)
+    try:
+        from cirtorch.datasets.genericdataset import ImagesFromList
+    except ImportError as exc:
+        raise RuntimeError("loading images from paths needs the reference's cirtorch package importable: %s" % exc)
+    model = getattr(net, "model", net)
+    if hasattr(net, "eval"):
+        net.eval()
+    loader = torch.utils.data.DataLoader(ImagesFromList(root='', images=images, imsize=image_size, bbxs=bbxs, transform=transform),
+                                         batch_size=1, shuffle=False, num_workers=num_workers, pin_memory=True)
+
+    def stream():
+        for i, inp in enumerate(loader):
+            if (i + 1) % print_freq == 0 or (i + 1) == len(images):
+                sys.stdout.write('\r>>>> {}/{} done...'.format(i + 1, len(images)))
+            yield inp
+        sys.stdout.write('\n')
+
+    dev = device if device is not None else next(model.parameters()).device
+    return extract_from_tensors(net, stream(), ms, msp, dev, group, return_device)

@@ -442,6 +442,54 @@ def test_graphed_search_replays(m):
         assert np.array_equal(i.cpu().numpy()[:, 0], src)
 
 
+# ------------------------------------------------------------------ batched extract_vectors (section 8f, f2)
+class _TinyRetrievalNet(torch.nn.Module):
+    """Shaped like cirtorch's ImageRetrievalNet: features / pool / norm / meta, no whitening."""
+
+    def __init__(self, m, pooling="gem", p=2.9137):
+        super().__init__()
+        nn = torch.nn
+        self.features = nn.Sequential(nn.Conv2d(3, 32, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(32, 64, 3, stride=2, padding=1), nn.ReLU())
+        self.lwhiten, self.whiten = None, None
+        self.pool = {"gem": lambda: m.GeM(p=p), "mac": m.MAC, "spoc": m.SPoC}[pooling]()
+        self.norm = m.L2N()
+        self.meta = {"pooling": pooling, "regional": False, "whitening": False, "out_channels": 64, "outputdim": 64}
+
+
+def test_batched_extract_vectors(m, golden):
+    torch.manual_seed(3)
+    net = _TinyRetrievalNet(m).to(DEV).eval()
+    rs = np.random.RandomState(6)
+    imgs = [torch.from_numpy(rs.rand(3, h, w).astype(np.float32)) for h, w in ((64, 48), (57, 91), (128, 96), (40, 40), (33, 77))]
+    feats = lambda x: net.features(x.to(DEV).unsqueeze(0)).float().cpu().numpy()
+    # ImageRetrievalNet semantics: single scale (extract_ss) and multi-scale with explicit msp (extract_ms)
+    with torch.no_grad():
+        v1 = m.extract_vectors(net, imgs, None, None, ms=[1], msp=1, group=2)
+        assert tuple(v1.shape) == (64, 5) and v1.device.type == "cpu"
+        for i, im in enumerate(imgs):
+            close(v1[:, i], oracle.net_tail(feats(im), "gem", 2.9137)[:, 0], rtol=2e-5, atol=1e-7)
+        ms = [1, 1 / np.sqrt(2), 1 / 2]
+        v3 = m.extract_vectors(net, imgs, None, None, ms=ms, msp=2.9137, group=4)
+        for i, im in enumerate(imgs):
+            x = im.to(DEV).unsqueeze(0)
+            outs = []
+            for s in ms:
+                xs = x if s == 1 else torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+                outs.append(oracle.net_tail(net.features(xs).float().cpu().numpy(), "gem", 2.9137)[:, 0])
+            close(v3[:, i], oracle.aggregate_tensor(outs, 3, 64, 2.9137), rtol=2e-5, atol=1e-7)
+        # mdir CirNetwork semantics: wrappers carry the scales (msp rule) and the Lw whitening
+        g = golden("head")
+        lw = {"m": g["lw_m"][:64], "P": g["lw_P"][:64, :64]}
+        comp = types.SimpleNamespace(wrappers=[m.CirtorchWhiten(lw, 32, DEV), m.CirMultiscaleAggregation(True, DEV)])
+        cirnet = types.SimpleNamespace(model=net, wrappers={"eval": comp}, stage="eval")
+        vw = m.extract_vectors(cirnet, imgs, None, None, group=3, return_device=True)
+        assert tuple(vw.shape) == (5, 32) and vw.is_cuda
+        for i, im in enumerate(imgs):
+            x = im.to(DEV).unsqueeze(0)
+            fm = [net.features(torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)).float().cpu().numpy() for s in ms]
+            close(vw[i], oracle.gem_head(fm, 2.9137, 1e-6, lw["m"], lw["P"], 32), rtol=5e-5, atol=5e-7)
+
+
 # ------------------------------------------------------------------ mAP on the device (section 8f, f3)
 def test_compute_map_device(m, golden):
     g = golden("search")
