@@ -7,7 +7,7 @@ Nothing here imports the reference at module import time: ``install()`` needs an
 ``mdir`` package (the user's checkout) and raises otherwise."""
 import numpy as np
 
-from . import layers, wrappers, clahe, search, evaluate
+from . import layers, wrappers, clahe, search, evaluate, extract
 
 
 def rank_and_evaluate(dataset, vecs, qvecs, gnd, compute_map_and_print=None, device="cuda"):
@@ -52,7 +52,19 @@ def make_cirdatasetap(base_cls, extract_vectors, compute_map_and_print, stopwatc
     return CirDatasetAp
 
 
-def install():
+def _batched_or_reference(reference_extract):
+    """extract_vectors that uses the batched device path and falls back to the reference's per-image loop
+    for networks outside the hot path (local / in-model whitening, regional pooling, other wrappers)."""
+    def extract_vectors(net, images, image_size, transform, bbxs=None, ms=[1], msp=1, print_freq=10, device=None):
+        try:
+            return extract.extract_vectors(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq,
+                                           device=device)
+        except NotImplementedError:
+            return reference_extract(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq, device=device)
+    return extract_vectors
+
+
+def install(batched_extract=True):
     """Patch POOLING, WRAPPERS_LABELS, TRANSFORMS and SCORES of an importable ``mdir`` in place
     (SURVEY.md 8b).  Returns the dict of patched registry entries."""
     try:
@@ -81,7 +93,8 @@ def install():
         if key in mtrans.TRANSFORMS:
             mtrans.TRANSFORMS[key] = cls
             patched["TRANSFORMS[%s]" % key] = cls
-    new_cls = make_cirdatasetap(cirscore.CirDatasetAp, cirscore.extract_vectors, cirscore.compute_map_and_print, StopWatch)
+    ev = _batched_or_reference(cirscore.extract_vectors) if batched_extract else cirscore.extract_vectors
+    new_cls = make_cirdatasetap(cirscore.CirDatasetAp, ev, cirscore.compute_map_and_print, StopWatch)
     mscore.SCORES["cirdatasetap"] = new_cls
     patched["SCORES[cirdatasetap]"] = new_cls
     return patched
