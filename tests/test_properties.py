@@ -1,0 +1,51 @@
+"""Property tests (hypothesis) of the host-side ordering / merge logic: the 64-bit key order is exactly the
+stable descending argsort, and merging per-shard top-k lists is independent of how the rows were sharded."""
+import numpy as np
+from hypothesis import given, settings, strategies as st
+
+from oracle import oracle
+from mdir_b200.search import ShardedIndex, make_keys_host, keys_to_host, merge_keys_host, default_shortlist
+
+scores_st = st.lists(st.one_of(st.floats(-4, 4, width=32), st.sampled_from([0.0, -0.0, 1.0, 1.0, -1.0, float("inf"), float("-inf")])),
+                     min_size=1, max_size=200)
+
+
+@settings(max_examples=60, deadline=None)
+@given(scores_st)
+def test_key_order_is_stable_descending_argsort(vals):
+    s = np.asarray(vals, dtype=np.float32)
+    keys = make_keys_host(s, np.arange(s.shape[0]))
+    assert len(set(keys.tolist())) == s.shape[0]                         # keys are unique
+    assert np.array_equal(np.argsort(keys, kind="stable"), oracle.ranks_from_scores(s[:, None])[:, 0])
+    sc, idx = keys_to_host(keys)
+    assert np.array_equal(idx, np.arange(s.shape[0])) and np.array_equal(sc, np.where(s == 0, np.float32(0), s))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 400), st.integers(1, 30), st.integers(0, 2 ** 31 - 1))
+def test_shard_merge_is_partition_independent(n, k, seed):
+    rs = np.random.RandomState(seed)
+    sc = (np.round(rs.randn(n, 3) * 4) / 4).astype(np.float32)            # heavy ties
+    ref_i, ref_v = oracle.topk_from_scores(sc, min(k, n))
+    for world in (1, 2, 4, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = ShardedIndex.shard_bounds(n, world, r)
+            pad = np.full((3, k), np.uint64(0xffffffffffffffff))
+            if hi > lo:
+                idx, val = oracle.topk_from_scores(sc[lo:hi], min(k, hi - lo))
+                keys = make_keys_host(val.T, idx.T + lo)
+                pad[:, :keys.shape[1]] = keys
+            parts.append(pad)
+        msc, midx = keys_to_host(merge_keys_host(np.stack(parts), k))
+        kk = min(k, n)
+        assert np.array_equal(midx[:, :kk], ref_i.T) and np.array_equal(msc[:, :kk], ref_v.T)
+        assert np.all(midx[:, kk:] == -1)
+
+
+def test_default_shortlist_monotone():
+    prev = 0
+    for k in range(1, 2000, 7):
+        s = default_shortlist(k)
+        assert s >= k + 32 and s >= prev
+        prev = s
