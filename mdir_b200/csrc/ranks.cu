@@ -4,13 +4,16 @@
 // Layout: everything is query-major (n_q segments of n_db keys) on the device so all
 // streams are coalesced; the reference's (n_db, n_q) C-order appears only in the first
 // (score transpose -> u32 keys) and last (u32 ranks -> int64 transpose) kernels.
-// 4 passes x {digit histogram per 4096-key chunk, per-segment scan, stable scatter}.
+// 4 passes x {digit histogram per 2048-key chunk, per-segment scan, stable scatter staged through
+// shared memory so each digit's keys leave as one coalesced run}.
 #include "common.cuh"
 
 namespace mdir {
 
-constexpr int kChunk = 2048;          // keys per CTA
-constexpr int kItems = 8;             // keys per thread (256 threads)
+constexpr int kItems = 8;             // keys per thread in the scatter kernel
+constexpr int kScatterThreads = 256;
+constexpr int kChunk = kScatterThreads * kItems;   // 2048 keys per CTA
+constexpr int kScatterWarps = kScatterThreads / 32;
 
 __device__ __forceinline__ uint32_t rank_key(float s) { return desc_key(s); }   // ascending key == descending score, NaN last
 
@@ -100,25 +103,36 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__
 }
 
 // Stable scatter of one chunk.  vals_in == nullptr means "value = position" (first pass).
-__global__ void __launch_bounds__(256) radix_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                                            int64_t n_db, int n_chunks, int shift,
-                                                            const uint32_t* __restrict__ offsets, uint32_t* __restrict__ keys_out,
-                                                            uint32_t* __restrict__ vals_out) {
-    __shared__ uint32_t cnt[8][256];
+// Two phases: (1) every key gets its position inside the CHUNK sorted by digit (per-warp counters +
+// match.any ranking, then a scan over warps and digits) and is staged there in shared memory;
+// (2) the staged chunk is written out in order, so the keys of one digit go to consecutive global
+// addresses (runs of ~32 keys = full 128-byte lines instead of 32 scattered 4-byte stores).
+__global__ void __launch_bounds__(kScatterThreads, 4) radix_scatter_kernel(const uint32_t* __restrict__ keys_in,
+                                                                        const uint32_t* __restrict__ vals_in, int64_t n_db, int n_chunks,
+                                                                        int shift, const uint32_t* __restrict__ offsets,
+                                                                        uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    extern __shared__ uint32_t sm[];
+    uint32_t* skey = sm;                               // kChunk
+    uint32_t* sval = sm + kChunk;                      // kChunk
+    uint32_t* cnt = sm + 2 * kChunk;                   // kScatterWarps x 256
+    uint32_t* delta = cnt + kScatterWarps * 256;       // 256: global offset - local base of each digit
+    uint32_t* wsum = delta + 256;                      // 8 (digit scan over 256 threads)
     const int chunk = blockIdx.x, q = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&cnt[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < kScatterWarps * 256; i += kScatterThreads) cnt[i] = 0u;
     __syncthreads();
     const int64_t seg = (int64_t)q * n_db;
-    const int64_t base = (int64_t)chunk * kChunk + (int64_t)w * (kItems * 32);
+    const int64_t cbase = (int64_t)chunk * kChunk;
+    const int64_t base = cbase + (int64_t)w * (kItems * 32);
+    const int n_valid = (int)min((int64_t)kChunk, n_db - cbase);
     uint32_t key[kItems], rank[kItems];
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
         const int64_t i = base + it * 32 + lane;
-        const bool valid = i < n_db;
-        key[it] = valid ? keys_in[seg + i] : 0u;
+        key[it] = i < n_db ? keys_in[seg + i] : 0u;
     }
+    uint32_t* mycnt = cnt + w * 256;
 #pragma unroll
     for (int it = 0; it < kItems; ++it) {
         const int64_t i = base + it * 32 + lane;
@@ -126,24 +140,44 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint32_t* __re
         const int d = (int)((key[it] >> shift) & 0xffu);
         const unsigned peers = match_digit8(d, valid);
         uint32_t r = 0;
-        if (valid) {
-            r = cnt[w][d] + __popc(peers & lt);
-        }
+        if (valid) r = mycnt[d] + __popc(peers & lt);
         __syncwarp();
-        if (valid && lane == (__ffs(peers) - 1)) cnt[w][d] += __popc(peers);
+        if (valid && lane == (__ffs(peers) - 1)) mycnt[d] += __popc(peers);
         __syncwarp();
         rank[it] = r;
     }
     __syncthreads();
-    {
+    // per digit: exclusive scan over the warps, then an exclusive scan of the digit totals over the 256 digits
+    if (threadIdx.x < 256) {
         const int d = threadIdx.x;
-        uint32_t run = offsets[((int64_t)q * 256 + d) * n_chunks + chunk];
+        uint32_t run = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t t = cnt[k][d];
-            cnt[k][d] = run;
+        for (int k = 0; k < kScatterWarps; ++k) {
+            const uint32_t t = cnt[k * 256 + d];
+            cnt[k * 256 + d] = run;
             run += t;
         }
+        uint32_t incl = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        // (threads 256..511 skip this block; the barrier below is outside it)
+        delta[d] = incl - run;                          // exclusive within the warp for now
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const int d = threadIdx.x;
+        uint32_t pre = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < w) pre += wsum[k];
+        const uint32_t local_base = delta[d] + pre;
+#pragma unroll
+        for (int k = 0; k < kScatterWarps; ++k) cnt[k * 256 + d] += local_base;      // warp offsets become chunk positions
+        delta[d] = offsets[((int64_t)q * 256 + d) * n_chunks + chunk] - local_base;
     }
     __syncthreads();
 #pragma unroll
@@ -151,10 +185,17 @@ __global__ void __launch_bounds__(256) radix_scatter_kernel(const uint32_t* __re
         const int64_t i = base + it * 32 + lane;
         if (i < n_db) {
             const int d = (int)((key[it] >> shift) & 0xffu);
-            const uint32_t pos = cnt[w][d] + rank[it];
-            keys_out[seg + pos] = key[it];
-            vals_out[seg + pos] = vals_in ? vals_in[seg + i] : (uint32_t)i;
+            const uint32_t l = mycnt[d] + rank[it];
+            skey[l] = key[it];
+            sval[l] = vals_in ? vals_in[seg + i] : (uint32_t)i;
         }
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < n_valid; l += kScatterThreads) {
+        const uint32_t k = skey[l];
+        const uint32_t pos = (uint32_t)l + delta[(k >> shift) & 0xffu];
+        keys_out[seg + pos] = k;
+        vals_out[seg + pos] = sval[l];
     }
 }
 
@@ -213,6 +254,12 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         keys_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, kA);
     }
     MDIR_LAUNCH_CHECK();
+    constexpr size_t kScatterSmem = (size_t)(2 * kChunk + kScatterWarps * 256 + 256 + 8) * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        MDIR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
+        attr_set = true;
+    }
     uint32_t *kin = kA, *kout = kB, *vin = nullptr, *vout = vA;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;
@@ -220,7 +267,7 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         MDIR_LAUNCH_CHECK();
         radix_scan_kernel<<<n_q, 1024, 0, st>>>(counts, n_chunks);
         MDIR_LAUNCH_CHECK();
-        radix_scatter_kernel<<<dim3(n_chunks, n_q), 256, 0, st>>>(kin, vin, n_db, n_chunks, shift, counts, kout, vout);
+        radix_scatter_kernel<<<dim3(n_chunks, n_q), kScatterThreads, kScatterSmem, st>>>(kin, vin, n_db, n_chunks, shift, counts, kout, vout);
         MDIR_LAUNCH_CHECK();
         uint32_t* t = kin; kin = kout; kout = t;
         vin = vout;
