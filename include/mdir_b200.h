@@ -150,6 +150,24 @@ int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int 
                        const uint64_t* tau, uint32_t idx_base,
                        uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream);
 
+/* Threshold + filter in ONE launch (the large-database route of the top-k search; replaces the
+ * SAMPLE scan -> mdir_select_kth -> FILTER scan chain and its two extra launches).  Every
+ * persistent CTA first scans one sample tile (tiles c * (n_tiles / grid)), publishes the two best
+ * keys of each of its eight 32-row groups, and after a grid-wide arrival counter CTA q selects the
+ * kth smallest of query q's grid*16 values: a valid threshold, because those values are keys of
+ * kth distinct rows.  After a second arrival counter every CTA filters its sample tile (still in
+ * TMEM) and then the rest of the database exactly like MDIR_SCAN_FILTER.  Writes tau[q], the
+ * candidate segments 1.. and ALL n_q * MDIR_CAND_SEGS segment counters (segment 0 stays empty).
+ * ws: mdir_sim_scan_fused_workspace_bytes(n_q) bytes, 16-byte aligned, ZEROED ONCE by the caller
+ * before first use (the kernel re-arms its counters itself).  Needs n_db >= 512 rows and the
+ * whole grid co-resident (one CTA per SM, nothing else occupying the device); if an arrival
+ * counter is not reached within ~4 s the segments report overflow instead of hanging.       */
+size_t mdir_sim_scan_fused_workspace_bytes(int n_q);
+int mdir_sim_scan_fused_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
+                             int kth, uint64_t* tau, uint32_t idx_base,
+                             uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l,
+                             void* ws, void* stream);
+
 /* The same scan with fp32 operands consumed as TF32 (tcgen05 kind::tf32, fp32 accumulate):
  * db (n_db, D) and q (n_q, D) row-major fp32, D % 4 == 0.  Used directly it is the TF32
  * similarity variant; fed the (n, 3D) matrices written by mdir_split_tf32x3 (role 0 for the

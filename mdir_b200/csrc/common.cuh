@@ -82,6 +82,38 @@ __device__ __forceinline__ unsigned match_digit8(int d, bool valid) {
     return peers;
 }
 
+// One-warp helper: given hist[256] and the remaining rank k (1-based), find the bin where the
+// running count reaches k.  Returns the bin; *before = items in earlier bins.
+__device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, uint32_t* before) {
+    const int lane = threadIdx.x & 31;
+    uint32_t loc[8], sum = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const uint32_t excl = incl - sum;
+    const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
+    const int src = hit ? (__ffs(hit) - 1) : 31;
+    int bin = 0;
+    uint32_t acc = excl;
+    if (lane == src) {
+        int j = 0;
+        for (; j < 7; ++j) {
+            if (acc + loc[j] >= k) break;
+            acc += loc[j];
+        }
+        bin = lane * 8 + j;
+    }
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    acc = __shfl_sync(0xffffffffu, acc, src);
+    *before = acc;
+    return bin;
+}
+
 // ---- 64-bit candidate keys: smaller key == better (score desc, index asc) --------
 __host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
 #ifdef __CUDA_ARCH__

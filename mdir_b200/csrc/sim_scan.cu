@@ -122,10 +122,19 @@ struct ScanParams {
     // dense_out + ks * split_stride (the caller adds the k_split partial planes in a fixed order)
     int k_split, kb_per_split;
     int64_t split_stride;
+    // FUSED mode only (threshold + filter in one launch): every CTA's first tile is a sample tile; the best two keys
+    // of each 32-row group go to grp_top (n_q, grid, 8, 2); CTA q selects the kth smallest of query q's grid*16
+    // values as the threshold, published through tau_rw; sync = {arrivals 1, arrivals 2, unused, exits}
+    int kth;
+    uint32_t* grp_top;
+    uint32_t* sync;
+    uint64_t* tau_rw;
 };
 
+constexpr int MDIR_SCAN_FUSED = 3;      // internal mode behind mdir_sim_scan_fused_bf16
+
 struct WorkItem {
-    int tile, ks, kb0, nkb;
+    int tile, ks, kb0, nkb, j;
 };
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j);
@@ -143,7 +152,39 @@ __device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
         w.kb0 = 0;
         w.nkb = p.num_k_blocks;
     }
+    w.j = j;
     return w;
+}
+
+// The it-th work item of this CTA (persistent round-robin); false when the CTA is done.  In FUSED mode item 0 is
+// the CTA's own sample tile and the rest walk the non-sample tiles exactly like FILTER mode.
+__device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem& w) {
+    int j = (int)blockIdx.x + it * (int)gridDim.x;
+    if (p.mode == MDIR_SCAN_FUSED) {
+        if (it == 0) {
+            w.tile = (int)blockIdx.x * p.sample_stride;
+            w.ks = 0;
+            w.kb0 = 0;
+            w.nkb = p.num_k_blocks;
+            w.j = (int)blockIdx.x;
+            return true;
+        }
+        j -= (int)gridDim.x;
+    }
+    if (j >= p.n_work) return false;
+    w = decode_work(p, j);
+    return true;
+}
+
+// Bounded spin on a device-scope arrival counter (one thread).  ~4 s worst case, then gives up: the caller turns
+// that into a candidate overflow, which the host recovers through the dense route instead of hanging.
+__device__ __forceinline__ bool spin_until(const uint32_t* ctr, uint32_t target) {
+    const volatile uint32_t* c = ctr;
+    for (int i = 0; i < (1 << 25); ++i) {
+        if (*c >= target) return true;
+        __nanosleep(100);
+    }
+    return false;
 }
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j) {
@@ -196,7 +237,9 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (p.mode == MDIR_SCAN_FILTER) {
+    if (p.mode == MDIR_SCAN_FUSED) {
+        for (int c = threadIdx.x; c < kMaxN; c += kThreads) cand_n[c] = 0u;
+    } else if (p.mode == MDIR_SCAN_FILTER) {
         for (int c = threadIdx.x; c < kMaxN; c += kThreads) {
             uint64_t t = c < p.n_q ? p.tau[c] : 0ull;
             tau_s[c] = t;
@@ -214,8 +257,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int j = blockIdx.x; j < p.n_work; j += gridDim.x) {
-                const WorkItem w = decode_work(p, j);
+            WorkItem w;
+            for (int it = 0; next_item(p, it, w); ++it) {
                 const int row0 = w.tile * kBlockM;
                 for (int kb = w.kb0; kb < w.kb0 + w.nkb; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
@@ -238,13 +281,13 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_pad >> 3) << 17) | ((128u >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
-            for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
+            WorkItem w;
+            for (int it = 0; next_item(p, it, w); ++it) {
                 const int b = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(smem_u32(&tmem_empty_bar[b]), acc_phase ^ 1u);
                 tc_fence_after();
-                const int nkb = decode_work(p, j).nkb;
+                const int nkb = w.nkb;
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(smem_u32(&full_bar[stage]), phase);
                     tc_fence_after();
@@ -271,29 +314,130 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         const int quarter = warp & 3;                  // TMEM lane quarter this warp may read
         const int64_t cand_row = (int64_t)p.cap_s + (int64_t)kNumSMs * p.cap_l;
         const int64_t cand_seg_off = (int64_t)p.cap_s + (int64_t)blockIdx.x * p.cap_l;
-        int it = 0;
-        for (int j = blockIdx.x; j < p.n_work; j += gridDim.x, ++it) {
+        const int emode = p.mode == MDIR_SCAN_FUSED ? MDIR_SCAN_FILTER : p.mode;
+        WorkItem w;
+        for (int it = 0; next_item(p, it, w); ++it) {
             const int b = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-            const WorkItem w = decode_work(p, j);
             const int tile = w.tile;
             float* dense_out = p.dense_out + (int64_t)w.ks * p.split_stride;
             mbar_wait(smem_u32(&tmem_full_bar[b]), acc_phase);
             tc_fence_after();
+            if (p.mode == MDIR_SCAN_FUSED && it == 0) {
+                // ---- pass A over the sample tile: best two keys of each 32-row group (this warp x half), per query
+                const int et = (int)threadIdx.x - 64;
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int64_t row = (int64_t)tile * kBlockM + h * 128 + quarter * 32 + lane;
+                    const bool row_ok = row < p.n_db;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * 128u;
+#pragma unroll 1
+                    for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
+                        uint32_t v[16];
+                        tmem_ld16(taddr + (uint32_t)c0, v);
+                        tmem_ld_wait();
+                        uint32_t m1 = 0xffffffffu, m2 = 0xffffffffu;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t key = row_ok ? desc_key(__uint_as_float(v[i])) : 0xffffffffu;
+                            const uint32_t a = __reduce_min_sync(0xffffffffu, key);
+                            const unsigned who = __ballot_sync(0xffffffffu, key == a);
+                            const uint32_t key2 = (lane == __ffs(who) - 1) ? 0xffffffffu : key;
+                            const uint32_t bb = __reduce_min_sync(0xffffffffu, key2);
+                            if (lane == i) { m1 = a; m2 = bb; }
+                        }
+                        if (lane < 16 && c0 + lane < p.n_q) {
+                            uint32_t* dst = p.grp_top + (((int64_t)(c0 + lane) * gridDim.x + blockIdx.x) * 8 + (quarter * 2 + h)) * 2;
+                            *reinterpret_cast<uint2*>(dst) = make_uint2(m1, m2);
+                        }
+                    }
+                }
+                // ---- grid-wide arrival 1, then CTA q turns query q's grid*16 values into its threshold
+                __shared__ uint32_t sel_hist[256];
+                __shared__ uint32_t sel_prefix, sel_k, sel_ok;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    __threadfence();
+                    atomicAdd(&p.sync[0], 1u);
+                    sel_ok = 1u;
+                }
+                const int n_val = (int)gridDim.x * 16;
+                for (int q = blockIdx.x; q < p.n_q; q += gridDim.x) {
+                    if (et == 0) {
+                        if (!spin_until(&p.sync[0], gridDim.x)) sel_ok = 0u;
+                        __threadfence();
+                        sel_prefix = 0u;
+                        sel_k = (uint32_t)p.kth;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    constexpr int kPer = (kNumSMs * 16 + 127) / 128;
+                    uint32_t vals[kPer];
+                    const uint32_t* src = p.grp_top + (int64_t)q * n_val;
+#pragma unroll
+                    for (int k = 0; k < kPer; ++k) {
+                        const int i = et + 128 * k;
+                        vals[k] = i < n_val ? __ldcg(src + i) : 0xffffffffu;
+                    }
+                    uint32_t result = 0xffffffffu;
+                    if (p.kth <= n_val) {
+                        for (int pass = 0; pass < 4; ++pass) {
+                            const int shift = 24 - 8 * pass;
+                            sel_hist[et] = 0u;
+                            sel_hist[et + 128] = 0u;
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            const uint32_t prefix = sel_prefix;
+                            const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+#pragma unroll
+                            for (int k = 0; k < kPer; ++k)
+                                if (et + 128 * k < n_val && (vals[k] & himask) == prefix) atomicAdd(&sel_hist[(vals[k] >> shift) & 255u], 1u);
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            if (warp == 2) {
+                                uint32_t before;
+                                const int bin = find_bin_warp0(sel_hist, sel_k, &before);
+                                if (lane == 0) {
+                                    sel_prefix = prefix | ((uint32_t)bin << shift);
+                                    sel_k -= before;
+                                }
+                            }
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                        }
+                        result = sel_prefix;
+                    }
+                    if (et == 0) {
+                        p.tau_rw[q] = sel_ok ? (((uint64_t)result << 32) | 0xffffffffull) : 0ull;
+                        __threadfence();
+                        atomicAdd(&p.sync[1], 1u);
+                    }
+                }
+                // ---- grid-wide arrival 2: every threshold is published
+                if (et == 0) {
+                    if (!spin_until(&p.sync[1], (uint32_t)p.n_q)) sel_ok = 0u;
+                    __threadfence();
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                {
+                    const bool ok = sel_ok != 0u;
+                    const uint64_t tq = (ok && et < p.n_q) ? __ldcg(reinterpret_cast<const unsigned long long*>(p.tau_rw) + et) : 0ull;
+                    tau_s[et] = tq;
+                    tau_f[et] = ((uint32_t)(tq >> 32) == 0xffffffffu) ? -INFINITY : key_score(tq);
+                    if (!ok) cand_n[et] = (uint32_t)p.cap_l + 1u;        // barrier timed out: report overflow, never hang
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
                 const int r_in_tile = h * 128 + quarter * 32 + lane;
                 const int64_t row = (int64_t)tile * kBlockM + r_in_tile;
                 const bool row_ok = row < p.n_db;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * 128u;
-                const int64_t out_row = (p.mode == MDIR_SCAN_SAMPLE ? (int64_t)j * kBlockM : (int64_t)tile * kBlockM) + r_in_tile;
+                const int64_t out_row = (p.mode == MDIR_SCAN_SAMPLE ? (int64_t)w.j * kBlockM : (int64_t)tile * kBlockM) + r_in_tile;
                 const uint32_t gidx = p.idx_base + (uint32_t)row;
 #pragma unroll 1
                 for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
                     uint32_t v[16];
                     tmem_ld16(taddr + (uint32_t)c0, v);
                     tmem_ld_wait();
-                    if (p.mode != MDIR_SCAN_FILTER) {
+                    if (emode != MDIR_SCAN_FILTER) {
                         // rows past the end of the database only exist in the compact SAMPLE buffer: mark them -inf
                         if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
 #pragma unroll
@@ -321,10 +465,17 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&tmem_empty_bar[b]));
         }
-        if (p.mode == MDIR_SCAN_FILTER) {
+        if (emode == MDIR_SCAN_FILTER) {
             asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
             const int t = threadIdx.x - 64;
-            if (t < p.n_q) p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + 1 + blockIdx.x] = cand_n[t];
+            if (t < p.n_q) {
+                p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + 1 + blockIdx.x] = cand_n[t];
+                if (p.mode == MDIR_SCAN_FUSED && blockIdx.x == 0) {
+                    // no select kernel in this route: segment 0 and the segments of absent CTAs are empty
+                    p.seg_counts[(int64_t)t * MDIR_CAND_SEGS] = 0u;
+                    for (int s = 1 + (int)gridDim.x; s < MDIR_CAND_SEGS; ++s) p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + s] = 0u;
+                }
+            }
         }
     }
 
@@ -333,6 +484,15 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+    if (p.mode == MDIR_SCAN_FUSED && threadIdx.x == 0) {
+        // the last CTA out re-arms the arrival counters for the next launch on this workspace
+        if (atomicAdd(&p.sync[3], 1u) == gridDim.x - 1) {
+            p.sync[0] = 0u;
+            p.sync[1] = 0u;
+            p.sync[3] = 0u;
+            __threadfence();
+        }
     }
 }
 
@@ -380,11 +540,12 @@ using namespace mdir;
 
 static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, int n_q, int D, int mode, int sample_stride, int n_sample,
                        float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base, uint64_t* cand,
-                       uint32_t* seg_counts, int cap_s, int cap_l, void* stream, int k_split = 1, int64_t split_stride = 0) {
+                       uint32_t* seg_counts, int cap_s, int cap_l, void* stream, int k_split = 1, int64_t split_stride = 0,
+                       int kth = 0, uint32_t* fused_ws = nullptr, uint64_t* tau_rw = nullptr) {
     const int esz = tf32 ? 4 : 2;
     MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 16 / esz && (D % (16 / esz)) == 0);
     MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
-    MDIR_CHECK_ARG(mode >= 0 && mode <= 2);
+    MDIR_CHECK_ARG(mode >= 0 && mode <= MDIR_SCAN_FUSED);
     MDIR_CHECK_ARG(n_db + (int64_t)idx_base <= ((int64_t)1 << 32));
     ScanParams p;
     p.n_db = n_db;
@@ -401,6 +562,10 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.k_split = 1;
     p.kb_per_split = p.num_k_blocks;
     p.split_stride = split_stride;
+    p.kth = 0;
+    p.grp_top = nullptr;
+    p.sync = nullptr;
+    p.tau_rw = nullptr;
     if (mode == MDIR_SCAN_DENSE) {
         MDIR_CHECK_ARG(dense_out && dense_ld >= n_db);
         if (k_split > 1) {
@@ -413,6 +578,25 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CHECK_ARG((int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
         MDIR_CHECK_ARG(dense_ld >= (int64_t)n_sample * kBlockM);
         p.n_work = n_sample;
+    } else if (mode == MDIR_SCAN_FUSED) {
+        // one sample tile per CTA, all CTAs co-resident (the in-kernel arrival counters rely on it)
+        MDIR_CHECK_ARG(tau_rw && fused_ws && cand && seg_counts && cap_l >= 1 && kth >= 1);
+        static int sm_count = 0;
+        if (!sm_count) {
+            int dev = 0;
+            MDIR_CUDA(cudaGetDevice(&dev));
+            MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        }
+        int g = sm_count < kNumSMs ? sm_count : kNumSMs;
+        if (g > p.n_tiles / 2) g = p.n_tiles / 2;
+        MDIR_CHECK_ARG(g >= 1);
+        p.n_sample = g;
+        p.sample_stride = p.n_tiles / g;
+        p.n_work = p.n_tiles - g;
+        p.kth = kth;
+        p.grp_top = fused_ws + 4;
+        p.sync = fused_ws;
+        p.tau_rw = tau_rw;
     } else {
         MDIR_CHECK_ARG(tau && cand && seg_counts && cap_s >= 0 && cap_l >= 1);
         MDIR_CHECK_ARG(n_sample >= 0 && (n_sample == 0 || sample_stride >= 2));
@@ -429,7 +613,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.cap_l = cap_l;
     // a database that fits L2 (126 MB) is worth keeping there across query blocks / passes
     p.db_hint = ((int64_t)n_db * D * esz > (int64_t)96 * 1024 * 1024) ? kEvictFirst : kEvictNormal;
-    if (p.n_work <= 0) return 0;
+    if (p.n_work <= 0 && mode != MDIR_SCAN_FUSED) return 0;
 
     const int stage_bytes = kABytes + p.n_pad * 128;
     int stages = (232448 - 1024 - 4096) / stage_bytes;
@@ -450,7 +634,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
         attr_set = true;
     }
-    const int grid = p.n_work < kNumSMs ? p.n_work : kNumSMs;
+    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (p.n_work < kNumSMs ? p.n_work : kNumSMs);
     if (tf32) sim_scan_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     else sim_scan_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     MDIR_LAUNCH_CHECK();
@@ -462,6 +646,18 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
                                   uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
     return launch_scan(false, db, n_db, q, n_q, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts,
                        cap_s, cap_l, stream);
+}
+
+extern "C" size_t mdir_sim_scan_fused_workspace_bytes(int n_q) {
+    return (4 + (size_t)(n_q > 0 ? n_q : 0) * kNumSMs * 16) * sizeof(uint32_t);
+}
+
+extern "C" int mdir_sim_scan_fused_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int kth, uint64_t* tau,
+                                        uint32_t idx_base, uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* ws,
+                                        void* stream) {
+    MDIR_CHECK_ARG(ws && (((uintptr_t)ws) & 15) == 0);
+    return launch_scan(false, db, n_db, q, n_q, D, MDIR_SCAN_FUSED, 0, 0, nullptr, 0, nullptr, idx_base, cand, seg_counts, cap_s, cap_l,
+                       stream, 1, 0, kth, static_cast<uint32_t*>(ws), tau);
 }
 
 extern "C" int mdir_sim_scan_tf32(const float* db, int64_t n_db, const float* q, int n_q, int D, int mode, int sample_stride,

@@ -14,38 +14,6 @@ __device__ __forceinline__ uint32_t sample_pos_to_idx(int64_t i, int sample_stri
     return idx_base + (uint32_t)(j * sample_stride * MDIR_SCAN_TILE_ROWS + r);
 }
 
-// Warp 0 helper: given hist[256] and the remaining rank k (1-based), find the bin where the
-// running count reaches k.  Returns the bin; *before = items in earlier bins.
-__device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, uint32_t* before) {
-    const int lane = threadIdx.x & 31;
-    uint32_t loc[8], sum = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { loc[j] = hist[lane * 8 + j]; sum += loc[j]; }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    const uint32_t excl = incl - sum;
-    const unsigned hit = __ballot_sync(0xffffffffu, incl >= k);
-    const int src = hit ? (__ffs(hit) - 1) : 31;
-    int bin = 0;
-    uint32_t acc = excl;
-    if (lane == src) {
-        int j = 0;
-        for (; j < 7; ++j) {
-            if (acc + loc[j] >= k) break;
-            acc += loc[j];
-        }
-        bin = lane * 8 + j;
-    }
-    bin = __shfl_sync(0xffffffffu, bin, src);
-    acc = __shfl_sync(0xffffffffu, acc, src);
-    *before = acc;
-    return bin;
-}
-
 // kth smallest (1-based) of ONE 32-bit value per thread of a 1024-thread block (4 radix passes of
 // one element each).  Used to bound the selection: the kth smallest of the per-thread minima is an
 // upper bound B of the kth smallest key overall, so only the few keys <= B take part in the real

@@ -28,6 +28,7 @@ CAP_L = 96            # capacity of each scan CTA's private segment
 CAND_ROW = CAP_S + 148 * CAP_L
 STAGE_CAP = 16384     # keys mdir_topk_finalize can stage in shared memory
 MAX_SAMPLE_TILES = 512
+FUSED_CAP_L = CAND_ROW // 148   # one-launch route: no select segment, so each CTA segment gets the whole row's share
 TARGET_CAND = 4500    # candidates per query the sampling plan aims for (kth * n_tiles / n_sample), ~30 per CTA segment
 
 
@@ -66,6 +67,9 @@ def pack_bf16(x, dxn=False):
 
 class Index:
     """A (shard of a) descriptor database on one GPU."""
+
+    fused = True      # allow the one-launch threshold + filter route (False: always sample -> select -> filter)
+    _sms = None
 
     def __init__(self, vecs, dxn=False, device="cuda", keep_fp32=True, idx_base=0):
         """vecs: (n, D) fp32 rows (torch/numpy, host or device), or (D, n) with dxn=True
@@ -118,6 +122,21 @@ class Index:
             return None
         return n_sample, stride
 
+    def _fused_ok(self, kth):
+        """One-launch route (mdir_sim_scan_fused_bf16): each of the g persistent CTAs samples one tile, so the
+        threshold is about the kth best of g*256 rows and ~1.25 * kth * n_tiles / g rows survive, spread over g
+        segments.  Taken when that keeps the segments at most half full; larger k or databases use the
+        three-launch route, whose sample grows with the database."""
+        if not self.fused:
+            return False
+        n_tiles = (self.n + TILE - 1) // TILE
+        if self._sms is None:
+            self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        g = min(148, self._sms, n_tiles // 2)
+        if n_tiles < 64 or g * 16 < 2 * kth:
+            return False
+        return 1.25 * kth * n_tiles / (g * g) <= FUSED_CAP_L / 2
+
     def _scan(self, q16, mode, stride, n_sample, dense, dense_ld, tau, cand, cnt):
         _lib.check(_lib.lib().mdir_sim_scan_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16), q16.shape[0], self.D, mode, stride,
                                                  n_sample, _lib.ptr(dense), dense_ld, _lib.ptr(tau), self.idx_base, _lib.ptr(cand),
@@ -127,8 +146,10 @@ class Index:
         return (self._buf("tau", (MAX_Q,), torch.int64), self._buf("cand", (MAX_Q, CAND_ROW), torch.int64),
                 self._buf("segcnt", (MAX_Q, N_SEGS), torch.int32))
 
-    def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore=None):
+    def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore=None, caps=(CAP_S, CAP_L)):
         """rescore = (q32_block, k_out): fused exact fp32 re-scoring of the kth-long bf16 shortlist."""
+        CAP_S, CAP_L = caps
+        CAND_ROW = CAP_S + 148 * CAP_L            # the row stride the scan kernels derive from the two capacities
         if rescore is None:
             _lib.check(_lib.lib().mdir_topk_finalize(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth,
                                                      _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
@@ -160,7 +181,21 @@ class Index:
         plan = self._plan(kth)
         if plan is None:
             return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf, rescore)
-        tau, cand, cnt = self._cand_bufs()       # the select kernel (re)initialises every segment counter
+        tau, cand, cnt = self._cand_bufs()       # the select / fused kernel (re)initialises every segment counter
+        prof = getattr(self, "prof", None)       # bench.py: CUDA events around the dominant kernel, on its own stream
+        if self._fused_ok(kth):
+            ws = self._ws.get("fused_ws")
+            if ws is None:                       # zeroed once; the kernel re-arms its arrival counters itself
+                ws = torch.zeros((lib.mdir_sim_scan_fused_workspace_bytes(MAX_Q) // 4,), dtype=torch.int32, device=self.device)
+                self._ws["fused_ws"] = ws
+            if prof is not None:
+                prof.begin()
+            _lib.check(lib.mdir_sim_scan_fused_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16), nq, self.D, kth, _lib.ptr(tau),
+                                                    self.idx_base, _lib.ptr(cand), _lib.ptr(cnt), 0, FUSED_CAP_L, _lib.ptr(ws),
+                                                    _lib.stream()), "mdir_sim_scan_fused_bf16")
+            if prof is not None:
+                prof.end(self.n * self.D * 2)
+            return self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore, caps=(0, FUSED_CAP_L))
         n_sample, stride = plan
         rows = n_sample * TILE
         sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
@@ -168,8 +203,7 @@ class Index:
         self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
                                        _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 1, _lib.stream()), "mdir_select_kth")
-        prof = getattr(self, "prof", None)
-        if prof is not None:      # bench.py: CUDA events around the dominant kernel, on its own stream
+        if prof is not None:
             prof.begin()
         self._scan(q16, 2, stride, n_sample, None, 0, tau, cand, cnt)
         if prof is not None:

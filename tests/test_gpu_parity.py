@@ -345,6 +345,22 @@ def test_search_bf16_equals_topk_of_own_scores(m, n_db, n_q, D, k):
     assert np.all(i.cpu().numpy()[:, 0] == src + 1000)            # planted neighbour found first
 
 
+@pytest.mark.parametrize("n_db,n_q,D,k", [(16389, 70, 64, 100), (120000, 128, 64, 132), (300000, 33, 32, 10)])
+def test_search_one_launch_and_three_launch_routes_agree(m, n_db, n_q, D, k):
+    """The fused threshold+filter launch and the sample -> select -> filter chain are both exact."""
+    db = synth.descriptors(n_db, D, 300 + n_q, clusters=80)
+    q, _ = synth.planted_queries(db, n_q, 9)
+    index = m.Index(db, device=DEV, keep_fp32=False)
+    assert index._fused_ok(k)
+    sc = index.scores(q).cpu().numpy().T
+    ref_i, ref_v = oracle.topk_from_scores(sc, k)
+    for fused in (True, False, True):
+        index.fused = fused
+        s, i = index.search(q, k, precision="bf16")
+        assert np.array_equal(i.cpu().numpy().T, ref_i), fused
+        assert np.array_equal(s.cpu().numpy().T, ref_v), fused
+
+
 def test_search_fp32_matches_reference_topk(m):
     db = synth.descriptors(30000, 128, 41, clusters=200)
     q, _ = synth.planted_queries(db, 70, 42)

@@ -120,7 +120,7 @@ static void test_dense(int64_t n_db, int n_q, int D) {
 }
 
 // sample -> select -> filter -> finalize, compared with an exact sort of the GPU's own dense scores
-static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sample, int cap_s) {
+static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sample, int cap_s, bool fused = false) {
     const int cap_l = 96; const int64_t cap = cap_s + 148 * (int64_t)cap_l; const int NS = MDIR_CAND_SEGS;
     Scan s = make_scan(n_db, n_q, D);
     float *d_dense, *d_sample, *d_os; int32_t* d_oi; uint64_t *d_tau, *d_cand; uint32_t* d_cnt; int32_t* d_ovf;
@@ -132,12 +132,21 @@ static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sam
     CK(cudaMalloc(&d_cnt, n_q * NS * 4)); CK(cudaMalloc(&d_ovf, n_q * 4));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_DENSE, 0, 0, d_dense, n_db, nullptr, 0, nullptr,
                           nullptr, 0, 0, 0));
-    CK(cudaMemset(d_cnt, 0, n_q * NS * 4));
+    CK(cudaMemset(d_cnt, fused ? 0xff : 0, n_q * NS * 4));
+    void* d_ws = nullptr;
+    if (fused) {
+        const size_t wsb = mdir_sim_scan_fused_workspace_bytes(n_q);
+        CK(cudaMalloc(&d_ws, wsb));
+        CK(cudaMemset(d_ws, 0, wsb));
+        for (int rep = 0; rep < 3; ++rep)      // repeated launches: the kernel re-arms its own arrival counters
+            MD(mdir_sim_scan_fused_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, k, d_tau, 0, d_cand, d_cnt, cap_s, cap_l, d_ws, 0));
+    } else {
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_SAMPLE, stride, n_sample, d_sample, n_samp_rows,
                           nullptr, 0, nullptr, nullptr, 0, 0, 0));
     MD(mdir_select_kth(d_sample, n_samp_rows, n_samp_rows, n_q, k, stride, 0, d_tau, d_cand, cap, d_cnt, NS, cap_s, 1, 0));
     MD(mdir_sim_scan_bf16((uint16_t*)s.d_db, n_db, (uint16_t*)s.d_q, n_q, D, MDIR_SCAN_FILTER, stride, n_sample, nullptr, 0, d_tau, 0,
                           d_cand, d_cnt, cap_s, cap_l, 0));
+    }
     MD(mdir_topk_finalize(d_cand, cap, d_cnt, NS, cap_s, cap_l, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
     CK(cudaDeviceSynchronize());
     std::vector<float> dense((size_t)n_q * n_db), os((size_t)n_q * k);
@@ -163,7 +172,8 @@ static void test_topk(int64_t n_db, int n_q, int D, int k, int stride, int n_sam
             }
     }
     char name[128];
-    snprintf(name, sizeof name, "topk %lldx%dx%d k=%d (maxcand %u, ovf %d)", (long long)n_db, n_q, D, k, maxcnt, novf);
+    snprintf(name, sizeof name, "%s %lldx%dx%d k=%d (maxcand %u, ovf %d)", fused ? "fused" : "topk", (long long)n_db, n_q, D, k, maxcnt, novf);
+    if (d_ws) cudaFree(d_ws);
     report(name, bad == 0 && novf == 0, (double)bad);
     cudaFree(d_dense); cudaFree(d_sample); cudaFree(d_os); cudaFree(d_oi); cudaFree(d_tau); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_ovf);
     cudaFree(s.d_db); cudaFree(s.d_q);
@@ -240,6 +250,29 @@ static void bench_big(int64_t n_db, int n_q, int n_sample) {
         if (rep) printf("rep %d: sample %.3f ms  select %.3f ms  filter %.3f ms (%.0f GB/s)  finalize %.3f ms  total %.3f ms  maxcand %u\n", rep,
                t[0], t[1], t[2], gb / (t[2] * 1e-3), t[3], t[0] + t[1] + t[2] + t[3], mx);
     }
+    {   // the one-launch route
+        void* d_ws; const size_t wsb = mdir_sim_scan_fused_workspace_bytes(n_q);
+        CK(cudaMalloc(&d_ws, wsb)); CK(cudaMemset(d_ws, 0, wsb));
+        for (int rep = 0; rep < 4; ++rep) {
+            CK(cudaEventRecord(e[0]));
+            MD(mdir_sim_scan_fused_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, k, d_tau, 0, d_cand, d_cnt, cap_s, cap_l, d_ws, 0));
+            CK(cudaEventRecord(e[1]));
+            MD(mdir_topk_finalize(d_cand, cap, d_cnt, NS, cap_s, cap_l, n_q, k, d_os, d_oi, nullptr, d_tau, d_ovf, 0));
+            CK(cudaEventRecord(e[2]));
+            CK(cudaDeviceSynchronize());
+            float t0, t1;
+            CK(cudaEventElapsedTime(&t0, e[0], e[1])); CK(cudaEventElapsedTime(&t1, e[1], e[2]));
+            std::vector<uint32_t> cnt((size_t)n_q * NS);
+            CK(cudaMemcpy(cnt.data(), d_cnt, (size_t)n_q * NS * 4, cudaMemcpyDeviceToHost));
+            uint32_t mx = 0, mxseg = 0;
+            for (int qi = 0; qi < n_q; ++qi) { uint32_t tot = 0; for (int sg = 0; sg < NS; ++sg) { tot += cnt[(size_t)qi * NS + sg]; mxseg = std::max(mxseg, cnt[(size_t)qi * NS + sg]); } mx = std::max(mx, tot); }
+            std::vector<int32_t> ovf(n_q); CK(cudaMemcpy(ovf.data(), d_ovf, n_q * 4, cudaMemcpyDeviceToHost));
+            int novf = 0; for (auto o : ovf) novf += o;
+            if (rep) printf("fused rep %d: scan %.3f ms (%.0f GB/s)  finalize %.3f ms  total %.3f ms  maxcand %u maxseg %u ovf %d\n", rep, t0,
+                            (double)n_db * D * 2 / 1e9 / (t0 * 1e-3), t1, t0 + t1, mx, mxseg, novf);
+        }
+        cudaFree(d_ws);
+    }
     cudaFree(d_db); cudaFree(d_q); cudaFree(d_sample); cudaFree(d_os); cudaFree(d_oi); cudaFree(d_tau); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_ovf);
 }
 
@@ -254,6 +287,10 @@ int main(int argc, char** argv) {
     test_topk(20000, 70, 256, 100, 8, 8, 8192);
     test_topk(5000, 5, 64, 10, 2, 3, 1024);
     test_topk(100000, 128, 128, 200, 12, 32, 8192);
+    test_topk(20000, 70, 256, 100, 0, 0, 0, true);
+    test_topk(100000, 128, 128, 200, 0, 0, 0, true);
+    test_topk(513, 5, 64, 10, 0, 0, 0, true);
+    test_topk(300000, 70, 64, 132, 0, 0, 0, true);
     test_ranks(5000, 7, false);
     test_ranks(4993, 70, true);
     test_ranks(100, 3, true);
