@@ -252,6 +252,42 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
                     const int32_t* item_class, int64_t n_items, const int32_t* n_pos, const int32_t* kappas,
                     int n_kappa, double* aps, double* prs, void* ws, void* stream);
 
+/* ---------------------------------------------- hard-negative mining (f4) ---
+ * The consumer of a full ranking inside TuplesDataset.create_epoch_tuples
+ * (mdir/external/cirtorch/datasets/traindataset.py:250-267): for query q walk ranks[:, q]
+ * (ranks (n_pool, n_q) int64 C-order, pitch ranks_ld, as mdir_rank_scores writes them) from the
+ * best score down and keep the first nnum pool positions whose cluster differs from
+ * q_cluster[q] and from every cluster already kept.  out_pos (n_q, nnum) pool positions (-1
+ * where the pool ran out), out_found (n_q) how many were found.  nnum <= 63.
+ * mdir_pair_l2dist: out[q, j] = sqrt(sum_d (q[q, d] - pool[pos[q, j], d] + eps)^2), the
+ * reference's torch.pow(q - p + 1e-6, 2).sum().sqrt() (traindataset.py:263); q (n_q, D) and
+ * pool (n_pool, D) row-major fp32; NaN where pos < 0.                                        */
+int mdir_mine_negatives(const int64_t* ranks, int64_t ranks_ld, int64_t n_pool, int n_q,
+                        const int32_t* pool_cluster, const int32_t* q_cluster, int nnum,
+                        int64_t* out_pos, int32_t* out_found, void* stream);
+int mdir_pair_l2dist(const float* q, const float* pool, const int64_t* pos, int n_q, int nnum, int D,
+                     float eps, float* out, void* stream);
+
+/* --------------------------------------------- learning the whitening (f4) ---
+ * The O(D^2 N) fp64 contractions of whitenlearn / pcawhitenlearn
+ * (mdir/external/cirtorch/utils/whiten.py:14-53) on (D, N) matrices whose columns are images.
+ * mdir_gemm_f64: C (M, N) = alpha * (A - a_sub) * op(B - b_sub); A (M, K) row-major pitch lda;
+ * b_is_kxn == 0: B (N, K) row-major (np.dot(A, B.T), the covariance shape), else B (K, N)
+ * row-major (np.dot(A, B)); a_sub / b_sub: optional per-row constants of A / B in their own
+ * storage (the fused "X - m").  Deterministic (split-K partial planes summed in order);
+ * ws: mdir_gemm_f64_workspace_bytes(M, N, K) bytes (may be 0 -> NULL).
+ * mdir_pair_diff_f64: out (D, n_pairs) = X[:, qidx] - X[:, pidx] (whiten.py:41).
+ * mdir_cols_mean_f64: mean[d] = mean_j X[d, idx[j]]  (idx NULL: the first n_idx columns).    */
+size_t mdir_gemm_f64_workspace_bytes(int M, int N, int64_t K);
+int mdir_gemm_f64(const double* A, int64_t lda, const double* a_sub, const double* B, int64_t ldb,
+                  const double* b_sub, int b_is_kxn, int M, int N, int64_t K, double alpha,
+                  double* C, int64_t ldc, void* ws, void* stream);
+int mdir_pair_diff_f64(const double* X, int64_t ldx, int D, int64_t n_cols, const int64_t* qidx,
+                       const int64_t* pidx, int64_t n_pairs, double* out, void* stream);
+int mdir_cols_mean_f64(const double* X, int64_t ldx, int D, int64_t n_cols, const int64_t* idx,
+                       int64_t n_idx, double* mean, void* stream);
+int mdir_f32_to_f64(const float* src, int64_t n, double* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

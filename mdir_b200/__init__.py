@@ -20,5 +20,7 @@ from .search import Index, ShardedIndex, rank, ranks_from_scores, topk_from_scor
 from .extract import extract_vectors, extract_from_tensors  # noqa: F401
 from .evaluate import compute_map, compute_map_and_print  # noqa: F401
 from .score import install  # noqa: F401
+from .mining import mine_hard_negatives, search_hard_negatives  # noqa: F401
+from .whiten_learn import whitenlearn, pcawhitenlearn, gemm_f64  # noqa: F401
 
 __version__ = "0.1.0"

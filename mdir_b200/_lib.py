@@ -50,6 +50,13 @@ PROTOTYPES = {
     "mdir_add_l2n": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "mdir_map_workspace_bytes": (_sz, [_i64, _i]),
     "mdir_compute_ap": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "mdir_mine_negatives": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "mdir_pair_l2dist": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
+    "mdir_gemm_f64_workspace_bytes": (_sz, [_i, _i, _i64]),
+    "mdir_gemm_f64": (_i, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i64, _d, _vp, _i64, _vp, _vp]),
+    "mdir_pair_diff_f64": (_i, [_vp, _i64, _i, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "mdir_cols_mean_f64": (_i, [_vp, _i64, _i, _i64, _vp, _i64, _vp, _vp]),
+    "mdir_f32_to_f64": (_i, [_vp, _i64, _vp, _vp]),
     "mdir_rank_workspace_bytes": (_sz, [_i64, _i]),
     "mdir_rank_scores": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
 }

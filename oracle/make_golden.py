@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Generate tests/golden/*.npz from the LIVE reference (build container only).
 
-Usage:  python oracle/make_golden.py            (needs /root/reference; cv2 4.13)
+Usage:  python oracle/make_golden.py [section ...]   (needs /root/reference; cv2 4.13)
+        sections: base (pooling/head/clahe/search), mining, whitenlearn; default: all
 
 Every array written here is an OUTPUT OF THE REFERENCE'S OWN CODE (mdir/cirtorch
 functions, or the cv2/numpy calls at the reference's call sites) on the seeded
@@ -24,8 +25,109 @@ from oracle import ref_import, synth  # noqa: E402
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
 
+def make_mining():
+    """Hard-negative mining: the LIVE TuplesDataset.create_epoch_tuples (cirtorch/datasets/traindataset.py:178-272)
+    run on CPU over a synthetic image folder with a recording descriptor network."""
+    import tempfile
+    import torch
+    import torch.nn as nn
+    from PIL import Image
+    from cirtorch.datasets.traindataset import TuplesDataset
+
+    D, n_img, n_clu = 32, 400, 40
+    rs = np.random.RandomState(31)
+    tmp = tempfile.mkdtemp(prefix="mdir_mining_")
+    base = rs.randint(0, 256, size=(n_clu, 8, 8, 3))
+    clusters = [i % n_clu for i in range(n_img)]
+    images = []
+    for i in range(n_img):
+        px = np.clip(base[clusters[i]] + rs.randint(-60, 61, size=(8, 8, 3)), 0, 255).astype(np.uint8)
+        fn = os.path.join(tmp, "im%04d.png" % i)
+        Image.fromarray(px).save(fn)
+        images.append(fn)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(5)
+            self.W = torch.randn(D, 192, generator=g)
+            self.meta = {"out_channels": D}
+            self.seen = []
+
+        def forward(self, x):
+            v = self.W @ (x.reshape(-1) - 0.5)
+            v = v / v.norm()
+            self.seen.append(v.clone())
+            return v.reshape(1, D, 1, 1)
+
+    def to_tensor(img):
+        return torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1).contiguous()
+
+    out = {}
+    for case, (qsize, poolsize, nnum) in enumerate([(60, 300, 5), (25, 400, 8), (40, 120, 3)]):
+        ds = TuplesDataset.__new__(TuplesDataset)
+        ds.name, ds.mode, ds.imsize, ds.transform, ds.print_freq = "synthetic", "train", None, to_tensor, 1000
+        ds.images, ds.clusters = images, clusters
+        qp = list(range(0, 240, 2))
+        ds.qpool = qp
+        ds.ppool = [(q + n_clu) % n_img for q in qp]            # same cluster, other image
+        ds.qsize, ds.poolsize, ds.nnum = qsize, poolsize, nnum
+        net = Net()
+        torch.manual_seed(100 + case)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ret = ds.create_epoch_tuples(net, device=torch.device("cpu"))
+        torch.manual_seed(100 + case)                           # replay the method's two randperm draws
+        idxs2qpool = torch.randperm(len(ds.qpool))[:qsize]
+        idxs2images = torch.randperm(len(images))[:poolsize]
+        assert [ds.qpool[i] for i in idxs2qpool] == ds.qidxs
+        vec = torch.stack(net.seen, 1).numpy()                  # (D, qsize + poolsize) in call order
+        tag = "c%d_" % case
+        out[tag + "qvecs"] = vec[:, :qsize].copy()
+        out[tag + "poolvecs"] = vec[:, qsize:].copy()
+        out[tag + "qclusters"] = np.array([clusters[i] for i in ds.qidxs], np.int32)
+        out[tag + "poolclusters"] = np.array([clusters[int(i)] for i in idxs2images], np.int32)
+        out[tag + "idxs2images"] = idxs2images.numpy().astype(np.int64)
+        out[tag + "nidxs"] = np.array([[int(x) for x in row] for row in ds.nidxs], np.int64)
+        out[tag + "ndist"] = np.array(ret["average_negative_distance"], np.float32)
+        out[tag + "nnum"] = np.array(nnum)
+    np.savez_compressed(os.path.join(OUT, "mining.npz"), **out)
+
+
+def make_whitenlearn():
+    """Lw / PCA whitening learning: cirtorch/utils/whiten.py:14-53 (pure numpy, fp64)."""
+    from cirtorch.utils.whiten import whitenlearn, pcawhitenlearn, whitenapply
+    out = {}
+    for case, (D, N, npair) in enumerate([(32, 600, 200), (128, 3000, 1200)]):
+        X = synth.descriptors(N, D, 40 + case, clusters=30).T.astype(np.float64)      # (D, N), columns = images
+        rs = np.random.RandomState(50 + case)
+        qidxs = rs.randint(0, N, npair)
+        pidxs = (qidxs + 30 * rs.randint(1, 5, npair)) % N       # arbitrary 'matching' pairs: only the algebra is under test
+        m, P = whitenlearn(X, qidxs, pidxs)
+        mp, Pp = pcawhitenlearn(X)
+        tag = "c%d_" % case
+        out[tag + "X_recipe"] = np.array([N, D, 40 + case, 30])    # X = synth.descriptors(N, D, seed, clusters).T as fp64
+        out[tag + "qidxs"], out[tag + "pidxs"] = qidxs, pidxs
+        out[tag + "m"], out[tag + "P"] = m, np.real(P)
+        out[tag + "applied"] = whitenapply(X[:, :50], m, np.real(P))
+        out[tag + "pca_m"], out[tag + "pca_P"] = mp, np.real(Pp)
+    np.savez_compressed(os.path.join(OUT, "whitenlearn.npz"), **out)
+
+
 def main():
     ref_import.import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    sections = sys.argv[1:] or ["base", "mining", "whitenlearn"]
+    if "mining" in sections:
+        make_mining()
+    if "whitenlearn" in sections:
+        make_whitenlearn()
+    if "base" in sections:
+        make_base()
+    for f in sorted(os.listdir(OUT)):
+        print("%-14s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+def make_base():
     import cv2
     import torch
     import torch.nn as nn
@@ -144,9 +246,6 @@ def main():
     for k_, v_ in per.items():
         srch["emh_" + k_] = v_
     np.savez_compressed(os.path.join(OUT, "search.npz"), **srch)
-
-    for f in sorted(os.listdir(OUT)):
-        print("%-14s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 
 
 if __name__ == "__main__":

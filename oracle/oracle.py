@@ -500,3 +500,83 @@ def dba(db, alpha=3.0, k_dba=10, chunk=4096):
         acc = np.einsum("kb,kbd->bd", w, db[idx].astype(np.float64))
         out[s:s + chunk] = acc / np.sqrt((acc ** 2).sum(1, keepdims=True))
     return out.astype(np.float32)
+
+
+# ----------------------------------------------------------------------------
+# f4: hard-negative mining and whitening learning
+# ----------------------------------------------------------------------------
+
+
+def mine_negatives(qvecs, poolvecs, qclusters, poolclusters, nnum):
+    """cirtorch/datasets/traindataset.py:242-267.  qvecs (D,Nq), poolvecs (D,Np) fp32 (columns =
+    images); cluster ids per query / pool image.  Walk every query's ranking (best score first),
+    keep the first nnum pool positions whose cluster is neither the query's nor already kept.
+    Returns (pos (Nq,nnum) int64 pool positions, ndist (Nq,nnum) fp32) with
+    ndist = sqrt(sum((q - p + 1e-6)**2)) (traindataset.py:263)."""
+    qvecs = np.asarray(qvecs, dtype=np.float32)
+    poolvecs = np.asarray(poolvecs, dtype=np.float32)
+    rk = ranks_from_scores(np.dot(poolvecs.T, qvecs))
+    nq = qvecs.shape[1]
+    pos = np.full((nq, nnum), -1, dtype=np.int64)
+    ndist = np.full((nq, nnum), np.nan, dtype=np.float32)
+    for q in range(nq):
+        used = [qclusters[q]]
+        r = 0
+        n = 0
+        while n < nnum:
+            cand = rk[r, q]                      # IndexError when the pool runs out, like the reference
+            if poolclusters[cand] not in used:
+                used.append(poolclusters[cand])
+                pos[q, n] = cand
+                d = qvecs[:, q] - poolvecs[:, cand] + np.float32(1e-6)
+                ndist[q, n] = np.sqrt(np.sum(d * d, dtype=np.float32))
+                n += 1
+            r += 1
+    return pos, ndist
+
+
+def _eig_desc(S):
+    """Eigenpairs by descending eigenvalue (whiten.py:25-28, 46-49; the reference calls the general
+    np.linalg.eig on a symmetric matrix -- same pairs up to sign and rounding)."""
+    w, v = np.linalg.eigh((S + S.T) * 0.5)
+    return w[::-1], v[:, ::-1]
+
+
+def whitenlearn(X, qidxs, pidxs):
+    """cirtorch/utils/whiten.py:37-53 (Lw whitening from matching pairs), fp64.  X (D,N)."""
+    X = np.asarray(X, dtype=np.float64)
+    m = X[:, qidxs].mean(axis=1, keepdims=True)
+    df = X[:, qidxs] - X[:, pidxs]
+    S = df @ df.T / df.shape[1]
+    alpha = 0.0                                   # whiten.py:55-70: jitter the diagonal until positive definite
+    while True:
+        try:
+            L = np.linalg.cholesky(S + alpha * np.eye(S.shape[0]))
+            break
+        except np.linalg.LinAlgError:
+            alpha = 1e-10 if alpha == 0 else alpha * 10
+    Pc = np.linalg.inv(L)
+    Y = Pc @ (X - m)
+    _, vec = _eig_desc(Y @ Y.T)
+    return m, vec.T @ Pc
+
+
+def pcawhitenlearn(X, shrink=None):
+    """cirtorch/utils/whiten.py:14-35, fp64."""
+    X = np.asarray(X, dtype=np.float64)
+    N = X.shape[1]
+    m = X.mean(axis=1, keepdims=True)
+    Xc = X - m
+    cov = Xc @ Xc.T
+    w, v = _eig_desc((cov + cov.T) / (2 * N))
+    if shrink:
+        b = w[shrink - 1]
+        w = (1 - b) * w + b
+    return m, (v / np.sqrt(w)[None, :]).T
+
+
+def whitening_rows_aligned(P, P_ref):
+    """Rows of P with the sign of each flipped to agree with P_ref (eigenvector signs are arbitrary)."""
+    s = np.sign(np.sum(P * P_ref, axis=1, keepdims=True))
+    s[s == 0] = 1
+    return P * s

@@ -558,3 +558,93 @@ def test_qe_and_dba(m):
     small = synth.descriptors(600, 64, 23, clusters=10)
     aug = qe.dba(m.Index(small, device=DEV), alpha=3.0, k_dba=5)
     close(aug.db32, oracle.dba(small, 3.0, 5), rtol=1e-4, atol=2e-6)
+
+
+# ---- f4: hard-negative mining, whitening learning ----------------------------------------------------
+
+def test_mining_matches_reference_create_epoch_tuples(m, golden):
+    g = golden("mining")
+    for case in range(3):
+        t = "c%d_" % case
+        nnum = int(g[t + "nnum"])
+        pos, dist = m.mine_hard_negatives(g[t + "qvecs"], g[t + "poolvecs"], g[t + "qclusters"], g[t + "poolclusters"], nnum, device=DEV)
+        assert np.array_equal(g[t + "idxs2images"][pos.cpu().numpy()], g[t + "nidxs"])
+        np.testing.assert_allclose(dist.cpu().numpy().reshape(-1), g[t + "ndist"], rtol=0, atol=2e-6)
+    # the reference-variable form (traindataset.py:242-267 as one call)
+    clusters = np.arange(400) % 40
+    qidxs = [int(np.where(clusters == c)[0][0]) for c in g["c0_qclusters"]]
+    nidxs, ndist = m.search_hard_negatives(g["c0_qvecs"], g["c0_poolvecs"], qidxs, g["c0_idxs2images"], clusters, 5, device=DEV)
+    assert nidxs == g["c0_nidxs"].tolist() and len(ndist) == 300
+
+
+def test_mining_larger_pool_and_exhaustion(m):
+    D, n_pool, n_q, nnum = 64, 6000, 333, 7
+    pool = synth.descriptors(n_pool, D, 81, clusters=150)
+    q, src = synth.planted_queries(pool, n_q, 82)
+    rs = np.random.RandomState(83)
+    pc = rs.randint(0, 400, n_pool).astype(np.int32)
+    qc = pc[src]
+    pos, dist = m.mine_hard_negatives(q.T.copy(), pool.T.copy(), qc, pc, nnum, device=DEV)
+    ref_pos, ref_dist = oracle.mine_negatives(q.T, pool.T, qc, pc, nnum)
+    pos = pos.cpu().numpy()
+    assert np.mean(pos == ref_pos) > 0.995            # fp32 summation-order noise may swap near-equal scores
+    got_c = pc[pos]
+    assert not np.any(got_c == qc[:, None]) and all(len(set(r)) == nnum for r in got_c)
+    same = (pos == ref_pos)
+    np.testing.assert_allclose(dist.cpu().numpy()[same], ref_dist[same], rtol=0, atol=3e-6)
+    # only 3 clusters besides the query's: the 4th negative does not exist
+    pc3 = (np.arange(n_pool) % 4).astype(np.int32)
+    with pytest.raises(IndexError):
+        m.mine_hard_negatives(q.T.copy(), pool.T.copy(), np.zeros(n_q, np.int32), pc3, 4, device=DEV)
+    p3, _ = m.mine_hard_negatives(q.T.copy(), pool.T.copy(), np.zeros(n_q, np.int32), pc3, 3, device=DEV)
+    assert np.all(np.sort(pc3[p3.cpu().numpy()], axis=1) == np.array([1, 2, 3]))
+
+
+@pytest.mark.parametrize("M,N,K,kxn", [(128, 128, 64, False), (37, 211, 1000, False), (300, 70, 5000, True), (32, 32, 20000, False),
+                                       (257, 129, 17, True), (1, 1, 1, False)])
+def test_gemm_f64_matches_numpy(m, M, N, K, kxn):
+    import torch
+    rs = np.random.RandomState(M + N)
+    A = rs.randn(M, K)
+    B = rs.randn(K, N) if kxn else rs.randn(N, K)
+    a_sub, b_sub = rs.randn(M), rs.randn(B.shape[0])
+    ref = 0.37 * (A - a_sub[:, None]) @ ((B - b_sub[:, None]) if kxn else (B - b_sub[:, None]).T)
+    dev = torch.device(DEV)
+    got = m.gemm_f64(torch.tensor(A, device=dev), torch.tensor(B, device=dev), kxn, alpha=0.37,
+                     a_sub=torch.tensor(a_sub, device=dev), b_sub=torch.tensor(b_sub, device=dev))
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=0, atol=1e-12 * max(1.0, np.abs(ref).max()) * np.sqrt(K))
+    got2 = m.gemm_f64(torch.tensor(A, device=dev), torch.tensor(B, device=dev), kxn)
+    ref2 = A @ (B if kxn else B.T)
+    np.testing.assert_allclose(got2.cpu().numpy(), ref2, rtol=0, atol=1e-12 * max(1.0, np.abs(ref2).max()) * np.sqrt(K))
+
+
+def test_whitenlearn_matches_reference(m, golden):
+    g = golden("whitenlearn")
+    for case in range(2):
+        t = "c%d_" % case
+        N, D, seed, clusters = [int(x) for x in g[t + "X_recipe"]]
+        X = synth.descriptors(N, D, seed, clusters=clusters).T.astype(np.float64)
+        mm, P = m.whitenlearn(X, g[t + "qidxs"], g[t + "pidxs"], device=DEV)
+        assert mm.shape == (D, 1) and P.shape == (D, D) and P.dtype == np.float64
+        np.testing.assert_allclose(mm, g[t + "m"], rtol=0, atol=1e-13)
+        scale = np.abs(g[t + "P"]).max()
+        np.testing.assert_allclose(oracle.whitening_rows_aligned(P, g[t + "P"]), g[t + "P"], rtol=0, atol=1e-6 * scale)
+        app = oracle.whitenapply(X[:, :50], mm, P)
+        np.testing.assert_allclose(app.T @ app, g[t + "applied"].T @ g[t + "applied"], rtol=0, atol=1e-8)
+        mp, Pp = m.pcawhitenlearn(X, device=DEV)
+        np.testing.assert_allclose(mp, g[t + "pca_m"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(oracle.whitening_rows_aligned(Pp, g[t + "pca_P"]), g[t + "pca_P"], rtol=0,
+                                   atol=1e-6 * np.abs(g[t + "pca_P"]).max())
+    # fp32 input (what extract_vectors hands over), shrinkage, and the learnt dict feeding the Lw head
+    X32 = synth.descriptors(2000, 64, 91, clusters=40).T.copy()
+    rs = np.random.RandomState(92)
+    qi, pi = rs.randint(0, 2000, 500), rs.randint(0, 2000, 500)
+    mm, P = m.whitenlearn(X32, qi, pi, device=DEV)
+    mo, Po = oracle.whitenlearn(X32, qi, pi)
+    np.testing.assert_allclose(mm, mo, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(oracle.whitening_rows_aligned(P, Po), Po, rtol=0, atol=1e-6 * np.abs(Po).max())
+    mp, Pp = m.pcawhitenlearn(X32, shrink=10, device=DEV)
+    mo, Po = oracle.pcawhitenlearn(X32, shrink=10)
+    np.testing.assert_allclose(oracle.whitening_rows_aligned(Pp, Po), Po, rtol=0, atol=1e-6 * np.abs(Po).max())
+    out = m.whitenapply(X32[:, :20].astype(np.float64), mm, P, 32)
+    np.testing.assert_allclose(np.abs(out), np.abs(oracle.whitenapply(X32[:, :20].astype(np.float64), mm, P, 32)), rtol=0, atol=1e-5)

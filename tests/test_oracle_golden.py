@@ -143,3 +143,36 @@ def test_qe_dba_properties():
     d2 = oracle.dba(db, alpha=3.0, k_dba=5, chunk=128)
     close(np.linalg.norm(d2, axis=1), np.ones(300), rtol=1e-6)
     close(d2, oracle.dba(db, alpha=3.0, k_dba=5, chunk=300), rtol=1e-6, atol=1e-7)
+
+
+# ---- f4: hard-negative mining and whitening learning ----------------------------------------------
+
+def test_mining_oracle_matches_reference_create_epoch_tuples(golden):
+    g = golden("mining")
+    for case in range(3):
+        t = "c%d_" % case
+        nnum = int(g[t + "nnum"])
+        pos, ndist = oracle.mine_negatives(g[t + "qvecs"], g[t + "poolvecs"], g[t + "qclusters"], g[t + "poolclusters"], nnum)
+        assert np.array_equal(g[t + "idxs2images"][pos], g[t + "nidxs"])
+        np.testing.assert_allclose(ndist.reshape(-1), g[t + "ndist"], rtol=0, atol=2e-6)
+        # the rule itself: never the query's cluster, never two from one cluster
+        pc = g[t + "poolclusters"][pos]
+        assert not np.any(pc == g[t + "qclusters"][:, None])
+        assert all(len(set(row)) == nnum for row in pc)
+
+
+def test_whitenlearn_oracle_matches_reference(golden):
+    g = golden("whitenlearn")
+    for case in range(2):
+        t = "c%d_" % case
+        N, D, seed, clusters = [int(x) for x in g[t + "X_recipe"]]
+        X = synth.descriptors(N, D, seed, clusters=clusters).T.astype(np.float64)
+        m, P = oracle.whitenlearn(X, g[t + "qidxs"], g[t + "pidxs"])
+        np.testing.assert_allclose(m, g[t + "m"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(oracle.whitening_rows_aligned(P, g[t + "P"]), g[t + "P"], rtol=0, atol=1e-7 * np.abs(g[t + "P"]).max())
+        app = oracle.whitenapply(X[:, :50], m, P)
+        np.testing.assert_allclose(app.T @ app, g[t + "applied"].T @ g[t + "applied"], rtol=0, atol=1e-9)   # sign-free
+        mp, Pp = oracle.pcawhitenlearn(X)
+        np.testing.assert_allclose(mp, g[t + "pca_m"], rtol=0, atol=1e-14)
+        np.testing.assert_allclose(oracle.whitening_rows_aligned(Pp, g[t + "pca_P"]), g[t + "pca_P"], rtol=0,
+                                   atol=1e-7 * np.abs(g[t + "pca_P"]).max())
