@@ -531,6 +531,70 @@ def side_measurements(torch, mdir_b200, dev):
                     "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "hbm_floor_frac": pairs * 12 / 1e9 / (ms * 1e-3) / peak,
                     "note": "floor = 12 B/pair (4 B score + 8 B int64 rank) at the measured HBM peak"}
         del idx, db, r
+    out.update(training_side_measurements(torch, mdir_b200, dev, g, ev))
+    return out
+
+
+def training_side_measurements(torch, mdir_b200, dev, g, ev):
+    """Row f4: hard-negative mining at the reference's default epoch shape (2000 queries x 20000 pool images,
+    2048-D, 5 negatives; traindataset.py:54) and whitening learning (2048-D, 20000 images, 10000 pairs)."""
+    import numpy as np
+    from oracle import oracle
+    out = {}
+    D, n_q, n_pool, nnum = 2048, 2000, 20000, 5
+    pool = torch.randn((D, n_pool), device=dev, generator=g)
+    pool = pool / pool.norm(dim=0, keepdim=True)
+    qv = pool[:, :n_q] + 0.05 * torch.randn((D, n_q), device=dev, generator=g)
+    qv = qv / qv.norm(dim=0, keepdim=True)
+    rs = np.random.RandomState(3)
+    pc = rs.randint(0, 700, n_pool).astype(np.int32)
+    qc = pc[:n_q].copy()
+    for _ in range(2):
+        mdir_b200.mine_hard_negatives(qv, pool, qc, pc, nnum, device=dev)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(3):
+        mdir_b200.mine_hard_negatives(qv, pool, qc, pc, nnum, device=dev)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 3
+    sub = 100                                              # CPU: the reference's mm + sort + walk on 100 of the 2000 queries
+    ph, qh = pool.cpu().numpy(), qv[:, :sub].cpu().numpy()
+    t0 = time.perf_counter()
+    oracle.mine_negatives(qh, ph, qc[:sub], pc, nnum)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 * (n_q / sub)
+    out["mining"] = {"metric": "hard-negative mining (scores + full ranks + cluster walk + distances)", "shape": "%d q x %d pool x %d-D, %d negatives" % (n_q, n_pool, D, nnum),
+                     "ms": ms, "queries_per_s": n_q / (ms * 1e-3), "cpu_port_ms": cpu_ms, "cpu_sample": "%d of %d queries, time scaled" % (sub, n_q)}
+    del pool, qv
+    N, n_pairs = 20000, 10000
+    X = torch.randn((D, N), device=dev, generator=g, dtype=torch.float32)
+    X = X / X.norm(dim=0, keepdim=True)
+    qi, pi = rs.randint(0, N, n_pairs), rs.randint(0, N, n_pairs)
+    mdir_b200.whitenlearn(X, qi, pi, device=dev)
+    torch.cuda.synchronize()
+    ev[0].record()
+    mdir_b200.whitenlearn(X, qi, pi, device=dev)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1])
+    X64 = X.double()
+    for _ in range(2):
+        mdir_b200.gemm_f64(X64, X64, False)
+    torch.cuda.synchronize()
+    ev[0].record()
+    for _ in range(3):
+        mdir_b200.gemm_f64(X64, X64, False)
+    ev[1].record()
+    torch.cuda.synchronize()
+    gms = ev[0].elapsed_time(ev[1]) / 3
+    Xh = X[:512, :5000].cpu().numpy()                      # CPU: the numpy algorithm on a 512-D x 5000 slice (O(D^2 N + D^3))
+    t0 = time.perf_counter()
+    oracle.whitenlearn(Xh, qi[:2500] % 5000, pi[:2500] % 5000)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    out["whitenlearn"] = {"metric": "whitenlearn (fp64): pair covariance, Cholesky, data covariance, eigendecomposition", "shape": "%d-D x %d images, %d pairs" % (D, N, n_pairs),
+                          "ms": ms, "gemm_f64_ms_2048x2048x20000": gms, "gemm_f64_tflops": 2.0 * D * D * N / (gms * 1e-3) / 1e12,
+                          "cpu_port_ms_512d_x_5000": cpu_ms,
+                          "note": "O(D^2 N) contractions in mdir_gemm_f64 (SIMT DFMA); D x D factorisations are cuSOLVER via torch.linalg"}
     return out
 
 
