@@ -348,7 +348,7 @@ def run_ours(args):
         "e2e_cold_db_ms": {"pack_fp32_to_bf16_ms": pack_ms,
                            "note": "one-off index build for this shard; host->device upload of the fp32 rows would add %.1f GB over PCIe" % ((hi - lo) * DIM * 4 / 1e9)},
         "gpu_launches": int(launches), "gpu_launches_note": "%d libmdir_b200 kernels per step, replayed from one CUDA graph per step" % launches_per_step,
-        "roofline": {"bound": "hbm", "kernel": "sim_scan_kernel (FILTER pass)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "sim_scan_kernel (%s)" % ("threshold + filter in one launch: whole shard" if index._fused_ok(default_shortlist(TOPK)) else "FILTER pass"), "achieved": achieved, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": prof.bytes, "avg_launch_ms": scan_ms, "share_of_step": scan_ms / ms_step,
                      "timing": "CUDA events (external, recorded inside the step's CUDA graph on its stream), mean of %d replays" % len(scan_samples)},

@@ -3,8 +3,8 @@
 //
 //  kernel 1  clahe_lut_kernel    one CTA per (tile, image): the tile is read as aligned 16-byte
 //            chunks (4 in flight per thread), per-warp private uint32 histograms in shared memory
-//            updated with run-length-aggregated atomics (per-lane byte counters were tried and
-//            lost to their own zero/flush traffic), clip-limit redistribution, block scan,
+//            updated with unit-increment atomics (ATOMS.POPC.INC; run-length aggregation and per-lane
+//            byte counters were both tried and lost), clip-limit redistribution, block scan,
 //            LUT = sat_u8(rint(cdf * 255/area)).
 //  kernel 2  clahe_interp_kernel one CTA per interpolation cell (the rectangle between four
 //            tile centres, where the four contributing LUTs are fixed): the four LUTs are
@@ -13,6 +13,8 @@
 //            OpenCV's association (no FMA contraction) and round-half-even; a thread owns 8
 //            consecutive pixels (64-bit loads/stores, 4 rows in flight).
 //  The batch is processed in chunks of <= 48 MB of pixels so that pass 2 re-reads from L2.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mdir {
@@ -42,36 +44,64 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
-// run-length aggregated histogram update of the bytes [jlo, jhi) of a 16-byte chunk
-__device__ __forceinline__ void hist_chunk(uint32_t* h, const uint32_t (&w)[4], int jlo, int jhi) {
-    int prev = -1;
-    uint32_t run = 0;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        if (j >= jlo && j < jhi) {
-            const int v = (int)((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
-            if (v == prev) {
-                ++run;
-            } else {
-                if (run) atomicAdd(&h[prev], run);
-                prev = v;
-                run = 1;
-            }
-        }
+// Per-image constants, computed once per call by clahe_prep_kernel: the runtime integer divisions and the
+// double-precision clip limit cost ~500 instructions per warp when every CTA of the two big kernels redoes them
+// (a third of all instructions the interpolation kernel executed).
+struct ClahePrep {
+    int tw, th, ext_w, ext_h;
+    float inv_tw, inv_th, lut_scale;
+    int clip_limit;
+};
+
+__global__ void __launch_bounds__(256) clahe_prep_kernel(const mdir_image_desc* __restrict__ descs, int n_img, double clip, int tiles_x,
+                                                         int tiles_y, ClahePrep* __restrict__ prep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_img) return;
+    const ClaheGeom g = clahe_geom(descs[i].H, descs[i].W, tiles_x, tiles_y);
+    ClahePrep p;
+    p.tw = g.tw; p.th = g.th; p.ext_w = g.ext_w; p.ext_h = g.ext_h;
+    p.inv_tw = __fdiv_rn(1.0f, (float)g.tw);
+    p.inv_th = __fdiv_rn(1.0f, (float)g.th);
+    const int area = g.tw * g.th;
+    p.lut_scale = __fdiv_rn(255.0f, (float)area);
+    p.clip_limit = 0;
+    if (clip > 0.0) {
+        p.clip_limit = (int)(clip * (double)area / 256.0);
+        p.clip_limit = max(p.clip_limit, 1);
     }
-    if (run) atomicAdd(&h[prev], run);
+    prep[i] = p;
+}
+
+// histogram update of the bytes [jlo, jhi) of a 16-byte chunk (row ends only)
+__device__ __forceinline__ void hist_chunk_partial(uint32_t* h, const uint32_t (&w)[4], int jlo, int jhi) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+        if (j >= jlo && j < jhi) atomicAdd(&h[(w[j >> 2] >> (8 * (j & 3))) & 0xffu], 1u);
+}
+
+// all 16 bytes of a chunk: one unit-increment shared-memory atomic per pixel.  The unit increment matters: it
+// compiles to ATOMS.POPC.INC, which folds lanes that hit the same bin into one update, so dark images (a quarter
+// of a warp in bin 0) do not serialise the way a variable-increment ATOMS.ADD does.
+__device__ __forceinline__ void hist_chunk_full(uint32_t* h, const uint32_t (&w)[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        atomicAdd(&h[w[k] & 0xffu], 1u);
+        atomicAdd(&h[(w[k] >> 8) & 0xffu], 1u);
+        atomicAdd(&h[(w[k] >> 16) & 0xffu], 1u);
+        atomicAdd(&h[w[k] >> 24], 1u);
+    }
 }
 
 __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, const mdir_image_desc* __restrict__ descs,
-                                                        double clip, int tiles_x, int tiles_y, uint8_t* __restrict__ luts) {
+                                                        const ClahePrep* __restrict__ prep, uint8_t* __restrict__ luts) {
     __shared__ uint32_t whist[8][256];
     __shared__ int red_i[8];
     __shared__ int scan_w[8];
-    const int img = blockIdx.y;
-    const int tile = blockIdx.x;
-    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int img = blockIdx.z;
+    const int ty = blockIdx.y, tx = blockIdx.x;
+    const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const mdir_image_desc d = descs[img];
-    const ClaheGeom g = clahe_geom(d.H, d.W, tiles_x, tiles_y);
+    const ClahePrep g = prep[img];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0u;
     __syncthreads();
@@ -86,6 +116,9 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
         // 16-byte chunks: cpr per tile row (rows start at arbitrary alignment), 4 loads in flight per thread
         const int cpr = (vw + 15) / 16 + 1;
         const int total = g.th * cpr;
+        // chunk ci = (row r, chunk-in-row c); consecutive chunks of a thread are 256 apart: advance (r, c) instead of dividing
+        const int step_r = 256 / cpr, step_c = 256 - step_r * cpr;
+        int r = (int)threadIdx.x / cpr, c = (int)threadIdx.x - r * cpr;
         for (int c0 = threadIdx.x; c0 < total; c0 += 4 * 256) {
             uint32_t wv[4][4];
             int jlo[4], jhi[4];
@@ -94,7 +127,6 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
                 const int ci = c0 + u * 256;
                 jlo[u] = 0; jhi[u] = 0;
                 if (ci < total) {
-                    const int r = ci / cpr, c = ci - r * cpr;
                     const uint8_t* rowp = base + (int64_t)reflect101(y0 + r, d.H) * d.src_pitch;
                     const uint8_t* seg_lo = rowp + x0;
                     const uint8_t* seg_hi = seg_lo + vw;
@@ -115,10 +147,15 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
                         }
                     }
                 }
+                r += step_r;
+                c += step_c;
+                if (c >= cpr) { c -= cpr; ++r; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (jlo[u] < jhi[u]) hist_chunk(myh, wv[u], jlo[u], jhi[u]);
+            for (int u = 0; u < 4; ++u) {
+                if (jlo[u] == 0 && jhi[u] == 16) hist_chunk_full(myh, wv[u]);
+                else if (jlo[u] < jhi[u]) hist_chunk_partial(myh, wv[u], jlo[u], jhi[u]);
+            }
         }
     }
     const int rw = g.tw - vw;
@@ -137,12 +174,7 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
 #pragma unroll
     for (int k = 0; k < 8; ++k) h += (int)whist[k][i];
 
-    const int area = g.tw * g.th;
-    int clip_limit = 0;
-    if (clip > 0.0) {
-        clip_limit = (int)(clip * (double)area / 256.0);
-        clip_limit = max(clip_limit, 1);
-    }
+    const int clip_limit = g.clip_limit;
     if (clip_limit > 0) {
         int excess = max(h - clip_limit, 0);
         h = min(h, clip_limit);
@@ -174,21 +206,20 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     for (int k = 0; k < 8; ++k)
         if (k < w) pre += scan_w[k];
     s += pre;
-    const float lut_scale = __fdiv_rn(255.0f, (float)area);
-    int q = __float2int_rn(__fmul_rn((float)s, lut_scale));
+    int q = __float2int_rn(__fmul_rn((float)s, g.lut_scale));
     q = min(max(q, 0), 255);
     luts[(((int64_t)img * tiles_y + ty) * tiles_x + tx) * 256 + i] = (uint8_t)q;
 }
 
 __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                           const mdir_image_desc* __restrict__ descs, int tiles_x, int tiles_y,
+                                                           const mdir_image_desc* __restrict__ descs, const ClahePrep* __restrict__ prep,
                                                            const uint8_t* __restrict__ luts) {
     __shared__ float4 lutf[256];          // the four contributing LUTs, pre-converted: one LDS.128 per pixel
-    const int img = blockIdx.y;
-    const int cell = blockIdx.x;
-    const int cy = cell / (tiles_x + 1), cx = cell - cy * (tiles_x + 1);
+    const int img = blockIdx.z;
+    const int cy = blockIdx.y, cx = blockIdx.x;
+    const int tiles_x = (int)gridDim.x - 1, tiles_y = (int)gridDim.y - 1;
     const mdir_image_desc d = descs[img];
-    const ClaheGeom g = clahe_geom(d.H, d.W, tiles_x, tiles_y);
+    const ClahePrep g = prep[img];
     // nominal pixel ranges of this cell: raw tile index floor(x/tw - 0.5) == cx - 1.  The exact fp32
     // boundary can differ from the nominal one by a pixel, hence the margin + the per-pixel ownership test.
     const int margin = 1 + (max(g.tw, g.th) >> 9);
@@ -210,8 +241,18 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     }
     __syncthreads();
 
-    const float inv_tw = __fdiv_rn(1.0f, (float)g.tw);
-    const float inv_th = __fdiv_rn(1.0f, (float)g.th);
+    const float inv_tw = g.inv_tw;
+    const float inv_th = g.inv_th;
+    // shrink the nominal rectangle to the pixels this cell really owns (ownership is monotone in x and in y), so
+    // that the thread mapping below wastes no lanes on the safety margin
+    {
+        auto own = [](int v, float inv, int c) { return (int)floorf(__fsub_rn(__fmul_rn((float)v, inv), 0.5f)) == c - 1; };
+        while (xs < xe && !own(xs, inv_tw, cx)) ++xs;
+        while (xe > xs && !own(xe - 1, inv_tw, cx)) --xe;
+        while (ys < ye && !own(ys, inv_th, cy)) ++ys;
+        while (ye > ys && !own(ye - 1, inv_th, cy)) --ye;
+        if (xs >= xe || ys >= ye) return;
+    }
     const uint8_t* sbase = src + d.src_off;
     uint8_t* dbase = dst + d.dst_off;
     const bool vec_ok = (((uintptr_t)sbase | (uintptr_t)dbase | (uintptr_t)d.src_pitch | (uintptr_t)d.dst_pitch) & 7) == 0;
@@ -224,6 +265,9 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     const int rows_pp = 256 / gpp;                      // rows per pass
     const int gslot = threadIdx.x % gpp, rslot = threadIdx.x / gpp;
     if (rslot >= rows_pp) return;
+    // 4 or 6 rows in flight per thread, whichever leaves fewer idle row slots in the last sweep over the cell
+    const int n_rows = ye - ys;
+    const bool six_rows = ((n_rows + 6 * rows_pp - 1) / (6 * rows_pp)) * 6 <= ((n_rows + 4 * rows_pp - 1) / (4 * rows_pp)) * 4;
     for (int g0 = gslot; g0 < n_groups; g0 += gpp) {
         const int x8 = xs8 + g0 * 8;
         float xa[8], xa1[8];
@@ -240,11 +284,13 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
         if (!mine) continue;
         const bool in_row = x8 + 7 < d.W;
         const bool full = (mine == 0xffu) && in_row;
-        for (int yb = ys + rslot; yb < ye; yb += 4 * rows_pp) {
-            uint2 pix[4];
-            // 4 row loads in flight
+        auto rows = [&](auto U_) {
+        constexpr int U = decltype(U_)::value;
+        for (int yb = ys + rslot; yb < ye; yb += U * rows_pp) {
+            uint2 pix[U];
+            // U row loads in flight
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int y = yb + u * rows_pp;
                 pix[u] = make_uint2(0u, 0u);
                 if (y < ye) {
@@ -262,7 +308,7 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int y = yb + u * rows_pp;
                 if (y >= ye) continue;
                 const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
@@ -292,6 +338,8 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
                 }
             }
         }
+        };
+        if (six_rows) rows(std::integral_constant<int, 6>{}); else rows(std::integral_constant<int, 4>{});
     }
 }
 
@@ -301,18 +349,21 @@ using namespace mdir;
 
 extern "C" size_t mdir_clahe_workspace_bytes(int n_img, int tiles_x, int tiles_y) {
     if (n_img < 0 || tiles_x <= 0 || tiles_y <= 0) return 0;
-    return (size_t)n_img * tiles_x * tiles_y * 256;
+    return (size_t)n_img * tiles_x * tiles_y * 256 + (size_t)n_img * sizeof(ClahePrep);
 }
 
 extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_desc* descs, int n_img, int max_H, int max_W,
                              double clip, int tiles_x, int tiles_y, void* ws, void* stream) {
     MDIR_CHECK_ARG(src && dst && descs && ws);
     MDIR_CHECK_ARG(n_img >= 0 && n_img <= 65535);
-    MDIR_CHECK_ARG(tiles_x >= 1 && tiles_y >= 1 && tiles_x * tiles_y <= 4096);
+    MDIR_CHECK_ARG(tiles_x >= 1 && tiles_y >= 1 && tiles_x * tiles_y <= 4096 && (((uintptr_t)ws) & 15) == 0);
     MDIR_CHECK_ARG(max_H >= 1 && max_W >= 1);
     if (n_img == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t* luts = (uint8_t*)ws;
+    ClahePrep* prep = reinterpret_cast<ClahePrep*>(luts + (size_t)n_img * tiles_x * tiles_y * 256);
+    clahe_prep_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(descs, n_img, clip, tiles_x, tiles_y, prep);
+    MDIR_LAUNCH_CHECK();
 
     // Both passes read the source; processing the batch in chunks of <= ~48 MB of pixels lets the
     // interpolation pass of a chunk hit L2 (126 MB) for the pixels its LUT pass just streamed.
@@ -322,9 +373,9 @@ extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_
     for (int i0 = 0; i0 < n_img; i0 += chunk) {
         const int n = (n_img - i0) < chunk ? (n_img - i0) : chunk;
         uint8_t* l = luts + (size_t)i0 * tiles_x * tiles_y * 256;
-        clahe_lut_kernel<<<dim3(tiles_x * tiles_y, n), 256, 0, st>>>(src, descs + i0, clip, tiles_x, tiles_y, l);
+        clahe_lut_kernel<<<dim3(tiles_x, tiles_y, n), 256, 0, st>>>(src, descs + i0, prep + i0, l);
         MDIR_LAUNCH_CHECK();
-        clahe_interp_kernel<<<dim3((tiles_x + 1) * (tiles_y + 1), n), 256, 0, st>>>(src, dst, descs + i0, tiles_x, tiles_y, l);
+        clahe_interp_kernel<<<dim3(tiles_x + 1, tiles_y + 1, n), 256, 0, st>>>(src, dst, descs + i0, prep + i0, l);
         MDIR_LAUNCH_CHECK();
     }
     return 0;

@@ -276,7 +276,37 @@ static void bench_big(int64_t n_db, int n_q, int n_sample) {
     cudaFree(d_db); cudaFree(d_q); cudaFree(d_sample); cudaFree(d_os); cudaFree(d_oi); cudaFree(d_tau); cudaFree(d_cand); cudaFree(d_cnt); cudaFree(d_ovf);
 }
 
+// how the persistent scan's time depends on the number of 256-row tiles (rounds of 148 CTAs, tail rounds)
+static void bench_tiles() {
+    const int D = 2048, n_q = 70;
+    const int64_t max_rows = 256 * 1200;
+    __nv_bfloat16 *d_db, *d_q; float* d_out;
+    CK(cudaMalloc(&d_db, (size_t)max_rows * D * 2)); CK(cudaMalloc(&d_q, (size_t)n_q * D * 2));
+    CK(cudaMalloc(&d_out, (size_t)n_q * max_rows * 4));
+    fill_bf16<<<(unsigned)((max_rows * D + 255) / 256), 256>>>(d_db, max_rows * D, 1u);
+    fill_bf16<<<(n_q * D + 255) / 256, 256>>>(d_q, (int64_t)n_q * D, 7u);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int tiles[] = {1, 13, 74, 148, 161, 222, 296, 309, 444, 457, 592, 1184};
+    for (int nt : tiles) {
+        const int64_t n_db = (int64_t)nt * 256;
+        float best = 1e9f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(e0));
+            MD(mdir_sim_scan_bf16((uint16_t*)d_db, n_db, (uint16_t*)d_q, n_q, D, MDIR_SCAN_DENSE, 0, 0, d_out, n_db, nullptr, 0, nullptr,
+                                  nullptr, 0, 0, 0));
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep) best = std::min(best, ms);
+        }
+        printf("tiles %5d (%.2f rounds): %.1f us  -> %.0f GB/s\n", nt, nt / 148.0, best * 1e3, (double)n_db * D * 2 / 1e9 / (best * 1e-3));
+    }
+    cudaFree(d_db); cudaFree(d_q); cudaFree(d_out);
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "tiles")) { bench_tiles(); return 0; }
     MD(mdir_device_check());
     printf("abi %d\n", mdir_abi_version());
     test_pool();
