@@ -185,7 +185,7 @@ def run_ours(args):
     import torch
     import mdir_b200
     from mdir_b200 import _lib
-    from mdir_b200.search import Index, ShardedIndex, GraphedSearch, pack_bf16, default_shortlist
+    from mdir_b200.search import Index, ShardedIndex, GraphedSearch, SearchPipeline, pack_bf16, default_shortlist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,9 +223,13 @@ def run_ours(args):
     target = ShardedIndex.from_local(index) if world > 1 else index
     # the whole step (pack q, sample scan, select, filter scan, finalize, fp32 re-score, finalize,
     # [all-gather, merge]) captured once into a CUDA graph; every step below is one replay
-    gs = GraphedSearch(target, N_Q, TOPK, precision="fp32", prof=prof)
+    gs = GraphedSearch(target, N_Q, TOPK, precision="fp32")
     gs.q.copy_(q_host, non_blocking=True)
     q_dev = gs.q
+    # the same step with a CUDA event pair around the dominant kernel inside the graph: used only to read that
+    # kernel's duration (the two event-record nodes cost ~8 us per step, so `value` is timed on the plain graph)
+    gs_prof = GraphedSearch(target, N_Q, TOPK, precision="fp32", prof=prof)
+    gs_prof.q.copy_(q_host, non_blocking=True)
     out_host = torch.empty((N_Q, TOPK * 2), dtype=torch.float32).pin_memory()
 
     def step_device():
@@ -270,20 +274,34 @@ def run_ours(args):
     ms_total = ev[0].elapsed_time(ev[1])
     # dominant-kernel duration: the graph carries an event pair around the FILTER scan; read it after
     # individual replays of the same graph (a per-step read needs a sync, so not inside the loop above)
-    scan_samples = [prof.last_ms()]
-    for _ in range(min(50, args.steps)):
-        step_device()
+    scan_samples = []
+    for _ in range(min(50, args.steps) + 1):
+        gs_prof()
         torch.cuda.synchronize()
         scan_samples.append(prof.last_ms())
     scan_ms = sum(scan_samples) / len(scan_samples)
 
     # ---- timed region: e2e (host buffers in, host result out, every step) --------------------------
+    # (1) blocking: upload, replay, download, synchronize -- the latency of one step seen from the host
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     barrier()
+    e2e_blocking_s = time.perf_counter() - t0
+    # (2) the serving loop (SearchPipeline): the same three stages per step, two steps in flight, so the copies of
+    # one step overlap the scan of the next.  Every step's queries are uploaded and every result is read on the host.
+    pipe = SearchPipeline(target, N_Q, TOPK, depth=2, precision="fp32")
+    for _ in pipe.map([q_host] * 4):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    n_out = 0
+    for s_h, i_h in pipe.map(q_host for _ in range(args.steps)):
+        n_out += int(i_h[0, 0] >= 0)
+    barrier()
     e2e_s = time.perf_counter() - t0
+    assert n_out == args.steps
     sampler.stop_flag = True
 
     # bf16-only mode (no fp32 re-scoring), for the record
@@ -344,7 +362,8 @@ def run_ours(args):
                    "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
         "clocks": sampler.summary(),
         "e2e": {"value": N_Q * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N_Q * DIM * 4, "d2h_bytes_per_step": N_Q * TOPK * 8,
-                "ms_per_step": e2e_s / args.steps * 1e3, "timing": "wall clock around %d steps (H2D of pinned queries + graph replay + D2H of scores/idx + synchronize each step)" % args.steps},
+                "ms_per_step": e2e_s / args.steps * 1e3, "blocking_ms_per_step": e2e_blocking_s / args.steps * 1e3,
+                "timing": "wall clock around %d steps of SearchPipeline (per step: H2D of the pinned queries, graph replay, D2H of scores/idx, host read of the result; two steps in flight); blocking_ms_per_step = the same with a synchronize after every step" % args.steps},
         "e2e_cold_db_ms": {"pack_fp32_to_bf16_ms": pack_ms,
                            "note": "one-off index build for this shard; host->device upload of the fp32 rows would add %.1f GB over PCIe" % ((hi - lo) * DIM * 4 / 1e9)},
         "gpu_launches": int(launches), "gpu_launches_note": "%d libmdir_b200 kernels per step, replayed from one CUDA graph per step" % launches_per_step,

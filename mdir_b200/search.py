@@ -527,6 +527,7 @@ class GraphedSearch:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = step()
+                self.ovf = self.local._ovf[:n_q].clone()      # this graph's own copy of the overflow flags
             self.local.prof = None
 
     def __call__(self, q=None):
@@ -537,3 +538,99 @@ class GraphedSearch:
 
     def check_overflow(self):
         return self.local.check_overflow()
+
+
+class SearchPipeline:
+    """Host-facing serving loop: query batches arrive in (pinned) host memory, results go back to
+    pinned host memory, and the copies of one step overlap the scan of its neighbours.
+
+        pipe = SearchPipeline(index, n_q=70, k=100)            # Index or ShardedIndex
+        t0 = pipe.submit(q_host_0)                             # H2D -> graph replay -> D2H, all asynchronous
+        t1 = pipe.submit(q_host_1)
+        scores, idx = pipe.result(t0)                          # numpy views of pinned buffers, valid until
+        ...                                                    # `depth` more submits
+
+    `depth` CUDA graphs (one static query buffer and output set each) replay back to back on one
+    compute stream; uploads and downloads run on their own streams, ordered by events only.  A step
+    whose candidate lists overflowed is transparently redone through index.search() (exact recovery).
+    With a ShardedIndex every rank must submit the same sequence (the all-gather is inside the graphs)."""
+
+    def __init__(self, index, n_q, k, depth=2, precision="fp32", shortlist=None, prof=None):
+        self.index = index
+        self.local = index.local if isinstance(index, ShardedIndex) else index
+        dev = self.local.device
+        self.n_q, self.k, self.depth = int(n_q), int(k), int(depth)
+        self.precision, self.shortlist = precision, shortlist
+        self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None)
+                       for s in range(self.depth)]
+        with torch.cuda.device(dev):
+            self.compute, self.h2d, self.d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+            self.slots = []
+            for _ in range(self.depth):
+                self.slots.append({
+                    "scores": torch.empty((self.n_q, self.k), dtype=torch.float32).pin_memory(),
+                    "idx": torch.empty((self.n_q, self.k), dtype=torch.int32).pin_memory(),
+                    "ovf": torch.zeros((self.n_q,), dtype=torch.int32).pin_memory(),
+                    "up": torch.cuda.Event(), "done": torch.cuda.Event(), "down": torch.cuda.Event(),
+                    "q": None, "pending": False})
+            torch.cuda.synchronize(dev)
+        self.n_submitted = 0
+
+    def submit(self, q):
+        """q: (n_q, D) fp32, pinned host memory for a truly asynchronous upload (device tensors work too).
+        Returns a ticket for result().  The caller keeps q unchanged until result(ticket) returned."""
+        slot, gs = self.slots[self.n_submitted % self.depth], self.graphs[self.n_submitted % self.depth]
+        if slot["pending"]:
+            raise _lib.MdirError("SearchPipeline: collect result() of ticket %d before submitting more" % (self.n_submitted - self.depth))
+        q = torch.as_tensor(q)
+        if tuple(q.shape) != tuple(gs.q.shape):
+            raise _lib.MdirError("SearchPipeline expects query batches of shape %s" % (tuple(gs.q.shape),))
+        with torch.cuda.stream(self.h2d):
+            gs.q.copy_(q, non_blocking=True)            # this slot's previous replay was drained by result()
+            slot["up"].record()
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(slot["up"])
+            gs.graph.replay()
+            slot["done"].record()
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(slot["done"])
+            slot["scores"].copy_(gs.out[0], non_blocking=True)
+            slot["idx"].copy_(gs.out[1], non_blocking=True)
+            slot["ovf"].copy_(gs.ovf, non_blocking=True)
+            slot["down"].record()
+        slot["q"], slot["pending"] = q, True
+        self.n_submitted += 1
+        return self.n_submitted - 1
+
+    def result(self, ticket):
+        """Blocks until step `ticket` is in host memory; returns (scores (n_q, k) fp32, idx (n_q, k) int32) numpy views."""
+        if not (self.n_submitted - self.depth <= ticket < self.n_submitted):
+            raise _lib.MdirError("SearchPipeline: ticket %d is not in flight" % ticket)
+        slot = self.slots[ticket % self.depth]
+        if not slot["pending"]:
+            raise _lib.MdirError("SearchPipeline: result(%d) was already collected" % ticket)
+        slot["down"].synchronize()
+        slot["pending"] = False
+        if bool(slot["ovf"].any()):
+            if isinstance(self.index, ShardedIndex) and self.index.world > 1:
+                # the recovery is a collective (all-gather of keys); one rank cannot start it on its own
+                raise _lib.MdirError("SearchPipeline: candidate overflow on this rank for ticket %d; rerun the batch through "
+                                     "ShardedIndex.search() on every rank" % ticket)
+            # exact recovery, ordered after everything already queued on the compute stream (shared workspaces)
+            with torch.cuda.stream(self.compute):
+                s, i = self.index.search(slot["q"], self.k, precision=self.precision, shortlist=self.shortlist)
+                slot["scores"].copy_(s)
+                slot["idx"].copy_(i)
+            self.compute.synchronize()
+        slot["q"] = None
+        return slot["scores"].numpy(), slot["idx"].numpy()
+
+    def map(self, batches):
+        """Generator over an iterable of query batches, keeping `depth` steps in flight."""
+        tickets = []
+        for q in batches:
+            if len(tickets) == self.depth:
+                yield self.result(tickets.pop(0))
+            tickets.append(self.submit(q))
+        for t in tickets:
+            yield self.result(t)

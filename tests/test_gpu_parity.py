@@ -560,6 +560,42 @@ def test_qe_and_dba(m):
     close(aug.db32, oracle.dba(small, 3.0, 5), rtol=1e-4, atol=2e-6)
 
 
+def test_search_pipeline_matches_blocking_search(m):
+    """Double-buffered serving loop (async H2D / graph replay / D2H): same answers, in order, as index.search."""
+    import torch
+    db = synth.descriptors(80000, 64, 171, clusters=100)
+    index = m.Index(db, device=DEV)
+    pipe = m.SearchPipeline(index, n_q=40, k=50)
+    batches = [torch.from_numpy(synth.planted_queries(db, 40, 200 + b)[0]).pin_memory() for b in range(7)]
+    got = [(s.copy(), i.copy()) for s, i in pipe.map(batches)]
+    assert len(got) == 7
+    for b, (s, i) in enumerate(got):
+        rs, ri = index.search(batches[b], 50)
+        assert np.array_equal(i, ri.cpu().numpy()) and np.array_equal(s, rs.cpu().numpy()), b
+    # tickets: out-of-order collection inside the window, misuse is an error
+    t0, t1 = pipe.submit(batches[0]), pipe.submit(batches[1])
+    with pytest.raises(m.MdirError):
+        pipe.submit(batches[2])
+    s1, i1 = pipe.result(t1)
+    s0, i0 = pipe.result(t0)
+    assert np.array_equal(i0, got[0][1]) and np.array_equal(i1, got[1][1])
+    with pytest.raises(m.MdirError):
+        pipe.result(t0)
+    # a step whose candidate segments overflow is redone exactly (adversarial row order, as in the recovery test)
+    n_db, D = 40000, 64
+    rs_ = np.random.RandomState(5)
+    base = rs_.randn(D).astype(np.float32)
+    base /= np.linalg.norm(base)
+    adv = (np.linspace(0.1, 1.0, n_db, dtype=np.float32)[:, None] * base[None, :] + rs_.randn(n_db, D).astype(np.float32) * 0.01).astype(np.float32)
+    q = np.stack([base, -base, base + 0.1 * rs_.randn(D).astype(np.float32)]).astype(np.float32)
+    idx2 = m.Index(adv, device=DEV)
+    pipe2 = m.SearchPipeline(idx2, n_q=3, k=100, precision="bf16")
+    outs = [(s.copy(), i.copy()) for s, i in pipe2.map([q, q, q])]
+    ref_i, ref_v = oracle.topk_from_scores(idx2.scores(q).cpu().numpy().T, 100)
+    for s, i in outs:
+        assert np.array_equal(i.T, ref_i) and np.array_equal(s.T, ref_v)
+
+
 # ---- f4: hard-negative mining, whitening learning ----------------------------------------------------
 
 def test_mining_matches_reference_create_epoch_tuples(m, golden):
