@@ -313,6 +313,64 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
     }
 }
 
+// ---- thread-block-cluster helpers (distributed shared memory) for the split re-scoring in topk_finalize_kernel
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of `p` (a shared-memory object of this kernel) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(const void* p, uint32_t rank) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ uint64_t cluster_ld_u64(uint32_t a) {
+    uint64_t v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cluster_st_u64(uint32_t a, uint64_t v) {
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ int cluster_ld_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// fp32 dot product of one database row with the query staged in shared memory, one warp per row
+__device__ __forceinline__ float rescore_row(const float* __restrict__ a, const float* qs, int D, int lane) {
+    float acc = 0.f;
+    if ((D & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(a);
+        const float4* b4 = reinterpret_cast<const float4*>(qs);
+        const int n4 = D >> 2;
+        float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        int i = lane;
+        for (; i + 96 < n4; i += 128) {            // 4 independent 128-bit loads in flight per lane
+            const float4 x0 = __ldg(a4 + i), x1 = __ldg(a4 + i + 32), x2 = __ldg(a4 + i + 64), x3 = __ldg(a4 + i + 96);
+            const float4 y0 = b4[i], y1 = b4[i + 32], y2 = b4[i + 64], y3 = b4[i + 96];
+            acc = fmaf(x0.x, y0.x, acc); acc = fmaf(x0.y, y0.y, acc); acc = fmaf(x0.z, y0.z, acc); acc = fmaf(x0.w, y0.w, acc);
+            acc1 = fmaf(x1.x, y1.x, acc1); acc1 = fmaf(x1.y, y1.y, acc1); acc1 = fmaf(x1.z, y1.z, acc1); acc1 = fmaf(x1.w, y1.w, acc1);
+            acc2 = fmaf(x2.x, y2.x, acc2); acc2 = fmaf(x2.y, y2.y, acc2); acc2 = fmaf(x2.z, y2.z, acc2); acc2 = fmaf(x2.w, y2.w, acc2);
+            acc3 = fmaf(x3.x, y3.x, acc3); acc3 = fmaf(x3.y, y3.y, acc3); acc3 = fmaf(x3.z, y3.z, acc3); acc3 = fmaf(x3.w, y3.w, acc3);
+        }
+        for (; i < n4; i += 32) {
+            const float4 x = __ldg(a4 + i), y = b4[i];
+            acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
+        }
+        acc = (acc + acc1) + (acc2 + acc3);
+    } else {
+        for (int i = lane; i < D; i += 32) acc = fmaf(a[i], qs[i], acc);
+    }
+    return warp_sum(acc);
+}
+
 __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
     for (int kk = 2; kk <= n; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
@@ -334,6 +392,7 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
 // producer appended).  They are compacted into shared memory; when there are many more than k,
 // the k best are first isolated by an in-smem MSB radix select (keys are unique) and only those
 // are sorted.  dynamic smem = (smem_cap + kpow2) * 8 bytes.
+template <int CS>      // CS = CTAs per query (thread-block cluster size): rank 0 selects and sorts, all ranks share the fp32 re-scoring
 __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, int64_t cand_row,
                                                              const uint32_t* __restrict__ seg_counts, int n_seg, int cap0, int cap_l,
                                                              int k, int smem_cap, float* __restrict__ out_scores,
@@ -347,9 +406,33 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     __shared__ uint32_t s_k, s_done, s_out;
     __shared__ int s_off[MDIR_CAND_SEGS + 1];
     __shared__ int s_ovf;
+    __shared__ int s_hdr[2];                      // rank 0 -> helpers: {shortlist length, offset of the shortlist in skeys}
     uint64_t* sorted = skeys + smem_cap;          // kpow2 entries
-    const int q = blockIdx.x;
+    const int q = blockIdx.x / CS;
+    const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
     const int lane = threadIdx.x & 31;
+    int kpow2 = 32;
+    while (kpow2 < k) kpow2 <<= 1;
+    if (CS > 1 && crank != 0) {
+        // helper CTA of the cluster: stage the query, wait for rank 0's shortlist, re-score its share of the rows
+        float* qs = reinterpret_cast<float*>(sorted + kpow2);
+        for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = q32[(int64_t)q * D + i];
+        __syncthreads();
+        cluster_sync_all();                                            // (1) shortlist ready in rank 0's shared memory
+        const int nk = cluster_ld_s32(cluster_map(&s_hdr[0], 0));
+        const int off = cluster_ld_s32(cluster_map(&s_hdr[1], 0));
+        const uint32_t rk0 = cluster_map(skeys + off, 0);
+        for (int j = (threadIdx.x >> 5) * CS + crank; j < nk; j += 32 * CS) {
+            const uint64_t key = cluster_ld_u64(rk0 + 8u * (uint32_t)j);
+            const uint32_t gi = (uint32_t)key;
+            const int64_t row = (int64_t)gi - (int64_t)idx_base;
+            uint64_t nkey = ~0ull;
+            if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
+            if (lane == 0) cluster_st_u64(rk0 + 8u * (uint32_t)j, nkey);
+        }
+        cluster_sync_all();                                            // (2) every share is back in rank 0
+        return;
+    }
     // segment offsets (exclusive scan of the clamped counts) by warp 0
     if (threadIdx.x < 32) {
         int run = 0, ovf = 0;
@@ -388,8 +471,6 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         }
     }
     __syncthreads();
-    int kpow2 = 32;
-    while (kpow2 < k) kpow2 <<= 1;
     const uint64_t* res;       // ascending keys, at least min(k, cnt) valid
     int nres;
     if (cnt <= 2 * kpow2 || cnt <= 1024) {
@@ -466,43 +547,19 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         float* qs = reinterpret_cast<float*>(sorted + kpow2);
         for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = q32[(int64_t)q * D + i];
         const int nk = min(k, nres);
+        if (threadIdx.x == 0) { s_hdr[0] = nk; s_hdr[1] = (int)(rk - skeys); }
         __syncthreads();
-        for (int j = threadIdx.x >> 5; j < nk; j += 32) {
+        if (CS > 1) cluster_sync_all();                                // (1) helpers may read the shortlist
+        for (int j = (threadIdx.x >> 5) * CS; j < nk; j += 32 * CS) {
             const uint64_t key = rk[j];
             const uint32_t gi = (uint32_t)key;
             const int64_t row = (int64_t)gi - (int64_t)idx_base;
             uint64_t nkey = ~0ull;
-            if (key != ~0ull && row >= 0 && row < n_db) {
-                const float* a = db32 + row * D;
-                float acc = 0.f;
-                if ((D & 3) == 0) {
-                    const float4* a4 = reinterpret_cast<const float4*>(a);
-                    const float4* b4 = reinterpret_cast<const float4*>(qs);
-                    const int n4 = D >> 2;
-                    float acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-                    int i = lane;
-                    for (; i + 96 < n4; i += 128) {            // 4 independent 128-bit loads in flight per lane
-                        const float4 x0 = __ldg(a4 + i), x1 = __ldg(a4 + i + 32), x2 = __ldg(a4 + i + 64), x3 = __ldg(a4 + i + 96);
-                        const float4 y0 = b4[i], y1 = b4[i + 32], y2 = b4[i + 64], y3 = b4[i + 96];
-                        acc = fmaf(x0.x, y0.x, acc); acc = fmaf(x0.y, y0.y, acc); acc = fmaf(x0.z, y0.z, acc); acc = fmaf(x0.w, y0.w, acc);
-                        acc1 = fmaf(x1.x, y1.x, acc1); acc1 = fmaf(x1.y, y1.y, acc1); acc1 = fmaf(x1.z, y1.z, acc1); acc1 = fmaf(x1.w, y1.w, acc1);
-                        acc2 = fmaf(x2.x, y2.x, acc2); acc2 = fmaf(x2.y, y2.y, acc2); acc2 = fmaf(x2.z, y2.z, acc2); acc2 = fmaf(x2.w, y2.w, acc2);
-                        acc3 = fmaf(x3.x, y3.x, acc3); acc3 = fmaf(x3.y, y3.y, acc3); acc3 = fmaf(x3.z, y3.z, acc3); acc3 = fmaf(x3.w, y3.w, acc3);
-                    }
-                    for (; i < n4; i += 32) {
-                        const float4 x = __ldg(a4 + i), y = b4[i];
-                        acc = fmaf(x.x, y.x, acc); acc = fmaf(x.y, y.y, acc); acc = fmaf(x.z, y.z, acc); acc = fmaf(x.w, y.w, acc);
-                    }
-                    acc = (acc + acc1) + (acc2 + acc3);
-                } else {
-                    for (int i = lane; i < D; i += 32) acc = fmaf(a[i], qs[i], acc);
-                }
-                acc = warp_sum(acc);
-                nkey = make_key(acc, gi);
-            }
+            if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
             __syncwarp();
             if (lane == 0) rk[j] = nkey;
         }
+        if (CS > 1) cluster_sync_all();                                // (2) helpers' shares have landed
         for (int j = nk + threadIdx.x; j < kpow2; j += blockDim.x) rk[j] = ~0ull;
         __syncthreads();
         bitonic_sort_smem(rk, kpow2);
@@ -669,13 +726,39 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
         smem += (size_t)D * 4;
     }
     static bool attr_set = false;
+    static int sm_count = 0;
     if (!attr_set) {
-        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 4096) * 8 + 8192 * 4));
+        const int max_smem = (16384 + 4096) * 8 + 8192 * 4;
+        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        int dev = 0;
+        MDIR_CUDA(cudaGetDevice(&dev));
+        MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         attr_set = true;
     }
-    topk_finalize_kernel<<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap,
-                                                                     out_scores, out_idx, out_keys, tau, overflow, db32, n_db, idx_base,
-                                                                     q32, D, k_out);
+    // fp32 re-scoring gathers shortlist x D x 4 bytes per query from one CTA; while the batch leaves SMs idle, a
+    // 2-CTA cluster per query splits those rows (rank 1 reads / writes the shortlist through distributed shared memory)
+    if (db32 && 2 * n_q <= sm_count) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * n_q);
+        cfg.blockDim = dim3(1024);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MDIR_CUDA(cudaLaunchKernelEx(&cfg, topk_finalize_kernel<2>, cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap, out_scores,
+                                     out_idx, out_keys, tau, overflow, db32, n_db, idx_base, q32, D, k_out));
+        MDIR_LAUNCH_CHECK();
+        return 0;
+    }
+    topk_finalize_kernel<1><<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap,
+                                                                        out_scores, out_idx, out_keys, tau, overflow, db32, n_db, idx_base,
+                                                                        q32, D, k_out);
     MDIR_LAUNCH_CHECK();
     return 0;
 }
