@@ -252,6 +252,27 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
                     const int32_t* item_class, int64_t n_items, const int32_t* n_pos, const int32_t* kappas,
                     int n_kappa, double* aps, double* prs, void* ws, void* stream);
 
+/* ------------------------------------ shard merge over NVLink peer memory ---
+ * Multi-GPU top-k: every rank holds a row shard and its local top-k as sorted
+ * 64-bit keys (n_q, k).  mdir_shard_exchange_merge is the exchange AND the merge in one kernel: it
+ * stores the local keys into every rank's mailbox (peer-mapped device memory), publishes
+ * per-(rank, query) sequence flags with system-scope release, waits (bounded) for the world's flags
+ * and merges the world * k keys per query -> out_scores / out_idx (n_q, k), identical on every rank.
+ * No collective-library call; every rank must issue the same sequence of calls.
+ * Setup: each rank mdir_p2p_alloc()s a mailbox of mdir_shard_mailbox_bytes(world, max_q, max_k)
+ * bytes (zeroed), ships the 64-byte handle to its peers (any transport), and mdir_p2p_open()s theirs;
+ * mailboxes = host array of `world` device pointers, entry `rank` being the own allocation.
+ * mdir_shard_status: non-zero once a peer failed to arrive within the bounded wait (~2 s).      */
+size_t mdir_shard_mailbox_bytes(int world, int max_q, int max_k);
+int mdir_p2p_alloc(size_t bytes, void** ptr, void* handle64);
+int mdir_p2p_open(const void* handle64, void** ptr);
+int mdir_p2p_close(void* ptr);
+int mdir_p2p_free(void* ptr);
+int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world,
+                              int max_q, int max_k, void* const* mailboxes,
+                              float* out_scores, int32_t* out_idx, void* stream);
+int mdir_shard_status(const void* own_mailbox, int* status);
+
 /* ---------------------------------------------- hard-negative mining (f4) ---
  * The consumer of a full ranking inside TuplesDataset.create_epoch_tuples
  * (mdir/external/cirtorch/datasets/traindataset.py:250-267): for query q walk ranks[:, q]

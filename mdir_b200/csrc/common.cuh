@@ -114,6 +114,22 @@ __device__ __forceinline__ int find_bin_warp0(const uint32_t* hist, uint32_t k, 
     return bin;
 }
 
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
+    for (int kk = 2; kk <= n; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t x = a[i], y = a[ixj];
+                    const bool asc = (i & kk) == 0;
+                    if ((x > y) == asc) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ---- 64-bit candidate keys: smaller key == better (score desc, index asc) --------
 __host__ __device__ __forceinline__ uint32_t f32_bits(float f) {
 #ifdef __CUDA_ARCH__

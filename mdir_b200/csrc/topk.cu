@@ -371,22 +371,6 @@ __device__ __forceinline__ float rescore_row(const float* __restrict__ a, const 
     return warp_sum(acc);
 }
 
-__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, int n) {
-    for (int kk = 2; kk <= n; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t x = a[i], y = a[ixj];
-                    const bool asc = (i & kk) == 0;
-                    if ((x > y) == asc) { a[i] = y; a[ixj] = x; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 // One CTA (1024 threads) per query.  The candidates of a query live in n_seg segments of its
 // cand row (segment 0: cap0 slots, the others cap_l slots each; seg_counts holds how many each
 // producer appended).  They are compacted into shared memory; when there are many more than k,

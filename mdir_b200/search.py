@@ -407,6 +407,9 @@ class ShardedIndex:
     N_q*k 64-bit keys per rank (NCCL over NVLink), merge by (score desc, index asc): identical to
     the single-GPU answer by construction.  There is no other collective on the data path."""
 
+    p2p = True            # exchange + merge in one kernel over NVLink peer memory (False: ncclAllGather + merge kernel)
+    P2P_MAX_Q, P2P_MAX_K = 128, 1024
+
     def __init__(self, local_vecs, idx_base, group=None, device="cuda", keep_fp32=True, dxn=False):
         import torch.distributed as dist
         self.dist = dist
@@ -414,6 +417,7 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = Index(local_vecs, dxn=dxn, device=device, keep_fp32=keep_fp32, idx_base=idx_base)
         self.device = self.local.device
+        self._p2p_setup()
 
     @classmethod
     def from_local(cls, local_index, group=None):
@@ -425,7 +429,58 @@ class ShardedIndex:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.local = local_index
         self.device = local_index.device
+        self._p2p_setup()
         return self
+
+    def _p2p_setup(self):
+        """Mailboxes for mdir_shard_exchange_merge: one cudaMalloc'ed buffer per rank, mapped into every peer through
+        cudaIpc handles exchanged with one all-gather (setup time only).  Any failure (no peer access, a backend
+        without device tensors) leaves the NCCL all-gather route in place."""
+        self._mb, self._mb_own, self._mb_keep = None, None, None
+        dist = self.dist
+        if not (self.p2p and self.world > 1 and self.world <= 16 and self.device.type == "cuda" and dist.get_backend(self.group) == "nccl"):
+            return
+        import ctypes as C
+        lib = _lib.lib()
+        rank = dist.get_rank(self.group)
+        ok = 1
+        own = C.c_void_p(0)
+        handle = (C.c_ubyte * 64)()
+        with torch.cuda.device(self.device):
+            nbytes = lib.mdir_shard_mailbox_bytes(self.world, self.P2P_MAX_Q, self.P2P_MAX_K)
+            if lib.mdir_p2p_alloc(nbytes, C.byref(own), handle) != 0:
+                ok = 0
+            mine = torch.tensor(list(bytes(handle)) + [ok], dtype=torch.uint8, device=self.device)
+            allh = torch.empty((self.world, 65), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh.view(-1), mine, group=self.group)
+            allh = allh.cpu().numpy()
+            ptrs = (C.c_void_p * self.world)()
+            good = bool(allh[:, 64].all())
+            if good:
+                for r in range(self.world):
+                    if r == rank:
+                        ptrs[r] = own.value
+                        continue
+                    peer = C.c_void_p(0)
+                    hb = (C.c_ubyte * 64)(*[int(x) for x in allh[r, :64]])
+                    if lib.mdir_p2p_open(hb, C.byref(peer)) != 0:
+                        good = False
+                        break
+                    ptrs[r] = peer.value
+            flag = torch.tensor([1 if good else 0], dtype=torch.int32, device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)          # all or nobody
+            if int(flag.item()) == 1:
+                self._mb, self._mb_own, self._rank = ptrs, own, rank
+            torch.cuda.synchronize(self.device)
+
+    def exchange_status(self):
+        """0 = healthy; 1 = a peer did not arrive within the bounded wait of some step (results of that step are padding)."""
+        if self._mb is None:
+            return 0
+        import ctypes as C
+        st = C.c_int(0)
+        _lib.check(_lib.lib().mdir_shard_status(self._mb_own, C.byref(st)), "mdir_shard_status")
+        return int(st.value)
 
     @staticmethod
     def shard_bounds(n_total, world, rank):
@@ -437,7 +492,20 @@ class ShardedIndex:
         s, i, keys = self.local.search(q, k, precision=precision, shortlist=shortlist, check=check, return_keys=True)
         if self.world == 1:
             return s, i
-        return merge_keys(keys, self.world, self.group, k)
+        if self._mb is None or k > self.P2P_MAX_K:
+            return merge_keys(keys, self.world, self.group, k)
+        import ctypes as C
+        lib = _lib.lib()
+        nq_all = keys.shape[0]
+        out_s = torch.empty((nq_all, k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            for q0 in range(0, nq_all, self.P2P_MAX_Q):
+                q1 = min(q0 + self.P2P_MAX_Q, nq_all)
+                _lib.check(lib.mdir_shard_exchange_merge(_lib.ptr(keys[q0:q1]), q1 - q0, k, self._rank, self.world, self.P2P_MAX_Q,
+                                                         self.P2P_MAX_K, C.cast(self._mb, C.c_void_p), _lib.ptr(out_s[q0:q1]),
+                                                         _lib.ptr(out_i[q0:q1]), _lib.stream()), "mdir_shard_exchange_merge")
+        return out_s, out_i
 
 
 def merge_keys(local_keys, world, group, k):

@@ -42,11 +42,28 @@ def main():
     q, src = synth.planted_queries(db, nq, 82)
     lo, hi = ShardedIndex.shard_bounds(n, world, rank)
     sharded = ShardedIndex(db[lo:hi], idx_base=lo, device=dev)
+    check("peer-memory mailboxes mapped on every rank", sharded._mb is not None)
     single = mdir_b200.Index(db, device=dev)
     for prec in ("bf16", "fp32"):
         s1, i1 = single.search(q, k, precision=prec)
         s2, i2 = sharded.search(q, k, precision=prec)
-        check("sharded search == single (%s)" % prec, torch.equal(i1, i2) and torch.equal(s1, s2))
+        check("sharded search == single (%s, fused NVLink exchange + merge)" % prec, torch.equal(i1, i2) and torch.equal(s1, s2))
+    for rep in range(5):                                   # sequence numbers / parity buffers across back-to-back steps
+        qq, _ = synth.planted_queries(db, nq, 90 + rep)
+        s1, i1 = single.search(qq, k)
+        s2, i2 = sharded.search(qq, k)
+        check("  repeat %d" % rep, torch.equal(i1, i2) and torch.equal(s1, s2))
+    big_q, _ = synth.planted_queries(db, 300, 99)          # more than one exchange block of 128 queries
+    s1, i1 = single.search(big_q, 10)
+    s2, i2 = sharded.search(big_q, 10)
+    check("300 queries (3 exchange blocks)", torch.equal(i1, i2) and torch.equal(s1, s2))
+    check("exchange status clean", sharded.exchange_status() == 0)
+    ShardedIndex.p2p = False                               # the NCCL all-gather route stays available
+    nccl = ShardedIndex.from_local(sharded.local)
+    ShardedIndex.p2p = True
+    s1, i1 = single.search(q, k)
+    s2, i2 = nccl.search(q, k)
+    check("sharded search == single (ncclAllGather + merge kernel)", nccl._mb is None and torch.equal(i1, i2) and torch.equal(s1, s2))
     gs = GraphedSearch(sharded, nq, k)
     s3, i3 = gs(torch.from_numpy(q).pin_memory())
     torch.cuda.synchronize()
