@@ -268,8 +268,12 @@ int mdir_p2p_alloc(size_t bytes, void** ptr, void* handle64);
 int mdir_p2p_open(const void* handle64, void** ptr);
 int mdir_p2p_close(void* ptr);
 int mdir_p2p_free(void* ptr);
+#define MDIR_EXCHANGE_SYNC 0      /* push this step's keys, wait for the world's, merge them               */
+#define MDIR_EXCHANGE_DEFERRED 1  /* push this step's keys, merge the PREVIOUS step's (arrived a step ago):  */
+                                  /* exchange latency and rank skew hide behind the next scan                */
+#define MDIR_EXCHANGE_FLUSH 2     /* no push; merge the last pushed step (drain after deferred calls)        */
 int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world,
-                              int max_q, int max_k, void* const* mailboxes,
+                              int max_q, int max_k, int mode, void* const* mailboxes,
                               float* out_scores, int32_t* out_idx, void* stream);
 int mdir_shard_status(const void* own_mailbox, int* status);
 

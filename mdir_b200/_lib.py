@@ -55,7 +55,7 @@ PROTOTYPES = {
     "mdir_p2p_open": (_i, [_vp, _vp]),
     "mdir_p2p_close": (_i, [_vp]),
     "mdir_p2p_free": (_i, [_vp]),
-    "mdir_shard_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mdir_shard_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "mdir_shard_status": (_i, [_vp, _vp]),
     "mdir_mine_negatives": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mdir_pair_l2dist": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),

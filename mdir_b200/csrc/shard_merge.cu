@@ -6,15 +6,21 @@
 //
 // Mailbox (one per rank, cudaMalloc + cudaIpc, zero-initialised), all offsets in bytes:
 //   [0, 64)                         header: seq counter, exit counter, status (local use only)
-//   flags  [2][world][max_q] u32    sequence number of the last push per parity / source rank / query
-//   data   [2][world][max_q * max_k] u64
-// Parity = sequence & 1: a peer can be at most one step ahead (its step i+2 push needs our step i+1 flag, which our
-// stream issues only after our step-i merge finished), so two buffers suffice.
+//   flags  [4][world][max_q] u32    sequence number of the last push per buffer / source rank / query
+//   data   [4][world][max_q * max_k] u64
+// Buffer = sequence & 3.  Modes: SYNC pushes step s and merges step s; DEFERRED pushes step s and merges step s-1
+// (whose keys arrived a whole step ago: the exchange latency and the skew between ranks disappear behind the next
+// scan); FLUSH merges the last pushed step without pushing.  A peer's push of step s+4 (the buffer this rank reads
+// for step s) is ordered after the peer's step-(s+3) kernel, which waited for this rank's step-(s+2) flag, which
+// this rank's stream issues only after its step-(s+1) kernel -- the last reader of step s -- completed: 4 buffers
+// make the reuse safe in every mode.
 #include "common.cuh"
 
 namespace mdir {
 
 constexpr int kMaxWorld = 16;
+constexpr int kMailBufs = 4;
+enum { kExchangeSync = 0, kExchangeDeferred = 1, kExchangeFlush = 2 };
 
 struct Mailboxes {
     uint8_t* base[kMaxWorld];
@@ -24,7 +30,7 @@ __device__ __forceinline__ uint32_t* mb_flags(uint8_t* mb, int world, int max_q,
     return reinterpret_cast<uint32_t*>(mb + 64) + ((int64_t)parity * world + src) * max_q;
 }
 __device__ __forceinline__ uint64_t* mb_data(uint8_t* mb, int world, int max_q, int max_k, int parity, int src) {
-    const int64_t flag_bytes = ((int64_t)2 * world * max_q * 4 + 63) & ~(int64_t)63;
+    const int64_t flag_bytes = ((int64_t)kMailBufs * world * max_q * 4 + 63) & ~(int64_t)63;
     return reinterpret_cast<uint64_t*>(mb + 64 + flag_bytes) + ((int64_t)parity * world + src) * ((int64_t)max_q * max_k);
 }
 
@@ -39,38 +45,48 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 
 // grid = n_q CTAs of 256 threads; dynamic smem = world * k * 8 bytes
 __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int n_q, int k, int rank, int world,
-                                                                   int max_q, int max_k, Mailboxes mbs, float* __restrict__ out_scores,
-                                                                   int32_t* __restrict__ out_idx) {
+                                                                   int max_q, int max_k, int mode, Mailboxes mbs,
+                                                                   float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
     extern __shared__ uint64_t sk[];
     __shared__ int s_fail;
     const int q = blockIdx.x;
     uint8_t* mine = mbs.base[rank];
     uint32_t* hdr = reinterpret_cast<uint32_t*>(mine);
-    const uint32_t seq = *reinterpret_cast<volatile uint32_t*>(hdr) + 1u;      // same for every CTA: bumped by the last one out
-    const int parity = (int)(seq & 1u);
+    const uint32_t last = *reinterpret_cast<volatile uint32_t*>(hdr);          // same for every CTA: bumped by the last one out
+    const uint32_t seq = mode == kExchangeFlush ? last : last + 1u;            // step pushed by this launch (none when flushing)
+    const uint32_t mseq = mode == kExchangeDeferred ? seq - 1u : seq;          // step merged by this launch
+    const int parity = (int)(seq & (kMailBufs - 1));
     if (threadIdx.x == 0) s_fail = 0;
 
     // 1. push this rank's keys of query q into every mailbox (own included), then publish the flag
-    for (int r = 0; r < world; ++r) {
-        uint64_t* dst = mb_data(mbs.base[r], world, max_q, max_k, parity, rank) + (int64_t)q * max_k;
-        for (int j = threadIdx.x; j < k; j += blockDim.x) dst[j] = local_keys[(int64_t)q * k + j];
+    if (mode != kExchangeFlush) {
+        for (int r = 0; r < world; ++r) {
+            uint64_t* dst = mb_data(mbs.base[r], world, max_q, max_k, parity, rank) + (int64_t)q * max_k;
+            for (int j = threadIdx.x; j < k; j += blockDim.x) dst[j] = local_keys[(int64_t)q * k + j];
+        }
     }
     __syncthreads();                      // CTA-scope: every thread's stores happen-before the flag writers below
     if (threadIdx.x < world) {
-        __threadfence_system();           // one cumulative system-scope fence per flag writer, not one per thread
-        st_release_sys(mb_flags(mbs.base[threadIdx.x], world, max_q, parity, rank) + q, seq);
-        // 2. wait for source rank threadIdx.x's keys of query q (bounded: ~2 s, then report instead of hanging)
-        const uint32_t* f = mb_flags(mine, world, max_q, parity, threadIdx.x) + q;
-        bool ok = false;
-        for (int it = 0; it < (1 << 24); ++it) {
-            if (ld_acquire_sys(f) == seq) { ok = true; break; }
-            __nanosleep(100);
+        if (mode != kExchangeFlush) {
+            __threadfence_system();       // one cumulative system-scope fence per flag writer, not one per thread
+            st_release_sys(mb_flags(mbs.base[threadIdx.x], world, max_q, parity, rank) + q, seq);
         }
-        if (!ok) s_fail = 1;
+        // 2. wait for source rank threadIdx.x's keys of query q of the step being merged (bounded: ~2 s, then report
+        //    instead of hanging)
+        if (mseq != 0u) {
+            const uint32_t* f = mb_flags(mine, world, max_q, (int)(mseq & (kMailBufs - 1)), threadIdx.x) + q;
+            bool ok = false;
+            for (int it = 0; it < (1 << 24); ++it) {
+                if (ld_acquire_sys(f) == mseq) { ok = true; break; }
+                __nanosleep(100);
+            }
+            if (!ok) s_fail = 1;
+        }
     }
     __syncthreads();
-    if (s_fail) {
-        if (threadIdx.x == 0) hdr[2] = 1u;                                      // status: a peer never arrived
+    const int mpar = (int)(mseq & (kMailBufs - 1));
+    if (s_fail || mseq == 0u) {
+        if (threadIdx.x == 0 && s_fail) hdr[2] = 1u;                            // status: a peer never arrived
         for (int j = threadIdx.x; j < k; j += blockDim.x) {
             out_scores[(int64_t)q * k + j] = -INFINITY;
             out_idx[(int64_t)q * k + j] = -1;
@@ -81,7 +97,7 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
         const int n = world * k;
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int r = i / k, j = i - r * k;
-            sk[i] = __ldcg(mb_data(mine, world, max_q, max_k, parity, r) + (int64_t)q * max_k + j);   // written by a peer: bypass L1
+            sk[i] = __ldcg(mb_data(mine, world, max_q, max_k, mpar, r) + (int64_t)q * max_k + j);   // written by a peer: bypass L1
         }
         __syncthreads();
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -129,7 +145,7 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
         if (atomicAdd(&hdr[1], 1u) == gridDim.x - 1) {
             hdr[1] = 0u;
             __threadfence();
-            *reinterpret_cast<volatile uint32_t*>(hdr) = seq;
+            *reinterpret_cast<volatile uint32_t*>(hdr) = seq;                  // unchanged by a flush
         }
     }
 }
@@ -140,8 +156,8 @@ using namespace mdir;
 
 extern "C" size_t mdir_shard_mailbox_bytes(int world, int max_q, int max_k) {
     if (world < 1 || max_q < 1 || max_k < 1) return 0;
-    const size_t flag_bytes = ((size_t)2 * world * max_q * 4 + 63) & ~(size_t)63;
-    return 64 + flag_bytes + (size_t)2 * world * max_q * max_k * 8;
+    const size_t flag_bytes = ((size_t)kMailBufs * world * max_q * 4 + 63) & ~(size_t)63;
+    return 64 + flag_bytes + (size_t)kMailBufs * world * max_q * max_k * 8;
 }
 
 // cudaMalloc'ed (not from a caching allocator: the IPC handle must describe the whole allocation), zeroed.
@@ -175,14 +191,16 @@ extern "C" int mdir_p2p_free(void* ptr) {
 }
 
 // mailboxes: host array of `world` device pointers (entry `rank` = this rank's own allocation, the others peer-mapped
-// with mdir_p2p_open).  Every rank must call this with the same (n_q, k) in the same order.  status = word 2 of the
+// with mdir_p2p_open).  Every rank must call this with the same (n_q, k, mode) in the same order.  mode 0: exchange
+// and merge this step; 1: push this step, merge the previous one (same n_q, k) into out_*; 2: merge the last pushed
+// step without pushing (the drain after a run of mode-1 calls).  status = word 2 of the
 // own mailbox header (mdir_shard_status): non-zero after a peer failed to arrive within the bounded wait.
-extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world, int max_q, int max_k,
+extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world, int max_q, int max_k, int mode,
                                          void* const* mailboxes, float* out_scores, int32_t* out_idx, void* stream) {
     MDIR_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && n_q >= 0 && n_q <= max_q && k >= 1 && k <= max_k);
-    MDIR_CHECK_ARG(world * (int64_t)k <= 16384);
+    MDIR_CHECK_ARG(world * (int64_t)k <= 16384 && mode >= kExchangeSync && mode <= kExchangeFlush);
     if (n_q == 0) return 0;
-    MDIR_CHECK_ARG(local_keys && mailboxes && out_scores && out_idx);
+    MDIR_CHECK_ARG((local_keys || mode == kExchangeFlush) && mailboxes && out_scores && out_idx);
     Mailboxes mbs;
     for (int r = 0; r < kMaxWorld; ++r) mbs.base[r] = r < world ? static_cast<uint8_t*>(mailboxes[r]) : nullptr;
     for (int r = 0; r < world; ++r) MDIR_CHECK_ARG(mbs.base[r] != nullptr);
@@ -192,7 +210,7 @@ extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, in
         MDIR_CUDA(cudaFuncSetAttribute(shard_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
         attr_set = true;
     }
-    shard_exchange_merge_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(local_keys, n_q, k, rank, world, max_q, max_k, mbs, out_scores, out_idx);
+    shard_exchange_merge_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(local_keys, n_q, k, rank, world, max_q, max_k, mode, mbs, out_scores, out_idx);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

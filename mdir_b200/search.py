@@ -488,24 +488,43 @@ class ShardedIndex:
         lo = min(rank * per, n_total)
         return lo, min(lo + per, n_total)
 
-    def search(self, q, k, precision="fp32", shortlist=None, check=True):
+    def search(self, q, k, precision="fp32", shortlist=None, check=True, exchange="sync"):
+        """exchange="sync": the merged global top-k of THIS call.  exchange="deferred" (peer-memory route only, at most
+        128 queries): pushes this call's keys and returns the merged result of the PREVIOUS deferred call with the same
+        (n_q, k) -- its keys arrived a whole step ago, so neither the exchange latency nor the skew between ranks is
+        ever waited for; drain() returns the last one."""
         s, i, keys = self.local.search(q, k, precision=precision, shortlist=shortlist, check=check, return_keys=True)
         if self.world == 1:
             return s, i
+        if exchange not in ("sync", "deferred"):
+            raise ValueError("exchange must be 'sync' or 'deferred'")
         if self._mb is None or k > self.P2P_MAX_K:
+            if exchange == "deferred":
+                raise _lib.MdirError("exchange='deferred' needs the peer-memory mailboxes (and k <= %d)" % self.P2P_MAX_K)
             return merge_keys(keys, self.world, self.group, k)
-        import ctypes as C
-        lib = _lib.lib()
         nq_all = keys.shape[0]
+        if exchange == "deferred" and nq_all > self.P2P_MAX_Q:
+            raise _lib.MdirError("exchange='deferred' handles at most %d queries per call" % self.P2P_MAX_Q)
         out_s = torch.empty((nq_all, k), dtype=torch.float32, device=self.device)
         out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
-        with torch.cuda.device(self.device):
-            for q0 in range(0, nq_all, self.P2P_MAX_Q):
-                q1 = min(q0 + self.P2P_MAX_Q, nq_all)
-                _lib.check(lib.mdir_shard_exchange_merge(_lib.ptr(keys[q0:q1]), q1 - q0, k, self._rank, self.world, self.P2P_MAX_Q,
-                                                         self.P2P_MAX_K, C.cast(self._mb, C.c_void_p), _lib.ptr(out_s[q0:q1]),
-                                                         _lib.ptr(out_i[q0:q1]), _lib.stream()), "mdir_shard_exchange_merge")
+        for q0 in range(0, nq_all, self.P2P_MAX_Q):
+            q1 = min(q0 + self.P2P_MAX_Q, nq_all)
+            self._exchange(keys[q0:q1], q1 - q0, k, 1 if exchange == "deferred" else 0, out_s[q0:q1], out_i[q0:q1])
         return out_s, out_i
+
+    def _exchange(self, keys, nq, k, mode, out_s, out_i):
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().mdir_shard_exchange_merge(_lib.ptr(keys), nq, k, self._rank, self.world, self.P2P_MAX_Q, self.P2P_MAX_K, mode,
+                                                            C.cast(self._mb, C.c_void_p), _lib.ptr(out_s), _lib.ptr(out_i), _lib.stream()),
+                       "mdir_shard_exchange_merge")
+
+    def drain(self, n_q, k, out=None):
+        """Merged result of the last exchange='deferred' call (every rank calls it; nothing is pushed)."""
+        if out is None:
+            out = (torch.empty((n_q, k), dtype=torch.float32, device=self.device), torch.empty((n_q, k), dtype=torch.int32, device=self.device))
+        self._exchange(None, n_q, k, 2, out[0], out[1])
+        return out
 
 
 def merge_keys(local_keys, world, group, k):
@@ -572,16 +591,20 @@ class GraphedSearch:
         gs.check_overflow()            # after a sync: True -> rerun through index.search()
     """
 
-    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None):
+    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None, deferred=False):
+        """deferred=True (ShardedIndex with peer-memory mailboxes): every replay pushes its keys and returns the merged
+        result of the PREVIOUS replay (see ShardedIndex.search); drain() returns the last one."""
         self.index = index
         self.local = index.local if isinstance(index, ShardedIndex) else index
         dev = self.local.device
-        self.k, self.precision, self.shortlist = int(k), precision, shortlist
+        self.n_q, self.k, self.precision, self.shortlist = int(n_q), int(k), precision, shortlist
+        self.deferred = bool(deferred) and isinstance(index, ShardedIndex) and index.world > 1
         self.q = torch.zeros((n_q, self.local.D), dtype=torch.float32, device=dev)
         self.local.prof = None
+        extra = {"exchange": "deferred"} if self.deferred else {}
 
         def step():
-            return index.search(self.q, self.k, precision=self.precision, shortlist=self.shortlist, check=False)
+            return index.search(self.q, self.k, precision=self.precision, shortlist=self.shortlist, check=False, **extra)
 
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -604,6 +627,12 @@ class GraphedSearch:
         self.graph.replay()
         return self.out
 
+    def drain(self):
+        """deferred mode: the merged result of the last replay, written into this graph's static outputs."""
+        if self.deferred:
+            self.index.drain(self.n_q, self.k, out=self.out)
+        return self.out
+
     def check_overflow(self):
         return self.local.check_overflow()
 
@@ -623,14 +652,23 @@ class SearchPipeline:
     whose candidate lists overflowed is transparently redone through index.search() (exact recovery).
     With a ShardedIndex every rank must submit the same sequence (the all-gather is inside the graphs)."""
 
-    def __init__(self, index, n_q, k, depth=2, precision="fp32", shortlist=None, prof=None):
+    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None):
+        """deferred (default: on for a ShardedIndex with peer-memory mailboxes): the merge of step t runs inside the
+        replay of step t+1 (or in a drain when nothing follows), hiding the exchange behind the next scan.
+        depth = steps in flight (default 2; 3 when deferred, because result(t) then needs replay t+1 finished and the
+        host still wants a whole step of slack to queue the next one)."""
         self.index = index
         self.local = index.local if isinstance(index, ShardedIndex) else index
         dev = self.local.device
-        self.n_q, self.k, self.depth = int(n_q), int(k), int(depth)
+        self.n_q, self.k = int(n_q), int(k)
         self.precision, self.shortlist = precision, shortlist
-        self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None)
-                       for s in range(self.depth)]
+        sharded = isinstance(index, ShardedIndex) and index.world > 1
+        if deferred is None:
+            deferred = sharded and index._mb is not None and self.k <= index.P2P_MAX_K and self.n_q <= index.P2P_MAX_Q
+        self.deferred = bool(deferred) and sharded
+        self.depth = int(depth) if depth else (3 if self.deferred else 2)
+        self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None,
+                                     deferred=self.deferred) for s in range(self.depth)]
         with torch.cuda.device(dev):
             self.compute, self.h2d, self.d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
             self.slots = []
@@ -640,16 +678,30 @@ class SearchPipeline:
                     "idx": torch.empty((self.n_q, self.k), dtype=torch.int32).pin_memory(),
                     "ovf": torch.zeros((self.n_q,), dtype=torch.int32).pin_memory(),
                     "up": torch.cuda.Event(), "done": torch.cuda.Event(), "down": torch.cuda.Event(),
-                    "q": None, "pending": False})
+                    "q": None, "pending": False, "merged": False})
+            if self.deferred:
+                self.drain_out = (torch.empty((self.n_q, self.k), dtype=torch.float32, device=dev),
+                                  torch.empty((self.n_q, self.k), dtype=torch.int32, device=dev))
+                with torch.cuda.stream(self.compute):          # forget the graphs' warm-up pushes
+                    index.drain(self.n_q, self.k, out=self.drain_out)
             torch.cuda.synchronize(dev)
         self.n_submitted = 0
+
+    def _download(self, slot, src):
+        """Queue the D2H of a merged result into `slot`'s pinned buffers (ordered after the compute stream's last event)."""
+        with torch.cuda.stream(self.d2h):
+            slot["scores"].copy_(src[0], non_blocking=True)
+            slot["idx"].copy_(src[1], non_blocking=True)
+            slot["down"].record()
+        slot["merged"] = True
 
     def submit(self, q):
         """q: (n_q, D) fp32, pinned host memory for a truly asynchronous upload (device tensors work too).
         Returns a ticket for result().  The caller keeps q unchanged until result(ticket) returned."""
-        slot, gs = self.slots[self.n_submitted % self.depth], self.graphs[self.n_submitted % self.depth]
+        t_new = self.n_submitted
+        slot, gs = self.slots[t_new % self.depth], self.graphs[t_new % self.depth]
         if slot["pending"]:
-            raise _lib.MdirError("SearchPipeline: collect result() of ticket %d before submitting more" % (self.n_submitted - self.depth))
+            raise _lib.MdirError("SearchPipeline: collect result() of ticket %d before submitting more" % (t_new - self.depth))
         q = torch.as_tensor(q)
         if tuple(q.shape) != tuple(gs.q.shape):
             raise _lib.MdirError("SearchPipeline expects query batches of shape %s" % (tuple(gs.q.shape),))
@@ -660,15 +712,16 @@ class SearchPipeline:
             self.compute.wait_event(slot["up"])
             gs.graph.replay()
             slot["done"].record()
+        slot["q"], slot["pending"], slot["merged"] = q, True, False
         with torch.cuda.stream(self.d2h):
             self.d2h.wait_event(slot["done"])
-            slot["scores"].copy_(gs.out[0], non_blocking=True)
-            slot["idx"].copy_(gs.out[1], non_blocking=True)
             slot["ovf"].copy_(gs.ovf, non_blocking=True)
-            slot["down"].record()
-        slot["q"], slot["pending"] = q, True
+        if not self.deferred:
+            self._download(slot, gs.out)
+        elif t_new >= 1 and self.slots[(t_new - 1) % self.depth]["pending"]:
+            self._download(self.slots[(t_new - 1) % self.depth], gs.out)        # this replay merged the previous ticket
         self.n_submitted += 1
-        return self.n_submitted - 1
+        return t_new
 
     def result(self, ticket):
         """Blocks until step `ticket` is in host memory; returns (scores (n_q, k) fp32, idx (n_q, k) int32) numpy views."""
@@ -677,6 +730,16 @@ class SearchPipeline:
         slot = self.slots[ticket % self.depth]
         if not slot["pending"]:
             raise _lib.MdirError("SearchPipeline: result(%d) was already collected" % ticket)
+        if not slot["merged"]:
+            # deferred exchange and nothing was submitted after this ticket: merge it now (every rank does the same)
+            if ticket != self.n_submitted - 1:
+                raise _lib.MdirError("SearchPipeline: collect deferred results in submission order")
+            with torch.cuda.stream(self.compute):
+                self.index.drain(self.n_q, self.k, out=self.drain_out)
+                ev = torch.cuda.Event()
+                ev.record()
+            self.d2h.wait_event(ev)
+            self._download(slot, self.drain_out)
         slot["down"].synchronize()
         slot["pending"] = False
         if bool(slot["ovf"].any()):

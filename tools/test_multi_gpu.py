@@ -70,6 +70,35 @@ def main():
     s1, i1 = single.search(q, k)
     check("CUDA-graph sharded search == single", torch.equal(i1, i3) and torch.equal(s1, s3) and not gs.check_overflow())
     check("planted neighbour first", bool(np.array_equal(i3.cpu().numpy()[:, 0], src)))
+    # deferred exchange: replay t returns the merged result of replay t-1, drain() the last one
+    gd = GraphedSearch(sharded, nq, k, deferred=True)
+    batches = [torch.from_numpy(synth.planted_queries(db, nq, 120 + b)[0]).to(dev) for b in range(5)]
+    refs = [single.search(b, k) for b in batches]
+    good = True
+    for b in range(5):
+        s_prev, i_prev = gd(batches[b])
+        torch.cuda.synchronize()
+        if b >= 1:
+            good &= torch.equal(i_prev, refs[b - 1][1]) and torch.equal(s_prev, refs[b - 1][0])
+    s_last, i_last = gd.drain()
+    torch.cuda.synchronize()
+    good &= torch.equal(i_last, refs[4][1]) and torch.equal(s_last, refs[4][0])
+    check("deferred-exchange graph: step t returns step t-1, drain returns the last", good)
+    pipe = mdir_b200.SearchPipeline(sharded, nq, k)
+    hb = [b.cpu().pin_memory() for b in batches]
+    outs = [(s.copy(), i.copy()) for s, i in pipe.map(hb)]
+    good = pipe.deferred and len(outs) == 5
+    for b in range(5):
+        good &= bool(np.array_equal(outs[b][1], refs[b][1].cpu().numpy()) and np.array_equal(outs[b][0], refs[b][0].cpu().numpy()))
+    t_a = pipe.submit(hb[0])
+    sa, ia = pipe.result(t_a)                              # latest ticket collected right away -> drain path
+    good &= bool(np.array_equal(ia, refs[0][1].cpu().numpy()))
+    outs2 = [(s.copy(), i.copy()) for s, i in pipe.map(hb[1:3])]
+    good &= bool(np.array_equal(outs2[0][1], refs[1][1].cpu().numpy()) and np.array_equal(outs2[1][1], refs[2][1].cpu().numpy()))
+    check("SearchPipeline over the sharded index (deferred exchange) == single, in order", good)
+    s2, i2 = sharded.search(q, k)
+    s1, i1 = single.search(q, k)
+    check("sync search after deferred traffic still exact", torch.equal(i1, i2) and torch.equal(s1, s2) and sharded.exchange_status() == 0)
     q1 = qe.expand_queries(single, q, 3.0, 10)
     q2 = qe.expand_queries(sharded, q, 3.0, 10)
     check("sharded alpha-QE expansion == single (1e-6)", bool(torch.allclose(q1, q2, rtol=0, atol=1e-6)))

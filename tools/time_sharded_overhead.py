@@ -39,6 +39,45 @@ def timeit(gs, n=300):
     return ev[0].elapsed_time(ev[1]) / n
 
 
+# the exchange + merge kernel alone, back to back (its intrinsic cost, without the per-step skew between ranks)
+import ctypes as C  # noqa: E402
+from mdir_b200 import _lib  # noqa: E402
+sh0 = ShardedIndex.from_local(index)
+_, _, keys0 = index.search(q, K, return_keys=True)
+o_s = torch.empty((NQ, K), dtype=torch.float32, device=dev)
+o_i = torch.empty((NQ, K), dtype=torch.int32, device=dev)
+
+
+def exch():
+    _lib.check(_lib.lib().mdir_shard_exchange_merge(_lib.ptr(keys0), NQ, K, rank, world, sh0.P2P_MAX_Q, sh0.P2P_MAX_K, C.cast(sh0._mb, C.c_void_p),
+                                                    _lib.ptr(o_s), _lib.ptr(o_i), _lib.stream()), "x")
+
+
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    exch()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+gx = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gx):
+    for _ in range(20):
+        exch()
+dist.barrier()
+torch.cuda.synchronize()
+evx = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+gx.replay()
+torch.cuda.synchronize()
+dist.barrier()
+torch.cuda.synchronize()
+evx[0].record()
+for _ in range(10):
+    gx.replay()
+evx[1].record()
+torch.cuda.synchronize()
+if rank == 0:
+    print("exchange+merge kernel alone: %.1f us per call (20 per graph, 10 replays)" % (evx[0].elapsed_time(evx[1]) / 200 * 1e3), flush=True)
+
 t_local = timeit(GraphedSearch(index, NQ, K))
 t_local16 = timeit(GraphedSearch(index, NQ, K, precision="bf16"))
 t_shard = timeit(GraphedSearch(ShardedIndex.from_local(index), NQ, K))
