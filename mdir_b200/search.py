@@ -473,6 +473,19 @@ class ShardedIndex:
                 self._mb, self._mb_own, self._rank = ptrs, own, rank
             torch.cuda.synchronize(self.device)
 
+    def close(self):
+        """Unmap the peers' mailboxes and free the own one (every rank, after the last search; optional at exit)."""
+        if self._mb is None:
+            return
+        lib = _lib.lib()
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)                # nobody is still pushing into a mailbox about to disappear
+        for r in range(self.world):
+            if r != self._rank:
+                lib.mdir_p2p_close(self._mb[r])
+        lib.mdir_p2p_free(self._mb_own)
+        self._mb, self._mb_own = None, None
+
     def exchange_status(self):
         """0 = healthy; 1 = a peer did not arrive within the bounded wait of some step (results of that step are padding)."""
         if self._mb is None:

@@ -560,6 +560,30 @@ def test_qe_and_dba(m):
     close(aug.db32, oracle.dba(small, 3.0, 5), rtol=1e-4, atol=2e-6)
 
 
+def test_rescore_f32_entry_point(m):
+    """mdir_rescore_f32 directly: exact fp32 dot products of a shortlist, as keys; out-of-shard / negative ids pad."""
+    import torch
+    from mdir_b200 import _lib
+    from mdir_b200.search import keys_to_host
+    n_db, D, n_q, kk, base = 700, 136, 9, 17, 1000
+    db = synth.descriptors(n_db, D, 301)
+    q = synth.descriptors(n_q, D, 302)
+    rs = np.random.RandomState(303)
+    idx = (rs.randint(0, n_db, size=(n_q, kk)) + base).astype(np.int32)
+    idx[0, 0], idx[1, 3], idx[2, 5] = -1, base + n_db, base - 1           # padding, past the shard, before the shard
+    dev = torch.device(DEV)
+    d_db, d_q, d_idx = torch.tensor(db, device=dev), torch.tensor(q, device=dev), torch.tensor(idx, device=dev)
+    keys = torch.empty((n_q, kk), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mdir_rescore_f32(_lib.ptr(d_db), n_db, base, _lib.ptr(d_q), n_q, D, _lib.ptr(d_idx), kk, _lib.ptr(keys), _lib.stream()))
+    sc, gi = keys_to_host(keys.cpu().numpy().view(np.uint64))
+    bad = (idx < base) | (idx >= base + n_db)
+    assert np.all(gi[bad] == -1) and np.all(np.isneginf(sc[bad]))
+    ref = np.einsum("qkd,qd->qk", db[np.clip(idx - base, 0, n_db - 1)].astype(np.float64), q.astype(np.float64))
+    assert np.array_equal(gi[~bad], idx[~bad])
+    np.testing.assert_allclose(sc[~bad], ref[~bad], rtol=0, atol=2e-6)
+
+
 def test_search_pipeline_matches_blocking_search(m):
     """Double-buffered serving loop (async H2D / graph replay / D2H): same answers, in order, as index.search."""
     import torch

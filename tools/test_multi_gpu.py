@@ -111,6 +111,9 @@ def main():
     check("sharded DBA rows == single (1e-6)", bool(torch.allclose(aug_sh.local.db32, aug_single.db32[lo2:hi2], rtol=0, atol=1e-6)))
     torch.cuda.synchronize()
     dist.barrier()
+    sh2.close()
+    sharded.close()
+    check("mailboxes closed", sharded._mb is None)
     if rank == 0:
         print("MULTI-GPU %s" % ("PASSED" if ok_all else "FAILED"), flush=True)
     sys.stdout.flush()
