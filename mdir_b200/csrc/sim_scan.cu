@@ -752,6 +752,40 @@ __global__ void __launch_bounds__(256) row_l2n_kernel(float* x, int dims, float 
     for (int j = threadIdx.x; j < dims; j += blockDim.x) row[j] *= inv;
 }
 
+// sum of the k_split partial planes (fixed order) fused with the row renormalisation: one CTA per descriptor.
+// dims % 4 == 0 and 16-byte aligned planes (always true here: dims comes from the 256-row tiles of the scan).
+__global__ void __launch_bounds__(256) sum_partials_l2n_kernel(const float* __restrict__ partial, int k_split, int64_t split_stride, int dims,
+                                                               float eps, float* __restrict__ out) {
+    __shared__ float red[32];
+    const float* src = partial + (int64_t)blockIdx.x * dims;
+    float* row = out + (int64_t)blockIdx.x * dims;
+    float s = 0.f;
+    for (int j = threadIdx.x * 4; j < dims; j += blockDim.x * 4) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ks = 0;
+        for (; ks + 7 < k_split; ks += 8) {                       // 8 independent 128-bit loads in flight, summed in plane order
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (int64_t)(ks + u) * split_stride + j);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+        }
+        for (; ks < k_split; ++ks) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)ks * split_stride + j);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        *reinterpret_cast<float4*>(row + j) = a;
+        s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    s = block_sum(s, red);
+    const float inv = 1.0f / (sqrtf(s) + eps);
+    for (int j = threadIdx.x * 4; j < dims; j += blockDim.x * 4) {              // each thread re-reads only its own writes
+        float4 a = *reinterpret_cast<float4*>(row + j);
+        a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+        *reinterpret_cast<float4*>(row + j) = a;
+    }
+}
+
 static int whiten_plan(int D, int dims, int* k_split) {
     const int tiles = (dims + kBlockM - 1) / kBlockM;
     const int nkb = (3 * D + 31) / 32;
@@ -798,12 +832,16 @@ extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int
         const int per = (nkb + ks - 1) / ks;
         const int ks_eff = ks > 1 ? (nkb + per - 1) / per : 1;
         float* o = out + (size_t)r0 * dims;
-        sum_partials_kernel<<<(unsigned)((split_stride / 4 + 256) / 256), 256, 0, st>>>(partial, ks_eff, split_stride, split_stride, o);
-        MDIR_LAUNCH_CHECK();
-        if (renorm_eps >= 0.f) {
-            row_l2n_kernel<<<nb, 256, 0, st>>>(o, dims, renorm_eps);
+        if (renorm_eps >= 0.f && (dims & 3) == 0 && (((uintptr_t)o | (uintptr_t)partial) & 15) == 0) {
+            sum_partials_l2n_kernel<<<nb, 256, 0, st>>>(partial, ks_eff, split_stride, dims, renorm_eps, o);
+        } else if (renorm_eps >= 0.f) {
+            sum_partials_kernel<<<(unsigned)((split_stride / 4 + 256) / 256), 256, 0, st>>>(partial, ks_eff, split_stride, split_stride, o);
             MDIR_LAUNCH_CHECK();
+            row_l2n_kernel<<<nb, 256, 0, st>>>(o, dims, renorm_eps);
+        } else {
+            sum_partials_kernel<<<(unsigned)((split_stride / 4 + 256) / 256), 256, 0, st>>>(partial, ks_eff, split_stride, split_stride, o);
         }
+        MDIR_LAUNCH_CHECK();
     }
     return 0;
 }

@@ -5,7 +5,6 @@ unchanged with the similarity + ranking (and pooling / whitening / CLAHE) on the
 
 Nothing here imports the reference at module import time: ``install()`` needs an importable
 ``mdir`` package (the user's checkout) and raises otherwise."""
-import numpy as np
 
 from . import layers, wrappers, clahe, search, evaluate, extract
 
