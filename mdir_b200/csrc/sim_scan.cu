@@ -786,10 +786,22 @@ __global__ void __launch_bounds__(256) sum_partials_l2n_kernel(const float* __re
     }
 }
 
-static int whiten_plan(int D, int dims, int* k_split) {
+// Blocks of <= 128 descriptors; with more than one block two of them run concurrently (caller's stream + an internal
+// one), each on half of the SMs, instead of back to back on all of them: the chain of small kernels per block is
+// latency-bound, so two half-width chains finish in about the time of one.
+static void whiten_blocks(int n, int* n_blocks, int* block_rows) {
+    const int nblk = (n + kMaxN - 1) / kMaxN;
+    int rows = (n + nblk - 1) / nblk;
+    rows = (rows + 15) & ~15;
+    if (rows > kMaxN) rows = kMaxN;
+    *n_blocks = (n + rows - 1) / rows;
+    *block_rows = rows;
+}
+
+static int whiten_plan(int D, int dims, int n_concurrent, int* k_split) {
     const int tiles = (dims + kBlockM - 1) / kBlockM;
     const int nkb = (3 * D + 31) / 32;
-    int ks = kNumSMs / tiles;
+    int ks = (kNumSMs / n_concurrent) / tiles;
     if (ks < 1) ks = 1;
     if (ks > nkb) ks = nkb;
     const int per = (nkb + ks - 1) / ks;
@@ -799,12 +811,17 @@ static int whiten_plan(int D, int dims, int* k_split) {
 
 }  // namespace mdir
 
+static size_t whiten_slot_floats(int rows, int D, int dims, int ks) {
+    return (((size_t)rows * 3 * D + (size_t)ks * rows * dims) + 63) & ~(size_t)63;
+}
+
 extern "C" size_t mdir_whiten_tc_workspace_bytes(int n, int D, int dims) {
     if (n <= 0 || D <= 0 || dims <= 0) return 0;
-    int ks;
-    whiten_plan(D, dims, &ks);
-    const size_t nb = n < kMaxN ? n : kMaxN;
-    return nb * 3 * (size_t)D * 4 + (size_t)ks * nb * dims * 4 + 512;
+    int nblk, rows, ks;
+    whiten_blocks(n, &nblk, &rows);
+    const int conc = nblk > 1 ? 2 : 1;
+    whiten_plan(D, dims, conc, &ks);
+    return conc * whiten_slot_floats(rows, D, dims, ks) * 4 + 512;
 }
 
 extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int D, const float* Px3, int dims, float renorm_eps,
@@ -812,20 +829,39 @@ extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int
     MDIR_CHECK_ARG(v && Px3 && out && ws && n >= 0 && D > 0 && (D % 4) == 0 && dims > 0);
     MDIR_CHECK_ARG((((uintptr_t)Px3 | (uintptr_t)ws) & 15) == 0);
     if (n == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    int ks;
-    whiten_plan(D, dims, &ks);
-    const int nb_max = n < kMaxN ? n : kMaxN;
-    float* vx3 = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
-    float* partial = vx3 + (size_t)nb_max * 3 * D;
-    for (int r0 = 0; r0 < n; r0 += kMaxN) {
-        const int nb = (n - r0) < kMaxN ? (n - r0) : kMaxN;
+    int nblk, rows, ks;
+    whiten_blocks(n, &nblk, &rows);
+    const int conc = nblk > 1 ? 2 : 1;
+    whiten_plan(D, dims, conc, &ks);
+    const size_t slot = whiten_slot_floats(rows, D, dims, ks);
+    float* ws0 = (float*)(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+
+    // fork: odd blocks run on an internal stream (created once per process), joined before returning; both the fork
+    // and the join are event edges, so the whole thing is capturable into a CUDA graph
+    static cudaStream_t side = nullptr;
+    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t main_st = (cudaStream_t)stream;
+    if (conc > 1) {
+        if (!side) {
+            MDIR_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+            MDIR_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+            MDIR_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        }
+        MDIR_CUDA(cudaEventRecord(ev_fork, main_st));
+        MDIR_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    }
+    for (int b = 0; b < nblk; ++b) {
+        const int r0 = b * rows;
+        const int nb = (n - r0) < rows ? (n - r0) : rows;
+        cudaStream_t st = (b & 1) ? side : main_st;
+        float* vx3 = ws0 + (size_t)(b & 1) * slot;
+        float* partial = vx3 + (size_t)rows * 3 * D;
         const int64_t total = (int64_t)nb * D;
         center_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(v + (size_t)r0 * D, m, nb, D, vx3);
         MDIR_LAUNCH_CHECK();
         const int64_t split_stride = (int64_t)nb * dims;
         int rc = launch_scan(true, Px3, dims, vx3, nb, 3 * D, MDIR_SCAN_DENSE, 0, 0, partial, dims, nullptr, 0, nullptr, nullptr, 0, 0,
-                             stream, ks, split_stride);
+                             (void*)st, ks, split_stride);
         if (rc) return rc;
         // launch_scan may have reduced the split count; recompute it the same way
         const int nkb = (3 * D + 31) / 32;
@@ -842,6 +878,10 @@ extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int
             sum_partials_kernel<<<(unsigned)((split_stride / 4 + 256) / 256), 256, 0, st>>>(partial, ks_eff, split_stride, split_stride, o);
         }
         MDIR_LAUNCH_CHECK();
+    }
+    if (conc > 1) {
+        MDIR_CUDA(cudaEventRecord(ev_join, side));
+        MDIR_CUDA(cudaStreamWaitEvent(main_st, ev_join, 0));
     }
     return 0;
 }

@@ -226,6 +226,30 @@ class RetrievalHead:
                                      self.eps, _lib.ptr(out), _lib.stream()), "mdir_pool")
         return out
 
+    def capture(self, packed):
+        """Static shapes (a PackedMaps over a pre-allocated arena, or one uniform tensor): record the whole head once
+        into a CUDA graph.  Returns replay() -> the (n_img, dims) output tensor of the graph; the nine launches of the
+        head then cost one graph launch instead of nine host round trips (the small kernels are latency-bound)."""
+        dev = packed.device
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self(packed)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self(packed)
+
+        def replay():
+            graph.replay()
+            return out
+
+        replay.graph, replay.out = graph, out
+        return replay
+
     def __call__(self, fmaps):
         pooled = self.pool_maps(fmaps)
         n_maps, Cc = pooled.shape

@@ -140,6 +140,15 @@ def test_batched_head_vs_oracle(m, golden):
         for i, per in enumerate(fmaps):
             ref = oracle.gem_head(per, 2.9137, 1e-6, lw["m"], lw["P"], dims)
             close(out[i], ref, rtol=2e-5, atol=3e-7)
+    # the head recorded into a CUDA graph over a static arena: replays follow the arena's contents
+    head = m.RetrievalHead("gem", p=2.9137, whitening=lw, dimensions=None, nscales=3, device=DEV)
+    packed = head.pack(flat)
+    replay = head.capture(packed)
+    eager = head(packed).clone()
+    assert bool((replay() == eager).all())
+    flat[0].mul_(0.5)                                     # same storage, new contents
+    assert bool((replay() == head(packed)).all()) and not bool((replay()[0] == eager[0]).all())
+    flat[0].mul_(2.0)
     # single-scale, no whitening, packed NCHW input (C1 shape family)
     x = synth.fmap((5, C, 32, 24), 77)
     head = m.RetrievalHead("gem", p=3.0, nscales=1, device=DEV)
