@@ -252,6 +252,34 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
                     const int32_t* item_class, int64_t n_items, const int32_t* n_pos, const int32_t* kappas,
                     int n_kappa, double* aps, double* prs, void* ws, void* stream);
 
+/* ------------------------------------------------------------- composites ---
+ * One call per stage for hosts that do not want to chain the component launchers themselves
+ * (SURVEY.md section 8b).  Pure host-side planning + the launchers above on the caller's stream.
+ *
+ * mdir_sim_topk_bf16: the k best database rows for n_q <= 128 queries -- the first k rows of
+ * np.argsort(-np.dot(vecs.T, qvecs), axis=0) (cirscore.py:69-70) without materialising scores.
+ *   db16 (n_db, D) bf16 rows (mdir_pack_bf16); db32 (n_db, D) fp32 master or NULL;
+ *   q32 (n_q, D) fp32 queries.  db32 != NULL: bf16 shortlist of `shortlist` rows (0 = max(k+32,
+ *   1.25k)) re-scored exactly in fp32 (fp32-faithful ranking); NULL: exact top-k of the bf16 scores.
+ *   route 0 = automatic (one-launch threshold+filter scan, three-launch scan, or dense for small
+ *   databases), 1 = dense (every score; the exact recovery after overflow[q] != 0; n_db <= 131072).
+ *   out_scores / out_idx (n_q, k), out_keys (n_q, k) or NULL, overflow (n_q) int32.  k <= n_db.
+ *   ws: mdir_sim_topk_workspace_bytes(D) bytes (~115 MB), contents irrelevant.
+ * mdir_gem_head: pooling -> L2N -> multi-scale aggregation -> [Lw centre, project, renormalise] for
+ *   n_img images x S scales (maps image-major, scale-minor; off/hw as in mdir_pool).  P (>= dims, C)
+ *   and/or Px3 = mdir_split_tf32x3(P, role 0) select the projection (both NULL: out is (n_img, C));
+ *   msp = the GeM p when the reference's msp rule applies (wrapper.py:122-124), else 1.
+ *   out (n_img, dims).  ws: mdir_gem_head_workspace_bytes(n_img, S, C, dims) bytes.            */
+size_t mdir_sim_topk_workspace_bytes(int D);
+int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64_t n_db, const float* q32, int n_q,
+                       int D, int k, int shortlist, uint32_t idx_base, int route,
+                       float* out_scores, int32_t* out_idx, uint64_t* out_keys, int32_t* overflow,
+                       void* ws, void* stream);
+size_t mdir_gem_head_workspace_bytes(int n_img, int S, int C, int dims);
+int mdir_gem_head(int kind, const float* x, const int64_t* off, const int32_t* hw, int n_img, int S, int C,
+                  int hw_uniform, float p, float eps, float msp, const float* m, const float* P,
+                  const float* Px3, int dims, float* out, void* ws, void* stream);
+
 /* ------------------------------------ shard merge over NVLink peer memory ---
  * Multi-GPU top-k: every rank holds a row shard and its local top-k as sorted
  * 64-bit keys (n_q, k).  mdir_shard_exchange_merge is the exchange AND the merge in one kernel: it

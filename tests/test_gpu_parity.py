@@ -569,6 +569,64 @@ def test_qe_and_dba(m):
     close(aug.db32, oracle.dba(small, 3.0, 5), rtol=1e-4, atol=2e-6)
 
 
+@pytest.mark.parametrize("n_db,n_q,D,k", [(3000, 5, 64, 10), (70000, 70, 64, 100), (300000, 33, 32, 1200), (20000, 128, 136, 64)])
+def test_c_abi_topk_composite_equals_index_search(m, n_db, n_q, D, k):
+    """mdir_sim_topk_bf16 (one C call: plan + pack + scan + select + finalize) == Index.search, every route."""
+    import torch
+    from mdir_b200 import _lib
+    db = synth.descriptors(n_db, D, 400 + n_q, clusters=60)
+    q, _ = synth.planted_queries(db, n_q, 11)
+    dev = torch.device(DEV)
+    index = m.Index(db, device=dev, idx_base=77)
+    lib = _lib.lib()
+    d_q = torch.tensor(q, device=dev)
+    ws = torch.empty((lib.mdir_sim_topk_workspace_bytes(D),), dtype=torch.uint8, device=dev)
+    for prec, routes in (("bf16", (0, 1)), ("fp32", (0,))):
+        if prec == "fp32" and k > 1024:
+            continue
+        ref_s, ref_i = index.search(q, k, precision=prec)
+        for route in routes:
+            if route == 1 and n_db > 131072:
+                continue
+            o_s = torch.empty((n_q, k), dtype=torch.float32, device=dev)
+            o_i = torch.empty((n_q, k), dtype=torch.int32, device=dev)
+            o_k = torch.empty((n_q, k), dtype=torch.int64, device=dev)
+            ovf = torch.ones((n_q,), dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.mdir_sim_topk_bf16(_lib.ptr(index.db16), _lib.ptr(index.db32) if prec == "fp32" else None, n_db, _lib.ptr(d_q),
+                                                  n_q, D, k, 0, 77, route, _lib.ptr(o_s), _lib.ptr(o_i), _lib.ptr(o_k), _lib.ptr(ovf),
+                                                  _lib.ptr(ws), _lib.stream()), "mdir_sim_topk_bf16")
+            assert int(ovf.sum().item()) == 0
+            assert torch.equal(o_i, ref_i) and torch.equal(o_s, ref_s), (prec, route)
+            assert torch.equal((o_k & 0xffffffff).to(torch.int32), ref_i)
+
+
+def test_c_abi_gem_head_composite_equals_retrieval_head(m, golden):
+    import ctypes
+    import torch
+    from mdir_b200 import _lib
+    g = golden("head")
+    C = 128
+    lw = {"m": g["lw_m"], "P": g["lw_P"]}
+    hws = [[(32, 24), (23, 17), (16, 12)], [(24, 32), (17, 23), (12, 16)], [(8, 8), (6, 6), (4, 4)]]
+    flat = []
+    for i, hw in enumerate(hws * 4):                      # 12 ragged images x 3 scales
+        flat += [dev(synth.fmap((1, C, h, w), 950 + 7 * i + s, "relu")) for s, (h, w) in enumerate(hw)]
+    lib = _lib.lib()
+    for dims, whiten in ((64, True), (C, True), (C, False)):
+        head = m.RetrievalHead("gem", p=2.9137, whitening=lw if whiten else None, dimensions=dims if whiten else None, nscales=3, device=DEV)
+        ref = head(flat)
+        pm = head.pack(flat)
+        out = torch.empty((12, dims), dtype=torch.float32, device=ref.device)
+        ws = torch.empty((lib.mdir_gem_head_workspace_bytes(12, 3, C, dims if whiten else 0),), dtype=torch.uint8, device=ref.device)
+        with torch.cuda.device(ref.device):
+            _lib.check(lib.mdir_gem_head(0, ctypes.c_void_p(pm.base), _lib.ptr(pm.off), _lib.ptr(pm.hw), 12, 3, C, 0, 2.9137, 1e-6, head.msp,
+                                         _lib.ptr(head.m) if whiten else None, _lib.ptr(head.P) if whiten else None,
+                                         _lib.ptr(head.Px3) if whiten else None, dims if whiten else 0, _lib.ptr(out), _lib.ptr(ws), _lib.stream()),
+                       "mdir_gem_head")
+        assert torch.equal(out, ref), (dims, whiten)
+
+
 def test_rescore_f32_entry_point(m):
     """mdir_rescore_f32 directly: exact fp32 dot products of a shortlist, as keys; out-of-shard / negative ids pad."""
     import torch
