@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                             if (warp == 2) {
                                 uint32_t before;
                                 const int bin = find_bin_warp0(sel_hist, sel_k, &before);
+                                __syncwarp();                       // every lane has read sel_k before lane 0 rewrites it
                                 if (lane == 0) {
                                     sel_prefix = prefix | ((uint32_t)bin << shift);
                                     sel_k -= before;
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                             }
                             asm volatile("bar.sync 1, 128;" ::: "memory");
                         }
-                        result = sel_prefix;
+                        if (et == 0) result = sel_prefix;       // only the publishing thread reads it (it also rewrites it next round)
                     }
                     if (et == 0) {
                         p.tau_rw[q] = sel_ok ? (((uint64_t)result << 32) | 0xffffffffull) : 0ull;

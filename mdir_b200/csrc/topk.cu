@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(1024) select_kth_kernel(const float* __restric
         }
     }
     const uint64_t tau_key = ((uint64_t)result << 32) | (uint64_t)idx_limit;
+    __syncthreads();          // s_prefix / s_k / s_ties share a vector word with s_n: every read of them is done
     if (threadIdx.x == 0) { tau[q] = tau_key; s_n = 0u; }
     if (cand) {
         __syncthreads();
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(1024, 1) select_kth_reg_kernel(const float* __
         }
     }
     const uint64_t tau_key = ((uint64_t)result << 32) | (uint64_t)idx_limit;
+    __syncthreads();          // s_prefix / s_k / s_ties share a vector word with s_n: every read of them is done
     if (threadIdx.x == 0) { tau[q] = tau_key; s_n = 0u; }
     if (cand) {
         __syncthreads();
