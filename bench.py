@@ -575,8 +575,50 @@ def side_measurements(torch, mdir_b200, dev):
                     "ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "hbm_floor_frac": pairs * 12 / 1e9 / (ms * 1e-3) / peak,
                     "note": "floor = 12 B/pair (4 B score + 8 B int64 rank) at the measured HBM peak"}
         del idx, db, r
+    out["c3_full"] = c3_full_measurement(torch, mdir_b200, dev, g)
     out.update(training_side_measurements(torch, mdir_b200, dev, g, ev))
     return out
+
+
+def c3_full_measurement(torch, mdir_b200, dev, g):
+    """BASELINE.json config C3 at full size: 10,000 queries x 100,000 database rows x 512-D -> the (N_db, N_q) int64
+    ranks array (8 GB) and mAP from it, everything on the device; the reference's np.dot + np.argsort timed on a
+    64-query sample of the same matrices for scale."""
+    import numpy as np
+    from mdir_b200.search import Index
+    from mdir_b200.evaluate import compute_map
+    n_db, D, nq = 100000, 512, 10000
+    db = torch.randn((n_db, D), device=dev, generator=g)
+    db = db / db.norm(dim=1, keepdim=True)
+    src = torch.randperm(n_db, device=dev, generator=g)[:nq]
+    q = db[src] + 0.7 * torch.randn((nq, D), device=dev, generator=g) / D ** 0.5
+    q = q / q.norm(dim=1, keepdim=True)
+    src_h = src.cpu().numpy()
+    rs = np.random.RandomState(11)
+    gnd = [{"ok": np.array([int(src_h[i])] + rs.randint(0, n_db, 3).tolist()), "junk": rs.randint(0, n_db, 2)} for i in range(nq)]
+    idx = Index(db, device=dev, keep_fp32=False)
+    ranks = idx.ranks(q, precision="bf16")               # first call: cudaMalloc of the 8 GB result + 5 GB of workspace
+    del ranks
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    ranks = idx.ranks(q, precision="bf16")
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms_ranks = ev[0].elapsed_time(ev[1])
+    t0 = time.perf_counter()
+    mp, aps, _, _ = compute_map(ranks, gnd, device=dev)
+    torch.cuda.synchronize()
+    ms_map = (time.perf_counter() - t0) * 1e3
+    first_ok = bool((ranks[0] == src).float().mean().item() > 0.99)
+    dbh, qh = db.cpu().numpy(), q[:64].cpu().numpy()
+    t0 = time.perf_counter()
+    np.argsort(-np.dot(dbh, qh.T), axis=0)
+    cpu_ms = (time.perf_counter() - t0) * 1e3 * (nq / 64)
+    del ranks, idx, db, q
+    return {"metric": "C3 full size: scores + full ranks (N_db, N_q) int64 + mAP on the device", "shape": "%d q x %d db x %d-D, bf16 scores" % (nq, n_db, D),
+            "ranks_ms": ms_ranks, "map_ms_incl_host_flatten": ms_map, "pairs_per_s": n_db * nq / (ms_ranks * 1e-3), "mAP": mp,
+            "planted_neighbour_ranked_first": first_ok, "cpu_port_ms_dot_argsort": cpu_ms, "cpu_sample": "64 of %d queries, time scaled" % nq}
 
 
 def training_side_measurements(torch, mdir_b200, dev, g, ev):
