@@ -172,6 +172,20 @@ class KernelProf:
         return self.e0.elapsed_time(self.e1)
 
 
+class QuietStdout:
+    """Everything libraries print to fd 1 while the benchmark runs (NCCL's version banner, ...) goes to stderr, so
+    that stdout carries exactly one line: the JSON result written through emit()."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+
 # ------------------------------------------------------------------ our arm
 def count_launches_per_step(lib, target, q_dev):
     """Kernels of libmdir_b200 launched by one step (counted on an un-captured run of the same call)."""
@@ -187,6 +201,7 @@ def run_ours(args):
     from mdir_b200 import _lib
     from mdir_b200.search import Index, ShardedIndex, GraphedSearch, SearchPipeline, pack_bf16, default_shortlist
 
+    out = QuietStdout()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,7 +408,7 @@ def run_ours(args):
     if per_rank is not None:
         line["per_rank"] = per_rank
     line.update(extras)
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     sys.stdout.flush()
     finish(dist, world)
 
