@@ -30,6 +30,7 @@ constexpr int kMaxN = 128;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kMaxAccBufs = 3;          // accumulator tiles resident in TMEM (2 halves x acc_stride columns each)
 
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
@@ -125,6 +126,7 @@ struct ScanParams {
     // FUSED mode only (threshold + filter in one launch): every CTA's first tile is a sample tile; the best two keys
     // of each 32-row group go to grp_top (n_q, grid, 8, 2); CTA q selects the kth smallest of query q's grid*16
     // values as the threshold, published through tau_rw; sync = {arrivals 1, arrivals 2, unused, exits}
+    int acc_bufs, acc_stride;     // TMEM: acc_bufs accumulator tiles of 2 x acc_stride columns (3 x 2 x 80 when N <= 80, else 2 x 2 x 128)
     int kth;
     uint32_t* grp_top;
     uint32_t* sync;
@@ -207,8 +209,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-    __shared__ __align__(8) uint64_t tmem_full_bar[2];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t tmem_full_bar[kMaxAccBufs];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[kMaxAccBufs];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint64_t tau_s[kMaxN];
     __shared__ float tau_f[kMaxN];
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             mbar_init(smem_u32(&full_bar[s]), 1);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < p.acc_bufs; ++b) {
             mbar_init(smem_u32(&tmem_full_bar[b]), 1);
             mbar_init(smem_u32(&tmem_empty_bar[b]), 4);
         }
@@ -283,8 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             uint32_t phase = 0;
             WorkItem w;
             for (int it = 0; next_item(p, it, w); ++it) {
-                const int b = it & 1;
-                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                const int b = it % p.acc_bufs;
+                const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
                 mbar_wait(smem_u32(&tmem_empty_bar[b]), acc_phase ^ 1u);
                 tc_fence_after();
                 const int nkb = w.nkb;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     const uint32_t b_base = a_base + kABytes;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 + h) * 128u;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(b * 2 + h) * (uint32_t)p.acc_stride;
 #pragma unroll
                         for (int k = 0; k < kKSteps; ++k) {
                             const uint64_t ad = umma_desc_sw128(a_base + (uint32_t)h * (128u * 128u) + (uint32_t)k * 32u);
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         const int emode = p.mode == MDIR_SCAN_FUSED ? MDIR_SCAN_FILTER : p.mode;
         WorkItem w;
         for (int it = 0; next_item(p, it, w); ++it) {
-            const int b = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int b = it % p.acc_bufs;
+            const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             const int tile = w.tile;
             float* dense_out = p.dense_out + (int64_t)w.ks * p.split_stride;
             mbar_wait(smem_u32(&tmem_full_bar[b]), acc_phase);
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                 for (int h = 0; h < 2; ++h) {
                     const int64_t row = (int64_t)tile * kBlockM + h * 128 + quarter * 32 + lane;
                     const bool row_ok = row < p.n_db;
-                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * 128u;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * (uint32_t)p.acc_stride;
 #pragma unroll 1
                     for (int c0 = 0; c0 < p.n_pad; c0 += 16) {
                         uint32_t v[16];
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                 const int r_in_tile = h * 128 + quarter * 32 + lane;
                 const int64_t row = (int64_t)tile * kBlockM + r_in_tile;
                 const bool row_ok = row < p.n_db;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * 128u;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(b * 2 + h) * (uint32_t)p.acc_stride;
                 const int64_t out_row = (p.mode == MDIR_SCAN_SAMPLE ? (int64_t)w.j * kBlockM : (int64_t)tile * kBlockM) + r_in_tile;
                 const uint32_t gidx = p.idx_base + (uint32_t)row;
 #pragma unroll 1
@@ -563,6 +565,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.k_split = 1;
     p.kb_per_split = p.num_k_blocks;
     p.split_stride = split_stride;
+    p.acc_bufs = p.n_pad <= 80 ? 3 : 2;
+    p.acc_stride = p.n_pad <= 80 ? 80 : 128;
     p.kth = 0;
     p.grp_top = nullptr;
     p.sync = nullptr;
