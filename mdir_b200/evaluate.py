@@ -11,16 +11,17 @@ _NAN = float("nan")
 
 
 def _flatten_gnd(gnd):
-    items, iq, ic, npos = [], [], [], []
-    for q, g in enumerate(gnd):
-        ok = np.asarray(g["ok"], dtype=np.int64).reshape(-1)
-        junk = np.asarray(g["junk"], dtype=np.int64).reshape(-1) if "junk" in g else np.empty(0, np.int64)
-        npos.append(ok.shape[0])
-        items += [ok, junk]
-        iq += [np.full(ok.shape[0], q, np.int32), np.full(junk.shape[0], q, np.int32)]
-        ic += [np.zeros(ok.shape[0], np.int32), np.ones(junk.shape[0], np.int32)]
-    cat = lambda xs, dt: np.concatenate(xs).astype(dt) if xs else np.empty(0, dt)
-    return cat(items, np.int64), cat(iq, np.int32), cat(ic, np.int32), np.asarray(npos, np.int32)
+    """list of {'ok', ['junk']} -> (items int64, query-of-item int32, class-of-item int32 (0 ok / 1 junk), n_pos int32);
+    one pass over the dicts, the per-item columns are built with np.repeat instead of per-query arrays."""
+    oks = [np.asarray(g["ok"], dtype=np.int64).reshape(-1) for g in gnd]
+    junks = [np.asarray(g["junk"], dtype=np.int64).reshape(-1) if "junk" in g else np.empty(0, np.int64) for g in gnd]
+    n_ok = np.fromiter((a.shape[0] for a in oks), dtype=np.int64, count=len(gnd))
+    n_junk = np.fromiter((a.shape[0] for a in junks), dtype=np.int64, count=len(gnd))
+    qs = np.arange(len(gnd), dtype=np.int32)
+    items = np.concatenate(oks + junks).astype(np.int64) if gnd else np.empty(0, np.int64)
+    iq = np.concatenate([np.repeat(qs, n_ok), np.repeat(qs, n_junk)]).astype(np.int32)
+    ic = np.concatenate([np.zeros(int(n_ok.sum()), np.int32), np.ones(int(n_junk.sum()), np.int32)])
+    return items, iq, ic, n_ok.astype(np.int32)
 
 
 def compute_map(ranks, gnd, kappas=(), device="cuda"):
