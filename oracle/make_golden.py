@@ -2,7 +2,7 @@
 """Generate tests/golden/*.npz from the LIVE reference (build container only).
 
 Usage:  python oracle/make_golden.py [section ...]   (needs /root/reference; cv2 4.13)
-        sections: base (pooling/head/clahe/search), mining, whitenlearn; default: all
+        sections: base (pooling/head/clahe/search), mining, whitenlearn, extract; default: all
 
 Every array written here is an OUTPUT OF THE REFERENCE'S OWN CODE (mdir/cirtorch
 functions, or the cv2/numpy calls at the reference's call sites) on the seeded
@@ -93,6 +93,50 @@ def make_mining():
     np.savez_compressed(os.path.join(OUT, "mining.npz"), **out)
 
 
+def make_extract():
+    """Descriptor extraction: the LIVE cirtorch extract_vectors (networks/imageretrievalnet.py:277-324: DataLoader over
+    image files, extract_ss / extract_ms) on CPU with a small seeded ImageRetrievalNet.  The fixture keeps the network's
+    weights, the exact tensors the loader fed to it, and the (D, N) results."""
+    import tempfile
+    import torch
+    import torch.nn as nn
+    from PIL import Image
+    from cirtorch.layers.pooling import GeM
+    from cirtorch.networks.imageretrievalnet import ImageRetrievalNet, extract_vectors
+
+    torch.manual_seed(17)
+    feats = [nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 48, 3, stride=2, padding=1), nn.ReLU()]
+    meta = {"architecture": "tiny", "local_whitening": False, "pooling": "gem", "regional": False, "whitening": False,
+            "mean": [0.485, 0.456, 0.406], "std": [0.229, 0.224, 0.225], "outputdim": 48, "out_channels": 48}
+    p = 2.9137
+    net = ImageRetrievalNet(feats, None, GeM(p=p), None, meta).eval()
+    rs = np.random.RandomState(23)
+    tmp = tempfile.mkdtemp(prefix="mdir_extract_")
+    files = []
+    for i, (h, w) in enumerate(((64, 48), (57, 91), (120, 96), (40, 40), (33, 77), (96, 128))):
+        fn = os.path.join(tmp, "im%d.png" % i)
+        Image.fromarray(rs.randint(0, 256, size=(h, w, 3)).astype(np.uint8)).save(fn)
+        files.append(fn)
+    mean, std = torch.tensor(meta["mean"]).view(3, 1, 1), torch.tensor(meta["std"]).view(3, 1, 1)
+
+    def transform(img):
+        x = torch.from_numpy(np.asarray(img, dtype=np.float32) / 255.0).permute(2, 0, 1).contiguous()
+        return (x - mean) / std
+
+    out = {"p": np.array(p)}
+    for k, v in net.features.state_dict().items():
+        out["w_" + k] = v.numpy()
+    for i, fn in enumerate(files):
+        out["input_%d" % i] = transform(Image.open(fn).convert("RGB")).numpy()
+    ms = [1, 1 / np.sqrt(2), 1 / 2]
+    with contextlib.redirect_stdout(io.StringIO()):
+        out["vecs_ss"] = extract_vectors(net, files, None, transform, device=torch.device("cpu")).numpy()
+        out["vecs_ms"] = extract_vectors(net, files, None, transform, ms=ms, msp=p, device=torch.device("cpu")).numpy()
+        out["vecs_ms_msp1"] = extract_vectors(net, files, None, transform, ms=ms, msp=1, device=torch.device("cpu")).numpy()
+    out["ms"] = np.array(ms)
+    np.savez_compressed(os.path.join(OUT, "extract.npz"), **out)
+
+
 def make_whitenlearn():
     """Lw / PCA whitening learning: cirtorch/utils/whiten.py:14-53 (pure numpy, fp64)."""
     from cirtorch.utils.whiten import whitenlearn, pcawhitenlearn, whitenapply
@@ -116,7 +160,9 @@ def make_whitenlearn():
 def main():
     ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    sections = sys.argv[1:] or ["base", "mining", "whitenlearn"]
+    sections = sys.argv[1:] or ["base", "mining", "whitenlearn", "extract"]
+    if "extract" in sections:
+        make_extract()
     if "mining" in sections:
         make_mining()
     if "whitenlearn" in sections:

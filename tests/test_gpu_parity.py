@@ -515,6 +515,34 @@ def test_batched_extract_vectors(m, golden):
             close(vw[i], oracle.gem_head(fm, 2.9137, 1e-6, lw["m"], lw["P"], 32), rtol=5e-5, atol=5e-7)
 
 
+def test_extract_vectors_matches_reference_extract_vectors(m, golden):
+    """tests/golden/extract.npz: outputs of the live cirtorch extract_vectors (single- and multi-scale) for a seeded
+    network; the same weights and the same input tensors through the batched device path."""
+    g = golden("extract")
+    p = float(g["p"])
+    net = _TinyRetrievalNet(m, "gem", p)
+    nn = torch.nn
+    net.features = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 48, 3, stride=2, padding=1), nn.ReLU())
+    net.features.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")})
+    net.meta.update(out_channels=48, outputdim=48)
+    net = net.to(DEV).eval()
+    imgs = [torch.from_numpy(g["input_%d" % i]) for i in range(6)]
+    ms = [float(s) for s in g["ms"]]
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False            # the reference ran its convolutions in fp32 on the CPU
+    try:
+        with torch.no_grad():
+            v_ss = m.extract_vectors(net, imgs, None, None, ms=[1], msp=1, group=4)
+            v_ms = m.extract_vectors(net, imgs, None, None, ms=ms, msp=p, group=3)
+            v_m1 = m.extract_vectors(net, imgs, None, None, ms=ms, msp=1, group=6)
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert tuple(v_ss.shape) == (48, 6)
+    close(v_ss, g["vecs_ss"], rtol=1e-4, atol=2e-6)
+    close(v_ms, g["vecs_ms"], rtol=1e-4, atol=2e-6)
+    close(v_m1, g["vecs_ms_msp1"], rtol=1e-4, atol=2e-6)
+
+
 # ------------------------------------------------------------------ mAP on the device (section 8f, f3)
 def test_compute_map_device(m, golden):
     g = golden("search")

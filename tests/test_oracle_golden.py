@@ -176,3 +176,25 @@ def test_whitenlearn_oracle_matches_reference(golden):
         np.testing.assert_allclose(mp, g[t + "pca_m"], rtol=0, atol=1e-14)
         np.testing.assert_allclose(oracle.whitening_rows_aligned(Pp, g[t + "pca_P"]), g[t + "pca_P"], rtol=0,
                                    atol=1e-7 * np.abs(g[t + "pca_P"]).max())
+
+
+def test_extract_vectors_oracle_matches_reference(golden):
+    """extract_ss / extract_ms of the live reference (cirtorch extract_vectors on CPU) == oracle tail + aggregation on the
+    same feature maps (the backbone is stock torch on both sides)."""
+    import torch
+    g = golden("extract")
+    nn = torch.nn
+    feats = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 48, 3, stride=2, padding=1), nn.ReLU())
+    feats.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")})
+    p = float(g["p"])
+    ms = [float(s) for s in g["ms"]]
+    with torch.no_grad():
+        for i in range(6):
+            x = torch.from_numpy(g["input_%d" % i]).unsqueeze(0)
+            close(oracle.net_tail(feats(x).numpy(), "gem", p)[:, 0], g["vecs_ss"][:, i], rtol=5e-6, atol=1e-7)
+            outs = []
+            for s in ms:
+                xs = x if s == 1 else torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+                outs.append(oracle.net_tail(feats(xs).numpy(), "gem", p)[:, 0])
+            close(oracle.aggregate_tensor(outs, 3, 48, p), g["vecs_ms"][:, i], rtol=1e-5, atol=1e-7)
+            close(oracle.aggregate_tensor(outs, 3, 48, 1.0), g["vecs_ms_msp1"][:, i], rtol=1e-5, atol=1e-7)
