@@ -2,7 +2,7 @@
 """Generate tests/golden/*.npz from the LIVE reference (build container only).
 
 Usage:  python oracle/make_golden.py [section ...]   (needs /root/reference; cv2 4.13)
-        sections: base (pooling/head/clahe/search), mining, whitenlearn, extract; default: all
+        sections: base (pooling/head/clahe/search), mining, whitenlearn, extract, transforms; default: all
 
 Every array written here is an OUTPUT OF THE REFERENCE'S OWN CODE (mdir/cirtorch
 functions, or the cv2/numpy calls at the reference's call sites) on the seeded
@@ -137,6 +137,26 @@ def make_extract():
     np.savez_compressed(os.path.join(OUT, "extract.npz"), **out)
 
 
+def make_transforms():
+    """The three CLAHE transform classes of the reference's TRANSFORMS registry (photometric_transforms.py:10-43), built
+    from the string arguments of the "apply_clahe:4:lab:8" mini-language, on a float RGB picture whose sides are not
+    multiples of the 8 x 8 grid."""
+    from mdir.components.data.transform import TRANSFORMS
+    rs = np.random.RandomState(91)
+    pic = (rs.rand(61, 83, 3) ** 2.2).astype(np.float32)
+    pic[:9, :11] = 0.0
+    pic[20:30, 40:60] = 1.0
+    out = {"pic": pic}
+    out["apply_clahe_4_lab_8"] = TRANSFORMS["apply_clahe"]("4", "lab", "8")(pic.copy())[0]
+    out["apply_clahe_2_lab_4"] = TRANSFORMS["apply_clahe"]("2", "lab", "4")(pic.copy())[0]
+    two = TRANSFORMS["create_clahed"]()(pic.copy())
+    assert np.array_equal(two[0], pic)
+    out["create_clahed_1"] = two[1]
+    out["add_clahe_fromrgb"] = TRANSFORMS["add_clahe_fromrgb"]()(pic.copy())[0]
+    out["add_clahe_fromrgb_2_4"] = TRANSFORMS["add_clahe_fromrgb"]("2", "4")(pic.copy())[0]
+    np.savez_compressed(os.path.join(OUT, "transforms.npz"), **out)
+
+
 def make_whitenlearn():
     """Lw / PCA whitening learning: cirtorch/utils/whiten.py:14-53 (pure numpy, fp64)."""
     from cirtorch.utils.whiten import whitenlearn, pcawhitenlearn, whitenapply
@@ -160,7 +180,9 @@ def make_whitenlearn():
 def main():
     ref_import.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    sections = sys.argv[1:] or ["base", "mining", "whitenlearn", "extract"]
+    sections = sys.argv[1:] or ["base", "mining", "whitenlearn", "extract", "transforms"]
+    if "transforms" in sections:
+        make_transforms()
     if "extract" in sections:
         make_extract()
     if "mining" in sections:

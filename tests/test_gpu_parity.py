@@ -235,6 +235,24 @@ def test_apply_clahe_transform(m):
     assert four.shape == (120, 160, 4)
 
 
+def test_transform_classes_match_reference_registry(m, golden):
+    """tests/golden/transforms.npz: outputs of the reference's TRANSFORMS['apply_clahe' | 'create_clahed' |
+    'add_clahe_fromrgb'] built from the mini-language's string arguments; same calls on the drop-in classes."""
+    g = golden("transforms")
+    pic = g["pic"]
+    np.testing.assert_allclose(m.ApplyClahe("4", "lab", "8")(pic.copy())[0], g["apply_clahe_4_lab_8"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(m.ApplyClahe("2", "lab", "4")(pic.copy())[0], g["apply_clahe_2_lab_4"], rtol=0, atol=2e-5)
+    two = m.CreateClahedImage()(pic.copy())
+    assert len(two) == 2 and np.array_equal(two[0], pic)
+    np.testing.assert_allclose(two[1], g["create_clahed_1"], rtol=0, atol=2e-5)
+    for args, key in (((), "add_clahe_fromrgb"), (("2", "4"), "add_clahe_fromrgb_2_4")):
+        four = m.AddClaheFromRgb(*args)(pic.copy())
+        assert isinstance(four, list) and len(four) == 1 and four[0].dtype == np.float32
+        assert np.array_equal(four[0], g[key])                      # L channel: integer lattice + bit-exact CLAHE
+    with pytest.raises(NotImplementedError):
+        m.ApplyClahe("4", "luv", "8")(pic.copy())
+
+
 # ------------------------------------------------------------------ ranks / top-k on the reference's scores
 def test_ranks_from_reference_scores_bit_exact(m, golden):
     g = golden("search")

@@ -198,3 +198,18 @@ def test_extract_vectors_oracle_matches_reference(golden):
                 outs.append(oracle.net_tail(feats(xs).numpy(), "gem", p)[:, 0])
             close(oracle.aggregate_tensor(outs, 3, 48, p), g["vecs_ms"][:, i], rtol=1e-5, atol=1e-7)
             close(oracle.aggregate_tensor(outs, 3, 48, 1.0), g["vecs_ms_msp1"][:, i], rtol=1e-5, atol=1e-7)
+
+
+def test_transform_classes_oracle_matches_reference_registry(golden):
+    """ApplyClahe / CreateClahedImage / AddClaheFromRgb built by the reference's TRANSFORMS registry (golden) == the
+    oracle's Lab -> CLAHE(L) -> RGB restatement."""
+    pytest.importorskip("cv2")
+    g = golden("transforms")
+    pic = g["pic"]
+    lat = oracle.cv2_lab_lattice()
+    for key, clip, grid in (("apply_clahe_4_lab_8", 4, 8), ("apply_clahe_2_lab_4", 2, 4), ("create_clahed_1", 4, 8)):
+        np.testing.assert_allclose(oracle.image_clahe(pic, clip, grid, lat), g[key], rtol=0, atol=2e-5)
+    for key, clip, grid in (("add_clahe_fromrgb", 4, 8), ("add_clahe_fromrgb_2_4", 2, 4)):
+        L = oracle.rgb2lab_cv(pic, lat)[:, :, 0] / np.float32(100.0)
+        assert np.array_equal(g[key][:, :, :3], pic)
+        assert np.array_equal(oracle.channel_clahe(L.astype(np.float32), clip, grid), g[key][:, :, 3])
