@@ -103,6 +103,7 @@ def make_extract():
     from PIL import Image
     from cirtorch.layers.pooling import GeM
     from cirtorch.networks.imageretrievalnet import ImageRetrievalNet, extract_vectors
+    from mdir.components.data.wrapper import CirMultiscaleAggregation, CirtorchWhiten
 
     torch.manual_seed(17)
     feats = [nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 48, 3, stride=2, padding=1), nn.ReLU()]
@@ -134,6 +135,19 @@ def make_extract():
         out["vecs_ms"] = extract_vectors(net, files, None, transform, ms=ms, msp=p, device=torch.device("cpu")).numpy()
         out["vecs_ms_msp1"] = extract_vectors(net, files, None, transform, ms=ms, msp=1, device=torch.device("cpu")).numpy()
     out["ms"] = np.array(ms)
+    # mdir's own inference pattern: Compose([CirtorchWhiten, CirMultiscaleAggregation]) around the same network
+    # (mdir/components/data/wrapper.py:8-36 -- preprocess in order, postprocess in reverse)
+    from mdir.components.data.wrapper import Compose
+    lwd = synth.lw(48, 29)
+    out["lw_m"], out["lw_P"] = lwd["m"], lwd["P"]
+    wh = CirtorchWhiten.__new__(CirtorchWhiten)
+    wh.device = torch.device("cpu")
+    wh.P = torch.tensor(lwd["P"], dtype=torch.float32)
+    wh.m = torch.tensor(lwd["m"], dtype=torch.float32)
+    wh.dimensions = 32
+    comp = Compose([wh, CirMultiscaleAggregation(True, torch.device("cpu"))], torch.device("cpu"))
+    with torch.no_grad():
+        out["compose_wh32"] = np.stack([comp(torch.from_numpy(out["input_%d" % i]).unsqueeze(0), net, net).numpy() for i in range(len(files))])
     np.savez_compressed(os.path.join(OUT, "extract.npz"), **out)
 
 

@@ -553,8 +553,15 @@ def test_extract_vectors_matches_reference_extract_vectors(m, golden):
             v_ss = m.extract_vectors(net, imgs, None, None, ms=[1], msp=1, group=4)
             v_ms = m.extract_vectors(net, imgs, None, None, ms=ms, msp=p, group=3)
             v_m1 = m.extract_vectors(net, imgs, None, None, ms=ms, msp=1, group=6)
+            # mdir's CirNetwork pattern: the eval wrappers carry the scales (msp rule) and the Lw whitening
+            lw = {"m": g["lw_m"], "P": g["lw_P"]}
+            comp = types.SimpleNamespace(wrappers=[m.CirtorchWhiten(lw, 32, DEV), m.CirMultiscaleAggregation(True, DEV)])
+            cirnet = types.SimpleNamespace(model=net, wrappers={"eval": comp}, stage="eval")
+            v_wr = m.extract_vectors(cirnet, imgs, None, None, group=4, return_device=True)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
+    assert tuple(v_wr.shape) == (6, 32)
+    close(v_wr, g["compose_wh32"], rtol=2e-4, atol=5e-6)
     assert tuple(v_ss.shape) == (48, 6)
     close(v_ss, g["vecs_ss"], rtol=1e-4, atol=2e-6)
     close(v_ms, g["vecs_ms"], rtol=1e-4, atol=2e-6)

@@ -198,6 +198,9 @@ def test_extract_vectors_oracle_matches_reference(golden):
                 outs.append(oracle.net_tail(feats(xs).numpy(), "gem", p)[:, 0])
             close(oracle.aggregate_tensor(outs, 3, 48, p), g["vecs_ms"][:, i], rtol=1e-5, atol=1e-7)
             close(oracle.aggregate_tensor(outs, 3, 48, 1.0), g["vecs_ms_msp1"][:, i], rtol=1e-5, atol=1e-7)
+            # mdir's Compose([CirtorchWhiten(32), CirMultiscaleAggregation(True)]): every scale interpolated, msp rule, Lw
+            fm = [feats(torch.nn.functional.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)).numpy() for s in ms]
+            close(oracle.gem_head(fm, p, 1e-6, g["lw_m"], g["lw_P"], 32), g["compose_wh32"][i], rtol=2e-5, atol=2e-7)
 
 
 def test_transform_classes_oracle_matches_reference_registry(golden):
