@@ -265,11 +265,13 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
  *   databases), 1 = dense (every score; the exact recovery after overflow[q] != 0; n_db <= 131072).
  *   out_scores / out_idx (n_q, k), out_keys (n_q, k) or NULL, overflow (n_q) int32.  k <= n_db.
  *   ws: mdir_sim_topk_workspace_bytes(D) bytes (~115 MB), contents irrelevant.
+ *   mdir_topk_plan exposes the route choice (0 dense / 1 one-launch / 2 three-launch + its sampling plan).
  * mdir_gem_head: pooling -> L2N -> multi-scale aggregation -> [Lw centre, project, renormalise] for
  *   n_img images x S scales (maps image-major, scale-minor; off/hw as in mdir_pool).  P (>= dims, C)
  *   and/or Px3 = mdir_split_tf32x3(P, role 0) select the projection (both NULL: out is (n_img, C));
  *   msp = the GeM p when the reference's msp rule applies (wrapper.py:122-124), else 1.
  *   out (n_img, dims).  ws: mdir_gem_head_workspace_bytes(n_img, S, C, dims) bytes.            */
+int mdir_topk_plan(int64_t n_db, int kth, int sm_count, int* route, int* n_sample, int* stride);   /* host-only planner */
 size_t mdir_sim_topk_workspace_bytes(int D);
 int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64_t n_db, const float* q32, int n_q,
                        int D, int k, int shortlist, uint32_t idx_base, int route,

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "mdir_add_l2n": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "mdir_map_workspace_bytes": (_sz, [_i64, _i]),
     "mdir_compute_ap": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "mdir_topk_plan": (_i, [_i64, _i, _i, _vp, _vp, _vp]),
     "mdir_sim_topk_workspace_bytes": (_sz, [_i]),
     "mdir_sim_topk_bf16": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _i, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdir_gem_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),

@@ -56,6 +56,36 @@ extern "C" size_t mdir_sim_topk_workspace_bytes(int D) {
     return topk_layout(nullptr, D).total + 256;
 }
 
+// Host-only: which route a top-k over n_db rows with selection depth kth takes on a device with sm_count SMs.
+// route 0 = dense (every score, exact select), 1 = one-launch threshold + filter scan, 2 = sample / select / filter with
+// n_sample tiles at the given stride.  No CUDA call.
+extern "C" int mdir_topk_plan(int64_t n_db, int kth, int sm_count, int* route, int* n_sample, int* stride) {
+    MDIR_CHECK_ARG(route && n_sample && stride && n_db >= 0 && kth >= 1 && sm_count >= 1);
+    *route = 0;
+    *n_sample = 0;
+    *stride = 0;
+    const int64_t n_tiles = (n_db + kTile - 1) / kTile;
+    if (n_tiles < 64) return 0;
+    int64_t g = sm_count < 148 ? sm_count : 148;
+    if (g > n_tiles / 2) g = n_tiles / 2;
+    if (g * 16 >= 2 * (int64_t)kth && 1.25 * kth * (double)n_tiles / ((double)g * (double)g) <= kFusedCapL / 2.0) {
+        *route = 1;
+        return 0;
+    }
+    int64_t want = ((int64_t)kth * n_tiles + kTargetCand - 1) / kTargetCand;
+    if (want > 148) want = (want + 147) / 148 * 148;
+    int64_t ns = want < n_tiles / 4 ? want : n_tiles / 4;
+    if (ns > kMaxSampleTiles) ns = kMaxSampleTiles;
+    if (ns < 32) ns = 32;
+    const int64_t st = n_tiles / ns;
+    if (ns * kTile >= 2 * (int64_t)kth && st >= 2) {
+        *route = 2;
+        *n_sample = (int)ns;
+        *stride = (int)st;
+    }
+    return 0;
+}
+
 extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64_t n_db, const float* q32, int n_q, int D, int k, int shortlist,
                                   uint32_t idx_base, int route, float* out_scores, int32_t* out_idx, uint64_t* out_keys, int32_t* overflow,
                                   void* ws, void* stream) {
@@ -74,27 +104,17 @@ extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64
     if (rc) return rc;
     const int64_t n_tiles = (n_db + kTile - 1) / kTile;
 
-    // route planning (the same rules as mdir_b200/search.py:Index._plan / _fused_ok)
+    // route planning (the same rules as mdir_b200/search.py:Index._plan / _fused_ok; tests/test_cpu_boundary.py compares them)
     static int sm_count = 0;
     if (!sm_count) {
         int dev = 0;
         MDIR_CUDA(cudaGetDevice(&dev));
         MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
     }
-    int64_t g = sm_count < 148 ? sm_count : 148;
-    if (g > n_tiles / 2) g = n_tiles / 2;
-    const bool fused = route == 0 && n_tiles >= 64 && g * 16 >= 2 * (int64_t)kth &&
-                       1.25 * kth * (double)n_tiles / ((double)g * (double)g) <= kFusedCapL / 2.0;
-    int n_sample = 0, stride = 0;
-    if (route == 0 && !fused && n_tiles >= 64) {
-        int64_t want = ((int64_t)kth * n_tiles + kTargetCand - 1) / kTargetCand;
-        if (want > 148) want = (want + 147) / 148 * 148;
-        int64_t ns = want < n_tiles / 4 ? want : n_tiles / 4;
-        if (ns > kMaxSampleTiles) ns = kMaxSampleTiles;
-        if (ns < 32) ns = 32;
-        const int64_t st = n_tiles / ns;
-        if (ns * kTile >= 2 * (int64_t)kth && st >= 2) { n_sample = (int)ns; stride = (int)st; }
-    }
+    int plan_route = 0, n_sample = 0, stride = 0;
+    if (route == 0) mdir_topk_plan(n_db, kth, sm_count, &plan_route, &n_sample, &stride);
+    const bool fused = plan_route == 1;
+    if (plan_route != 2) n_sample = 0;
     int cap0 = kCapS, cap_l = kCapL;
     if (fused) {
         MDIR_CUDA(cudaMemsetAsync(w.fused, 0, 16, (cudaStream_t)stream));       // the kernel's arrival counters

@@ -141,3 +141,25 @@ def test_install_patches_registries():
     # the yaml-driven wrapper factory builds ours (wrapper.py:209-220)
     comp = mwrap.initialize_wrappers({"1_cirmultiscale": {"scales": True}}, torch.device("cpu"))
     assert isinstance(comp.wrappers[0], mdir_b200.CirMultiscaleAggregation)
+
+
+def test_topk_route_planner_c_equals_python(libpath):
+    """The route rules exist twice: search.py (Index._plan / _fused_ok, used by the Python face) and composite.cu
+    (mdir_topk_plan, used by mdir_sim_topk_bf16).  They must agree for every database size / depth / SM count."""
+    import ctypes as C
+    from mdir_b200 import search
+    l = C.CDLL(libpath)
+    l.mdir_topk_plan.argtypes = [C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    rs = np.random.RandomState(0)
+    sizes = [1, 255, 16383, 16384, 16385, 20000, 32768, 75000, 125126, 250251, 1001001, 2600000, 4000000, 20000000]
+    sizes += [int(x) for x in rs.randint(1, 5_000_000, 60)]
+    for n_db in sizes:
+        for kth in (1, 10, 100, 132, 200, 384, 700, 1184, 1185, 2048, 4096):
+            for sms in (148, 132, 60):
+                idx = search.Index.__new__(search.Index)
+                idx.n, idx._sms, idx.fused = n_db, sms, True
+                plan = idx._plan(kth)
+                want = (0, 0, 0) if plan is None else ((1, 0, 0) if idx._fused_ok(kth) else (2, plan[0], plan[1]))
+                r, ns, st = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+                assert l.mdir_topk_plan(n_db, kth, sms, C.byref(r), C.byref(ns), C.byref(st)) == 0
+                assert (r.value, ns.value, st.value) == want, (n_db, kth, sms, want, (r.value, ns.value, st.value))
