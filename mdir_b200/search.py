@@ -592,6 +592,29 @@ def merge_keys_host(gathered, k):
     return np.sort(allk, axis=1)[:, :k]
 
 
+def merge_keys_by_rank_host(gathered, k):
+    """numpy restatement of the merge inside csrc/shard_merge.cu (pure integer logic, for the CPU tests): the world
+    lists are sorted and their real keys unique, so the output slot of a key is its position in its own list plus,
+    for every other list, the number of keys smaller than it (lower_bound); all-ones keys are padding."""
+    g = np.asarray(gathered).astype(np.uint64)
+    world, nq, kk = g.shape
+    pad = np.uint64(0xffffffffffffffff)
+    out = np.full((nq, k), pad, dtype=np.uint64)
+    for q in range(nq):
+        for r in range(world):
+            for j in range(kk):
+                key = g[r, q, j]
+                if key == pad:
+                    continue
+                pos = j
+                for o in range(world):
+                    if o != r:
+                        pos += int(np.searchsorted(g[o, q], key, side="left"))
+                if pos < k:
+                    out[q, pos] = key
+    return out
+
+
 class GraphedSearch:
     """One search step captured in a CUDA graph (CUDA streams and graphs instead of per-call
     launches): static query buffer in, static (scores, idx) out.  Works for an Index or a

@@ -4,7 +4,7 @@ import numpy as np
 from hypothesis import given, settings, strategies as st
 
 from oracle import oracle
-from mdir_b200.search import ShardedIndex, make_keys_host, keys_to_host, merge_keys_host, default_shortlist
+from mdir_b200.search import ShardedIndex, make_keys_host, keys_to_host, merge_keys_host, merge_keys_by_rank_host, default_shortlist
 
 scores_st = st.lists(st.one_of(st.floats(-4, 4, width=32), st.sampled_from([0.0, -0.0, 1.0, 1.0, -1.0, float("inf"), float("-inf")])),
                      min_size=1, max_size=200)
@@ -37,7 +37,10 @@ def test_shard_merge_is_partition_independent(n, k, seed):
                 keys = make_keys_host(val.T, idx.T + lo)
                 pad[:, :keys.shape[1]] = keys
             parts.append(pad)
-        msc, midx = keys_to_host(merge_keys_host(np.stack(parts), k))
+        merged = merge_keys_host(np.stack(parts), k)
+        # the lower_bound-rank merge of csrc/shard_merge.cu (numpy restatement) gives the same keys as the sort
+        assert np.array_equal(merge_keys_by_rank_host(np.stack(parts), k), merged)
+        msc, midx = keys_to_host(merged)
         kk = min(k, n)
         assert np.array_equal(midx[:, :kk], ref_i.T) and np.array_equal(msc[:, :kk], ref_v.T)
         assert np.all(midx[:, kk:] == -1)
