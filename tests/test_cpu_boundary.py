@@ -163,3 +163,23 @@ def test_topk_route_planner_c_equals_python(libpath):
                 r, ns, st = C.c_int(-1), C.c_int(-1), C.c_int(-1)
                 assert l.mdir_topk_plan(n_db, kth, sms, C.byref(r), C.byref(ns), C.byref(st)) == 0
                 assert (r.value, ns.value, st.value) == want, (n_db, kth, sms, want, (r.value, ns.value, st.value))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host alone and prints exactly one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-rows", "3000"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "queries/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
+    for key in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
