@@ -4,6 +4,7 @@ golden vectors (outputs of the reference itself), on the same seeded inputs.
 Bars (BASELINE.json north_star): CLAHE and sort/top-k indexing bit-exact; pooled / whitened
 descriptors within 1e-5 relative; similarity scores within 2e-3 absolute on the bf16 path;
 mAP within 0.01."""
+import os
 import types
 
 import numpy as np
@@ -828,3 +829,30 @@ def test_whitenlearn_matches_reference(m, golden):
     np.testing.assert_allclose(oracle.whitening_rows_aligned(Pp, Po), Po, rtol=0, atol=1e-6 * np.abs(Po).max())
     out = m.whitenapply(X32[:, :20].astype(np.float64), mm, P, 32)
     np.testing.assert_allclose(np.abs(out), np.abs(oracle.whitenapply(X32[:, :20].astype(np.float64), mm, P, 32)), rtol=0, atol=1e-5)
+
+
+def test_bench_line_contract():
+    """python bench.py (short run): one JSON line on stdout with the metric, roofline, cpu_baseline, e2e, clocks and
+    gpu_launches objects the measurement contract asks for."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "20", "--warmup", "3", "--no-extras", "--cpu-rows", "4000"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["unit"] == "queries/s" and d["n_gpus"] == 1 and d["steps"] == 20 and d["higher_is_better"] is True
+    assert d["vs_baseline"] is None and d["dtype"] == "bf16" and d["data"] == "synthetic" and "workload" in d["config"]
+    assert d["value"] > 1e4 and abs(d["value"] - 70 / (d["ms_per_step"] * 1e-3)) < 1e-6 * d["value"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.3 < r["frac"] < 1.3 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0.9 * r["algorithmic_bytes_per_launch"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "queries/s" and c["sample"]
+    e = d["e2e"]
+    assert e["value"] > 1e4 and e["h2d_bytes_per_step"] == 70 * 2048 * 4 and e["d2h_bytes_per_step"] == 70 * 100 * 8
+    assert d["gpu_launches"] == 20 * 3                         # pack, fused scan, finalize+re-score per step
+    assert "sm_mhz" in d["clocks"] or "error" in d["clocks"]
