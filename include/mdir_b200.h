@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define MDIR_ABI_VERSION 1
+#define MDIR_ABI_VERSION 2
 
 #define MDIR_E_ARG      (-1)   /* invalid argument (shape/alignment/range) */
 #define MDIR_E_DRIVER   (-2)   /* driver entry point (cuTensorMapEncodeTiled) unavailable */
@@ -210,12 +210,27 @@ int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* s
 
 /* mdir_topk_finalize + exact fp32 re-scoring fused: selects the `shortlist` best keys (bf16
  * scores), recomputes their dot products in fp32 from db32 (rows idx - idx_base of this shard)
- * against q32[q], re-sorts and emits the best k_out (out_* are (n_q, k_out)).           */
+ * against q32[q], re-sorts and emits the best k_out (out_* are (n_q, k_out)).
+ * Shortlist CERTIFICATE (db_stats != NULL, then tau != NULL): with t = the k_out-th best fp32
+ * score and eps = a Cauchy-Schwarz bound on |bf16-path score - fp32 score| over the whole shard
+ * (from db_stats = mdir_pack_stats output and the query's own rounding residual), every candidate
+ * whose bf16 score is >= t - eps is re-scored as well, and status bit 1 is raised unless the
+ * candidate list provably holds all such rows (tau[q] not tighter than t - eps, no overflow):
+ * a clear status means the emitted rows ARE the exact fp32 top k_out of the shard.
+ * overflow[q] is a status word: bit 0 = a segment / the staging area overflowed (re-scan),
+ * bit 1 = not certified (widen the selection: larger shortlist, eventually the dense route). */
 int mdir_topk_finalize_rescore(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg,
                                int cap0, int cap_l, int n_q, int shortlist, int k_out,
                                const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int D,
+                               const float* db_stats,
                                float* out_scores, int32_t* out_idx, uint64_t* out_keys,
                                uint64_t* tau, int32_t* overflow, void* stream);
+#define MDIR_STATUS_OVERFLOW    1
+#define MDIR_STATUS_UNCERTIFIED 2
+
+/* stats[2] (device) = {max_r ||bf16(x_r) - x_r||_2^2, max_r ||x_r||_2^2} over the n rows of a shard:
+ * the database half of the certificate's error bound.  db16 = mdir_pack_bf16(db32).            */
+int mdir_pack_stats(const float* db32, const uint16_t* db16, int64_t n, int D, float* stats, void* stream);
 
 /* Exact fp32 re-scoring of a shortlist: out[q, j] = <db32[idx[q,j]-idx_base], q32[q]>
  * (idx < 0 or outside this shard -> -inf); then callers re-finalize.             */
@@ -259,11 +274,14 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
  * mdir_sim_topk_bf16: the k best database rows for n_q <= 128 queries -- the first k rows of
  * np.argsort(-np.dot(vecs.T, qvecs), axis=0) (cirscore.py:69-70) without materialising scores.
  *   db16 (n_db, D) bf16 rows (mdir_pack_bf16); db32 (n_db, D) fp32 master or NULL;
- *   q32 (n_q, D) fp32 queries.  db32 != NULL: bf16 shortlist of `shortlist` rows (0 = max(k+32,
- *   1.25k)) re-scored exactly in fp32 (fp32-faithful ranking); NULL: exact top-k of the bf16 scores.
+ *   q32 (n_q, D) fp32 queries.  db32 != NULL: bf16 shortlist of `shortlist` rows (0 = 1.25k rounded
+ *   up to a multiple of 64) re-scored exactly in fp32 (fp32-faithful ranking), certified when
+ *   db_stats (mdir_pack_stats) is given -- see mdir_topk_finalize_rescore; NULL: exact top-k of the
+ *   bf16 scores.
  *   route 0 = automatic (one-launch threshold+filter scan, three-launch scan, or dense for small
  *   databases), 1 = dense (every score; the exact recovery after overflow[q] != 0; n_db <= 131072).
- *   out_scores / out_idx (n_q, k), out_keys (n_q, k) or NULL, overflow (n_q) int32.  k <= n_db.
+ *   out_scores / out_idx (n_q, k), out_keys (n_q, k) or NULL, overflow (n_q) int32 status words
+ *   (MDIR_STATUS_*).  k <= n_db.
  *   ws: mdir_sim_topk_workspace_bytes(D) bytes (~115 MB), contents irrelevant.
  *   mdir_topk_plan exposes the route choice (0 dense / 1 one-launch / 2 three-launch + its sampling plan).
  * mdir_gem_head: pooling -> L2N -> multi-scale aggregation -> [Lw centre, project, renormalise] for
@@ -273,8 +291,8 @@ int mdir_compute_ap(const int64_t* ranks, int64_t n_db, int n_q, const int64_t* 
  *   out (n_img, dims).  ws: mdir_gem_head_workspace_bytes(n_img, S, C, dims) bytes.            */
 int mdir_topk_plan(int64_t n_db, int kth, int sm_count, int* route, int* n_sample, int* stride);   /* host-only planner */
 size_t mdir_sim_topk_workspace_bytes(int D);
-int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64_t n_db, const float* q32, int n_q,
-                       int D, int k, int shortlist, uint32_t idx_base, int route,
+int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, const float* db_stats, int64_t n_db,
+                       const float* q32, int n_q, int D, int k, int shortlist, uint32_t idx_base, int route,
                        float* out_scores, int32_t* out_idx, uint64_t* out_keys, int32_t* overflow,
                        void* ws, void* stream);
 size_t mdir_gem_head_workspace_bytes(int n_img, int S, int C, int dims);
@@ -302,9 +320,13 @@ int mdir_p2p_free(void* ptr);
 #define MDIR_EXCHANGE_DEFERRED 1  /* push this step's keys, merge the PREVIOUS step's (arrived a step ago):  */
                                   /* exchange latency and rank skew hide behind the next scan                */
 #define MDIR_EXCHANGE_FLUSH 2     /* no push; merge the last pushed step (drain after deferred calls)        */
+/* local_status (n_q) int32 or NULL: this rank's MDIR_STATUS_* word per query of the step being pushed (it rides in
+ * the flag word); out_status (n_q) int32 or NULL: OR of the world's status words for the step being MERGED, plus
+ * bit 2 (value 4) when a peer did not arrive -- identical on every rank except for that last bit.               */
 int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world,
                               int max_q, int max_k, int mode, void* const* mailboxes,
-                              float* out_scores, int32_t* out_idx, void* stream);
+                              float* out_scores, int32_t* out_idx,
+                              const int32_t* local_status, int32_t* out_status, void* stream);
 int mdir_shard_status(const void* own_mailbox, int* status);
 
 /* ---------------------------------------------- hard-negative mining (f4) ---

@@ -9,6 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmdir_b200.so")
 _lib = None
+ABI_VERSION = 2
 
 
 class ImageDesc(C.Structure):
@@ -44,7 +45,8 @@ PROTOTYPES = {
     "mdir_key_score": (_f, [_u64]),
     "mdir_select_kth": (_i, [_vp, _i64, _i64, _i, _i, _i, _u32, _vp, _vp, _i64, _vp, _i, _i, _i, _vp]),
     "mdir_topk_finalize": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "mdir_topk_finalize_rescore": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _u32, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mdir_topk_finalize_rescore": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp, _i64, _u32, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mdir_pack_stats": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "mdir_rescore_f32": (_i, [_vp, _i64, _u32, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "mdir_qe_accumulate": (_i, [_vp, _i64, _u32, _i, _vp, _vp, _i, _i, _f, _vp, _vp]),
     "mdir_add_l2n": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -52,7 +54,7 @@ PROTOTYPES = {
     "mdir_compute_ap": (_i, [_vp, _i64, _i, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "mdir_topk_plan": (_i, [_i64, _i, _i, _vp, _vp, _vp]),
     "mdir_sim_topk_workspace_bytes": (_sz, [_i]),
-    "mdir_sim_topk_bf16": (_i, [_vp, _vp, _i64, _vp, _i, _i, _i, _i, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "mdir_sim_topk_bf16": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _u32, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdir_gem_head_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mdir_gem_head": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "mdir_shard_mailbox_bytes": (_sz, [_i, _i, _i]),
@@ -60,7 +62,7 @@ PROTOTYPES = {
     "mdir_p2p_open": (_i, [_vp, _vp]),
     "mdir_p2p_close": (_i, [_vp]),
     "mdir_p2p_free": (_i, [_vp]),
-    "mdir_shard_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "mdir_shard_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mdir_shard_status": (_i, [_vp, _vp]),
     "mdir_mine_negatives": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "mdir_pair_l2dist": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp]),
@@ -90,7 +92,7 @@ def lib():
             fn = getattr(l, name)
             fn.restype = res
             fn.argtypes = args
-        if l.mdir_abi_version() != 1:
+        if l.mdir_abi_version() != ABI_VERSION:
             raise MdirError("libmdir_b200.so ABI mismatch")
         _lib = l
     return _lib

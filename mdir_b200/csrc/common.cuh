@@ -40,6 +40,33 @@ extern unsigned long long g_launches;   // kernels launched by this library (ben
 
 constexpr int kNumSMs = 148;
 
+// Per-device "already done" flag: cudaFuncSetAttribute and the SM count are per DEVICE, so a
+// process that drives cuda:0 and then cuda:1 must repeat them (a process-wide static would skip the second device).
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+    bool done[kMaxDevices] = {};
+    // true exactly once per device ordinal (the current device); -1 on a CUDA error
+    int first() {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+        if (done[dev]) return 0;
+        done[dev] = true;
+        return 1;
+    }
+};
+// SM count of the current device (cached per ordinal); 0 on error
+inline int device_sm_count() {
+    static int cache[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    if (!cache[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -42,9 +42,11 @@ static TopkWs topk_layout(void* ws, int D) {
     return w;
 }
 
+// 1.25 k rounded up to a multiple of 64 (whole rounds of the 2 x 32 re-scoring warps); the certified extension
+// of mdir_topk_finalize_rescore adds whatever else is needed.  Same rule as mdir_b200/search.py:default_shortlist.
 static int default_shortlist(int k) {
-    const int a = k + 32, b = (5 * k + 3) / 4;
-    return a > b ? a : b;
+    const int b = (5 * k + 3) / 4;
+    return (b + 63) / 64 * 64;
 }
 
 }  // namespace mdir
@@ -86,7 +88,7 @@ extern "C" int mdir_topk_plan(int64_t n_db, int kth, int sm_count, int* route, i
     return 0;
 }
 
-extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64_t n_db, const float* q32, int n_q, int D, int k, int shortlist,
+extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, const float* db_stats, int64_t n_db, const float* q32, int n_q, int D, int k, int shortlist,
                                   uint32_t idx_base, int route, float* out_scores, int32_t* out_idx, uint64_t* out_keys, int32_t* overflow,
                                   void* ws, void* stream) {
     MDIR_CHECK_ARG(db16 && q32 && ws && out_scores && out_idx && overflow);
@@ -105,12 +107,8 @@ extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64
     const int64_t n_tiles = (n_db + kTile - 1) / kTile;
 
     // route planning (the same rules as mdir_b200/search.py:Index._plan / _fused_ok; tests/test_cpu_boundary.py compares them)
-    static int sm_count = 0;
-    if (!sm_count) {
-        int dev = 0;
-        MDIR_CUDA(cudaGetDevice(&dev));
-        MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    const int sm_count = device_sm_count();
+    MDIR_CHECK_ARG(sm_count > 0);
     int plan_route = 0, n_sample = 0, stride = 0;
     if (route == 0) mdir_topk_plan(n_db, kth, sm_count, &plan_route, &n_sample, &stride);
     const bool fused = plan_route == 1;
@@ -144,7 +142,7 @@ extern "C" int mdir_sim_topk_bf16(const uint16_t* db16, const float* db32, int64
     const int64_t cand_row = cap0 + 148 * (int64_t)cap_l;
     if (db32)
         return mdir_topk_finalize_rescore(w.cand, cand_row, w.segcnt, MDIR_CAND_SEGS, cap0, cap_l, n_q, kth, k, db32, n_db, idx_base, q32, D,
-                                          out_scores, out_idx, out_keys, w.tau, overflow, stream);
+                                          db_stats, out_scores, out_idx, out_keys, w.tau, overflow, stream);
     return mdir_topk_finalize(w.cand, cand_row, w.segcnt, MDIR_CAND_SEGS, cap0, cap_l, n_q, k, out_scores, out_idx, out_keys, w.tau, overflow,
                               stream);
 }

@@ -255,11 +255,9 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
     }
     MDIR_LAUNCH_CHECK();
     constexpr size_t kScatterSmem = (size_t)(2 * kChunk + kScatterWarps * 256 + 256 + 8) * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first() != 0)
         MDIR_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem));
-        attr_set = true;
-    }
     uint32_t *kin = kA, *kout = kB, *vin = nullptr, *vout = vA;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 8 * pass;

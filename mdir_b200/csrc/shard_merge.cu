@@ -46,9 +46,11 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 // grid = n_q CTAs of 256 threads; dynamic smem = world * k * 8 bytes
 __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_t* __restrict__ local_keys, int n_q, int k, int rank, int world,
                                                                    int max_q, int max_k, int mode, Mailboxes mbs,
-                                                                   float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
+                                                                   float* __restrict__ out_scores, int32_t* __restrict__ out_idx,
+                                                                   const int32_t* __restrict__ local_status, int32_t* __restrict__ out_status) {
     extern __shared__ uint64_t sk[];
     __shared__ int s_fail;
+    __shared__ uint32_t s_status;
     const int q = blockIdx.x;
     uint8_t* mine = mbs.base[rank];
     uint32_t* hdr = reinterpret_cast<uint32_t*>(mine);
@@ -56,7 +58,11 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
     const uint32_t seq = mode == kExchangeFlush ? last : last + 1u;            // step pushed by this launch (none when flushing)
     const uint32_t mseq = mode == kExchangeDeferred ? seq - 1u : seq;          // step merged by this launch
     const int parity = (int)(seq & (kMailBufs - 1));
-    if (threadIdx.x == 0) s_fail = 0;
+    if (threadIdx.x == 0) { s_fail = 0; s_status = 0u; }
+    // The flag word carries the sequence number AND this rank's 2-bit status of the query (candidate overflow /
+    // failed shortlist certificate): every rank ORs the world's statuses, so all of them agree on which queries of
+    // the merged step need the (collective) recovery -- a rank never silently merges a peer's incomplete keys.
+    const uint32_t my_status = (local_status && mode != kExchangeFlush) ? ((uint32_t)local_status[q] & 3u) : 0u;
 
     // 1. push this rank's keys of query q into every mailbox (own included), then publish the flag
     if (mode != kExchangeFlush) {
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
     if (threadIdx.x < world) {
         if (mode != kExchangeFlush) {
             __threadfence_system();       // one cumulative system-scope fence per flag writer, not one per thread
-            st_release_sys(mb_flags(mbs.base[threadIdx.x], world, max_q, parity, rank) + q, seq);
+            st_release_sys(mb_flags(mbs.base[threadIdx.x], world, max_q, parity, rank) + q, (seq << 2) | my_status);
         }
         // 2. wait for source rank threadIdx.x's keys of query q of the step being merged (bounded: ~2 s, then report
         //    instead of hanging)
@@ -77,7 +83,8 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
             const uint32_t* f = mb_flags(mine, world, max_q, (int)(mseq & (kMailBufs - 1)), threadIdx.x) + q;
             bool ok = false;
             for (int it = 0; it < (1 << 24); ++it) {
-                if (ld_acquire_sys(f) == mseq) { ok = true; break; }
+                const uint32_t v = ld_acquire_sys(f);
+                if ((v >> 2) == (mseq & 0x3fffffffu)) { ok = true; if (v & 3u) atomicOr(&s_status, v & 3u); break; }
                 __nanosleep(100);
             }
             if (!ok) s_fail = 1;
@@ -85,6 +92,7 @@ __global__ void __launch_bounds__(256) shard_exchange_merge_kernel(const uint64_
     }
     __syncthreads();
     const int mpar = (int)(mseq & (kMailBufs - 1));
+    if (threadIdx.x == 0 && out_status) out_status[q] = (int32_t)(s_status | (s_fail ? 4u : 0u));
     if (s_fail || mseq == 0u) {
         if (threadIdx.x == 0 && s_fail) hdr[2] = 1u;                            // status: a peer never arrived
         for (int j = threadIdx.x; j < k; j += blockDim.x) {
@@ -196,7 +204,8 @@ extern "C" int mdir_p2p_free(void* ptr) {
 // step without pushing (the drain after a run of mode-1 calls).  status = word 2 of the
 // own mailbox header (mdir_shard_status): non-zero after a peer failed to arrive within the bounded wait.
 extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, int k, int rank, int world, int max_q, int max_k, int mode,
-                                         void* const* mailboxes, float* out_scores, int32_t* out_idx, void* stream) {
+                                         void* const* mailboxes, float* out_scores, int32_t* out_idx, const int32_t* local_status,
+                                         int32_t* out_status, void* stream) {
     MDIR_CHECK_ARG(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world && n_q >= 0 && n_q <= max_q && k >= 1 && k <= max_k);
     MDIR_CHECK_ARG(world * (int64_t)k <= 16384 && mode >= kExchangeSync && mode <= kExchangeFlush);
     if (n_q == 0) return 0;
@@ -205,12 +214,11 @@ extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, in
     for (int r = 0; r < kMaxWorld; ++r) mbs.base[r] = r < world ? static_cast<uint8_t*>(mailboxes[r]) : nullptr;
     for (int r = 0; r < world; ++r) MDIR_CHECK_ARG(mbs.base[r] != nullptr);
     const size_t smem = (size_t)world * k * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first() != 0)
         MDIR_CUDA(cudaFuncSetAttribute(shard_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-        attr_set = true;
-    }
-    shard_exchange_merge_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(local_keys, n_q, k, rank, world, max_q, max_k, mode, mbs, out_scores, out_idx);
+    shard_exchange_merge_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(local_keys, n_q, k, rank, world, max_q, max_k, mode, mbs, out_scores, out_idx,
+                                                                          local_status, out_status);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

@@ -586,12 +586,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     } else if (mode == MDIR_SCAN_FUSED) {
         // one sample tile per CTA, all CTAs co-resident (the in-kernel arrival counters rely on it)
         MDIR_CHECK_ARG(tau_rw && fused_ws && cand && seg_counts && cap_l >= 1 && kth >= 1);
-        static int sm_count = 0;
-        if (!sm_count) {
-            int dev = 0;
-            MDIR_CUDA(cudaGetDevice(&dev));
-            MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        }
+        const int sm_count = device_sm_count();
+        MDIR_CHECK_ARG(sm_count > 0);
         int g = sm_count < kNumSMs ? sm_count : kNumSMs;
         if (g > p.n_tiles / 2) g = p.n_tiles / 2;
         MDIR_CHECK_ARG(g >= 1);
@@ -633,11 +629,10 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     rc = make_tmap(&tmap_q, tf32, q, (uint64_t)n_q, (uint64_t)D, (uint32_t)p.n_pad);
     if (rc) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce once;
+    if (once.first() != 0) {
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
-        attr_set = true;
     }
     const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (p.n_work < kNumSMs ? p.n_work : kNumSMs);
     if (tf32) sim_scan_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
@@ -843,8 +838,13 @@ extern "C" int mdir_whiten_project_tc(const float* v, const float* m, int n, int
 
     // fork: odd blocks run on an internal stream (created once per process), joined before returning; both the fork
     // and the join are event edges, so the whole thing is capturable into a CUDA graph
-    static cudaStream_t side = nullptr;
-    static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    static cudaStream_t side_dev[kMaxDevices] = {};
+    static cudaEvent_t ev_fork_dev[kMaxDevices] = {}, ev_join_dev[kMaxDevices] = {};
+    int cur_dev = 0;
+    MDIR_CUDA(cudaGetDevice(&cur_dev));
+    MDIR_CHECK_ARG(cur_dev >= 0 && cur_dev < kMaxDevices);
+    cudaStream_t& side = side_dev[cur_dev];
+    cudaEvent_t &ev_fork = ev_fork_dev[cur_dev], &ev_join = ev_join_dev[cur_dev];
     cudaStream_t main_st = (cudaStream_t)stream;
     if (conc > 1) {
         if (!side) {

@@ -373,52 +373,86 @@ __device__ __forceinline__ float rescore_row(const float* __restrict__ a, const 
     return warp_sum(acc);
 }
 
+// Rescore entries [j0, j0 + n) of the key list at shared-memory address `list` of cluster rank 0 (DSMEM when this
+// CTA is a helper): one warp per row, rows interleaved over the CS CTAs of the cluster.
+template <int CS>
+__device__ __forceinline__ void rescore_share(uint64_t* local_list, uint32_t remote_list, bool remote, int j0, int n, int crank,
+                                              const float* __restrict__ db32, int64_t n_db, uint32_t idx_base, const float* qs, int D) {
+    const int lane = threadIdx.x & 31;
+    for (int j = (threadIdx.x >> 5) * CS + crank; j < n; j += 32 * CS) {
+        const uint64_t key = remote ? cluster_ld_u64(remote_list + 8u * (uint32_t)(j0 + j)) : local_list[j0 + j];
+        const uint32_t gi = (uint32_t)key;
+        const int64_t row = (int64_t)gi - (int64_t)idx_base;
+        uint64_t nkey = ~0ull;
+        if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
+        __syncwarp();
+        if (lane == 0) {
+            if (remote) cluster_st_u64(remote_list + 8u * (uint32_t)(j0 + j), nkey);
+            else local_list[j0 + j] = nkey;
+        }
+    }
+}
+
 // One CTA (1024 threads) per query.  The candidates of a query live in n_seg segments of its
 // cand row (segment 0: cap0 slots, the others cap_l slots each; seg_counts holds how many each
 // producer appended).  They are compacted into shared memory; when there are many more than k,
 // the k best are first isolated by an in-smem MSB radix select (keys are unique) and only those
-// are sorted.  dynamic smem = (smem_cap + kpow2) * 8 bytes.
+// are sorted.  dynamic smem = (smem_cap + sl_cap) * 8 (+ D * 4 when re-scoring) bytes.
+//
+// Re-scoring (db32 != NULL) with the shortlist CERTIFICATE (db_stats != NULL).  The k best keys by bf16 score are
+// re-scored exactly in fp32 (one warp per row).  Let t be the k_out-th best fp32 score among them and eps a bound
+// on |bf16-path score - fp32 score| for any database row against this query:
+//     eps = max_r ||bf16(x_r) - x_r|| * ||bf16(q)||  +  max_r ||x_r|| * ||bf16(q) - q||        (Cauchy-Schwarz on the
+//           + 1.25 * D * 2^-24 * max_r ||x_r|| * ||q||                                          two rounding residuals,
+// (db_stats = {max_r ||bf16(x_r) - x_r||^2, max_r ||x_r||^2}, from mdir_pack_stats).           + fp32 accumulation)
+// A row whose bf16 score is below t - eps cannot reach the fp32 top k_out.  Every candidate at or above t - eps that
+// is not yet in the shortlist is appended ("extension") and re-scored too; t can only rise, so one round suffices.
+// The answer is then PROVEN equal to the exact fp32 top k_out of the whole shard provided the candidate list
+// contains every row with bf16 score >= t - eps, i.e. the filter threshold tau[q] is not tighter than that bound
+// and nothing overflowed.  Otherwise status bit 1 (uncertified) is raised and the host widens the selection.
+// status[q]: bit 0 = a candidate segment / the staging area overflowed, bit 1 = not certified.
 template <int CS>      // CS = CTAs per query (thread-block cluster size): rank 0 selects and sorts, all ranks share the fp32 re-scoring
 __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __restrict__ cand, int64_t cand_row,
                                                              const uint32_t* __restrict__ seg_counts, int n_seg, int cap0, int cap_l,
-                                                             int k, int smem_cap, float* __restrict__ out_scores,
+                                                             int k, int smem_cap, int sl_cap, float* __restrict__ out_scores,
                                                              int32_t* __restrict__ out_idx, uint64_t* __restrict__ out_keys,
                                                              uint64_t* __restrict__ tau, int32_t* __restrict__ overflow,
                                                              const float* __restrict__ db32, int64_t n_db, uint32_t idx_base,
-                                                             const float* __restrict__ q32, int D, int k_out) {
+                                                             const float* __restrict__ q32, int D, int k_out,
+                                                             const float* __restrict__ db_stats) {
     extern __shared__ uint64_t skeys[];
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_k, s_done, s_out;
     __shared__ int s_off[MDIR_CAND_SEGS + 1];
     __shared__ int s_ovf;
-    __shared__ int s_hdr[2];                      // rank 0 -> helpers: {shortlist length, offset of the shortlist in skeys}
-    uint64_t* sorted = skeys + smem_cap;          // kpow2 entries
+    __shared__ int s_hdr[3];                      // rank 0 -> helpers: {shortlist length, offset of the list in skeys, extension length}
+    __shared__ uint64_t s_tkey;
+    __shared__ float s_red[32];
+    uint64_t* sorted = skeys + smem_cap;          // sl_cap entries: the sorted selection; with re-scoring the shortlist + its extension
     const int q = blockIdx.x / CS;
     const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
     const int lane = threadIdx.x & 31;
     int kpow2 = 32;
     while (kpow2 < k) kpow2 <<= 1;
     if (CS > 1 && crank != 0) {
-        // helper CTA of the cluster: stage the query, wait for rank 0's shortlist, re-score its share of the rows
-        float* qs = reinterpret_cast<float*>(sorted + kpow2);
+        // helper CTA of the cluster: stage the query, then re-score its share of the shortlist and of the extension
+        float* qs = reinterpret_cast<float*>(sorted + sl_cap);
         for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = q32[(int64_t)q * D + i];
         __syncthreads();
         cluster_sync_all();                                            // (1) shortlist ready in rank 0's shared memory
         const int nk = cluster_ld_s32(cluster_map(&s_hdr[0], 0));
         const int off = cluster_ld_s32(cluster_map(&s_hdr[1], 0));
         const uint32_t rk0 = cluster_map(skeys + off, 0);
-        for (int j = (threadIdx.x >> 5) * CS + crank; j < nk; j += 32 * CS) {
-            const uint64_t key = cluster_ld_u64(rk0 + 8u * (uint32_t)j);
-            const uint32_t gi = (uint32_t)key;
-            const int64_t row = (int64_t)gi - (int64_t)idx_base;
-            uint64_t nkey = ~0ull;
-            if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
-            if (lane == 0) cluster_st_u64(rk0 + 8u * (uint32_t)j, nkey);
-        }
+        rescore_share<CS>(nullptr, rk0, true, 0, nk, crank, db32, n_db, idx_base, qs, D);
         cluster_sync_all();                                            // (2) every share is back in rank 0
+        cluster_sync_all();                                            // (3) extension ready
+        const int n_ext = cluster_ld_s32(cluster_map(&s_hdr[2], 0));
+        rescore_share<CS>(nullptr, rk0, true, nk, n_ext, crank, db32, n_db, idx_base, qs, D);
+        cluster_sync_all();                                            // (4) extension shares are back
         return;
     }
+    const uint64_t tau_in = tau ? tau[q] : ~0ull;
     // segment offsets (exclusive scan of the clamped counts) by warp 0
     if (threadIdx.x < 32) {
         int run = 0, ovf = 0;
@@ -520,38 +554,113 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         res = sorted;
         nres = min(cnt, k);
     }
-    if (threadIdx.x == 0 && overflow) {
-        overflow[q] = ovf_any ? 1 : 0;
-        if (ovf_any && tau && nres > 0) tau[q] = res[min(k, nres) - 1];
-    }
+    int status = ovf_any ? 1 : 0;
+    if (threadIdx.x == 0 && ovf_any && tau && nres > 0) tau[q] = res[min(k, nres) - 1];
     int k_emit = k;
     if (db32) {
-        // fused exact re-scoring: the k best keys by bf16 score are a shortlist; recompute their dot
-        // products in fp32 from the master copy (one warp per row, the query staged in shared memory),
-        // re-sort, and emit the best k_out.
-        uint64_t* rk = const_cast<uint64_t*>(res);
-        float* qs = reinterpret_cast<float*>(sorted + kpow2);
-        for (int i = threadIdx.x; i < D; i += blockDim.x) qs[i] = q32[(int64_t)q * D + i];
+        // ---- exact fp32 re-scoring of the bf16 shortlist (+ certified extension) ----
+        uint64_t* sl = sorted;
+        float* qs = reinterpret_cast<float*>(sorted + sl_cap);
         const int nk = min(k, nres);
-        if (threadIdx.x == 0) { s_hdr[0] = nk; s_hdr[1] = (int)(rk - skeys); }
+        if (res != sl) {                           // small candidate sets were sorted in place: move the shortlist out
+            for (int j = threadIdx.x; j < nk; j += blockDim.x) sl[j] = res[j];
+        }
+        float q2 = 0.f, qt2 = 0.f, qf2 = 0.f;
+        for (int i = threadIdx.x; i < D; i += blockDim.x) {
+            const float v = q32[(int64_t)q * D + i];
+            qs[i] = v;
+            const float vt = __bfloat162float(__float2bfloat16_rn(v));
+            q2 = fmaf(v, v, q2);
+            qt2 = fmaf(vt, vt, qt2);
+            qf2 = fmaf(v - vt, v - vt, qf2);
+        }
+        if (threadIdx.x == 0) { s_hdr[0] = nk; s_hdr[1] = (int)(sl - skeys); s_hdr[2] = 0; s_out = 0u; s_tkey = ~0ull; }
+        __syncthreads();
+        const uint64_t last16 = nk > 0 ? sl[nk - 1] : 0ull;          // worst bf16 key inside the shortlist
+        float eps = 0.f;
+        if (db_stats) {
+            q2 = block_sum(q2, s_red);
+            qt2 = block_sum(qt2, s_red);
+            qf2 = block_sum(qf2, s_red);
+            const float e_max = sqrtf(db_stats[0]), x_max = sqrtf(db_stats[1]);
+            eps = e_max * sqrtf(qt2) + x_max * sqrtf(qf2) + 1.25f * (float)D * 5.9604645e-8f * x_max * sqrtf(q2);
+            eps = eps * 1.001f + 1e-7f;                              // slack for evaluating the bound itself in fp32
+        }
         __syncthreads();
         if (CS > 1) cluster_sync_all();                                // (1) helpers may read the shortlist
-        for (int j = (threadIdx.x >> 5) * CS; j < nk; j += 32 * CS) {
-            const uint64_t key = rk[j];
-            const uint32_t gi = (uint32_t)key;
-            const int64_t row = (int64_t)gi - (int64_t)idx_base;
-            uint64_t nkey = ~0ull;
-            if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
-            __syncwarp();
-            if (lane == 0) rk[j] = nkey;
-        }
+        rescore_share<CS>(sl, 0u, false, 0, nk, 0, db32, n_db, idx_base, qs, D);
         if (CS > 1) cluster_sync_all();                                // (2) helpers' shares have landed
-        for (int j = nk + threadIdx.x; j < kpow2; j += blockDim.x) rk[j] = ~0ull;
         __syncthreads();
-        bitonic_sort_smem(rk, kpow2);
-        nres = nk;
+        int n_ext = 0;
+        if (db_stats) {
+            // t = k_out-th best re-scored key (rank counting; the in-place bitonic sort when the shortlist is long)
+            if (nk >= k_out) {
+                if (nk <= 1024) {
+                    if ((int)threadIdx.x < nk) {
+                        const uint64_t mine = sl[threadIdx.x];
+                        int r = 0;
+                        for (int j = 0; j < nk; ++j) {
+                            const uint64_t o = sl[j];
+                            r += (o < mine || (o == mine && j < (int)threadIdx.x)) ? 1 : 0;
+                        }
+                        if (r == k_out - 1) s_tkey = mine;
+                    }
+                } else {
+                    for (int j = nk + threadIdx.x; j < kpow2; j += blockDim.x) sl[j] = ~0ull;
+                    __syncthreads();
+                    bitonic_sort_smem(sl, kpow2);
+                    if (threadIdx.x == 0) s_tkey = sl[k_out - 1];
+                }
+            }
+            __syncthreads();
+            const uint64_t tkey = s_tkey;
+            // every row whose bf16 score is >= t - eps must be re-scored: bound key B (all index bits set)
+            const uint64_t bound = tkey == ~0ull ? ~0ull : ((uint64_t)desc_key(key_score(tkey) - eps) << 32) | 0xffffffffull;
+            const int ext_cap = sl_cap - nk;
+            for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const uint64_t key = skeys[i];
+                if (key > last16 && key <= bound && key != ~0ull) {
+                    const uint32_t pos = atomicAdd(&s_out, 1u);
+                    if (pos < (uint32_t)ext_cap) sl[nk + pos] = key;
+                }
+            }
+            __syncthreads();
+            n_ext = min((int)s_out, ext_cap);
+            // complete iff the candidate list holds every row with key <= bound: tau not tighter, nothing dropped
+            if ((int)s_out > ext_cap || bound > tau_in || ovf_any) status |= 2;
+            if (threadIdx.x == 0) s_hdr[2] = n_ext;
+            __syncthreads();
+        }
+        if (CS > 1) cluster_sync_all();                                // (3) helpers may read the extension
+        rescore_share<CS>(sl, 0u, false, nk, n_ext, 0, db32, n_db, idx_base, qs, D);
+        if (CS > 1) cluster_sync_all();                                // (4) extension shares have landed
+        __syncthreads();
+        const int n_all = nk + n_ext;
+        if (n_all <= 1024) {
+            // rank-counting sort into the (no longer needed) candidate staging area
+            if ((int)threadIdx.x < n_all) {
+                const uint64_t mine = sl[threadIdx.x];
+                int r = 0;
+                for (int j = 0; j < n_all; ++j) {
+                    const uint64_t o = sl[j];
+                    r += (o < mine || (o == mine && j < (int)threadIdx.x)) ? 1 : 0;
+                }
+                skeys[r] = mine;
+            }
+            __syncthreads();
+            res = skeys;
+        } else {
+            int n = 32;
+            while (n < n_all) n <<= 1;
+            for (int j = n_all + threadIdx.x; j < n; j += blockDim.x) sl[j] = ~0ull;
+            __syncthreads();
+            bitonic_sort_smem(sl, n);
+            res = sl;
+        }
+        nres = n_all;
         k_emit = k_out;
     }
+    if (threadIdx.x == 0 && overflow) overflow[q] = status;
     for (int j = threadIdx.x; j < k_emit; j += blockDim.x) {
         const uint64_t key = j < nres ? res[j] : ~0ull;
         const bool ok = j < nres && key != ~0ull;
@@ -693,7 +802,8 @@ extern "C" int mdir_select_kth(const float* scores, int64_t ld, int64_t n, int n
 
 static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0, int cap_l, int n_q,
                            int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau, int32_t* overflow,
-                           const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int D, int k_out, void* stream) {
+                           const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int D, int k_out, const float* db_stats,
+                           void* stream) {
     MDIR_CHECK_ARG(cand && seg_counts && n_seg >= 1 && n_seg <= MDIR_CAND_SEGS && cap0 >= 0 && n_q >= 0 && k >= 1 && k <= 4096);
     MDIR_CHECK_ARG(n_seg == 1 || cap_l >= 1);
     MDIR_CHECK_ARG(cand_row >= (int64_t)cap0 + (int64_t)(n_seg - 1) * cap_l);
@@ -705,23 +815,22 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
     int smem_cap = 1024;
     while (smem_cap < want && smem_cap < 16384) smem_cap <<= 1;
     if (smem_cap < 2 * kpow2) smem_cap = 2 * kpow2;
-    size_t smem = (size_t)(smem_cap + kpow2) * 8;
+    // with re-scoring the selection area also takes the certified extension of the shortlist (as many keys again)
+    const int sl_cap = db32 ? 2 * kpow2 : kpow2;
+    size_t smem = (size_t)(smem_cap + sl_cap) * 8;
     if (db32) {
         MDIR_CHECK_ARG(q32 && D > 0 && D <= 8192 && k_out >= 1 && k_out <= k && n_db >= 0);
         MDIR_CHECK_ARG((((uintptr_t)db32 | (uintptr_t)q32) & 15) == 0);
+        MDIR_CHECK_ARG(db_stats == nullptr || tau != nullptr);          // the certificate compares against the filter threshold
         smem += (size_t)D * 4;
     }
-    static bool attr_set = false;
-    static int sm_count = 0;
-    if (!attr_set) {
-        const int max_smem = (16384 + 4096) * 8 + 8192 * 4;
+    static PerDeviceOnce once;
+    if (once.first() != 0) {
+        const int max_smem = (16384 + 8192) * 8 + 8192 * 4;
         MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        int dev = 0;
-        MDIR_CUDA(cudaGetDevice(&dev));
-        MDIR_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-        attr_set = true;
     }
+    const int sm_count = device_sm_count();
     // fp32 re-scoring gathers shortlist x D x 4 bytes per query from one CTA; while the batch leaves SMs idle, a
     // 2-CTA cluster per query splits those rows (rank 1 reads / writes the shortlist through distributed shared memory)
     if (db32 && 2 * n_q <= sm_count) {
@@ -737,14 +846,14 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        MDIR_CUDA(cudaLaunchKernelEx(&cfg, topk_finalize_kernel<2>, cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap, out_scores,
-                                     out_idx, out_keys, tau, overflow, db32, n_db, idx_base, q32, D, k_out));
+        MDIR_CUDA(cudaLaunchKernelEx(&cfg, topk_finalize_kernel<2>, cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap, sl_cap, out_scores,
+                                     out_idx, out_keys, tau, overflow, db32, n_db, idx_base, q32, D, k_out, db_stats));
         MDIR_LAUNCH_CHECK();
         return 0;
     }
-    topk_finalize_kernel<1><<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap,
+    topk_finalize_kernel<1><<<n_q, 1024, smem, (cudaStream_t)stream>>>(cand, cand_row, seg_counts, n_seg, cap0, cap_l, k, smem_cap, sl_cap,
                                                                         out_scores, out_idx, out_keys, tau, overflow, db32, n_db, idx_base,
-                                                                        q32, D, k_out);
+                                                                        q32, D, k_out, db_stats);
     MDIR_LAUNCH_CHECK();
     return 0;
 }
@@ -753,16 +862,56 @@ extern "C" int mdir_topk_finalize(const uint64_t* cand, int64_t cand_row, const 
                                   int n_q, int k, float* out_scores, int32_t* out_idx, uint64_t* out_keys, uint64_t* tau,
                                   int32_t* overflow, void* stream) {
     return launch_finalize(cand, cand_row, seg_counts, n_seg, cap0, cap_l, n_q, k, out_scores, out_idx, out_keys, tau, overflow, nullptr, 0,
-                           0, nullptr, 0, 0, stream);
+                           0, nullptr, 0, 0, nullptr, stream);
 }
 
 extern "C" int mdir_topk_finalize_rescore(const uint64_t* cand, int64_t cand_row, const uint32_t* seg_counts, int n_seg, int cap0,
                                           int cap_l, int n_q, int shortlist, int k_out, const float* db32, int64_t n_db,
-                                          uint32_t idx_base, const float* q32, int D, float* out_scores, int32_t* out_idx,
-                                          uint64_t* out_keys, uint64_t* tau, int32_t* overflow, void* stream) {
+                                          uint32_t idx_base, const float* q32, int D, const float* db_stats, float* out_scores,
+                                          int32_t* out_idx, uint64_t* out_keys, uint64_t* tau, int32_t* overflow, void* stream) {
     MDIR_CHECK_ARG(db32 != nullptr);
     return launch_finalize(cand, cand_row, seg_counts, n_seg, cap0, cap_l, n_q, shortlist, out_scores, out_idx, out_keys, tau, overflow,
-                           db32, n_db, idx_base, q32, D, k_out, stream);
+                           db32, n_db, idx_base, q32, D, k_out, db_stats, stream);
+}
+
+// db_stats for the shortlist certificate: {max_r ||bf16(x_r) - x_r||^2, max_r ||x_r||^2} over the rows of a shard.
+// Non-negative floats order like their bit patterns, so the maxima are atomicMax on the uint view.
+namespace mdir {
+__global__ void __launch_bounds__(256) pack_stats_kernel(const float* __restrict__ db32, const __nv_bfloat16* __restrict__ db16, int64_t n, int D,
+                                                         uint32_t* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float e_max = 0.f, x_max = 0.f;
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += warps) {
+        const float* a = db32 + r * D;
+        const __nv_bfloat16* b = db16 + r * D;
+        float e2 = 0.f, x2 = 0.f;
+        for (int i = lane; i < D; i += 32) {
+            const float x = a[i];
+            const float d = __bfloat162float(b[i]) - x;
+            e2 = fmaf(d, d, e2);
+            x2 = fmaf(x, x, x2);
+        }
+        e_max = fmaxf(e_max, warp_sum(e2));
+        x_max = fmaxf(x_max, warp_sum(x2));
+    }
+    if (lane == 0) {
+        // 1 ulp-scale head room for the order of the fp32 summation above
+        atomicMax(&stats[0], __float_as_uint(e_max * 1.0001f));
+        atomicMax(&stats[1], __float_as_uint(x_max * 1.0001f));
+    }
+}
+}  // namespace mdir
+
+extern "C" int mdir_pack_stats(const float* db32, const uint16_t* db16, int64_t n, int D, float* stats, void* stream) {
+    MDIR_CHECK_ARG(db32 && db16 && stats && n >= 0 && D > 0);
+    MDIR_CUDA(cudaMemsetAsync(stats, 0, 2 * sizeof(float), (cudaStream_t)stream));
+    if (n == 0) return 0;
+    const int64_t blocks = (n + 7) / 8;
+    pack_stats_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        db32, reinterpret_cast<const __nv_bfloat16*>(db16), n, D, reinterpret_cast<uint32_t*>(stats));
+    MDIR_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int mdir_rescore_f32(const float* db32, int64_t n_db, uint32_t idx_base, const float* q32, int n_q, int D,

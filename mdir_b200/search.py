@@ -32,11 +32,16 @@ FUSED_CAP_L = CAND_ROW // 148   # one-launch route: no select segment, so each C
 TARGET_CAND = 4500    # candidates per query the sampling plan aims for (kth * n_tiles / n_sample), ~30 per CTA segment
 
 
+STATUS_OVERFLOW, STATUS_UNCERTIFIED, STATUS_PEER_TIMEOUT = 1, 2, 4     # MDIR_STATUS_* (+ the exchange's own bit)
+MAX_KTH = 4096        # deepest selection the finalize kernel stages
+
+
 def default_shortlist(k):
-    """bf16 shortlist size for an exact fp32 top-k: bf16 score noise (~3e-5 at D=2048 on unit vectors)
-    is ~40x smaller than the score gap between rank k and rank k+32 of a 1M-row database, so the true
-    fp32 top-k lies inside the bf16 top-(k+32)."""
-    return max(int(k) + 32, -(-5 * int(k) // 4))
+    """Initial bf16 shortlist for an exact fp32 top-k: 1.25 k rounded up to a multiple of 64 (whole rounds of the
+    2 x 32 re-scoring warps).  It only has to be a good first guess: the finalize kernel extends it with every
+    candidate whose bf16 score is within the certified error bound of the k-th fp32 score, and flags the query
+    when even the candidate list is not provably deep enough (mdir_topk_finalize_rescore)."""
+    return -(-(-(-5 * int(k) // 4)) // 64) * 64
 
 
 def _as_dev_f32(x, device):
@@ -69,6 +74,7 @@ class Index:
     """A (shard of a) descriptor database on one GPU."""
 
     fused = True      # allow the one-launch threshold + filter route (False: always sample -> select -> filter)
+    certify = True    # precision="fp32": prove the shortlist complete (status bit 2 + widening when it cannot be)
     _sms = None
 
     def __init__(self, vecs, dxn=False, device="cuda", keep_fp32=True, idx_base=0):
@@ -85,6 +91,8 @@ class Index:
         if keep_fp32:
             self.db32 = v.t().contiguous() if dxn else v
         self._ws = {}
+        self._stats = None
+        self.cert = {"queries": 0, "flagged": 0, "widened_blocks": 0, "uncertified": 0}
 
     @classmethod
     def from_packed(cls, db16, db32=None, idx_base=0):
@@ -95,7 +103,22 @@ class Index:
         self.db32 = db32
         self.idx_base = int(idx_base)
         self._ws = {}
+        self._stats = None
+        self.cert = {"queries": 0, "flagged": 0, "widened_blocks": 0, "uncertified": 0}
         return self
+
+    def stats(self):
+        """Device float32[2] = {max_r ||bf16(x_r) - x_r||^2, max_r ||x_r||^2}: the database half of the shortlist
+        certificate's error bound (mdir_pack_stats; one pass over the shard, cached)."""
+        if self._stats is None:
+            if self.db32 is None:
+                raise _lib.MdirError("the shortlist certificate needs the fp32 master copy (keep_fp32=True)")
+            st = torch.zeros((2,), dtype=torch.float32, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().mdir_pack_stats(_lib.ptr(self.db32), _lib.ptr(self.db16), self.n, self.D, _lib.ptr(st), _lib.stream()),
+                           "mdir_pack_stats")
+            self._stats = st
+        return self._stats
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name, shape, dtype):
@@ -156,10 +179,11 @@ class Index:
                                                      _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize")
         else:
             q32, k_out = rescore
+            stats = self.stats() if self.certify else None
             _lib.check(_lib.lib().mdir_topk_finalize_rescore(_lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, CAP_L, nq, kth, k_out,
                                                              _lib.ptr(self.db32), self.n, self.idx_base, _lib.ptr(q32), self.D,
-                                                             _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys), _lib.ptr(tau),
-                                                             _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize_rescore")
+                                                             _lib.ptr(stats), _lib.ptr(out_scores), _lib.ptr(out_idx), _lib.ptr(out_keys),
+                                                             _lib.ptr(tau), _lib.ptr(ovf), _lib.stream()), "mdir_topk_finalize_rescore")
 
     def _dense_block(self, q16, kth, out_scores, out_idx, out_keys, ovf, rescore=None):
         """All scores of the block -> exact kth-key select -> sort.  The route for small databases
@@ -272,15 +296,42 @@ class Index:
 
     def _run_block(self, q16, kth, out_s, out_i, out_k, ovf, check, rescore=None):
         self._topk_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
-        if check and bool(ovf.any().item()):
+        if not check:
+            return
+        st = ovf.cpu()
+        self.cert["queries"] += int(st.numel())
+        if bool((st & STATUS_OVERFLOW).any()):
             # a candidate segment overflowed (adversarial row order / massive ties): exact dense route
             self._dense_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
-            if bool(ovf.any().item()):
+            st = ovf.cpu()
+            if bool((st & STATUS_OVERFLOW).any()):
                 raise _lib.MdirError("dense recovery overflowed (internal error)")
+        if rescore is None:
+            return
+        self.cert["flagged"] += int((st & STATUS_UNCERTIFIED).ne(0).sum())
+        # the shortlist certificate failed for some query: the candidate list was not provably deep enough.  Widen the
+        # selection (x2 per round; deeper kth = lower threshold = more candidates) until it is, at most MAX_KTH rows.
+        k_max = min(self.n, MAX_KTH)
+        while bool((st & STATUS_UNCERTIFIED).any()) and kth < k_max:
+            kth = min(2 * kth, k_max)
+            self.cert["widened_blocks"] += 1
+            self._topk_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
+            st = ovf.cpu()
+            if bool((st & STATUS_OVERFLOW).any()):
+                self._dense_block(q16, kth, out_s, out_i, out_k, ovf, rescore)
+                st = ovf.cpu()
+        # still flagged: more than ~MAX_KTH rows lie within the error bound of the k-th score (massive near-ties).
+        # The best-effort answer stands; the flag stays raised in status() and the counter records it.
+        self.cert["uncertified"] += int((st & STATUS_UNCERTIFIED).ne(0).sum())
 
     def check_overflow(self):
-        """True if the last search(check=False) overflowed a candidate list (results then invalid)."""
+        """True if the last search(check=False) raised a status flag for some query (candidate overflow or a failed
+        shortlist certificate): rerun that batch through search(check=True), which recovers / widens."""
         return bool(self._ovf.any().item())
+
+    def status(self):
+        """Per-query status words of the last search (0 = exact and, for precision='fp32', certified)."""
+        return self._ovf
 
     def _split3(self, x, role):
         """(n, D) fp32 -> (n, 3D) fp32 [hi|hi|lo] (role 0) / [hi|lo|hi] (role 1) for the 3xTF32 scan."""
@@ -505,38 +556,71 @@ class ShardedIndex:
         """exchange="sync": the merged global top-k of THIS call.  exchange="deferred" (peer-memory route only, at most
         128 queries): pushes this call's keys and returns the merged result of the PREVIOUS deferred call with the same
         (n_q, k) -- its keys arrived a whole step ago, so neither the exchange latency nor the skew between ranks is
-        ever waited for; drain() returns the last one."""
+        ever waited for; drain() returns the last one.
+        status() afterwards = OR over all ranks of the per-query status words of the merged step (identical on every
+        rank): with check=False a rank whose candidate lists overflowed, or whose shortlist certificate failed, marks
+        the query for EVERY rank instead of being merged silently."""
         s, i, keys = self.local.search(q, k, precision=precision, shortlist=shortlist, check=check, return_keys=True)
+        nq_all = keys.shape[0]
+        local_status = self.local._ovf[:nq_all]
         if self.world == 1:
+            self._status = local_status
             return s, i
         if exchange not in ("sync", "deferred"):
             raise ValueError("exchange must be 'sync' or 'deferred'")
         if self._mb is None or k > self.P2P_MAX_K:
             if exchange == "deferred":
                 raise _lib.MdirError("exchange='deferred' needs the peer-memory mailboxes (and k <= %d)" % self.P2P_MAX_K)
+            bits = torch.stack([local_status & STATUS_OVERFLOW, local_status & STATUS_UNCERTIFIED])
+            if nq_all:
+                self.dist.all_reduce(bits, op=self.dist.ReduceOp.MAX, group=self.group)      # per-bit MAX = OR over the ranks
+            self._status = bits[0] | bits[1]
             return merge_keys(keys, self.world, self.group, k)
-        nq_all = keys.shape[0]
         if exchange == "deferred" and nq_all > self.P2P_MAX_Q:
             raise _lib.MdirError("exchange='deferred' handles at most %d queries per call" % self.P2P_MAX_Q)
         out_s = torch.empty((nq_all, k), dtype=torch.float32, device=self.device)
         out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
+        self._status = torch.empty((max(nq_all, 1),), dtype=torch.int32, device=self.device)[:nq_all]
         for q0 in range(0, nq_all, self.P2P_MAX_Q):
             q1 = min(q0 + self.P2P_MAX_Q, nq_all)
-            self._exchange(keys[q0:q1], q1 - q0, k, 1 if exchange == "deferred" else 0, out_s[q0:q1], out_i[q0:q1])
+            self._exchange(keys[q0:q1], q1 - q0, k, 1 if exchange == "deferred" else 0, out_s[q0:q1], out_i[q0:q1],
+                           local_status[q0:q1], self._status[q0:q1])
         return out_s, out_i
 
-    def _exchange(self, keys, nq, k, mode, out_s, out_i):
+    def status(self):
+        """Per-query status words of the step the last search()/drain() MERGED, OR-ed over the ranks (0 = exact and
+        certified everywhere; bit 0 overflow, bit 1 uncertified on some rank, bit 2 a peer never arrived)."""
+        return self._status
+
+    def check_overflow(self):
+        return bool(self._status.any().item())
+
+    def search_collective_recovery(self, q, k, precision="fp32", shortlist=None):
+        """The exact redo of a flagged batch, called by EVERY rank (the global status is identical on all of them):
+        local search with recovery / widening, then the NCCL all-gather + merge route, which does not touch the
+        mailboxes' sequence numbers and so may run between deferred steps."""
+        s, i, keys = self.local.search(q, k, precision=precision, shortlist=shortlist, check=True, return_keys=True)
+        if self.world == 1:
+            return s, i
+        return merge_keys(keys, self.world, self.group, k)
+
+    def _exchange(self, keys, nq, k, mode, out_s, out_i, local_status=None, out_status=None):
         import ctypes as C
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().mdir_shard_exchange_merge(_lib.ptr(keys), nq, k, self._rank, self.world, self.P2P_MAX_Q, self.P2P_MAX_K, mode,
-                                                            C.cast(self._mb, C.c_void_p), _lib.ptr(out_s), _lib.ptr(out_i), _lib.stream()),
+                                                            C.cast(self._mb, C.c_void_p), _lib.ptr(out_s), _lib.ptr(out_i),
+                                                            _lib.ptr(local_status), _lib.ptr(out_status), _lib.stream()),
                        "mdir_shard_exchange_merge")
 
-    def drain(self, n_q, k, out=None):
-        """Merged result of the last exchange='deferred' call (every rank calls it; nothing is pushed)."""
+    def drain(self, n_q, k, out=None, status=None):
+        """Merged result of the last exchange='deferred' call (every rank calls it; nothing is pushed).
+        status: optional (n_q) int32 device tensor receiving that step's global status words."""
         if out is None:
             out = (torch.empty((n_q, k), dtype=torch.float32, device=self.device), torch.empty((n_q, k), dtype=torch.int32, device=self.device))
-        self._exchange(None, n_q, k, 2, out[0], out[1])
+        if status is None:
+            status = torch.empty((n_q,), dtype=torch.int32, device=self.device)
+        self._status = status
+        self._exchange(None, n_q, k, 2, out[0], out[1], None, status)
         return out
 
 
@@ -654,7 +738,10 @@ class GraphedSearch:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = step()
-                self.ovf = self.local._ovf[:n_q].clone()      # this graph's own copy of the overflow flags
+                self.ovf = self.local._ovf[:n_q].clone()      # this graph's own copy of the LOCAL status words of this step
+                # status words of the step whose result `out` holds: the world's OR for a sharded index (in deferred
+                # mode that is the previous step, like `out`)
+                self.status = index._status[:n_q].clone() if isinstance(index, ShardedIndex) and index.world > 1 else self.ovf
             self.local.prof = None
 
     def __call__(self, q=None):
@@ -666,11 +753,13 @@ class GraphedSearch:
     def drain(self):
         """deferred mode: the merged result of the last replay, written into this graph's static outputs."""
         if self.deferred:
-            self.index.drain(self.n_q, self.k, out=self.out)
+            self.index.drain(self.n_q, self.k, out=self.out, status=self.status)
         return self.out
 
     def check_overflow(self):
-        return self.local.check_overflow()
+        """True when some query of the step `out` holds was flagged (overflow / uncertified shortlist, on any rank):
+        rerun that batch through index.search() (ShardedIndex: search_collective_recovery on every rank)."""
+        return bool(self.status.any().item())
 
 
 class SearchPipeline:
@@ -718,16 +807,20 @@ class SearchPipeline:
             if self.deferred:
                 self.drain_out = (torch.empty((self.n_q, self.k), dtype=torch.float32, device=dev),
                                   torch.empty((self.n_q, self.k), dtype=torch.int32, device=dev))
+                self.drain_status = torch.zeros((self.n_q,), dtype=torch.int32, device=dev)
                 with torch.cuda.stream(self.compute):          # forget the graphs' warm-up pushes
-                    index.drain(self.n_q, self.k, out=self.drain_out)
+                    index.drain(self.n_q, self.k, out=self.drain_out, status=self.drain_status)
             torch.cuda.synchronize(dev)
         self.n_submitted = 0
+        self.n_recovered = 0          # steps redone exactly because a status word was raised
 
-    def _download(self, slot, src):
-        """Queue the D2H of a merged result into `slot`'s pinned buffers (ordered after the compute stream's last event)."""
+    def _download(self, slot, src, status):
+        """Queue the D2H of a merged result and its status words into `slot`'s pinned buffers (ordered after the compute
+        stream's last event)."""
         with torch.cuda.stream(self.d2h):
             slot["scores"].copy_(src[0], non_blocking=True)
             slot["idx"].copy_(src[1], non_blocking=True)
+            slot["ovf"].copy_(status, non_blocking=True)
             slot["down"].record()
         slot["merged"] = True
 
@@ -749,13 +842,11 @@ class SearchPipeline:
             gs.graph.replay()
             slot["done"].record()
         slot["q"], slot["pending"], slot["merged"] = q, True, False
-        with torch.cuda.stream(self.d2h):
-            self.d2h.wait_event(slot["done"])
-            slot["ovf"].copy_(gs.ovf, non_blocking=True)
+        self.d2h.wait_event(slot["done"])
         if not self.deferred:
-            self._download(slot, gs.out)
+            self._download(slot, gs.out, gs.status)
         elif t_new >= 1 and self.slots[(t_new - 1) % self.depth]["pending"]:
-            self._download(self.slots[(t_new - 1) % self.depth], gs.out)        # this replay merged the previous ticket
+            self._download(self.slots[(t_new - 1) % self.depth], gs.out, gs.status)        # this replay merged the previous ticket
         self.n_submitted += 1
         return t_new
 
@@ -771,21 +862,26 @@ class SearchPipeline:
             if ticket != self.n_submitted - 1:
                 raise _lib.MdirError("SearchPipeline: collect deferred results in submission order")
             with torch.cuda.stream(self.compute):
-                self.index.drain(self.n_q, self.k, out=self.drain_out)
+                self.index.drain(self.n_q, self.k, out=self.drain_out, status=self.drain_status)
                 ev = torch.cuda.Event()
                 ev.record()
             self.d2h.wait_event(ev)
-            self._download(slot, self.drain_out)
+            self._download(slot, self.drain_out, self.drain_status)
         slot["down"].synchronize()
         slot["pending"] = False
         if bool(slot["ovf"].any()):
-            if isinstance(self.index, ShardedIndex) and self.index.world > 1:
-                # the recovery is a collective (all-gather of keys); one rank cannot start it on its own
-                raise _lib.MdirError("SearchPipeline: candidate overflow on this rank for ticket %d; rerun the batch through "
-                                     "ShardedIndex.search() on every rank" % ticket)
+            # some query of this step was flagged (candidate overflow or a failed shortlist certificate; for a sharded
+            # index on ANY rank -- the status words are the world's OR, so every rank takes this branch together)
+            self.n_recovered += 1
+            sharded = isinstance(self.index, ShardedIndex) and self.index.world > 1
+            if sharded and bool((slot["ovf"] & STATUS_PEER_TIMEOUT).any()):
+                raise _lib.MdirError("SearchPipeline: a peer rank did not deliver its keys for ticket %d within the bounded wait" % ticket)
             # exact recovery, ordered after everything already queued on the compute stream (shared workspaces)
             with torch.cuda.stream(self.compute):
-                s, i = self.index.search(slot["q"], self.k, precision=self.precision, shortlist=self.shortlist)
+                if sharded:
+                    s, i = self.index.search_collective_recovery(slot["q"], self.k, precision=self.precision, shortlist=self.shortlist)
+                else:
+                    s, i = self.index.search(slot["q"], self.k, precision=self.precision, shortlist=self.shortlist)
                 slot["scores"].copy_(s)
                 slot["idx"].copy_(i)
             self.compute.synchronize()

@@ -34,7 +34,7 @@ def test_header_symbols_exported(libpath):
         assert hasattr(l, n), "missing export " + n
     from mdir_b200 import _lib
     assert sorted(_lib.PROTOTYPES) == names, "ctypes prototypes out of sync with the header"
-    assert _lib.lib().mdir_abi_version() == 1
+    assert _lib.lib().mdir_abi_version() == _lib.ABI_VERSION
 
 
 def test_key_helpers_match_c(libpath):

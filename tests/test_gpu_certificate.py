@@ -1,0 +1,225 @@
+"""Identical top-100 on the headline configuration, and the shortlist certificate behind it.
+
+north_star: "70 queries ranked against a 1M x 2048 database ... with identical top-100 indices" to
+np.dot + np.argsort (mdir/components/optim/score/cirscore.py:69-70).  The product path is bf16 scan ->
+shortlist -> exact fp32 re-scoring; what makes that *identical* instead of *probably identical* is the
+certificate in mdir_topk_finalize_rescore (csrc/topk.cu): a Cauchy-Schwarz bound eps on |bf16 score - fp32
+score|, every candidate within eps of the k-th fp32 score re-scored, and a status bit + widening whenever the
+candidate list is not provably deep enough.
+
+The reference ranking used here is INDEPENDENT of that path: dense 3xTF32 scores of the whole database
+(mdir_sim_scan_tf32), exact k-th select, then the top rows re-scored in fp64 by torch -- itself cross-checked
+against host np.dot + a stable argsort on a 65,536-row slice.  Swaps are accepted only where the reference's own
+scores are within 2e-6 (the noise between two fp32 summation orders)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle, synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def m():
+    import mdir_b200
+    return mdir_b200
+
+
+def _unit(x):
+    return x / x.norm(dim=1, keepdim=True)
+
+
+def _fill(db, gen, make_block, step=65536):
+    for r0 in range(0, db.shape[0], step):
+        n = min(step, db.shape[0] - r0)
+        db[r0:r0 + n] = make_block(n, gen)
+
+
+def build_case(dist, n_db, D, n_q, seed, dup_per_query=200):
+    """-> (db (n_db, D) fp32 unit rows on the device, q (n_q, D), planted (n_q, P) row indices or None)."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    db = torch.empty((n_db, D), dtype=torch.float32, device=DEV)
+    if dist == "randn":
+        _fill(db, g, lambda n, gen: _unit(torch.randn((n, D), device=DEV, generator=gen)))
+    elif dist == "clusters":                                        # 1k Gaussian clusters
+        cent = torch.randn((1000, D), device=DEV, generator=g)
+
+        def blk(n, gen):
+            c = torch.randint(0, 1000, (n,), device=DEV, generator=gen)
+            return _unit(cent[c] + 0.7 * torch.randn((n, D), device=DEV, generator=gen))
+        _fill(db, g, blk)
+    elif dist == "near_dup":
+        _fill(db, g, lambda n, gen: _unit(torch.randn((n, D), device=DEV, generator=gen)))
+    else:
+        raise ValueError(dist)
+    if dist == "near_dup":
+        # dup_per_query near-duplicates of every query: q + noise ORTHOGONAL to q, so all of them score 0.9 +- 3e-3
+        # (consecutive ranks ~3e-5 apart: below the bf16 score noise of ~6e-5, far below the certified bound)
+        q = _unit(torch.randn((n_q, D), device=DEV, generator=g))
+        pos = torch.randperm(n_db, device=DEV, generator=g)[:n_q * dup_per_query].view(n_q, dup_per_query)
+        for j in range(n_q):
+            nz = torch.randn((dup_per_query, D), device=DEV, generator=g)
+            nz = nz - (nz @ q[j])[:, None] * q[j][None, :]
+            db[pos[j]] = _unit(q[j][None, :] + 0.484 * nz / D ** 0.5)
+        return db, q, pos
+    src = torch.randperm(n_db, device=DEV, generator=g)[:n_q]
+    q = _unit(db[src] + 0.5 * torch.randn((n_q, D), device=DEV, generator=g) / D ** 0.5)
+    return db, q, src[:, None]
+
+
+def independent_ranking(m, index, db, q, k_ext):
+    """Top-k_ext per query by a path that shares nothing with the bf16 shortlist machinery: dense 3xTF32 scores ->
+    exact select -> fp64 re-scoring by torch -> (score desc, index asc).  -> (idx (k_ext, nq) int64, val (k_ext, nq) fp64) numpy."""
+    dense = index.scores(q, precision="fp32")                       # (nq, n_db), 3xTF32 on the tensor cores
+    idx, _ = m.topk_from_scores(dense.t().contiguous(), k_ext + 48)
+    idx = idx.t().contiguous()                                      # (nq, k_ext + 48)
+    v64 = (db[idx.reshape(-1)].double().view(idx.shape[0], idx.shape[1], -1) * q.double()[:, None, :]).sum(-1)
+    v64, idx = v64.cpu().numpy(), idx.cpu().numpy()
+    order = np.lexsort((idx, -v64), axis=1)
+    idx, v64 = np.take_along_axis(idx, order, 1), np.take_along_axis(v64, order, 1)
+    return idx[:, :k_ext].T.copy(), v64[:, :k_ext].T.copy(), dense
+
+
+def assert_same_topk(got_i, got_s, ref_i, ref_v, tol):
+    """got (k, nq); ref (k_ext >= k + 8, nq).  Scores equal to tol position by position; every index mismatch must be a
+    swap inside a reference gap <= tol.  Returns the number of mismatching positions (all inside such gaps)."""
+    k, nq = got_i.shape
+    assert np.abs(got_s - ref_v[:k]).max() <= tol, np.abs(got_s - ref_v[:k]).max()
+    swaps = 0
+    for j in range(nq):
+        for r in np.nonzero(got_i[:, j] != ref_i[:k, j])[0]:
+            near = np.abs(ref_v[:, j] - ref_v[r, j]) <= tol
+            assert got_i[r, j] in ref_i[near, j], (j, r, got_i[r, j], ref_i[r, j])
+            swaps += 1
+    return swaps
+
+
+@pytest.mark.parametrize("dist", ["randn", "clusters", "near_dup"])
+def test_r1m_identical_top100(m, dist):
+    """BASELINE.json configs[3] at FULL size, three database distributions."""
+    n_db, D, n_q, k = 1001001, 2048, 70, 100
+    db, q, planted = build_case(dist, n_db, D, n_q, {"randn": 41, "clusters": 42, "near_dup": 43}[dist])
+    index = m.Index.from_packed(m.search.pack_bf16(db), db32=db)
+    s, i = index.search(q, k, precision="fp32")
+    torch.cuda.synchronize()
+    ref_i, ref_v, dense = independent_ranking(m, index, db, q, k + 16)
+    # the independent ranking itself, pinned on a 65,536-row slice to the reference arithmetic on the host
+    # (np.dot + stable argsort, cirscore.py:69-70 with the canonical tie rule)
+    n_s = 65536
+    sl_h = oracle.scores(db[:n_s].cpu().numpy().T, q.cpu().numpy().T)           # (n_s, nq) fp32
+    np.testing.assert_allclose(dense[:, :n_s].cpu().numpy().T, sl_h, rtol=0, atol=2e-6)
+    h_i, h_v = oracle.topk_from_scores(sl_h, k + 16)
+    d_i, d_v = m.topk_from_scores(dense[:, :n_s].t().contiguous(), k)
+    assert_same_topk(d_i.cpu().numpy(), d_v.cpu().numpy(), h_i, h_v, 4e-6)
+    del dense
+    swaps = assert_same_topk(i.cpu().numpy().T.astype(np.int64), s.cpu().numpy().T, ref_i, ref_v, 2e-6)
+    assert index.cert["uncertified"] == 0, index.cert              # every query left with a certificate
+    assert not bool(index.status().any().item())
+    i_h = i.cpu().numpy()
+    pl = planted.cpu().numpy()
+    if dist == "near_dup":                                          # the 200 planted rows fill the whole top-100
+        for j in range(n_q):
+            assert set(i_h[j].tolist()) <= set(pl[j].tolist())
+    else:
+        assert np.array_equal(i_h[:, 0], pl[:, 0])
+    print("R1M %s: %d index swaps inside 2e-6 reference gaps; certificate counters %s" % (dist, swaps, index.cert))
+
+
+def _eps_bound(index, q):
+    """numpy restatement of the bound inside topk_finalize_kernel (csrc/topk.cu)."""
+    st = index.stats().cpu().numpy().astype(np.float64)
+    qh = q.astype(np.float32)
+    qt = torch.from_numpy(qh).to(torch.bfloat16).float().numpy()
+    D = qh.shape[1]
+    return (np.sqrt(st[0]) * np.linalg.norm(qt, axis=1) + np.sqrt(st[1]) * np.linalg.norm(qh - qt, axis=1)
+            + 1.25 * D * 2.0 ** -24 * np.sqrt(st[1]) * np.linalg.norm(qh, axis=1))
+
+
+@pytest.mark.parametrize("clusters", [0, 40])
+def test_error_bound_holds_and_is_not_vacuous(m, clusters):
+    """|bf16-path score - exact score| <= eps for EVERY (row, query) pair, and eps is within ~100x of what is observed."""
+    db = synth.descriptors(60000, 512, 5, clusters=clusters)
+    q, _ = synth.planted_queries(db, 64, 6)
+    index = m.Index(db, device=DEV)
+    s16 = index.scores(q, precision="bf16").cpu().numpy().astype(np.float64)           # (nq, n_db)
+    exact = q.astype(np.float64) @ db.astype(np.float64).T
+    err = np.abs(s16 - exact).max(axis=1)
+    eps = _eps_bound(index, q)
+    assert np.all(err <= eps), (err.max(), eps.min())
+    assert np.all(eps <= 200 * np.maximum(err, 1e-6)) and eps.max() < 5e-3, (err.max(), eps.max())
+    st = index.stats().cpu().numpy()
+    resid = torch.from_numpy(db).to(torch.bfloat16).float().numpy() - db
+    assert st[0] >= (resid.astype(np.float64) ** 2).sum(1).max() and st[0] <= 1.01 * (resid.astype(np.float64) ** 2).sum(1).max()
+    assert st[1] >= (db.astype(np.float64) ** 2).sum(1).max() and st[1] <= 1.01 * (db.astype(np.float64) ** 2).sum(1).max()
+
+
+def test_certificate_extends_and_widens(m):
+    """600 near-ties per query: more rows within eps of the k-th score than the first shortlist (128) plus its
+    extension area hold -> status bit 1 -> the selection is widened until the certificate closes; the answer equals
+    the exact ranking.  With the certificate switched off the same data returns a wrong top-100."""
+    n_db, D, n_q, k, dup = 120000, 256, 6, 100, 600
+    rs = np.random.RandomState(3)
+    db = synth.descriptors(n_db, D, 70)
+    q = synth.descriptors(n_q, D, 71)
+    pos = rs.permutation(n_db)[:n_q * dup].reshape(n_q, dup)
+    for j in range(n_q):
+        nz = rs.randn(dup, D).astype(np.float32)
+        nz -= (nz @ q[j])[:, None] * q[j][None, :]
+        v = q[j][None, :] + 0.3 * nz / np.sqrt(D)
+        db[pos[j]] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    index = m.Index(db, device=DEV)
+    s, i = index.search(q, k, precision="fp32")
+    exact = q.astype(np.float64) @ db.astype(np.float64).T                      # (nq, n_db)
+    order = np.lexsort((np.broadcast_to(np.arange(n_db), exact.shape), -exact), axis=1)[:, :k + 16]
+    ref_v = np.take_along_axis(exact, order, 1)
+    assert_same_topk(i.cpu().numpy().T.astype(np.int64), s.cpu().numpy().T, order.T, ref_v.T, 2e-6)
+    assert index.cert["flagged"] > 0 and index.cert["widened_blocks"] > 0 and index.cert["uncertified"] == 0, index.cert
+    assert not bool(index.status().any().item())
+    # check=False reports instead of recovering: the status words carry bit 1
+    index.search(q, k, precision="fp32", check=False)
+    assert index.check_overflow() and bool((index.status() & 2).any().item())
+    # certificate off (the round-1 behaviour): a fixed 128-row bf16 shortlist silently misses true neighbours here
+    index.certify = False
+    s0, i0 = index.search(q, k, precision="fp32")
+    missing = sum(len(set(order[j, :k].tolist()) - set(i0[j].cpu().tolist())) for j in range(n_q))
+    assert missing > 0
+    index.certify = True
+
+
+def test_certificate_terminal_case_exact_duplicates(m):
+    """5,000 IDENTICAL rows tie at the top: no bound can separate them, so the query ends flagged (bit 1) -- and the
+    answer is still the canonical one (ties by ascending index), because keys order by (score, index) end to end."""
+    base = synth.descriptors(30000, 64, 8)
+    dup_rows = np.arange(100, 30000, 6)[:5000]
+    base[dup_rows] = base[7]
+    index = m.Index(base, device=DEV)
+    s, i = index.search(base[7:8], 50, precision="fp32")
+    want = np.sort(np.concatenate([[7], dup_rows]))[:50]
+    assert np.array_equal(i.cpu().numpy()[0], want)
+    assert index.cert["uncertified"] == 1 and bool((index.status() & 2).all().item())
+
+
+def test_pipeline_recovers_flagged_steps(m):
+    """SearchPipeline / GraphedSearch (check=False inside the graph): a step whose certificate failed is redone through
+    search(check=True) transparently, and counted."""
+    n_db, D, n_q, k, dup = 100000, 128, 8, 100, 700
+    rs = np.random.RandomState(9)
+    db = synth.descriptors(n_db, D, 90)
+    q_hard = synth.descriptors(n_q, D, 91)
+    pos = rs.permutation(n_db)[:n_q * dup].reshape(n_q, dup)
+    for j in range(n_q):
+        nz = rs.randn(dup, D).astype(np.float32)
+        nz -= (nz @ q_hard[j])[:, None] * q_hard[j][None, :]
+        v = q_hard[j][None, :] + 0.3 * nz / np.sqrt(D)
+        db[pos[j]] = v / np.linalg.norm(v, axis=1, keepdims=True)
+    q_easy, _ = synth.planted_queries(synth.descriptors(n_db, D, 90), n_q, 92)
+    index = m.Index(db, device=DEV)
+    pipe = m.SearchPipeline(index, n_q, k)
+    batches = [torch.from_numpy(b).pin_memory() for b in (q_easy, q_hard, q_easy, q_hard)]
+    outs = [(s.copy(), i.copy()) for s, i in pipe.map(batches)]
+    assert pipe.n_recovered == 2
+    for b, (s, i) in zip(batches, outs):
+        s_ref, i_ref = index.search(b, k, precision="fp32")
+        assert np.array_equal(i, i_ref.cpu().numpy()) and np.array_equal(s, s_ref.cpu().numpy())

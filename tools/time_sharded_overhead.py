@@ -49,8 +49,8 @@ o_i = torch.empty((NQ, K), dtype=torch.int32, device=dev)
 
 
 def exch():
-    _lib.check(_lib.lib().mdir_shard_exchange_merge(_lib.ptr(keys0), NQ, K, rank, world, sh0.P2P_MAX_Q, sh0.P2P_MAX_K, C.cast(sh0._mb, C.c_void_p),
-                                                    _lib.ptr(o_s), _lib.ptr(o_i), _lib.stream()), "x")
+    _lib.check(_lib.lib().mdir_shard_exchange_merge(_lib.ptr(keys0), NQ, K, rank, world, sh0.P2P_MAX_Q, sh0.P2P_MAX_K, 0, C.cast(sh0._mb, C.c_void_p),
+                                                    _lib.ptr(o_s), _lib.ptr(o_i), None, None, _lib.stream()), "x")
 
 
 side = torch.cuda.Stream()
