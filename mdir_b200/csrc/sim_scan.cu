@@ -30,6 +30,7 @@ constexpr int kMaxN = 128;
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
+constexpr int kChainKBlocks = 4;        // k-blocks (16 MMAs) per chained accumulation chunk of the tf32 DENSE scan
 constexpr int kMaxAccBufs = 3;          // accumulator tiles resident in TMEM (2 halves x acc_stride columns each)
 
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -123,6 +124,12 @@ struct ScanParams {
     // dense_out + ks * split_stride (the caller adds the k_split partial planes in a fixed order)
     int k_split, kb_per_split;
     int64_t split_stride;
+    // DENSE mode only: CHAINED accumulation.  The tensor core's fp32 accumulator truncates once per MMA, so a long K
+    // loop drifts by up to (number of MMAs) x ulp(|score|) (~4.6e-5 relative at 3 x 2048 tf32 elements).  With
+    // chain > 1 the K loop of a tile is cut into `chain` chunks of kb_per_chain k-blocks that the SAME CTA runs back
+    // to back; the epilogue of chunk c > 0 adds its TMEM partial to what chunk c-1 left in dense_out (one rounded
+    // fp32 add per chunk), which keeps the drift at (MMAs per chunk) x ulp.
+    int chain, kb_per_chain;
     // FUSED mode only (threshold + filter in one launch): every CTA's first tile is a sample tile; the best two keys
     // of each 32-row group go to grp_top (n_q, grid, 8, 2); CTA q selects the kth smallest of query q's grid*16
     // values as the threshold, published through tau_rw; sync = {arrivals 1, arrivals 2, unused, exits}
@@ -136,7 +143,7 @@ struct ScanParams {
 constexpr int MDIR_SCAN_FUSED = 3;      // internal mode behind mdir_sim_scan_fused_bf16
 
 struct WorkItem {
-    int tile, ks, kb0, nkb, j;
+    int tile, ks, kb0, nkb, j, chunk;
 };
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j);
@@ -155,12 +162,25 @@ __device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
         w.nkb = p.num_k_blocks;
     }
     w.j = j;
+    w.chunk = 0;
     return w;
 }
 
 // The it-th work item of this CTA (persistent round-robin); false when the CTA is done.  In FUSED mode item 0 is
 // the CTA's own sample tile and the rest walk the non-sample tiles exactly like FILTER mode.
 __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem& w) {
+    if (p.chain > 1) {                    // DENSE, chained chunks: chunk c of the CTA's (it / chain)-th tile
+        const int t = it / p.chain, c = it - t * p.chain;
+        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+        if (tile >= p.n_tiles) return false;
+        w.tile = tile;
+        w.ks = 0;
+        w.kb0 = c * p.kb_per_chain;
+        w.nkb = min(p.kb_per_chain, p.num_k_blocks - w.kb0);
+        w.j = tile;
+        w.chunk = c;
+        return true;
+    }
     int j = (int)blockIdx.x + it * (int)gridDim.x;
     if (p.mode == MDIR_SCAN_FUSED) {
         if (it == 0) {
@@ -169,6 +189,7 @@ __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem&
             w.kb0 = 0;
             w.nkb = p.num_k_blocks;
             w.j = (int)blockIdx.x;
+            w.chunk = 0;
             return true;
         }
         j -= (int)gridDim.x;
@@ -443,10 +464,20 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     if (emode != MDIR_SCAN_FILTER) {
                         // rows past the end of the database only exist in the compact SAMPLE buffer: mark them -inf
                         if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
+                            if (w.chunk > 0) {
+                                // chained chunk: add to what this same thread stored for the previous chunk of the tile
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (c0 + i < p.n_q)
-                                    dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < p.n_q) {
+                                        float* o = dense_out + (int64_t)(c0 + i) * p.dense_ld + out_row;
+                                        *o = __fadd_rn(*o, __uint_as_float(v[i]));
+                                    }
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (c0 + i < p.n_q)
+                                        dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
+                            }
                         }
                     } else if (row_ok) {
 #pragma unroll
@@ -565,6 +596,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.k_split = 1;
     p.kb_per_split = p.num_k_blocks;
     p.split_stride = split_stride;
+    p.chain = 1;
+    p.kb_per_chain = p.num_k_blocks;
     p.acc_bufs = p.n_pad <= 80 ? 3 : 2;
     p.acc_stride = p.n_pad <= 80 ? 80 : 128;
     p.kth = 0;
@@ -578,6 +611,11 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
             p.k_split = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // every split gets >= 1 k-block
         }
         p.n_work = p.n_tiles * p.k_split;
+        if (tf32 && p.k_split == 1 && p.num_k_blocks > 2 * kChainKBlocks) {
+            // fp32-faithful path: at most 16 truncating MMAs per TMEM accumulation (see ScanParams::chain)
+            p.kb_per_chain = kChainKBlocks;
+            p.chain = (p.num_k_blocks + kChainKBlocks - 1) / kChainKBlocks;
+        }
     } else if (mode == MDIR_SCAN_SAMPLE) {
         MDIR_CHECK_ARG(dense_out && n_sample >= 1 && sample_stride >= 1);
         MDIR_CHECK_ARG((int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
@@ -634,7 +672,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
     }
-    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (p.n_work < kNumSMs ? p.n_work : kNumSMs);
+    const int n_ctas_wanted = p.chain > 1 ? p.n_tiles : p.n_work;
+    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (n_ctas_wanted < kNumSMs ? n_ctas_wanted : kNumSMs);
     if (tf32) sim_scan_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     else sim_scan_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     MDIR_LAUNCH_CHECK();

@@ -1,16 +1,27 @@
-"""Import the LIVE reference (/root/reference) for golden-vector generation.
+"""Import the LIVE reference: /root/reference in the build container, else the verbatim copy that
+``baseline/stage_ref.py`` placed under baseline/_ref/ (git-ignored; it travels to the GPU box with the gpurun
+snapshot, where /root/reference does not exist).
 
-TEST INFRASTRUCTURE ONLY, and only usable in the build container: the reference
-tree does not exist on the GPU box, so nothing in tests/, smoke() or bench.py
-calls this at run time -- only ``oracle/make_golden.py`` does, and its outputs
-are committed under tests/golden/.  Recipe: SURVEY.md App. B (stub two absent
-off-path modules, alias a Pillow constant that Pillow 12 dropped).
+TEST INFRASTRUCTURE ONLY: used by ``oracle/make_golden.py`` (golden vectors committed under tests/golden/),
+by the integration tests (validate() un-patched vs after mdir_b200.install()) and by bench.py's CPU-baseline
+legs.  Never imported by the product package.  Recipe: SURVEY.md App. B (stub two absent off-path modules,
+alias a Pillow constant that Pillow 12 dropped).
 """
 import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("MDIR_REF_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get("MDIR_REF_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "mdir")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def available():

@@ -167,7 +167,7 @@ def test_certificate_extends_and_widens(m):
     for j in range(n_q):
         nz = rs.randn(dup, D).astype(np.float32)
         nz -= (nz @ q[j])[:, None] * q[j][None, :]
-        v = q[j][None, :] + 0.3 * nz / np.sqrt(D)
+        v = q[j][None, :] + 0.1 * nz / np.sqrt(D)
         db[pos[j]] = v / np.linalg.norm(v, axis=1, keepdims=True)
     index = m.Index(db, device=DEV)
     s, i = index.search(q, k, precision="fp32")
@@ -212,7 +212,7 @@ def test_pipeline_recovers_flagged_steps(m):
     for j in range(n_q):
         nz = rs.randn(dup, D).astype(np.float32)
         nz -= (nz @ q_hard[j])[:, None] * q_hard[j][None, :]
-        v = q_hard[j][None, :] + 0.3 * nz / np.sqrt(D)
+        v = q_hard[j][None, :] + 0.1 * nz / np.sqrt(D)
         db[pos[j]] = v / np.linalg.norm(v, axis=1, keepdims=True)
     q_easy, _ = synth.planted_queries(synth.descriptors(n_db, D, 90), n_q, 92)
     index = m.Index(db, device=DEV)
