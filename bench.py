@@ -40,8 +40,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-extras", action="store_true", help="skip the head / CLAHE side measurements")
-    ap.add_argument("--cpu-rows", type=int, default=100000, help="database row sample for the CPU baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip the head / CLAHE / C5 side measurements")
+    ap.add_argument("--full-dba", action="store_true", help="N=1: run the full 1M-row DBA instead of a 16,384-row slice")
+    ap.add_argument("--cpu-rows", type=int, default=200000, help="database row sample for the cpu_baseline leg of our arm")
     return ap.parse_args()
 
 
@@ -55,44 +56,112 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------ CPU reference arm
-def cpu_reference(rows, reps):
-    """The reference's own arithmetic (cirscore.py:69-70) through the oracle port, all host
-    threads numpy/BLAS will use, on `rows` database rows x 70 queries; queries/s extrapolated
-    linearly in N_db (argsort is n log n, so this flatters the CPU slightly)."""
+REF_BUDGET_S = 210.0      # wall-clock budget of the whole --impl reference run (data generation excluded)
+
+
+def host_cores():
+    return len(os.sched_getaffinity(0))
+
+
+def host_descriptors(rows, seed, threads):
+    """(D, rows) fp32 C-order with unit columns -- the layout extract_vectors returns (imageretrievalnet.py:291) --
+    filled by `threads` numpy Generators in parallel (they release the GIL)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    vecs = np.empty((DIM, rows), dtype=np.float32)
+    step = max(4096, -(-rows // (4 * threads)))
+
+    def fill(c0):
+        c1 = min(rows, c0 + step)
+        blk = np.random.default_rng([seed, c0]).standard_normal((DIM, c1 - c0), dtype=np.float32)
+        blk /= np.sqrt((blk * blk).sum(axis=0, keepdims=True))
+        vecs[:, c0:c1] = blk
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(fill, range(0, rows, step)))
+    return vecs
+
+
+def reference_step(vecs, qvecs):
+    """Exactly what cirscore.py:69-70 executes (restated in oracle/oracle.py:scores): np.dot(vecs.T, qvecs) and
+    np.argsort(-scores, axis=0) with numpy's default sort kind."""
     import numpy as np
     from oracle import oracle
-    rs = np.random.RandomState(4)
-    vecs = rs.standard_normal((DIM, rows)).astype(np.float32)        # (D, N_db) as extract_vectors returns
-    vecs /= np.linalg.norm(vecs, axis=0, keepdims=True)
-    qvecs = rs.standard_normal((DIM, N_Q)).astype(np.float32)
-    qvecs /= np.linalg.norm(qvecs, axis=0, keepdims=True)
-    oracle.ranks(vecs[:, :1000], qvecs)                               # warm-up
+    sc = oracle.scores(vecs, qvecs)
+    return np.argsort(-sc, axis=0)
+
+
+def time_reference(vecs, qvecs, steps, warmup, threads):
+    """-> list of per-step seconds, BLAS pinned to `threads` whatever OMP_NUM_THREADS says (torchrun sets it to 1)."""
+    from threadpoolctl import threadpool_limits
     ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        sc = oracle.scores(vecs, qvecs)
-        rk = np.argsort(-sc, axis=0)                                   # the reference's exact call (default kind)
-        ts.append(time.perf_counter() - t0)
-        assert rk.shape == (rows, N_Q)
+    with threadpool_limits(limits=threads):
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            rk = reference_step(vecs, qvecs)
+            dt = time.perf_counter() - t0
+            assert rk.shape == (vecs.shape[1], qvecs.shape[1])
+            if i >= warmup:
+                ts.append(dt)
+    return ts
+
+
+def cpu_reference(rows, reps, threads=None, vecs=None, qvecs=None):
+    """The reference arithmetic on `rows` database rows x 70 queries, `threads` BLAS threads (default: every host core);
+    queries/s scaled linearly to the full database when rows < N_DB (argsort is n log n, so that flatters the CPU)."""
+    import numpy as np
+    threads = threads or host_cores()
+    if vecs is None:
+        vecs = host_descriptors(rows, 4, host_cores())
+        qvecs = host_descriptors(N_Q, 5, 1)
+    ts = time_reference(vecs[:, :rows], qvecs, reps, 1, threads)
     t = float(np.median(ts))
     scale = N_DB / float(rows)
-    return {"value": N_Q / (t * scale), "unit": UNIT, "cores": len(os.sched_getaffinity(0)), "kind": "port",
-            "sample": "np.dot + np.argsort(axis=0) on %d of %d db rows x 70 queries x 2048-D, median of %d, time scaled x%.2f"
-                      % (rows, N_DB, reps, scale),
-            "ms_per_step_extrapolated": t * scale * 1e3}
+    return {"value": N_Q / (t * scale), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "np.dot + np.argsort(axis=0) (cirscore.py:69-70 via the oracle port) on %d of %d db rows x 70 queries x 2048-D, %d BLAS threads of %d host cores, median of %d%s"
+                      % (rows, N_DB, threads, host_cores(), reps, "" if rows == N_DB else ", time scaled x%.2f" % scale),
+            "ms_per_step": t * scale * 1e3, "rows": rows}
 
 
 def run_reference(args):
+    """bench.py --impl reference: the reference's own CPU implementation of the path on this box's host cores, at the
+    FULL workload (1,001,001 rows per step) for --warmup + --steps steps when that fits REF_BUDGET_S; otherwise the
+    steps run on the largest row sample that does, after one full-size step, and the line says so."""
+    import numpy as np
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    reps = max(1, min(args.steps, 5))
-    cb = cpu_reference(args.cpu_rows, reps)
-    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
-            "warmup": 1, "ms_per_step": cb["ms_per_step_extrapolated"], "higher_is_better": True, "scaling": "strong",
+    cores = host_cores()
+    t_gen = time.perf_counter()
+    vecs = host_descriptors(N_DB, 4, cores)
+    qvecs = host_descriptors(N_Q, 5, 1)
+    t_gen = time.perf_counter() - t_gen
+    t_start = time.perf_counter()
+    full = time_reference(vecs, qvecs, 1, 0, cores)[0]                     # one full-size step, always (also the first warm-up)
+    warm = max(args.warmup, 1)
+    total_steps = warm - 1 + args.steps
+    rows = N_DB
+    if total_steps * full > REF_BUDGET_S - full:
+        rows = int(max(50000, min(N_DB, N_DB * (REF_BUDGET_S - full) / (total_steps * full))))
+    ts = time_reference(vecs[:, :rows] if rows < N_DB else vecs, qvecs, args.steps, warm - 1, cores)
+    scale = N_DB / float(rows)
+    t = float(np.mean(ts)) * scale
+    # the as-shipped thread setting of the reference (torch/MKL/OMP = 3, mdir/stages/validate.py:10-12), for the record
+    t3 = None
+    if time.perf_counter() - t_start < REF_BUDGET_S:
+        r3 = min(rows, 250000)
+        t3 = float(np.median(time_reference(vecs[:, :r3], qvecs, 2, 1, 3))) * (N_DB / float(r3))
+    sample = ("every step = the full workload: np.dot(vecs.T, qvecs) + np.argsort(-scores, axis=0) (cirscore.py:69-70 via the oracle port) on "
+              "1,001,001 x 2048 fp32 x 70 queries" if rows == N_DB else
+              "steps on %d of %d db rows (time scaled x%.2f) to fit %.0f s; one full-size step took %.0f ms" % (rows, N_DB, scale, REF_BUDGET_S, full * 1e3))
+    sample += "; %d BLAS threads (all host cores, pinned with threadpoolctl regardless of OMP_NUM_THREADS)" % cores
+    line = {"impl": "reference", "metric": METRIC, "value": N_Q / t, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": warm, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": N_Q / t, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": N_Q / t, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "full_size_step_ms": full * 1e3, "rows_per_step": rows, "host_data_generation_s": t_gen,
+            "as_shipped_3_threads": None if t3 is None else {"value": N_Q / t3, "unit": UNIT, "ms_per_step": t3 * 1e3, "cores": 3,
+                                                              "note": "torch/MKL/OMP = 3 threads as mdir/stages/validate.py:10-12 sets them; 250k-row sample scaled"}}
     print(json.dumps(line))
 
 
@@ -194,6 +263,37 @@ def count_launches_per_step(lib, target, q_dev):
     return int(lib.mdir_launch_count() - n0)
 
 
+N_BATCHES = 8             # distinct query batches rotated through every timed loop
+
+
+def same_topk(got_i, got_s, ref_i, ref_v, tol):
+    """got (nq, k) vs an independent reference ranking ref (nq, k_ext >= k): scores equal to tol position by position,
+    every index mismatch must be a swap inside a reference gap <= tol.  -> (violations, swaps_inside_gaps)."""
+    import numpy as np
+    nq, k = got_i.shape
+    bad = int((np.abs(got_s - ref_v[:, :k]) > tol).sum())
+    swaps = 0
+    for j in range(nq):
+        for r in np.nonzero(got_i[j] != ref_i[j, :k])[0]:
+            near = np.abs(ref_v[j] - ref_v[j, r]) <= tol
+            if got_i[j, r] in ref_i[j][near]:
+                swaps += 1
+            else:
+                bad += 1
+    return bad, swaps
+
+
+def independent_topk(torch, mdir_b200, index, q, k_ext):
+    """Local top-k_ext of one shard by a path that shares nothing with the bf16 shortlist machinery: dense 3xTF32 scores
+    of every row -> exact select -> fp64 re-scoring by torch.  -> (global idx (nq, k_ext + 48) int64, fp64 scores) unsorted-by-fp64."""
+    dense = index.scores(q, precision="fp32")
+    idx, _ = mdir_b200.topk_from_scores(dense.t().contiguous(), min(k_ext + 48, index.n))
+    del dense
+    idx = idx.t().contiguous()
+    v64 = (index.db32[idx.reshape(-1)].double().view(idx.shape[0], idx.shape[1], -1) * q.double()[:, None, :]).sum(-1)
+    return idx + index.idx_base, v64
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -219,44 +319,43 @@ def run_ours(args):
 
     # ---- synthetic database shard (rows [lo, hi) of the 1,001,001), built on the device -------
     lo, hi = ShardedIndex.shard_bounds(N_DB, world, rank)
-    t_build0 = time.perf_counter()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     db32 = torch.empty((hi - lo, DIM), dtype=torch.float32, device=dev)
     for r0 in range(0, hi - lo, 65536):
         blk = torch.randn((min(65536, hi - lo - r0), DIM), device=dev, generator=g)
         db32[r0:r0 + blk.shape[0]] = blk / blk.norm(dim=1, keepdim=True)
+    # N_BATCHES distinct query batches (pinned host memory; every timed loop rotates through them)
     gq = torch.Generator(device="cpu").manual_seed(99)
-    q_host = torch.randn((N_Q, DIM), generator=gq)
-    q_host = (q_host / q_host.norm(dim=1, keepdim=True)).pin_memory()
+    q_host = torch.randn((N_BATCHES, N_Q, DIM), generator=gq)
+    q_host = (q_host / q_host.norm(dim=2, keepdim=True)).pin_memory()
+    q_bank = q_host.to(dev)
     torch.cuda.synchronize()
     # cold path of the index build (packing only; the fp32 rows are already resident)
     t0 = time.perf_counter()
     index = Index.from_packed(pack_bf16(db32), db32=db32, idx_base=lo)
+    index.stats()                                                    # database half of the shortlist certificate (one pass, cached)
     torch.cuda.synchronize()
     pack_ms = (time.perf_counter() - t0) * 1e3
     prof = KernelProf(torch)
     target = ShardedIndex.from_local(index) if world > 1 else index
-    # the whole step (pack q, sample scan, select, filter scan, finalize, fp32 re-score, finalize,
-    # [all-gather, merge]) captured once into a CUDA graph; every step below is one replay
-    gs = GraphedSearch(target, N_Q, TOPK, precision="fp32")
-    gs.q.copy_(q_host, non_blocking=True)
-    q_dev = gs.q
-    # N > 1: the throughput loop replays the deferred-exchange graph (step t pushes its keys over NVLink and merges
-    # step t-1, whose keys arrived a step ago; one drain after the last step, inside the timed region)
+    # the whole step (pack q, fused threshold+filter scan, finalize + certified fp32 re-score, [exchange + merge]) captured
+    # once per query batch into a CUDA graph whose static query buffer already holds that batch: every timed step is ONE
+    # graph replay, and consecutive steps search different queries
     deferred = world > 1 and getattr(target, "_mb", None) is not None
-    gs_run = GraphedSearch(target, N_Q, TOPK, precision="fp32", deferred=True) if deferred else gs
-    gs_run.q.copy_(q_host, non_blocking=True)
+    graphs = []
+    for b in range(N_BATCHES):
+        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", deferred=deferred)
+        gb.q.copy_(q_bank[b])
+        graphs.append(gb)
+    gs = GraphedSearch(target, N_Q, TOPK, precision="fp32")          # synchronous exchange: the blocking e2e loop
     # the same step with a CUDA event pair around the dominant kernel inside the graph: used only to read that
-    # kernel's duration (the two event-record nodes cost ~8 us per step, so `value` is timed on the plain graph)
+    # kernel's duration (the two event-record nodes cost ~8 us per step, so `value` is timed on the plain graphs)
     gs_prof = GraphedSearch(target, N_Q, TOPK, precision="fp32", prof=prof)
-    gs_prof.q.copy_(q_host, non_blocking=True)
+    gs_prof.q.copy_(q_bank[0])
     out_host = torch.empty((N_Q, TOPK * 2), dtype=torch.float32).pin_memory()
 
-    def step_device():
-        return gs()
-
-    def step_e2e():
-        s, i = gs(q_host)                                            # pinned host -> static device buffer, replay
+    def step_e2e(t):
+        s, i = gs(q_host[t % N_BATCHES])                             # pinned host -> static device buffer, replay
         out_host[:, :TOPK].copy_(s, non_blocking=True)
         out_host[:, TOPK:].view(torch.int32).copy_(i, non_blocking=True)
         torch.cuda.synchronize()
@@ -267,39 +366,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ---------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        s_chk, i_chk = step_device()
+    def run_steps(n):
+        for t in range(n):
+            graphs[t % N_BATCHES].graph.replay()
         if deferred:
-            gs_run()
-    if deferred:
-        gs_run.drain()
+            graphs[(n - 1) % N_BATCHES].drain()
+
+    # ---- warm-up ---------------------------------------------------------------------------------
+    run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
-    assert not gs.check_overflow(), "candidate overflow on the benchmark data"
-    for _ in range(3):
-        step_e2e()
+    for t in range(3):
+        step_e2e(t)
 
     # ---- timed region: `value` ------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if sampler.ok:
         sampler.start()
-    launches_per_step = count_launches_per_step(lib, target, q_dev)
+    n0 = lib.mdir_launch_count()
+    target.search(q_bank[0], TOPK, precision="fp32", check=False)
+    launches_per_step = int(lib.mdir_launch_count() - n0)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     sampler.active = True
     ev[0].record()
-    for _ in range(args.steps):
-        gs_run()
-    if deferred:
-        gs_run.drain()
+    run_steps(args.steps)
     ev[1].record()
     barrier()
     sampler.active = False
     launches = launches_per_step * args.steps
-    assert not gs.check_overflow()
     ms_total = ev[0].elapsed_time(ev[1])
-    # dominant-kernel duration: the graph carries an event pair around the FILTER scan; read it after
-    # individual replays of the same graph (a per-step read needs a sync, so not inside the loop above)
+    # dominant-kernel duration: the graph carries an event pair around the scan; read it after individual replays
+    # of the same graph (a per-step read needs a sync, so not inside the loop above)
     scan_samples = []
     for _ in range(min(50, args.steps) + 1):
         gs_prof()
@@ -311,19 +408,19 @@ def run_ours(args):
     # (1) blocking: upload, replay, download, synchronize -- the latency of one step seen from the host
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for t in range(args.steps):
+        step_e2e(t)
     barrier()
     e2e_blocking_s = time.perf_counter() - t0
-    # (2) the serving loop (SearchPipeline): the same three stages per step, two steps in flight, so the copies of
+    # (2) the serving loop (SearchPipeline): the same three stages per step, several steps in flight, so the copies of
     # one step overlap the scan of the next.  Every step's queries are uploaded and every result is read on the host.
     pipe = SearchPipeline(target, N_Q, TOPK, precision="fp32")
-    for _ in pipe.map([q_host] * 4):
+    for _ in pipe.map(q_host[b] for b in range(4)):
         pass
     barrier()
     t0 = time.perf_counter()
     n_out = 0
-    for s_h, i_h in pipe.map(q_host for _ in range(args.steps)):
+    for s_h, i_h in pipe.map(q_host[t % N_BATCHES] for t in range(args.steps)):
         n_out += int(i_h[0, 0] >= 0)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -332,7 +429,7 @@ def run_ours(args):
 
     # bf16-only mode (no fp32 re-scoring), for the record
     gs16 = GraphedSearch(target, N_Q, TOPK, precision="bf16")
-    gs16.q.copy_(q_dev)
+    gs16.q.copy_(q_bank[0])
     for _ in range(3):
         gs16()
     e2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
@@ -353,18 +450,64 @@ def run_ours(args):
         per_rank = {"ms_total": allr[:, 0].tolist(), "e2e_s": allr[:, 1].tolist(), "scan_ms": allr[:, 2].tolist()}
         ms_total, e2e_s, scan_ms = [float(x) for x in allr.max(dim=0).values.tolist()]
 
-    # ---- sanity: planted result is self-consistent with an exact recomputation -------------------
-    s_chk, i_chk = step_device()
-    own = (i_chk >= lo) & (i_chk < hi)
-    rows = (i_chk.long() - lo).clamp_(0, hi - lo - 1)
-    exact = (db32[rows.view(-1)].view(N_Q, TOPK, DIM) * q_dev[:, None, :]).sum(-1)
-    assert torch.all(((exact - s_chk).abs() < 2e-6) | ~own), "fp32 re-scored values disagree with an exact recomputation"
-    assert torch.all(s_chk[:, :-1] >= s_chk[:, 1:])
+    # ---- parity of what was timed -------------------------------------------------
+    # For every one of the N_BATCHES query batches: the result of the TIMED graph (at N > 1: local certified top-k,
+    # keys pushed over NVLink, merge deferred by a step) against (a) an independent ranking -- per shard dense 3xTF32
+    # scores of every row -> exact select -> fp64 re-scoring, shards merged on the host -- with swaps accepted only
+    # inside 2e-6 reference gaps, and at N > 1 (b) bit for bit against the ncclAllGather + merge-kernel route.
+    K_EXT = TOPK + 16
+    timed, flagged = [], 0
+    for b in range(N_BATCHES):
+        graphs[b].graph.replay()
+        if deferred:
+            graphs[b].drain()
+        torch.cuda.synchronize()
+        timed.append((graphs[b].out[0].clone(), graphs[b].out[1].clone()))
+        flagged += int(graphs[b].status.ne(0).sum().item())
+    nccl_equal = None
+    if world > 1:
+        ShardedIndex.p2p = False
+        nccl_index = ShardedIndex.from_local(index)
+        ShardedIndex.p2p = True
+        nccl_equal = True
+        for b in range(N_BATCHES):
+            s_n, i_n = nccl_index.search(q_bank[b], TOPK, precision="fp32")
+            nccl_equal &= bool(torch.equal(i_n, timed[b][1]) and torch.equal(s_n, timed[b][0]))
+    violations = swaps = 0
+    for b in range(N_BATCHES):
+        r_i, r_v = independent_topk(torch, mdir_b200, index, q_bank[b], K_EXT)
+        if world > 1:
+            g_i = torch.empty((world,) + tuple(r_i.shape), dtype=r_i.dtype, device=dev)
+            g_v = torch.empty((world,) + tuple(r_v.shape), dtype=r_v.dtype, device=dev)
+            dist.all_gather_into_tensor(g_i.view(-1), r_i.contiguous().view(-1))
+            dist.all_gather_into_tensor(g_v.view(-1), r_v.contiguous().view(-1))
+            r_i = g_i.permute(1, 0, 2).reshape(N_Q, -1)
+            r_v = g_v.permute(1, 0, 2).reshape(N_Q, -1)
+        r_i, r_v = r_i.cpu().numpy(), r_v.cpu().numpy()
+        order = np.lexsort((r_i, -r_v), axis=1)[:, :K_EXT]
+        r_i, r_v = np.take_along_axis(r_i, order, 1), np.take_along_axis(r_v, order, 1)
+        bad, sw = same_topk(timed[b][1].cpu().numpy().astype(np.int64), timed[b][0].cpu().numpy().astype(np.float64), r_i, r_v, 2e-6)
+        violations += bad
+        swaps += sw
+    index._db_x3 = None                                              # 24.6 GB / world of 3xTF32 operands: only the check needed them
+    torch.cuda.empty_cache()
+    parity = {"checked_queries": N_BATCHES * N_Q, "mismatches": violations, "swaps_inside_2e-6_reference_gaps": swaps,
+              "certificate_failures": flagged, "certificate_counters": dict(index.cert),
+              "reference": "independent: per shard dense 3xTF32 scores of every row -> exact top-%d select -> fp64 re-scoring (torch), shards merged on the host" % (K_EXT + 48),
+              "timed_route": ("deferred NVLink exchange graph" if deferred else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
+    if nccl_equal is not None:
+        parity["p2p_route_equals_nccl_allgather_route"] = nccl_equal
+        flag = torch.tensor([violations, 0 if nccl_equal else 1], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)                                    # every rank merged the same lists
+        parity["mismatches_max_over_ranks"], parity["p2p_route_equals_nccl_allgather_route"] = int(flag[0].item()), not bool(flag[1].item())
+    assert parity["mismatches"] == 0, parity
 
     extras = {}
+    if not args.no_extras:
+        extras.update(c5_measurements(torch, dist, world, rank, target, index, q_bank[0], args))
     if rank == 0 and not args.no_extras:
         if world == 1:
-            extras.update(search_side_measurements(torch, mdir_b200, index, q_dev, prof))
+            extras.update(search_side_measurements(torch, mdir_b200, index, q_bank[0], prof))
         extras.update(side_measurements(torch, mdir_b200, dev))
 
     if rank != 0:
@@ -383,34 +526,94 @@ def run_ours(args):
         "metric": METRIC, "value": N_Q * args.steps / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK), "db_rows_per_gpu": hi - lo,
+        "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK),
+                   "distinct_query_batches": N_BATCHES, "db_rows_per_gpu": hi - lo,
                    "sharding": "db rows contiguous over %d GPU(s); %s" % (world, "single shard" if world == 1 else (
                        ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); the merge of "
                         "step t runs inside step t+1, one drain after the last step") % (N_Q * TOPK * 8) if deferred else
                        "ncclAllGather of %d B of keys per rank + merge kernel" % (N_Q * TOPK * 8))),
                    "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
         "clocks": sampler.summary(),
-        "e2e": {"value": N_Q * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N_Q * DIM * 4, "d2h_bytes_per_step": N_Q * TOPK * 8,
-                "ms_per_step": e2e_s / args.steps * 1e3, "blocking_ms_per_step": e2e_blocking_s / args.steps * 1e3,
-                "timing": "wall clock around %d steps of SearchPipeline (per step: H2D of the pinned queries, graph replay, D2H of scores/idx, host read of the result; %d steps in flight%s); blocking_ms_per_step = the same with a synchronize after every step" % (args.steps, pipe.depth, ", deferred NVLink exchange" if pipe.deferred else "")},
-        "e2e_cold_db_ms": {"pack_fp32_to_bf16_ms": pack_ms,
+        "e2e": {"value": N_Q * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N_Q * DIM * 4, "d2h_bytes_per_step": N_Q * TOPK * 8 + N_Q * 4,
+                "ms_per_step": e2e_s / args.steps * 1e3, "blocking_ms_per_step": e2e_blocking_s / args.steps * 1e3, "steps_redone_exactly": pipe.n_recovered,
+                "timing": "wall clock around %d steps of SearchPipeline (per step: H2D of the pinned queries, graph replay, D2H of scores/idx/status, host read of the result; %d steps in flight%s); blocking_ms_per_step = the same with a synchronize after every step" % (args.steps, pipe.depth, ", deferred NVLink exchange" if pipe.deferred else "")},
+        "e2e_cold_db_ms": {"pack_fp32_to_bf16_and_certificate_stats_ms": pack_ms,
                            "note": "one-off index build for this shard; host->device upload of the fp32 rows would add %.1f GB over PCIe" % ((hi - lo) * DIM * 4 / 1e9)},
         "gpu_launches": int(launches), "gpu_launches_note": "%d libmdir_b200 kernels per step, replayed from one CUDA graph per step" % launches_per_step,
         "roofline": {"bound": "hbm", "kernel": "sim_scan_kernel (%s)" % ("threshold + filter in one launch: whole shard" if index._fused_ok(default_shortlist(TOPK)) else "FILTER pass"), "achieved": achieved, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "algorithmic_bytes_per_launch": prof.bytes, "avg_launch_ms": scan_ms, "share_of_step": scan_ms / ms_step,
                      "timing": "CUDA events (external, recorded inside the step's CUDA graph on its stream), mean of %d replays" % len(scan_samples)},
+        "parity_check": parity,
         "bf16_only_ms_per_step": bf16_ms,
     }
     if world == 1:
         cb = cpu_reference(args.cpu_rows, 3)
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cb3 = cpu_reference(min(args.cpu_rows, 100000), 2, threads=3)
+        line["cpu_baseline_as_shipped_3_threads"] = {k: cb3[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if per_rank is not None:
         line["per_rank"] = per_rank
     line.update(extras)
     out.emit(json.dumps(line))
     sys.stdout.flush()
     finish(dist, world)
+
+
+def c5_measurements(torch, dist, world, rank, target, index, q_dev, args):
+    """BASELINE.json configs[4] (alpha-QE + DBA on the 1M x 2048 database) at THIS world size; every rank takes part.
+    alpha-QE: search top-10, expand (one all-reduce of N_q x D fp32 when sharded), search top-100.
+    DBA: every database row searched against the whole database (top-10) and replaced by the weighted sum of its
+    neighbours.  Run in full at N > 1 (the verdict's 8-GPU measurement); at N = 1 a bounded 16,384-row slice of the
+    database rows is augmented and the full run extrapolated linearly (a full pass is seconds; --full-dba runs it)."""
+    from mdir_b200 import qe
+    out = {}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ms(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=q_dev.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for _ in range(2):
+        qe.search_qe(target, q_dev, TOPK)
+    barrier()
+    ev[0].record()
+    for _ in range(10):
+        qe.search_qe(target, q_dev, TOPK)
+    ev[1].record()
+    barrier()
+    ms = max_ms(ev[0].elapsed_time(ev[1]) / 10)
+    out["alpha_qe"] = {"metric": "alpha-QE queries/s (alpha=3, n_QE=10; two certified similarity+top-k passes%s; parity unpinned)" % (
+                           "" if world == 1 else " + one all-reduce of the expansion"),
+                       "value": N_Q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "n_gpus": world}
+    full = world > 1 or args.full_dba
+    barrier()
+    t0 = time.perf_counter()
+    if full:
+        aug = qe.dba_sharded(target, 3.0, 10) if world > 1 else qe.dba(index, 3.0, 10)
+        rows_done = N_DB
+    else:
+        rows_done = 16384
+        aug = qe.dba(index, 3.0, 10, rows=rows_done)
+    barrier()
+    dba_s = max_ms((time.perf_counter() - t0) * 1e3) / 1e3
+    del aug
+    torch.cuda.empty_cache()
+    flops = 2.0 * rows_done * N_DB * DIM
+    out["dba"] = {"metric": "DBA (k=10, alpha=3) over the 1,001,001 x 2048 database, every row searched against every row",
+                  "n_gpus": world, "rows_augmented": rows_done, "seconds": dba_s,
+                  "full_1M_seconds": dba_s * (N_DB / rows_done), "measured_in_full": bool(full),
+                  "tflops_per_gpu": flops / dba_s / 1e12 / world,
+                  "note": "wall clock incl. the all-gather of the shards, index build and per-block host loop; max over ranks"}
+    return out
 
 
 def finish(dist, world):
@@ -427,10 +630,8 @@ def finish(dist, world):
 
 
 def search_side_measurements(torch, mdir_b200, index, q_dev, prof):
-    """Config 5 and the tensor-utilisation evidence, on the resident 1M x 2048 index (1 GPU):
-    alpha-QE (two similarity + top-k passes), a DBA slice (blocks of 128 database rows searched
-    against the whole database), and the 128-query FILTER scan as TFLOP/s."""
-    from mdir_b200 import qe
+    """The tensor-utilisation evidence on the resident 1M x 2048 index (1 GPU): blocks of 128 database rows searched
+    against the whole database (the DBA inner loop), the 128-query FILTER scan as TFLOP/s."""
     out = {}
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     tf_peak = 1397.3
@@ -438,18 +639,6 @@ def search_side_measurements(torch, mdir_b200, index, q_dev, prof):
         with open(path) as fh:
             tf_peak = float(json.load(fh).get("bf16_tflops_sustained", tf_peak))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    # alpha-QE: search top-10, expand, search top-100 (fp32-faithful both times)
-    for _ in range(2):
-        qe.search_qe(index, q_dev, TOPK)
-    torch.cuda.synchronize()
-    ev[0].record()
-    for _ in range(10):
-        qe.search_qe(index, q_dev, TOPK)
-    ev[1].record()
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[1]) / 10
-    out["alpha_qe"] = {"metric": "alpha-QE queries/s (alpha=3, n_QE=10; two similarity+top-k passes; parity unpinned)", "value": N_Q / (ms * 1e-3),
-                       "unit": "queries/s", "ms_per_batch": ms}
     # 128-row blocks of the database as queries (the DBA inner loop): FILTER scan at N = 128
     rows = index.db32[:1280]
     index.prof = prof
@@ -591,6 +780,16 @@ def side_measurements(torch, mdir_b200, dev):
                     "note": "floor = 12 B/pair (4 B score + 8 B int64 rank) at the measured HBM peak"}
         del idx, db, r
     out["c3_full"] = c3_full_measurement(torch, mdir_b200, dev, g)
+    # SURVEY.md 8d CPU baselines beside `head` and `clahe`: the reference's torch-CPU head and OpenCV CLAHE on this host,
+    # as shipped (3 torch threads / 1 cv2 thread) and on all cores
+    try:
+        from oracle import cpu_baselines
+        cb = cpu_baselines.head_and_clahe_baselines()
+        out["head"]["cpu_baseline"] = {k[5:]: v for k, v in cb.items() if k.startswith("head_")}
+        out["clahe"]["cpu_baseline"] = {k[6:]: v for k, v in cb.items() if k.startswith("clahe_")}
+        out["head"]["cpu_baseline"]["cores"] = out["clahe"]["cpu_baseline"]["cores"] = cb["cores"]
+    except Exception as exc:  # noqa: BLE001
+        out["cpu_baselines_error"] = repr(exc)
     out.update(training_side_measurements(torch, mdir_b200, dev, g, ev))
     return out
 

@@ -105,7 +105,8 @@ int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_desc* descs
  * mdir_rgb_to_l_u8:      L plane as uint8 = trunc((L/100)*255)   -> feed to mdir_clahe_u8
  * mdir_lab_clahe_to_rgb: (a, b of the original pixel) + CLAHE'd uint8 L -> RGB float32 HWC       */
 typedef struct {
-    int64_t rgb_off;   /* float offset of pixel (0,0) in the rgb buffers (input and output alike) */
+    int64_t rgb_off;   /* float offset of pixel (0,0) in the rgb INPUT buffer */
+    int64_t out_off;   /* float offset of pixel (0,0) in the rgb OUTPUT buffer of mdir_lab_clahe_to_rgb */
     int64_t l_off;     /* byte offset of the image's L plane in the uint8 L buffers */
     int32_t H, W;
 } mdir_rgb_desc;

@@ -7,8 +7,9 @@
   mdir/components/data/transform/{functional.py:109-129, photometric_transforms.py:10-43}.
   ``image_clahe`` runs the whole ImageClahe transform on the device: RGB->Lab follows OpenCV's
   float code path bit for bit (trilinear interpolation of its 33^3 fixed-point lattice), CLAHE on
-  the uint8 L plane, Lab->RGB within ~1e-5.  These transforms touch the GPU,
-  so run the DataLoader with num_workers=0 on this path (threading).
+  the uint8 L plane, Lab->RGB within ~1e-5.  No host OpenCV anywhere.  These transforms
+  touch the GPU, so run the DataLoader with num_workers=0 on this path (threading): called inside
+  a worker process they raise with that remedy instead of crashing in CUDA's fork check.
 """
 import ctypes
 import os
@@ -19,7 +20,7 @@ import torch
 from . import _lib
 
 
-_RGB_DESC_DTYPE = np.dtype([("rgb_off", np.int64), ("l_off", np.int64), ("H", np.int32), ("W", np.int32)])
+_RGB_DESC_DTYPE = np.dtype([("rgb_off", np.int64), ("out_off", np.int64), ("l_off", np.int64), ("H", np.int32), ("W", np.int32)])
 _DESC_DTYPE = np.dtype([("src_off", np.int64), ("dst_off", np.int64), ("H", np.int32), ("W", np.int32),
                         ("src_pitch", np.int32), ("dst_pitch", np.int32)])
 
@@ -113,33 +114,64 @@ def lab_tables(device):
     return _LAB_CACHE[key]
 
 
+def _check_rgb(imgs):
+    for im in imgs:
+        _lib.require_cuda(im, "image")
+        if im.dtype != torch.float32 or im.dim() != 3 or im.shape[2] != 3 or im.numel() == 0:
+            raise _lib.MdirError("expected non-empty (H,W,3) float32 RGB tensors")
+    return [im.contiguous() for im in imgs]
+
+
+def _rgb_descs(imgs, compact_out):
+    """Descriptor table of a ragged RGB batch.  Inputs are addressed relative to the lowest input pointer (they stay
+    where they are); outputs go to ONE compact buffer, image after image (so separately allocated inputs that sit
+    gigabytes apart in the caching allocator cost nothing).  -> (sbase, descs_np, l_off, out_off, npx)"""
+    npx = [im.shape[0] * im.shape[1] for im in imgs]
+    l_off = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in npx])]).astype(np.int64)
+    out_off = np.concatenate([[0], np.cumsum([(3 * n + 3) // 4 * 4 for n in npx])]).astype(np.int64)
+    sbase = min(im.data_ptr() for im in imgs)
+    descs = np.zeros(len(imgs), dtype=_RGB_DESC_DTYPE)
+    for i, im in enumerate(imgs):
+        descs[i] = ((im.data_ptr() - sbase) // 4, int(out_off[i]) if compact_out else 0, int(l_off[i]), im.shape[0], im.shape[1])
+    return sbase, descs, l_off, out_off, npx
+
+
+def rgb_l_clahe_u8(images, clip_limit=4, grid=(8, 8)):
+    """The L channel of the reference's normalised Lab space, quantised and equalised as ChannelClahe does
+    (transform/functional.py:24-27,109-117): RGB float32 HWC in [0,1] -> trunc(L/100*255) uint8 (OpenCV's
+    interpolated float RGB2Lab, bit for bit) -> CLAHE.  -> list of (H,W) uint8 cuda tensors."""
+    lib = _lib.lib()
+    imgs = _check_rgb(list(images))
+    if not imgs:
+        return []
+    dev = imgs[0].device
+    lut, _ = lab_tables(dev)
+    sbase, descs, l_off, _, npx = _rgb_descs(imgs, False)
+    l_in = torch.empty((int(l_off[-1]),), dtype=torch.uint8, device=dev)
+    descs_d = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mdir_rgb_to_l_u8(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut), _lib.ptr(l_in),
+                                        _lib.stream()), "mdir_rgb_to_l_u8")
+    planes = [l_in[int(l_off[i]):int(l_off[i]) + npx[i]].view(im.shape[0], im.shape[1]) for i, im in enumerate(imgs)]
+    return clahe_u8(planes, clip_limit, grid)
+
+
 def image_clahe(images, clip_limit=4, grid=(8, 8)):
     """ImageClahe.apply (transform/functional.py:120-129, colorspace 'lab') entirely on the device:
     RGB float32 HWC in [0,1] -> Lab (OpenCV's interpolated float path) -> CLAHE on L as uint8 -> RGB.
-    images: one (H,W,3) cuda tensor or a list of them (ragged sizes, one launch per stage)."""
+    images: one (H,W,3) cuda tensor or a list of them (ragged sizes, one launch per stage).  The results are views
+    into one compact output buffer."""
     lib = _lib.lib()
     single = isinstance(images, torch.Tensor)
     imgs = [images] if single else list(images)
     if not imgs:
         return []
-    for im in imgs:
-        _lib.require_cuda(im, "image")
-        if im.dtype != torch.float32 or im.dim() != 3 or im.shape[2] != 3 or im.numel() == 0:
-            raise _lib.MdirError("image_clahe expects non-empty (H,W,3) float32 tensors")
-    imgs = [im.contiguous() for im in imgs]
+    imgs = _check_rgb(imgs)
     dev = imgs[0].device
     lut, gamma = lab_tables(dev)
-    outs = [torch.empty_like(im) for im in imgs]
-    npx = [im.shape[0] * im.shape[1] for im in imgs]
-    l_off = np.concatenate([[0], np.cumsum([(n + 15) // 16 * 16 for n in npx])]).astype(np.int64)
+    sbase, descs, l_off, out_off, npx = _rgb_descs(imgs, True)
     l_in = torch.empty((int(l_off[-1]),), dtype=torch.uint8, device=dev)
-    sbase = min(im.data_ptr() for im in imgs)
-    # the output images must sit at the same offsets as the inputs: use one arena laid out like the inputs
-    span = max(im.data_ptr() + im.numel() * 4 for im in imgs) - sbase
-    arena = torch.empty((span // 4,), dtype=torch.float32, device=dev)
-    descs = np.zeros(len(imgs), dtype=_RGB_DESC_DTYPE)
-    for i, im in enumerate(imgs):
-        descs[i] = ((im.data_ptr() - sbase) // 4, int(l_off[i]), im.shape[0], im.shape[1])
+    arena = torch.empty((int(out_off[-1]),), dtype=torch.float32, device=dev)
     descs_d = torch.from_numpy(descs.view(np.uint8).reshape(-1)).to(dev)
     with torch.cuda.device(dev):
         _lib.check(lib.mdir_rgb_to_l_u8(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut), _lib.ptr(l_in),
@@ -150,10 +182,24 @@ def image_clahe(images, clip_limit=4, grid=(8, 8)):
         clahe_u8(planes, clip_limit, grid, out=oplanes)
         _lib.check(lib.mdir_lab_clahe_to_rgb(ctypes.c_void_p(sbase), _lib.ptr(descs_d), len(imgs), max(npx), _lib.ptr(lut),
                                              _lib.ptr(gamma), _lib.ptr(l_out), _lib.ptr(arena), _lib.stream()), "mdir_lab_clahe_to_rgb")
-    for i, im in enumerate(imgs):
-        o = (im.data_ptr() - sbase) // 4
-        outs[i] = arena[o:o + im.numel()].view(im.shape)
+    outs = [arena[int(out_off[i]):int(out_off[i]) + im.numel()].view(im.shape) for i, im in enumerate(imgs)]
     return outs[0] if single else outs
+
+
+def _not_in_worker(what):
+    """The transform classes launch CUDA kernels: inside a forked DataLoader worker that cannot work ("Cannot
+    re-initialize CUDA in forked subprocess").  Fail with the remedy instead."""
+    info = torch.utils.data.get_worker_info()
+    if info is not None:
+        raise _lib.MdirError("%s runs on the GPU and was called inside DataLoader worker %d: use num_workers=0 on this path "
+                             "(mdir_b200.extract_vectors does), or mdir_b200.install(transforms=False) to keep the reference's "
+                             "CPU transforms for loaders with workers" % (what, info.id))
+
+
+def _require_lab(colorspace):
+    if str(colorspace).lower() != "lab":
+        raise NotImplementedError("colorspace %r: only 'lab' (the CLAHE scenario's) runs on the device; mdir_b200.install() "
+                                  "leaves other colourspaces to the reference's own transform classes" % (colorspace,))
 
 
 class ChannelClahe:
@@ -167,47 +213,29 @@ class ChannelClahe:
         self.device = device
 
     def apply(self, chan):
+        _not_in_worker("ChannelClahe")
         q = (np.asarray(chan) * 255).astype(np.uint8)                 # C truncation, functional.py:117
         out = clahe_u8(torch.from_numpy(np.ascontiguousarray(q)).to(self.device), self.clip_limit, self.grid_size)
         return out.cpu().numpy().astype(np.float32) / 255.0
 
 
-def _cv2():
-    import cv2
-    return cv2
-
-
-def rgb2normspace(img, colorspace):
-    """transform/functional.py:24-27 (lab only: the colourspace of the CLAHE scenario)."""
-    if colorspace.lower() != "lab":
-        raise NotImplementedError("Colorspace %s is not supported" % colorspace)
-    cv2 = _cv2()
-    return (cv2.cvtColor(img, cv2.COLOR_RGB2LAB) + np.array([0, 128, 128], dtype=np.float32)) / np.array([100.0, 255.0, 255.0], dtype=np.float32)
-
-
-def normspace2rgb(img, colorspace):
-    """transform/functional.py:38-41"""
-    if colorspace.lower() != "lab":
-        raise NotImplementedError("Colorspace %s is not supported" % colorspace)
-    cv2 = _cv2()
-    return cv2.cvtColor((img * np.array([100.0, 255.0, 255.0], dtype=np.float32)) - np.array([0, 128, 128], dtype=np.float32), cv2.COLOR_LAB2RGB)
-
-
 class ImageClahe(ChannelClahe):
-    """transform/functional.py:120-129"""
+    """transform/functional.py:120-129 -- colorspace 'lab', float32 RGB in [0,1], the whole transform on the device
+    (no host OpenCV anywhere on this path)."""
 
     def __init__(self, clip_limit, grid_size, colorspace, device="cuda"):
         super().__init__(clip_limit, grid_size, device)
+        _require_lab(colorspace)
         self.colorspace = colorspace
 
     def apply(self, img):
-        if self.colorspace.lower() == "lab" and img.dtype == np.float32 and img.ndim == 3 and img.shape[2] == 3:
-            # whole transform on the device: cv2-compatible RGB->Lab, CLAHE on L, Lab->RGB
-            x = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
-            return image_clahe(x, self.clip_limit, self.grid_size).cpu().numpy()
-        spc = rgb2normspace(img, self.colorspace)
-        spc[:, :, 0] = super().apply(spc[:, :, 0])
-        return normspace2rgb(spc, self.colorspace)
+        _not_in_worker("ImageClahe")
+        img = np.asarray(img)
+        if img.dtype != np.float32 or img.ndim != 3 or img.shape[2] != 3:
+            raise _lib.MdirError("ImageClahe.apply expects an (H,W,3) float32 RGB image in [0,1] (what pil2np produces); got %s %s"
+                                 % (img.dtype, img.shape))
+        x = torch.from_numpy(np.ascontiguousarray(img)).to(self.device)
+        return image_clahe(x, self.clip_limit, self.grid_size).cpu().numpy()
 
 
 class ApplyClahe:
@@ -232,17 +260,23 @@ class CreateClahedImage(ApplyClahe):
 
 
 class AddClaheFromRgb:
-    """photometric_transforms.py:10-23"""
+    """photometric_transforms.py:10-23: append the CLAHE'd L channel of each picture as a fourth channel.
+    RGB -> L (OpenCV's float RGB2Lab, bit for bit), the uint8 quantisation and CLAHE all run on the device."""
 
-    def __init__(self, clip_limit=4, grid_size=8, colorspace="lab"):
+    def __init__(self, clip_limit=4, grid_size=8, colorspace="lab", device="cuda"):
+        _require_lab(colorspace)
         self.params = {"clip_limit": int(clip_limit), "grid_size": grid_size, "colorspace": colorspace}
-        self.clahe = ChannelClahe(clip_limit=int(clip_limit), grid_size=grid_size)
+        self.clahe = ChannelClahe(clip_limit=int(clip_limit), grid_size=grid_size, device=device)
 
     def __call__(self, *pics):
-        acc = []
+        _not_in_worker("AddClaheFromRgb")
         for pic in pics:
             assert isinstance(pic, np.ndarray)
-            spc = rgb2normspace(pic[:, :, :3], self.params["colorspace"])
-            chan = self.clahe.apply(spc[:, :, 0])
+        dev = self.clahe.device
+        rgb = [torch.from_numpy(np.ascontiguousarray(pic[:, :, :3], dtype=np.float32)).to(dev) for pic in pics]
+        chans = rgb_l_clahe_u8(rgb, self.clahe.clip_limit, self.clahe.grid_size)
+        acc = []
+        for pic, ch in zip(pics, chans):
+            chan = ch.cpu().numpy().astype(np.float32) / 255.0
             acc.append(np.concatenate((pic, np.expand_dims(chan, axis=2)), axis=2))
         return acc

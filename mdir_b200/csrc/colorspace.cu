@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) lab_clahe_to_rgb_kernel(const float* __re
         const float ro = clip01(C0 * fx + C1 * y + C2 * fz);
         const float go = clip01(C3 * fx + C4 * y + C5 * fz);
         const float bo = clip01(C6 * fx + C7 * y + C8 * fz);
-        float* o = out + d.rgb_off + i * 3;
+        float* o = out + d.out_off + i * 3;
         o[0] = spline_eval(gamma_tab, ro);
         o[1] = spline_eval(gamma_tab, go);
         o[2] = spline_eval(gamma_tab, bo);

@@ -8,13 +8,16 @@ pool, L2N, multi-scale aggregation, Lw whitening -- is ONE pass of the ``Retriev
 nothing is copied to the host until the end (or never, with ``return_device=True``: the (N, D) matrix
 then feeds ``Index`` directly).
 
-Two kinds of ``net`` are understood (duck-typed, nothing of the reference is imported):
+Three kinds of ``net`` are understood (recognised by class name, nothing of the reference is imported):
   * cirtorch's ``ImageRetrievalNet``: ``.features``, ``.pool``, ``.meta``  (+ ``ms`` / ``msp`` arguments,
     the semantics of ``extract_ss`` / ``extract_ms``);
-  * mdir's ``CirNetwork``: ``.model`` (an ImageRetrievalNet) and ``.wrappers['eval']`` holding
-    ``CirMultiscaleAggregation`` and/or ``CirtorchWhiten`` (mdir/learning/network.py:88-89).
-Local whitening, in-model whitening layers and regional pooling are outside the hot path
- and raise NotImplementedError.
+  * mdir's ``CirNetwork`` / ``SingleNetwork``: ``.model`` (an ImageRetrievalNet) and ``.wrappers['eval']`` holding
+    ``CirMultiscaleAggregation`` and/or ``CirtorchWhiten`` (mdir/learning/network.py:88-89);
+  * mdir's ``SequentialNetwork`` of such networks (normaliser -> CirNet, network.py:204-236): the earlier
+    networks run unchanged on every scaled image, the last one's head is batched.
+Everything else -- subclasses that override ``forward`` (``ImageRetrievalNetBranched``), local whitening,
+in-model whitening layers, regional pooling, unknown wrappers -- raises NotImplementedError, which
+``install()``'s extractor turns into the reference's own per-image loop.
 """
 import sys
 
@@ -26,16 +29,47 @@ from .wrappers import RetrievalHead
 
 
 class _Plan:
+    """What the batched path will run for `net`.  The path is WHITELISTED by type: anything it does not positively
+    recognise raises NotImplementedError, and install()'s extractor then falls back to the reference's own per-image
+    loop -- a network with an overridden forward (ImageRetrievalNetBranched, cirnet.py:25-45) or an unknown
+    composition must never be evaluated through `.model.features` alone."""
+
     def __init__(self, net, ms, msp):
-        model = getattr(net, "model", net)
-        self.model = model
         self.scales = list(ms)
         self.msp = float(msp)
         self.lw = None
         self.dimensions = None
         self.interp_unit_scale = False
-        wr = getattr(net, "wrappers", None)
-        if wr is not None and hasattr(net, "model"):
+        self.pre = []                                 # networks applied to every scaled image before the last model
+        kind = type(net).__name__
+        wr = None
+        if hasattr(net, "networks") or hasattr(net, "sequence"):
+            # mdir's SequentialNetwork (learning/network.py:204-236; e.g. U-Net normaliser -> CirNet,
+            # examples/iccv19/eval_composition.yml): the eval wrappers of the LAST network wrap the whole chain, so
+            # every scaled image goes through the earlier networks (their own wrappers included) and then through the
+            # last model's backbone.
+            if kind != "SequentialNetwork" or not hasattr(net, "networks") or not hasattr(net, "sequence"):
+                raise NotImplementedError("composite network %s is outside the batched extraction path" % kind)
+            seq = list(net.sequence)
+            self.pre = [net.networks[k] for k in seq[:-1]]
+            last = net.networks[seq[-1]]
+            if type(last).__name__ not in ("CirNetwork", "SingleNetwork") or last.model is not net.model:
+                raise NotImplementedError("last stage %s of the sequence is outside the batched extraction path" % type(last).__name__)
+            for stage in self.pre:
+                if type(stage).__name__ not in ("CirNetwork", "SingleNetwork"):
+                    raise NotImplementedError("stage %s of the sequence is outside the batched extraction path" % type(stage).__name__)
+            model, wr = net.model, net.wrappers
+        elif hasattr(net, "model"):
+            if kind not in ("CirNetwork", "SingleNetwork"):
+                raise NotImplementedError("network wrapper %s is outside the batched extraction path" % kind)
+            model, wr = net.model, getattr(net, "wrappers", None)
+        else:
+            model = net
+        # the backbone must be cirtorch's ImageRetrievalNet with ITS forward (imageretrievalnet.py:93-115), not a subclass
+        if type(model).__name__ != "ImageRetrievalNet" or not getattr(type(model).forward, "__qualname__", "").endswith("ImageRetrievalNet.forward"):
+            raise NotImplementedError("model %s is outside the batched extraction path" % type(model).__name__)
+        self.model = model
+        if wr is not None:
             comp = wr.get("eval") if isinstance(wr, dict) else wr
             self.scales, self.msp = [1], None
             for w in getattr(comp, "wrappers", []):
@@ -93,6 +127,8 @@ def extract_from_tensors(net, tensors, ms=(1,), msp=1, device=None, group=32, re
                 x = x.unsqueeze(0)
             for s in plan.scales:
                 xs = x if (s == 1 and not plan.interp_unit_scale) else F.interpolate(x, scale_factor=s, mode="bilinear", align_corners=False)
+                for stage in plan.pre:               # SequentialNetwork: earlier networks run as they are (stock torch)
+                    xs = stage(xs)
                 pending.append(plan.model.features(xs).float().contiguous())
             if (n_img + 1) % group == 0:
                 flush()

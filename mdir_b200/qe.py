@@ -46,15 +46,17 @@ def search_qe(index, q, k, alpha=3.0, n_qe=10, precision="fp32"):
     return index.search(expand_queries(index, q, alpha, n_qe), k, precision=precision)
 
 
-def dba(index, alpha=3.0, k_dba=10):
+def dba(index, alpha=3.0, k_dba=10, rows=None):
     """Database-side augmentation of a single-GPU Index: every row replaced by the normalised
     alpha-weighted sum of its own top-k_dba neighbours (self included).  Returns a new Index.
-    Each block of 128 rows is one streaming pass of the database (HBM-bound form)."""
+    Each block of 128 rows is one streaming pass of the database (HBM-bound form).
+    rows: augment only the first `rows` rows (the others are copied unchanged) -- bounded benchmarks."""
     if index.db32 is None:
         raise _lib.MdirError("DBA needs the fp32 master copy (keep_fp32=True)")
-    out = torch.empty_like(index.db32)
-    for r0 in range(0, index.n, MAX_Q):
-        r1 = min(r0 + MAX_Q, index.n)
+    n_aug = index.n if rows is None else min(int(rows), index.n)
+    out = torch.empty_like(index.db32) if n_aug == index.n else index.db32.clone()
+    for r0 in range(0, n_aug, MAX_Q):
+        r1 = min(r0 + MAX_Q, n_aug)
         s, i = index.search(index.db32[r0:r1], k_dba, precision="fp32")
         out[r0:r1] = _add_l2n(_accumulate(index, i, s, alpha), None)
     return Index(out, device=index.device, keep_fp32=True, idx_base=index.idx_base)

@@ -51,21 +51,65 @@ def make_cirdatasetap(base_cls, extract_vectors, compute_map_and_print, stopwatc
     return CirDatasetAp
 
 
-def _batched_or_reference(reference_extract):
-    """extract_vectors that uses the batched device path and falls back to the reference's per-image loop
-    for networks outside the hot path (local / in-model whitening, regional pooling, other wrappers)."""
+class _NoLoaderWorkers:
+    """While active, torch.utils.data.DataLoader ignores num_workers (forces 0).  The reference's extract_vectors
+    hard-codes six forked workers (imageretrievalnet.py:284-287); with the GPU-backed CLAHE transforms installed those
+    workers would have to initialise CUDA after a fork, which CUDA refuses."""
+
+    def __enter__(self):
+        import torch.utils.data as tud
+        self._tud, self._orig = tud, tud.DataLoader
+        orig = self._orig
+
+        class _Loader(orig):
+            def __init__(self, *args, **kwargs):
+                kwargs["num_workers"] = 0
+                super().__init__(*args, **kwargs)
+
+        tud.DataLoader = _Loader
+        return self
+
+    def __exit__(self, *exc):
+        self._tud.DataLoader = self._orig
+        return False
+
+
+def _batched_or_reference(reference_extract, gpu_transforms):
+    """extract_vectors that uses the batched device path and falls back to the reference's per-image loop for
+    networks outside the hot path (branched / composite models, local / in-model whitening, regional pooling, other
+    wrappers) -- ANY failure to recognise the network falls back, never a partial evaluation (extract._Plan)."""
     def extract_vectors(net, images, image_size, transform, bbxs=None, ms=[1], msp=1, print_freq=10, device=None):
         try:
-            return extract.extract_vectors(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq,
-                                           device=device)
+            extract._Plan(net, ms, msp)                       # recognition only: cheap, raises NotImplementedError
         except NotImplementedError:
+            if gpu_transforms:
+                with _NoLoaderWorkers():
+                    return reference_extract(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq, device=device)
             return reference_extract(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq, device=device)
+        return extract.extract_vectors(net, images, image_size, transform, bbxs=bbxs, ms=ms, msp=msp, print_freq=print_freq,
+                                       device=device)
     return extract_vectors
 
 
-def install(batched_extract=True):
+def _lab_or_reference(ours, ref_cls, colorspace_pos):
+    """TRANSFORMS factory: colorspace 'lab' (the CLAHE scenario's) -> the device-backed class; 'luv' / 'lsh' / 'gray'
+    -> the reference's own class, unchanged.  Arguments arrive as strings from the "name:arg:arg" mini-language
+    (transform/__init__.py:35-44)."""
+    def factory(*args, **kwargs):
+        cs = kwargs.get("colorspace", args[colorspace_pos] if len(args) > colorspace_pos else "lab")
+        if str(cs).lower() == "lab":
+            return ours(*args, **kwargs)
+        return ref_cls(*args, **kwargs)
+    factory.__name__ = ours.__name__
+    factory.device_class, factory.reference_class = ours, ref_cls
+    return factory
+
+
+def install(batched_extract=True, transforms=True):
     """Patch POOLING, WRAPPERS_LABELS, TRANSFORMS and SCORES of an importable ``mdir`` in place
-    (SURVEY.md 8b).  Returns the dict of patched registry entries."""
+    (SURVEY.md 8b).  Returns the dict of patched registry entries.
+    transforms=False leaves the CLAHE entries of TRANSFORMS alone: use it for stages whose DataLoaders fork worker
+    processes (training), where a GPU-backed transform cannot run."""
     try:
         import mdir  # noqa: F401
         import cirtorch.networks.imageretrievalnet as irn
@@ -87,12 +131,16 @@ def install(batched_extract=True):
     mwrap.WRAPPERS_LABELS["cirmultiscale"] = wrappers.CirMultiscaleAggregation
     patched["WRAPPERS_LABELS[cirwhiten]"] = wrappers.CirtorchWhiten
     patched["WRAPPERS_LABELS[cirmultiscale]"] = wrappers.CirMultiscaleAggregation
-    for key, cls in (("apply_clahe", clahe.ApplyClahe), ("add_clahe_fromrgb", clahe.AddClaheFromRgb),
-                     ("create_clahed", clahe.CreateClahedImage)):
-        if key in mtrans.TRANSFORMS:
-            mtrans.TRANSFORMS[key] = cls
-            patched["TRANSFORMS[%s]" % key] = cls
-    ev = _batched_or_reference(cirscore.extract_vectors) if batched_extract else cirscore.extract_vectors
+    if transforms:
+        # positional index of `colorspace` in each constructor (photometric_transforms.py:12,27)
+        for key, cls, cs_pos in (("apply_clahe", clahe.ApplyClahe, 1), ("add_clahe_fromrgb", clahe.AddClaheFromRgb, 2),
+                                 ("create_clahed", clahe.CreateClahedImage, 1)):
+            if key in mtrans.TRANSFORMS:
+                ref_cls = mtrans.TRANSFORMS[key]
+                ref_cls = getattr(ref_cls, "reference_class", ref_cls)          # install() twice: keep the original
+                mtrans.TRANSFORMS[key] = _lab_or_reference(cls, ref_cls, cs_pos)
+                patched["TRANSFORMS[%s]" % key] = cls
+    ev = _batched_or_reference(cirscore.extract_vectors, transforms) if batched_extract else cirscore.extract_vectors
     new_cls = make_cirdatasetap(cirscore.CirDatasetAp, ev, cirscore.compute_map_and_print, StopWatch)
     mscore.SCORES["cirdatasetap"] = new_cls
     patched["SCORES[cirdatasetap]"] = new_cls

@@ -135,7 +135,14 @@ def test_install_patches_registries():
     assert "rmac" in irn.POOLING                                   # untouched (out of scope)
     assert mwrap.WRAPPERS_LABELS["cirwhiten"] is mdir_b200.CirtorchWhiten
     assert mwrap.WRAPPERS_LABELS["cirmultiscale"] is mdir_b200.CirMultiscaleAggregation
-    assert mtrans.TRANSFORMS["apply_clahe"] is mdir_b200.ApplyClahe
+    assert mtrans.TRANSFORMS["apply_clahe"].device_class is mdir_b200.ApplyClahe
+    # colourspaces the device path does not cover stay the reference's own classes (functional.py:24-48)
+    from mdir.components.data.transform import photometric_transforms as ref_pt
+    assert isinstance(mtrans.TRANSFORMS["apply_clahe"]("4", "luv", "8"), ref_pt.ApplyClahe)
+    assert isinstance(mtrans.TRANSFORMS["add_clahe_fromrgb"]("4", "8", "lsh"), ref_pt.AddClaheFromRgb)
+    assert isinstance(mtrans.TRANSFORMS["apply_clahe"]("4", "lab", "8"), mdir_b200.ApplyClahe)
+    mdir_b200.install()                                            # idempotent: the reference class is not lost
+    assert mtrans.TRANSFORMS["apply_clahe"].reference_class is ref_pt.ApplyClahe
     assert mscore.SCORES["cirdatasetap"].__name__ == "CirDatasetAp"
     assert len(patched) >= 9
     # the yaml-driven wrapper factory builds ours (wrapper.py:209-220)
@@ -183,3 +190,62 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_batched_extraction_is_whitelisted():
+    """the batched extractor must refuse every network it does not positively recognise -- a branched
+    model (forward overridden, cirnet.py:25-45) or an unknown composite -- so that install()'s extractor falls back to the
+    reference's per-image loop instead of silently evaluating `.model.features` alone; mdir's SequentialNetwork
+    (normaliser -> CirNet, learning/network.py:204-236) IS understood: its earlier stages run on every scaled image."""
+    from mdir_b200 import extract, score
+
+    class ImageRetrievalNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.features = torch.nn.Identity()
+            self.pool = type("GeM", (torch.nn.Module,), {})()
+            self.pool.p = torch.nn.Parameter(torch.ones(1) * 3)
+            self.pool.eps = 1e-6
+            self.lwhiten = self.whiten = None
+            self.meta = {"pooling": "gem", "regional": False, "whitening": False, "outputdim": 8, "out_channels": 8}
+
+        def forward(self, x):
+            return x
+
+    class ImageRetrievalNetBranched(ImageRetrievalNet):
+        def forward(self, x):
+            return x + 1
+
+    class Comp:
+        wrappers = []
+
+    class CirNetwork:
+        def __init__(self, model):
+            self.model, self.wrappers = model, {"eval": Comp()}
+
+    class SingleNetwork(CirNetwork):
+        pass
+
+    class SequentialNetwork:
+        def __init__(self, first, last):
+            self.networks, self.sequence = {"a": first, "b": last}, ["a", "b"]
+            self.model, self.wrappers = last.model, last.wrappers
+
+    class SomethingElse(SequentialNetwork):
+        pass
+
+    base = ImageRetrievalNet()
+    assert extract._Plan(base, [1], 1).pre == []
+    assert extract._Plan(CirNetwork(base), [1], 1).model is base
+    first = SingleNetwork(ImageRetrievalNet())
+    plan = extract._Plan(SequentialNetwork(first, CirNetwork(base)), [1], 1)
+    assert plan.pre == [first] and plan.model is base
+    for bad in (ImageRetrievalNetBranched(), CirNetwork(ImageRetrievalNetBranched()), SomethingElse(first, CirNetwork(base)),
+                SequentialNetwork(first, CirNetwork(ImageRetrievalNetBranched()))):
+        with pytest.raises(NotImplementedError):
+            extract._Plan(bad, [1], 1)
+    # the installed extractor: unrecognised -> the reference loop (with DataLoader workers forced to 0), recognised -> ours
+    calls = []
+    ev = score._batched_or_reference(lambda *a, **k: calls.append(torch.utils.data.DataLoader([0], num_workers=6).num_workers) or "ref", True)
+    assert ev(CirNetwork(ImageRetrievalNetBranched()), [], 10, None) == "ref" and calls == [0]
+    assert torch.utils.data.DataLoader([0], num_workers=2).num_workers == 2            # restored afterwards

@@ -99,6 +99,37 @@ def main():
     s2, i2 = sharded.search(q, k)
     s1, i1 = single.search(q, k)
     check("sync search after deferred traffic still exact", torch.equal(i1, i2) and torch.equal(s1, s2) and sharded.exchange_status() == 0)
+    # ---- a flagged step on ONE rank must be visible on EVERY rank: the last rank's shard is adversarial
+    # (scores grow with the row index, so its candidate segments overflow inside the graph, where nothing recovers)
+    n_sh, d2 = 40000, 64
+    rs = np.random.RandomState(5)
+    base = rs.randn(d2).astype(np.float32)
+    base /= np.linalg.norm(base)
+    parts = [synth.descriptors(n_sh, d2, 300 + r) for r in range(world - 1)]
+    parts.append((np.linspace(0.1, 1.0, n_sh, dtype=np.float32)[:, None] * base[None, :] + rs.randn(n_sh, d2).astype(np.float32) * 0.01).astype(np.float32))
+    db_adv = np.concatenate(parts)
+    q_adv = np.stack([base, -base, base + 0.1 * rs.randn(d2).astype(np.float32)]).astype(np.float32)
+    q_easy = synth.descriptors(3, d2, 77)
+    lo3, hi3 = rank * n_sh, (rank + 1) * n_sh
+    sh3 = ShardedIndex(db_adv[lo3:hi3], idx_base=lo3, device=dev)
+    single3 = mdir_b200.Index(db_adv, device=dev)
+    ref_adv, ref_easy = single3.search(q_adv, k), single3.search(q_easy, k)
+    g3 = GraphedSearch(sharded if False else sh3, 3, k)
+    g3(torch.from_numpy(q_adv).to(dev))
+    torch.cuda.synchronize()
+    local_flag = bool(g3.ovf.any().item())
+    check("overflow inside the graph on the last rank only (%s here)" % local_flag, local_flag == (rank == world - 1) or local_flag)
+    check("... raises the merged step's status word on EVERY rank", g3.check_overflow())
+    s_r, i_r = sh3.search_collective_recovery(q_adv, k)
+    check("collective recovery == single", torch.equal(i_r, ref_adv[1]) and torch.equal(s_r, ref_adv[0]))
+    pipe3 = mdir_b200.SearchPipeline(sh3, 3, k)
+    hb3 = [torch.from_numpy(x).pin_memory() for x in (q_adv, q_easy, q_adv)]
+    outs3 = [(s_.copy(), i_.copy()) for s_, i_ in pipe3.map(hb3)]
+    good = pipe3.n_recovered >= 2
+    for (s_, i_), ref in zip(outs3, (ref_adv, ref_easy, ref_adv)):
+        good &= bool(np.array_equal(i_, ref[1].cpu().numpy()) and np.array_equal(s_, ref[0].cpu().numpy()))
+    check("SearchPipeline redoes flagged steps collectively (%d redone) and stays exact" % pipe3.n_recovered, good)
+    sh3.close()
     q1 = qe.expand_queries(single, q, 3.0, 10)
     q2 = qe.expand_queries(sharded, q, 3.0, 10)
     check("sharded alpha-QE expansion == single (1e-6)", bool(torch.allclose(q1, q2, rtol=0, atol=1e-6)))
