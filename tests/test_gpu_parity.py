@@ -492,7 +492,7 @@ def test_graphed_search_replays(m):
 
 
 # ------------------------------------------------------------------ batched extract_vectors (section 8f, f2)
-class _TinyRetrievalNet(torch.nn.Module):
+class ImageRetrievalNet(torch.nn.Module):
     """Shaped like cirtorch's ImageRetrievalNet: features / pool / norm / meta, no whitening."""
 
     def __init__(self, m, pooling="gem", p=2.9137):
@@ -507,7 +507,7 @@ class _TinyRetrievalNet(torch.nn.Module):
 
 def test_batched_extract_vectors(m, golden):
     torch.manual_seed(3)
-    net = _TinyRetrievalNet(m).to(DEV).eval()
+    net = ImageRetrievalNet(m).to(DEV).eval()
     rs = np.random.RandomState(6)
     imgs = [torch.from_numpy(rs.rand(3, h, w).astype(np.float32)) for h, w in ((64, 48), (57, 91), (128, 96), (40, 40), (33, 77))]
     feats = lambda x: net.features(x.to(DEV).unsqueeze(0)).float().cpu().numpy()
@@ -544,7 +544,7 @@ def test_extract_vectors_matches_reference_extract_vectors(m, golden):
     network; the same weights and the same input tensors through the batched device path."""
     g = golden("extract")
     p = float(g["p"])
-    net = _TinyRetrievalNet(m, "gem", p)
+    net = ImageRetrievalNet(m, "gem", p)
     nn = torch.nn
     net.features = nn.Sequential(nn.Conv2d(3, 16, 3, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 48, 3, stride=2, padding=1), nn.ReLU())
     net.features.load_state_dict({k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w_")})
