@@ -62,13 +62,14 @@ __global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t* __restr
     counts[((int64_t)q * 256 + threadIdx.x) * n_chunks + chunk] = h[threadIdx.x];
 }
 
-// exclusive scan of counts[q] in (digit-major, chunk-minor) order, in place.  One CTA per q.
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ counts, int n_chunks) {
+// exclusive scan of counts[q] in (bin-major, chunk-minor) order, in place.  One CTA per q.  n_bins = 256 radix digits,
+// or the number of buckets of the sample-sort path below.
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ counts, int n_chunks, int n_bins) {
     __shared__ uint32_t wsum[32];
     __shared__ uint32_t carry_s;
     const int q = blockIdx.x;
-    uint32_t* c = counts + (int64_t)q * 256 * n_chunks;
-    const int total = 256 * n_chunks;
+    uint32_t* c = counts + (int64_t)q * n_bins * n_chunks;
+    const int total = n_bins * n_chunks;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (threadIdx.x == 0) carry_s = 0u;
     __syncthreads();
@@ -219,6 +220,230 @@ __global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __
     }
 }
 
+
+// ============================================================================================================
+// Sample-sort path (mdir_rank_scores_fast): one partition pass + one in-shared-memory sort per bucket.
+//
+// The LSD radix sort above moves every (key, index) pair through HBM four times.  A segment here is one query's
+// n_db scores (100,000 at BASELINE config C3): with data-adaptive splitters it can be cut, in ONE pass, into
+// buckets small enough to be sorted entirely in shared memory:
+//   1. ss_splitters_kernel   per query: a systematic sample of 16 x B composite keys (score key << 32 | row) is
+//                            sorted in shared memory; every 16th is a splitter.  Composite keys are unique, so ties
+//                            in the scores cannot unbalance the buckets.
+//   2. ss_count_kernel       per (query, 4096-key chunk): bucket of every key (binary search over the splitters in
+//                            shared memory), bucket histogram -> counts
+//   3. radix_scan_kernel     exclusive scan, bucket-major / chunk-minor -> where each chunk's share of a bucket goes
+//   4. ss_scatter_kernel     same chunks: pairs staged in shared memory grouped by bucket, written out as runs
+//   5. ss_bucket_sort_kernel per (query, bucket): <= 2048 pairs, bitonic sort on the 64-bit composite in shared
+//                            memory, row indices written at their final ranks (query-major u32)
+//   6. ranks_transpose_kernel (n_q, n_db) u32 -> (n_db, n_q) int64, the reference's layout
+// Traffic per pair: scores 4 (read twice: 8) + pairs 8 written + 8 read + ranks 4 + transpose 4 + 8 = 40 B, against
+// ~100 B for the four radix passes.  A bucket that exceeds the staging capacity (the sample misjudged a segment;
+// not observed on any test distribution) raises *status and the caller re-runs mdir_rank_scores.
+constexpr int kSsChunk = 4096;                         // keys per CTA in the count / scatter kernels
+constexpr int kSsThreads = 256;
+constexpr int kSsItems = kSsChunk / kSsThreads;        // 16
+constexpr int kBucketTarget = 768;                     // average bucket size aimed for
+constexpr int kBucketCap = 2048;                       // pairs the bucket sort stages (16 KB)
+constexpr int kOversample = 16;
+constexpr int kMaxBuckets = 512;
+constexpr int64_t kSsMaxRows = (int64_t)kMaxBuckets * kBucketTarget;      // longer segments take the LSD path
+
+__device__ __forceinline__ uint32_t ss_load_key(const void* src, int is_key, int64_t i) {
+    return is_key ? static_cast<const uint32_t*>(src)[i] : desc_key(static_cast<const float*>(src)[i]);
+}
+__device__ __forceinline__ uint64_t ss_composite(uint32_t key, uint32_t idx) { return ((uint64_t)key << 32) | (uint64_t)idx; }
+
+// number of splitters <= x  (splitters ascending, n_spl = B - 1 of them)  ->  bucket in [0, B - 1]
+__device__ __forceinline__ int ss_bucket_of(const uint64_t* spl, int n_spl, uint64_t x) {
+    int lo = 0, hi = n_spl;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (spl[mid] <= x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// bitonic sort of n (power of two) 64-bit keys in shared memory, every thread busy in every stage
+__device__ __forceinline__ void ss_bitonic(uint64_t* a, int n) {
+    for (int kk = 2; kk <= n; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const uint64_t x = a[i], y = a[p];
+                const bool asc = (i & kk) == 0;
+                if ((x > y) == asc) { a[i] = y; a[p] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) ss_splitters_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int m, int m_pow2,
+                                                           uint64_t* __restrict__ splitters) {
+    extern __shared__ uint64_t ss_smem[];
+    const int q = blockIdx.x;
+    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+    for (int j = threadIdx.x; j < m_pow2; j += blockDim.x) {
+        uint64_t v = ~0ull;
+        if (j < m) {
+            const int64_t i = (int64_t)j * n_db / m;
+            v = ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i);
+        }
+        ss_smem[j] = v;
+    }
+    __syncthreads();
+    ss_bitonic(ss_smem, m_pow2);
+    for (int b = threadIdx.x; b < B - 1; b += blockDim.x) splitters[(int64_t)q * B + b] = ss_smem[(int64_t)(b + 1) * m / B];
+}
+
+__global__ void __launch_bounds__(kSsThreads) ss_count_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int n_chunks,
+                                                              const uint64_t* __restrict__ splitters, uint32_t* __restrict__ counts) {
+    extern __shared__ uint64_t ss_smem[];
+    uint64_t* spl = ss_smem;                                   // B entries (B - 1 used)
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(spl + B);      // B
+    const int chunk = blockIdx.x, q = blockIdx.y;
+    for (int b = threadIdx.x; b < B; b += kSsThreads) {
+        spl[b] = b < B - 1 ? splitters[(int64_t)q * B + b] : ~0ull;
+        cnt[b] = 0u;
+    }
+    __syncthreads();
+    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+    const int64_t base = (int64_t)chunk * kSsChunk;
+    uint32_t key[kSsItems];
+#pragma unroll
+    for (int it = 0; it < kSsItems; ++it) {
+        const int64_t i = base + it * kSsThreads + threadIdx.x;
+        key[it] = i < n_db ? ss_load_key(seg, is_key, i) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < kSsItems; ++it) {
+        const int64_t i = base + it * kSsThreads + threadIdx.x;
+        if (i < n_db) atomicAdd(&cnt[ss_bucket_of(spl, B - 1, ss_composite(key[it], (uint32_t)i))], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += kSsThreads) counts[((int64_t)q * B + b) * n_chunks + chunk] = cnt[b];
+}
+
+__global__ void __launch_bounds__(kSsThreads) ss_scatter_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int n_chunks,
+                                                                const uint64_t* __restrict__ splitters, const uint32_t* __restrict__ offsets,
+                                                                uint64_t* __restrict__ pairs) {
+    extern __shared__ uint64_t ss_smem[];
+    uint64_t* stage = ss_smem;                                             // kSsChunk
+    uint64_t* spl = stage + kSsChunk;                                      // B
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(spl + B);                  // B: counts, then chunk-local bases
+    uint32_t* delta = cnt + B;                                             // B: global offset - local base
+    uint16_t* sbucket = reinterpret_cast<uint16_t*>(delta + B);            // kSsChunk
+    const int chunk = blockIdx.x, q = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    for (int b = threadIdx.x; b < B; b += kSsThreads) {
+        spl[b] = b < B - 1 ? splitters[(int64_t)q * B + b] : ~0ull;
+        cnt[b] = 0u;
+    }
+    __syncthreads();
+    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+    const int64_t base = (int64_t)chunk * kSsChunk;
+    uint32_t key[kSsItems], where[kSsItems];                               // where = bucket << 16 | rank inside (chunk, bucket)
+#pragma unroll
+    for (int it = 0; it < kSsItems; ++it) {
+        const int64_t i = base + it * kSsThreads + threadIdx.x;
+        key[it] = i < n_db ? ss_load_key(seg, is_key, i) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < kSsItems; ++it) {
+        const int64_t i = base + it * kSsThreads + threadIdx.x;
+        where[it] = 0u;
+        if (i < n_db) {
+            const int b = ss_bucket_of(spl, B - 1, ss_composite(key[it], (uint32_t)i));
+            where[it] = ((uint32_t)b << 16) | atomicAdd(&cnt[b], 1u);      // order inside a bucket is free: the bucket gets sorted
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {                                                // exclusive scan of the B counts by warp 0
+        uint32_t run = 0;
+        for (int b0 = 0; b0 < B; b0 += 32) {
+            const int b = b0 + lane;
+            const uint32_t c = b < B ? cnt[b] : 0u;
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (b < B) {
+                const uint32_t lbase = run + incl - c;
+                cnt[b] = lbase;
+                delta[b] = offsets[((int64_t)q * B + b) * n_chunks + chunk] - lbase;
+            }
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kSsItems; ++it) {
+        const int64_t i = base + it * kSsThreads + threadIdx.x;
+        if (i < n_db) {
+            const uint32_t b = where[it] >> 16;
+            const uint32_t l = cnt[b] + (where[it] & 0xffffu);
+            stage[l] = ss_composite(key[it], (uint32_t)i);
+            sbucket[l] = (uint16_t)b;
+        }
+    }
+    __syncthreads();
+    const int n_valid = (int)min((int64_t)kSsChunk, n_db - base);
+    uint64_t* out = pairs + (int64_t)q * n_db;
+    for (int l = threadIdx.x; l < n_valid; l += kSsThreads) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+}
+
+// direct != 0: B == 1, the pairs are built from the scores / keys themselves (short segments: no partition pass)
+__global__ void __launch_bounds__(256) ss_bucket_sort_kernel(const uint64_t* __restrict__ pairs, const void* __restrict__ src, int is_key, int direct,
+                                                             int64_t n_db, int B, int n_chunks, const uint32_t* __restrict__ offsets,
+                                                             uint32_t* __restrict__ vals, int32_t* __restrict__ status) {
+    extern __shared__ uint64_t ss_smem[];
+    const int b = blockIdx.x, q = blockIdx.y;
+    uint32_t off = 0u, end = (uint32_t)n_db;
+    if (!direct) {
+        off = offsets[((int64_t)q * B + b) * n_chunks];
+        if (b + 1 < B) end = offsets[((int64_t)q * B + b + 1) * n_chunks];
+    }
+    const int s = (int)(end - off);
+    if (s <= 0) return;
+    if (s > kBucketCap) {
+        if (threadIdx.x == 0) atomicOr(status, 1);
+        return;
+    }
+    int n = 32;
+    while (n < s) n <<= 1;
+    if (direct) {
+        const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) ss_smem[i] = i < s ? ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i) : ~0ull;
+    } else {
+        const uint64_t* in = pairs + (int64_t)q * n_db + off;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) ss_smem[i] = i < s ? in[i] : ~0ull;
+    }
+    __syncthreads();
+    ss_bitonic(ss_smem, n);
+    uint32_t* out = vals + (int64_t)q * n_db + off;
+    for (int i = threadIdx.x; i < s; i += blockDim.x) out[i] = (uint32_t)ss_smem[i];
+}
+
+struct SsPlan {
+    int B, m, m_pow2, n_chunks;
+};
+static SsPlan ss_plan(int64_t n_db) {
+    SsPlan p;
+    p.B = n_db <= kBucketCap ? 1 : (int)((n_db + kBucketTarget - 1) / kBucketTarget);
+    if (p.B > kMaxBuckets) p.B = kMaxBuckets;
+    int64_t m = (int64_t)p.B * kOversample;
+    if (m > n_db) m = n_db;
+    p.m = (int)m;
+    p.m_pow2 = 32;
+    while (p.m_pow2 < p.m) p.m_pow2 <<= 1;
+    p.n_chunks = (int)((n_db + kSsChunk - 1) / kSsChunk);
+    return p;
+}
+
 }  // namespace mdir
 
 using namespace mdir;
@@ -234,6 +459,7 @@ extern "C" size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q) {
 
 extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, int64_t ranks_ld,
                                 void* ws, void* stream) {
+    // the always-complete path: segmented stable LSD radix sort (4 x 8 bits)
     MDIR_CHECK_ARG(scores && ranks && ws && n_db >= 1 && n_q >= 1 && ranks_ld >= n_q);
     MDIR_CHECK_ARG(n_db < ((int64_t)1 << 32) && n_q <= 65535);
     cudaStream_t st = (cudaStream_t)stream;
@@ -263,7 +489,7 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         const int shift = 8 * pass;
         radix_hist_kernel<<<dim3(n_chunks, n_q), 256, 0, st>>>(kin, n_db, n_chunks, shift, counts);
         MDIR_LAUNCH_CHECK();
-        radix_scan_kernel<<<n_q, 1024, 0, st>>>(counts, n_chunks);
+        radix_scan_kernel<<<n_q, 1024, 0, st>>>(counts, n_chunks, 256);
         MDIR_LAUNCH_CHECK();
         radix_scatter_kernel<<<dim3(n_chunks, n_q), kScatterThreads, kScatterSmem, st>>>(kin, vin, n_db, n_chunks, shift, counts, kout, vout);
         MDIR_LAUNCH_CHECK();
@@ -272,6 +498,65 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         vout = (vout == vA) ? vB : vA;
     }
     ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vin, n_db, n_q, ranks, ranks_ld);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// ---- sample-sort path -------------------------------------------------------------------------------------------
+extern "C" size_t mdir_rank_fast_workspace_bytes(int64_t n_db, int n_q) {
+    if (n_db <= 0 || n_q <= 0) return 0;
+    if (n_db > kSsMaxRows) return mdir_rank_workspace_bytes(n_db, n_q);
+    const SsPlan p = ss_plan(n_db);
+    const size_t pairs = (size_t)n_db * n_q;
+    return align256((size_t)n_q * p.B * 8) + align256((size_t)n_q * p.B * p.n_chunks * 4) + align256(pairs * 8) + 2 * align256(pairs * 4);
+}
+
+extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, int64_t ranks_ld,
+                                     void* ws, int32_t* status, void* stream) {
+    MDIR_CHECK_ARG(scores && ranks && ws && status && n_db >= 1 && n_q >= 1 && ranks_ld >= n_q);
+    MDIR_CHECK_ARG(n_db < ((int64_t)1 << 32) && n_q <= 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    MDIR_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    if (n_db > kSsMaxRows) return mdir_rank_scores(scores, n_db, n_q, query_major, ranks, ranks_ld, ws, stream);
+    const SsPlan p = ss_plan(n_db);
+    const size_t n_pairs = (size_t)n_db * n_q;
+    uint8_t* w = (uint8_t*)ws;
+    uint64_t* splitters = (uint64_t*)w;          w += align256((size_t)n_q * p.B * 8);
+    uint32_t* counts = (uint32_t*)w;             w += align256((size_t)n_q * p.B * p.n_chunks * 4);
+    uint64_t* pairs = (uint64_t*)w;              w += align256(n_pairs * 8);
+    uint32_t* vals = (uint32_t*)w;               w += align256(n_pairs * 4);
+    uint32_t* keys_t = (uint32_t*)w;             // only for the (n_db, n_q) input layout
+    const unsigned gx = (unsigned)((n_db + 31) / 32), gy = (unsigned)((n_q + 31) / 32);
+    const void* src = scores;
+    int is_key = 0;
+    if (!query_major) {
+        keys_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, keys_t);
+        MDIR_LAUNCH_CHECK();
+        src = keys_t;
+        is_key = 1;
+    }
+    const size_t scatter_smem = (size_t)kSsChunk * 8 + (size_t)p.B * 8 + (size_t)p.B * 8 + (size_t)kSsChunk * 2;
+    static PerDeviceOnce once;
+    if (once.first() != 0) {
+        MDIR_CUDA(cudaFuncSetAttribute(ss_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)kSsChunk * 10 + (size_t)kMaxBuckets * 16)));
+        MDIR_CUDA(cudaFuncSetAttribute(ss_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * kOversample * 8));
+    }
+    if (p.B > 1) {
+        ss_splitters_kernel<<<n_q, 512, (size_t)p.m_pow2 * 8, st>>>(src, is_key, n_db, p.B, p.m, p.m_pow2, splitters);
+        MDIR_LAUNCH_CHECK();
+        ss_count_kernel<<<dim3(p.n_chunks, n_q), kSsThreads, (size_t)p.B * 12, st>>>(src, is_key, n_db, p.B, p.n_chunks, splitters, counts);
+        MDIR_LAUNCH_CHECK();
+        radix_scan_kernel<<<n_q, 1024, 0, st>>>(counts, p.n_chunks, p.B);
+        MDIR_LAUNCH_CHECK();
+        ss_scatter_kernel<<<dim3(p.n_chunks, n_q), kSsThreads, scatter_smem, st>>>(src, is_key, n_db, p.B, p.n_chunks, splitters, counts, pairs);
+        MDIR_LAUNCH_CHECK();
+    }
+    ss_bucket_sort_kernel<<<dim3(p.B, n_q), 256, (size_t)kBucketCap * 8, st>>>(pairs, src, is_key, p.B == 1 ? 1 : 0, n_db, p.B, p.n_chunks, counts,
+                                                                              vals, status);
+    MDIR_LAUNCH_CHECK();
+    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
     MDIR_LAUNCH_CHECK();
     return 0;
 }

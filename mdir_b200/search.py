@@ -377,35 +377,66 @@ class Index:
     def ranks(self, q, max_pairs=1 << 28, precision="bf16"):
         """Full ranking: (N_db, N_q) int64 C-order on the device (== np.argsort(-scores, axis=0,
         kind='stable') of this index's scores at the given precision, see scores()).  Queries are processed in chunks of at most
-        max_pairs // N_db to bound the radix-sort workspace (16 B per pair)."""
-        lib = _lib.lib()
+        max_pairs // N_db to bound the sort workspace (16 B per pair)."""
         with torch.cuda.device(self.device):
             q32 = _as_dev_f32(q, self.device)
             nq_all = q32.shape[0]
             out = torch.empty((self.n, nq_all), dtype=torch.int64, device=self.device)
             chunk = max(1, min(nq_all, max_pairs // max(self.n, 1)))
             chunk = max(1, min(chunk, 65535))
-            ws = torch.empty(lib.mdir_rank_workspace_bytes(self.n, chunk), dtype=torch.uint8, device=self.device)
+            ws = _rank_workspace(self.n, chunk, self.device)
             sc = torch.empty((chunk, self.n), dtype=torch.float32, device=self.device)
             for q0 in range(0, nq_all, chunk):
                 q1 = min(q0 + chunk, nq_all)
                 self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
-                _lib.check(lib.mdir_rank_scores(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
-                                                _lib.stream()), "mdir_rank_scores")
+                _rank_scores(sc, self.n, q1 - q0, 1, out[:, q0:], nq_all, ws)
             return out
 
 
-def ranks_from_scores(scores, device="cuda"):
+RANK_STATS = {"fast": 0, "fallback": 0}       # sample-sort calls / of those re-run through the radix path
+
+
+def _rank_workspace(n_db, n_q, device):
+    lib = _lib.lib()
+    return torch.empty(max(lib.mdir_rank_workspace_bytes(n_db, n_q), lib.mdir_rank_fast_workspace_bytes(n_db, n_q)) + 256,
+                       dtype=torch.uint8, device=device)
+
+
+def _rank_scores(scores, n_db, n_q, query_major, out, out_ld, ws):
+    """mdir_rank_scores_fast (sample sort), and the segmented radix sort when it reports a bucket it could not stage
+    (one status word read back per call: the price of never returning an incomplete ranking)."""
+    lib = _lib.lib()
+    status = torch.empty((1,), dtype=torch.int32, device=scores.device)
+    _lib.check(lib.mdir_rank_scores_fast(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.ptr(status),
+                                         _lib.stream()), "mdir_rank_scores_fast")
+    RANK_STATS["fast"] += 1
+    if int(status.item()) != 0:
+        RANK_STATS["fallback"] += 1
+        _lib.check(lib.mdir_rank_scores(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.stream()),
+                   "mdir_rank_scores")
+
+
+def ranks_from_scores(scores, device="cuda", method="auto"):
     """scores (N_db, N_q) fp32 in the reference layout (host or device) -> ranks (N_db, N_q) int64
-    on the device, bit-identical to np.argsort(-scores, axis=0, kind='stable')."""
+    on the device, bit-identical to np.argsort(-scores, axis=0, kind='stable').
+    method: "auto" = sample sort with the radix sort as its fallback, "radix" = the segmented LSD radix sort only."""
     lib = _lib.lib()
     dev = torch.device(device)
     s = _as_dev_f32(scores, dev)
     n_db, n_q = s.shape
     with torch.cuda.device(dev):
         out = torch.empty((n_db, n_q), dtype=torch.int64, device=dev)
-        ws = torch.empty(lib.mdir_rank_workspace_bytes(n_db, n_q), dtype=torch.uint8, device=dev)
-        _lib.check(lib.mdir_rank_scores(_lib.ptr(s), n_db, n_q, 0, _lib.ptr(out), n_q, _lib.ptr(ws), _lib.stream()), "mdir_rank_scores")
+        if n_db == 0 or n_q == 0:
+            return out
+        for q0 in range(0, n_q, 65535):
+            q1 = min(n_q, q0 + 65535)
+            blk = s if (q0 == 0 and q1 == n_q) else s[:, q0:q1].contiguous()
+            ws = _rank_workspace(n_db, q1 - q0, dev)
+            if method == "radix":
+                _lib.check(lib.mdir_rank_scores(_lib.ptr(blk), n_db, q1 - q0, 0, _lib.ptr(out[:, q0:]), n_q, _lib.ptr(ws), _lib.stream()),
+                           "mdir_rank_scores")
+            else:
+                _rank_scores(blk, n_db, q1 - q0, 0, out[:, q0:], n_q, ws)
     return out
 
 

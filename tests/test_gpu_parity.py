@@ -299,7 +299,44 @@ def test_ranks_edge_cases(m):
         if n_db > 3:
             sc[2, 0] = np.inf
             sc[3, 0] = -np.inf
-        assert np.array_equal(m.ranks_from_scores(sc).cpu().numpy(), oracle.ranks_from_scores(sc)), (n_db, n_q)
+        ref = oracle.ranks_from_scores(sc)
+        assert np.array_equal(m.ranks_from_scores(sc).cpu().numpy(), ref), (n_db, n_q)
+        assert np.array_equal(m.ranks_from_scores(sc, method="radix").cpu().numpy(), ref), (n_db, n_q)
+
+
+@pytest.mark.parametrize("case", ["gauss", "all_equal", "ascending", "descending", "periodic", "two_values", "spike"])
+@pytest.mark.parametrize("n_db", [2048, 2049, 100000, 393216, 393217])
+def test_ranks_sample_sort_distributions(m, case, n_db):
+    """mdir_rank_scores_fast (splitters from a systematic sample, one partition pass, shared-memory bucket sorts) against
+    the stable argsort on distributions chosen to stress the splitters: massive ties (composite (score, row) keys keep the
+    buckets balanced), monotone data, data periodic in the row index (aliases with the systematic sample), a dense spike.
+    Whatever the sample does, the result is exact: a bucket that cannot be staged falls back to the radix sort."""
+    from mdir_b200 import search
+    rs = np.random.RandomState(n_db % 1000 + len(case))
+    n_q = 3
+    i = np.arange(n_db, dtype=np.float64)
+    if case == "gauss":
+        sc = rs.randn(n_db, n_q) * 0.05
+    elif case == "all_equal":
+        sc = np.full((n_db, n_q), 0.25)
+    elif case == "ascending":
+        sc = np.repeat((i / n_db)[:, None], n_q, 1)
+    elif case == "descending":
+        sc = np.repeat((-i / n_db)[:, None], n_q, 1)
+    elif case == "periodic":
+        period = max(2, n_db // (16 * max(1, -(-n_db // 768))))            # the sampling stride of the splitter kernel
+        sc = np.stack([np.sin(2 * np.pi * i / period), (i % period) / period, ((i * 7) % period) / period], 1)
+    elif case == "two_values":
+        sc = (rs.rand(n_db, n_q) < 0.999).astype(np.float64)
+    else:
+        sc = rs.randn(n_db, n_q) * 1e-3
+        sc[rs.rand(n_db, n_q) < 0.9] = 0.7
+    sc = sc.astype(np.float32)
+    before = dict(search.RANK_STATS)
+    got = m.ranks_from_scores(sc).cpu().numpy()
+    assert np.array_equal(got, oracle.ranks_from_scores(sc)), (case, n_db)
+    if case in ("gauss", "all_equal", "ascending", "descending", "two_values", "spike"):
+        assert search.RANK_STATS["fallback"] == before["fallback"], "the sample sort needed its fallback on %s" % case
 
 
 # ------------------------------------------------------------------ similarity + search
