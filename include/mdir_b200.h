@@ -256,12 +256,13 @@ size_t mdir_rank_workspace_bytes(int64_t n_db, int n_q);
 int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int query_major,
                      int64_t* ranks, int64_t ranks_ld, void* ws, void* stream);
 
-/* The same result through a sample sort: per query one data-adaptive partition pass into buckets of <= 2048 pairs
- * (splitters = every 16th of a sorted systematic sample of (score key, row) composites, so ties cannot unbalance them)
- * and one shared-memory bitonic sort per bucket -- ~40 B of HBM traffic per pair instead of ~100 B for the four radix
- * passes.  *status (device int32) is cleared first and set non-zero when some bucket exceeded the staging capacity:
- * ranks is then incomplete and the caller re-runs mdir_rank_scores.  Segments longer than 393,216 rows take the
- * radix path directly.  ws: mdir_rank_fast_workspace_bytes() bytes.                                                */
+/* The same result through a sample sort: per query ONE data-adaptive partition pass into buckets of <= 2048 pairs
+ * (splitters = every 32nd of a sorted systematic sample of (score key, row) composites, so ties cannot unbalance
+ * them; every bucket owns a 2048-slot region, so no counting pass) and one shared-memory interpolation counting sort per
+ * bucket -- ~36 B of HBM traffic per pair instead of ~100 B for the four radix passes.  *status (device int32) is
+ * cleared first and set non-zero when a bucket overflowed its region: ranks is then incomplete and the caller re-runs
+ * mdir_rank_scores.  Segments longer than 196,608 rows take the radix path directly.
+ * ws: mdir_rank_fast_workspace_bytes() bytes.                                                                      */
 size_t mdir_rank_fast_workspace_bytes(int64_t n_db, int n_q);
 int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q, int query_major,
                           int64_t* ranks, int64_t ranks_ld, void* ws, int32_t* status, void* stream);

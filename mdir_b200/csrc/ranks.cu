@@ -222,125 +222,276 @@ __global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __
 
 
 // ============================================================================================================
-// Sample-sort path (mdir_rank_scores_fast): one partition pass + one in-shared-memory sort per bucket.
+// Sample-sort path (mdir_rank_scores_fast): ONE partition pass + one shared-memory sort per bucket.
 //
 // The LSD radix sort above moves every (key, index) pair through HBM four times.  A segment here is one query's
-// n_db scores (100,000 at BASELINE config C3): with data-adaptive splitters it can be cut, in ONE pass, into
+// n_db scores (100,000 at BASELINE config C3): with data-adaptive splitters it can be cut, in one pass, into
 // buckets small enough to be sorted entirely in shared memory:
-//   1. ss_splitters_kernel   per query: a systematic sample of 16 x B composite keys (score key << 32 | row) is
-//                            sorted in shared memory; every 16th is a splitter.  Composite keys are unique, so ties
+//   1. ss_splitters_kernel   per query: a systematic sample of 32 x B composite keys (score key << 32 | row) is
+//                            sorted in shared memory; every 32nd is a splitter.  Composite keys are unique, so ties
 //                            in the scores cannot unbalance the buckets.
-//   2. ss_count_kernel       per (query, 4096-key chunk): bucket of every key (binary search over the splitters in
-//                            shared memory), bucket histogram -> counts
-//   3. radix_scan_kernel     exclusive scan, bucket-major / chunk-minor -> where each chunk's share of a bucket goes
-//   4. ss_scatter_kernel     same chunks: pairs staged in shared memory grouped by bucket, written out as runs
-//   5. ss_bucket_sort_kernel per (query, bucket): <= 2048 pairs, bitonic sort on the 64-bit composite in shared
-//                            memory, row indices written at their final ranks (query-major u32)
-//   6. ranks_transpose_kernel (n_q, n_db) u32 -> (n_db, n_q) int64, the reference's layout
-// Traffic per pair: scores 4 (read twice: 8) + pairs 8 written + 8 read + ranks 4 + transpose 4 + 8 = 40 B, against
-// ~100 B for the four radix passes.  A bucket that exceeds the staging capacity (the sample misjudged a segment;
-// not observed on any test distribution) raises *status and the caller re-runs mdir_rank_scores.
-constexpr int kSsChunk = 4096;                         // keys per CTA in the count / scatter kernels
+//   2. ss_scatter_kernel     per (query, 4096-key chunk): bucket of every key (binary search over the splitters in
+//                            shared memory), pairs staged in shared memory grouped by bucket, one global atomicAdd per
+//                            (chunk, bucket) reserves the run's slots in the bucket's region (2048 slots, ~2.7x the
+//                            expected fill: no counting pass), runs written out coalesced
+//   3. ss_offsets_kernel     per query: exclusive scan of the B bucket fills -> rank offset of every bucket
+//   4. ss_bucket_sort_kernel per (query, bucket): interpolation counting sort in shared memory (fine bin = linear map
+//                            of the composite between the bucket's min and max, histogram, scan, place, exact rank
+//                            inside the ~0.5-element bins by comparison): O(n) for the smooth key distributions of
+//                            similarity scores, O(n^2 / 256) per CTA at worst (never wrong); row indices land at their
+//                            final ranks (query-major u32)
+//   5. ranks_transpose_kernel (n_q, n_db) u32 -> (n_db, n_q) int64, the reference's layout
+// Traffic per pair: scores 4 + pairs 8 written + 8 read + ranks 4 + transpose 4 + 8 = 36 B, against ~100 B for the four
+// radix passes.  A bucket that overflows its region (probability ~1e-9 per bucket for a random row order) raises
+// *status and the caller re-runs mdir_rank_scores.
+constexpr int kSsChunk = 2048;                         // keys per CTA in the scatter kernel
 constexpr int kSsThreads = 256;
-constexpr int kSsItems = kSsChunk / kSsThreads;        // 16
-constexpr int kBucketTarget = 768;                     // average bucket size aimed for
-constexpr int kBucketCap = 2048;                       // pairs the bucket sort stages (16 KB)
-constexpr int kOversample = 16;
-constexpr int kMaxBuckets = 512;
-constexpr int64_t kSsMaxRows = (int64_t)kMaxBuckets * kBucketTarget;      // longer segments take the LSD path
+constexpr int kSsItems = kSsChunk / kSsThreads;        // 8
+constexpr int kBucketTarget = 400;                     // average bucket size aimed for
+constexpr int kBucketCap = 1024;                       // slots per bucket region = pairs the bucket sort stages
+constexpr int kOversample = 32;
+constexpr int kMaxBuckets = 256;
+constexpr int kMaxSample = kMaxBuckets * kOversample;  // 8192
+static_assert(kMaxBuckets <= kSsThreads, "one bucket per thread in the scatter scan");
+constexpr int64_t kSsMaxRows = (int64_t)kMaxBuckets * kBucketTarget;      // 102,400: longer segments take the LSD path
+
+constexpr int kTab = 1024;              // cells of the score -> bucket-range lookup table (per query)
+struct SsTable {                        // written by ss_splitters_kernel, read by ss_scatter_kernel
+    float hi, scale;                    // cell(score) = clamp(int((hi - score) * scale)); scale == 0: one cell (plain binary search)
+    uint16_t lower[kTab + 2];           // lower[j] = number of splitters in cells < j; a key of cell j is in bucket [lower[j], lower[j + 1]]
+};
+// Monotone (non-decreasing) in the composite key: keys ascend as scores descend; NaN (last) -> last cell.
+__device__ __forceinline__ int ss_cell(float score, float hi, float scale) {
+    const float v = (hi - score) * scale;
+    return (v == v) ? min(kTab - 1, max(0, (int)v)) : kTab - 1;
+}
 
 __device__ __forceinline__ uint32_t ss_load_key(const void* src, int is_key, int64_t i) {
     return is_key ? static_cast<const uint32_t*>(src)[i] : desc_key(static_cast<const float*>(src)[i]);
 }
 __device__ __forceinline__ uint64_t ss_composite(uint32_t key, uint32_t idx) { return ((uint64_t)key << 32) | (uint64_t)idx; }
 
-// number of splitters <= x  (splitters ascending, n_spl = B - 1 of them)  ->  bucket in [0, B - 1]
-__device__ __forceinline__ int ss_bucket_of(const uint64_t* spl, int n_spl, uint64_t x) {
-    int lo = 0, hi = n_spl;
+// number of splitters <= x  (splitters ascending, n_spl = B - 1 of them)  ->  bucket in [0, B - 1].
+// The search runs on the 32-bit score keys; the row half of the composite only matters on an exact key tie.
+__device__ __forceinline__ int ss_bucket_of(const uint32_t* spl_key, const uint32_t* spl_idx, int lo, int hi, uint32_t key, uint32_t idx) {
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (spl[mid] <= x) lo = mid + 1; else hi = mid;
+        const uint32_t sk = spl_key[mid];
+        const bool le = sk < key || (sk == key && spl_idx[mid] <= idx);
+        if (le) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// bitonic sort of n (power of two) 64-bit keys in shared memory, every thread busy in every stage
-__device__ __forceinline__ void ss_bitonic(uint64_t* a, int n) {
-    for (int kk = 2; kk <= n; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
-                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-                const int p = i | j;
-                const uint64_t x = a[i], y = a[p];
-                const bool asc = (i & kk) == 0;
-                if ((x > y) == asc) { a[i] = y; a[p] = x; }
-            }
-            __syncthreads();
+__device__ __forceinline__ uint64_t ss_shfl_xor64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+// Interpolation counting sort of the s unique 64-bit keys a[0, s) (shared memory).  tmp: s keys of scratch, cur: F
+// counters (F a power of two >= s), red: 2 * 32 keys.  Calls emit(rank, key) exactly once per key with its rank.
+// Every thread of the block must call it.
+// by_score: bins linear in the SCORE between the extreme scores (the whole-segment sample: its keys span dozens of
+// float octaves, and bins linear in the key bits would put a third of a Gaussian sample into a few dozen bins);
+// otherwise (one bucket: a sub-octave key range, or a run of tied scores) linear in the composite itself.
+// bounds != nullptr: every key lies in [bounds[0], bounds[1]] (a bucket between two splitters): no min / max pass.
+template <int kRegKeys, typename Emit>
+__device__ __forceinline__ void ss_interp_sort(const uint64_t* a, uint64_t* tmp, uint32_t* cur, uint64_t* red, int s, int F, bool by_score,
+                                               const uint64_t* bounds, Emit emit) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint64_t mn = ~0ull, mx = 0ull;
+    if (bounds == nullptr) {
+        for (int i = threadIdx.x; i < s; i += blockDim.x) {
+            const uint64_t x = a[i];
+            mn = x < mn ? x : mn;
+            mx = x > mx ? x : mx;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint64_t a_ = ss_shfl_xor64(mn, o), b_ = ss_shfl_xor64(mx, o);
+            mn = a_ < mn ? a_ : mn;
+            mx = b_ > mx ? b_ : mx;
+        }
+        if (lane == 0) { red[w] = mn; red[32 + w] = mx; }
+    }
+    for (int f = threadIdx.x; f < F; f += blockDim.x) cur[f] = 0u;
+    __syncthreads();
+    if (bounds == nullptr) {
+        mn = red[0];
+        mx = red[32];
+        for (int k = 1; k < nw; ++k) {
+            mn = red[k] < mn ? red[k] : mn;
+            mx = red[32 + k] > mx ? red[32 + k] : mx;
+        }
+    } else {
+        mn = bounds[0];
+        mx = bounds[1];
+    }
+    // fine bin = floor(position(x) * F / (position(mx) + 1)) with position monotone (non-decreasing) in x, so the bins
+    // are ordered like the keys: position = x - mn, or score(mn) - score(x) (keys ascend as scores descend; NaN last)
+    const float s_hi = key_score(mn), s_lo = key_score(mx);
+    const bool use_score = by_score && (s_hi - s_lo) > 0.f && (s_hi - s_lo) < INFINITY;
+    const float scale = use_score ? (float)F / ((s_hi - s_lo) * 1.0001f) : (float)F / (__ull2float_rz(mx - mn) + 1.0f);
+    auto bin_of = [&](uint64_t x) {
+        const float v = use_score ? (s_hi - key_score(x)) : __ull2float_rz(x - mn);
+        return (v == v) ? min(F - 1, max(0, (int)(v * scale))) : F - 1;
+    };
+    // each thread keeps its first kRegKeys keys and their bins in registers across the phases (sized for the usual
+    // list: 2 per thread for a ~400-key bucket on 256 threads, 8 for the 8,000-key sample on 1024); the rest is re-read
+    uint64_t xr[kRegKeys];
+    int fr[kRegKeys];
+#pragma unroll
+    for (int k = 0; k < kRegKeys; ++k) {
+        const int i = threadIdx.x + k * blockDim.x;
+        fr[k] = -1;
+        if (i < s) {
+            xr[k] = a[i];
+            fr[k] = bin_of(xr[k]);
+            atomicAdd(&cur[fr[k]], 1u);
+        }
+    }
+    for (int i = threadIdx.x + kRegKeys * blockDim.x; i < s; i += blockDim.x) atomicAdd(&cur[bin_of(a[i])], 1u);
+    __syncthreads();
+    {   // exclusive scan of cur[0, F) in place: each thread owns F / blockDim consecutive counters
+        const int per = (F + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int f0 = threadIdx.x * per;
+        uint32_t sum = 0;
+        for (int k = 0; k < per; ++k)
+            if (f0 + k < F) sum += cur[f0 + k];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t* wsum = reinterpret_cast<uint32_t*>(red + 64);
+        __syncthreads();                                   // red[0..63] fully read
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        uint32_t pre = incl - sum;
+        for (int k = 0; k < w; ++k) pre += wsum[k];
+        for (int k = 0; k < per; ++k)
+            if (f0 + k < F) {
+                const uint32_t c = cur[f0 + k];
+                cur[f0 + k] = pre;
+                pre += c;
+            }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kRegKeys; ++k)
+        if (fr[k] >= 0) tmp[atomicAdd(&cur[fr[k]], 1u)] = xr[k];       // afterwards cur[f] = END of bin f
+    for (int i = threadIdx.x + kRegKeys * blockDim.x; i < s; i += blockDim.x) {
+        const uint64_t x = a[i];
+        tmp[atomicAdd(&cur[bin_of(x)], 1u)] = x;
+    }
+    __syncthreads();
+    // exact rank = first slot of the key's bin + the number of smaller keys in that bin (~0.5 keys per bin)
+    auto rank_of = [&](uint64_t x, int f) {
+        const int begin = f ? (int)cur[f - 1] : 0, end = (int)cur[f];
+        int r = begin;
+        for (int j = begin; j < end; ++j) r += tmp[j] < x ? 1 : 0;
+        return r;
+    };
+#pragma unroll
+    for (int k = 0; k < kRegKeys; ++k)
+        if (fr[k] >= 0) emit(rank_of(xr[k], fr[k]), xr[k]);
+    for (int i = threadIdx.x + kRegKeys * blockDim.x; i < s; i += blockDim.x) {
+        const uint64_t x = a[i];
+        emit(rank_of(x, bin_of(x)), x);
     }
 }
 
-__global__ void __launch_bounds__(512) ss_splitters_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int m, int m_pow2,
-                                                           uint64_t* __restrict__ splitters) {
+// dynamic smem: 2 * m keys + F counters + 64 keys + 32 counters
+__global__ void __launch_bounds__(1024) ss_splitters_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int m, int F,
+                                                            uint64_t* __restrict__ splitters, SsTable* __restrict__ table) {
     extern __shared__ uint64_t ss_smem[];
+    uint64_t* a = ss_smem;
+    uint64_t* tmp = a + m;
+    uint64_t* red = tmp + m;                              // 64 keys + 32 counters (= 16 keys)
+    uint32_t* cur = reinterpret_cast<uint32_t*>(red + 80);
     const int q = blockIdx.x;
     const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
-    for (int j = threadIdx.x; j < m_pow2; j += blockDim.x) {
-        uint64_t v = ~0ull;
-        if (j < m) {
-            const int64_t i = (int64_t)j * n_db / m;
-            v = ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i);
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        const int64_t i = (int64_t)j * n_db / m;
+        a[j] = ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i);
+    }
+    __syncthreads();
+    uint64_t* out = splitters + (int64_t)q * B;
+    __shared__ uint64_t s_ext[2];
+    __shared__ float s_tab[2];
+    __shared__ uint32_t s_hist[kTab + 2];
+    // splitter b = the sample's order statistic (b + 1) * m / B; ranks are unique, so each is written exactly once
+    ss_interp_sort<8>(a, tmp, cur, red, m, F, true, nullptr, [&](int r, uint64_t x) {
+        const int b = (int)(((int64_t)r * B + m - 1) / m);                 // the only b with (b * m) / B == r, if any (m >= B)
+        if (b >= 1 && b <= B - 1 && (int)(((int64_t)b * m) / B) == r) out[b - 1] = x;
+        if (r == 0) s_ext[0] = x;
+        if (r == m - 1) s_ext[1] = x;
+    });
+    // score -> bucket-range table for the scatter kernel: cells linear in the score between the sample's extremes;
+    // lower[j] = splitters in cells below j (they are smaller than every key of cell j, the map being monotone)
+    for (int j = threadIdx.x; j < kTab + 2; j += blockDim.x) s_hist[j] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float hi = key_score(s_ext[0]), range = hi - key_score(s_ext[1]);
+        s_tab[0] = hi;
+        s_tab[1] = (range > 0.f && range < INFINITY) ? (float)kTab / (range * 1.0001f) : 0.f;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < B - 1; b += blockDim.x) atomicAdd(&s_hist[ss_cell(key_score(out[b]), s_tab[0], s_tab[1]) + 1], 1u);
+    __syncthreads();
+    {   // inclusive scan of the kTab + 2 counters: 32 per lane of warp 0
+        constexpr int kPer = (kTab + 2 + 31) / 32;
+        if (threadIdx.x < 32) {
+            const int j0 = threadIdx.x * kPer;
+            uint32_t sum = 0;
+            for (int k = 0; k < kPer; ++k)
+                if (j0 + k < kTab + 2) sum += s_hist[j0 + k];
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)threadIdx.x >= o) incl += u;
+            }
+            uint32_t run = incl - sum;
+            for (int k = 0; k < kPer; ++k)
+                if (j0 + k < kTab + 2) {
+                    run += s_hist[j0 + k];
+                    s_hist[j0 + k] = run;
+                }
         }
-        ss_smem[j] = v;
     }
     __syncthreads();
-    ss_bitonic(ss_smem, m_pow2);
-    for (int b = threadIdx.x; b < B - 1; b += blockDim.x) splitters[(int64_t)q * B + b] = ss_smem[(int64_t)(b + 1) * m / B];
+    SsTable* t = table + q;
+    if (threadIdx.x == 0) { t->hi = s_tab[0]; t->scale = s_tab[1]; }
+    for (int j = threadIdx.x; j < kTab + 2; j += blockDim.x) t->lower[j] = (uint16_t)s_hist[j];
 }
 
-__global__ void __launch_bounds__(kSsThreads) ss_count_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int n_chunks,
-                                                              const uint64_t* __restrict__ splitters, uint32_t* __restrict__ counts) {
-    extern __shared__ uint64_t ss_smem[];
-    uint64_t* spl = ss_smem;                                   // B entries (B - 1 used)
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(spl + B);      // B
-    const int chunk = blockIdx.x, q = blockIdx.y;
-    for (int b = threadIdx.x; b < B; b += kSsThreads) {
-        spl[b] = b < B - 1 ? splitters[(int64_t)q * B + b] : ~0ull;
-        cnt[b] = 0u;
-    }
-    __syncthreads();
-    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
-    const int64_t base = (int64_t)chunk * kSsChunk;
-    uint32_t key[kSsItems];
-#pragma unroll
-    for (int it = 0; it < kSsItems; ++it) {
-        const int64_t i = base + it * kSsThreads + threadIdx.x;
-        key[it] = i < n_db ? ss_load_key(seg, is_key, i) : 0u;
-    }
-#pragma unroll
-    for (int it = 0; it < kSsItems; ++it) {
-        const int64_t i = base + it * kSsThreads + threadIdx.x;
-        if (i < n_db) atomicAdd(&cnt[ss_bucket_of(spl, B - 1, ss_composite(key[it], (uint32_t)i))], 1u);
-    }
-    __syncthreads();
-    for (int b = threadIdx.x; b < B; b += kSsThreads) counts[((int64_t)q * B + b) * n_chunks + chunk] = cnt[b];
-}
-
-__global__ void __launch_bounds__(kSsThreads) ss_scatter_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B, int n_chunks,
-                                                                const uint64_t* __restrict__ splitters, const uint32_t* __restrict__ offsets,
-                                                                uint64_t* __restrict__ pairs) {
+// dynamic smem: kSsChunk pairs + B x {splitter key, splitter row, counter, delta, fits} + kSsChunk bucket ids
+__global__ void __launch_bounds__(kSsThreads, 8) ss_scatter_kernel(const void* __restrict__ src, int is_key, int64_t n_db, int B,
+                                                                const uint64_t* __restrict__ splitters, const SsTable* __restrict__ table,
+                                                                uint32_t* __restrict__ fill, uint64_t* __restrict__ pairs,
+                                                                int32_t* __restrict__ status) {
     extern __shared__ uint64_t ss_smem[];
     uint64_t* stage = ss_smem;                                             // kSsChunk
-    uint64_t* spl = stage + kSsChunk;                                      // B
-    uint32_t* cnt = reinterpret_cast<uint32_t*>(spl + B);                  // B: counts, then chunk-local bases
-    uint32_t* delta = cnt + B;                                             // B: global offset - local base
-    uint16_t* sbucket = reinterpret_cast<uint16_t*>(delta + B);            // kSsChunk
+    uint32_t* spl_key = reinterpret_cast<uint32_t*>(stage + kSsChunk);     // B
+    uint32_t* spl_idx = spl_key + B;                                       // B
+    uint32_t* cnt = spl_idx + B;                                           // B: counts, then chunk-local bases
+    uint32_t* delta = cnt + B;                                             // B: slot in the bucket region - local base (mod 2^32)
+    uint32_t* fits = delta + B;                                            // B: 0 when the run overflowed the bucket region
+    uint16_t* sbucket = reinterpret_cast<uint16_t*>(fits + B);             // kSsChunk
+    __shared__ uint16_t lower[kTab + 2];
     const int chunk = blockIdx.x, q = blockIdx.y;
     const int lane = threadIdx.x & 31;
     for (int b = threadIdx.x; b < B; b += kSsThreads) {
-        spl[b] = b < B - 1 ? splitters[(int64_t)q * B + b] : ~0ull;
+        const uint64_t sp = b < B - 1 ? splitters[(int64_t)q * B + b] : ~0ull;
+        spl_key[b] = (uint32_t)(sp >> 32);
+        spl_idx[b] = (uint32_t)sp;
         cnt[b] = 0u;
     }
+    const SsTable* t = table + q;
+    for (int j = threadIdx.x; j < kTab + 2; j += kSsThreads) lower[j] = t->lower[j];
+    const float t_hi = t->hi, t_scale = t->scale;
     __syncthreads();
     const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
     const int64_t base = (int64_t)chunk * kSsChunk;
@@ -355,28 +506,40 @@ __global__ void __launch_bounds__(kSsThreads) ss_scatter_kernel(const void* __re
         const int64_t i = base + it * kSsThreads + threadIdx.x;
         where[it] = 0u;
         if (i < n_db) {
-            const int b = ss_bucket_of(spl, B - 1, ss_composite(key[it], (uint32_t)i));
+            const int cell = ss_cell(key_score((uint64_t)key[it] << 32), t_hi, t_scale);
+            const int b = ss_bucket_of(spl_key, spl_idx, (int)lower[cell], (int)lower[cell + 1], key[it], (uint32_t)i);
             where[it] = ((uint32_t)b << 16) | atomicAdd(&cnt[b], 1u);      // order inside a bucket is free: the bucket gets sorted
         }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {                                                // exclusive scan of the B counts by warp 0
-        uint32_t run = 0;
-        for (int b0 = 0; b0 < B; b0 += 32) {
-            const int b = b0 + lane;
-            const uint32_t c = b < B ? cnt[b] : 0u;
-            uint32_t incl = c;
+    // one thread per bucket reserves this chunk's run in the bucket's region (all the global atomics in flight at
+    // once); a run that does not fit is dropped and reported.  delta keeps (region slot - local base) mod 2^32.
+    for (int b = threadIdx.x; b < B; b += kSsThreads) {
+        const uint32_t c = cnt[b];
+        const uint32_t slot = c ? atomicAdd(&fill[(int64_t)q * B + b], c) : 0u;
+        const bool ok = slot + c <= (uint32_t)kBucketCap;
+        if (!ok) atomicOr(status, 1);
+        fits[b] = ok ? 1u : 0u;
+        delta[b] = (uint32_t)b * kBucketCap + slot;
+    }
+    __syncthreads();
+    {   // exclusive scan of the B <= kSsThreads counts, one bucket per thread
+        __shared__ uint32_t wsum[kSsThreads / 32];
+        const int b = threadIdx.x;
+        const uint32_t c = b < B ? cnt[b] : 0u;
+        uint32_t incl = c;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            if (b < B) {
-                const uint32_t lbase = run + incl - c;
-                cnt[b] = lbase;
-                delta[b] = offsets[((int64_t)q * B + b) * n_chunks + chunk] - lbase;
-            }
-            run += __shfl_sync(0xffffffffu, incl, 31);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        uint32_t lbase = incl - c;
+        for (int k = 0; k < (int)(threadIdx.x >> 5); ++k) lbase += wsum[k];
+        if (b < B) {
+            cnt[b] = lbase;
+            delta[b] -= lbase;
         }
     }
     __syncthreads();
@@ -392,55 +555,82 @@ __global__ void __launch_bounds__(kSsThreads) ss_scatter_kernel(const void* __re
     }
     __syncthreads();
     const int n_valid = (int)min((int64_t)kSsChunk, n_db - base);
-    uint64_t* out = pairs + (int64_t)q * n_db;
-    for (int l = threadIdx.x; l < n_valid; l += kSsThreads) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+    uint64_t* out = pairs + (int64_t)q * B * kBucketCap;
+    for (int l = threadIdx.x; l < n_valid; l += kSsThreads) {
+        const int b = sbucket[l];
+        if (fits[b]) out[(uint32_t)l + delta[b]] = stage[l];
+    }
 }
 
-// direct != 0: B == 1, the pairs are built from the scores / keys themselves (short segments: no partition pass)
-__global__ void __launch_bounds__(256) ss_bucket_sort_kernel(const uint64_t* __restrict__ pairs, const void* __restrict__ src, int is_key, int direct,
-                                                             int64_t n_db, int B, int n_chunks, const uint32_t* __restrict__ offsets,
-                                                             uint32_t* __restrict__ vals, int32_t* __restrict__ status) {
-    extern __shared__ uint64_t ss_smem[];
-    const int b = blockIdx.x, q = blockIdx.y;
-    uint32_t off = 0u, end = (uint32_t)n_db;
-    if (!direct) {
-        off = offsets[((int64_t)q * B + b) * n_chunks];
-        if (b + 1 < B) end = offsets[((int64_t)q * B + b + 1) * n_chunks];
-    }
-    const int s = (int)(end - off);
-    if (s <= 0) return;
-    if (s > kBucketCap) {
-        if (threadIdx.x == 0) atomicOr(status, 1);
-        return;
-    }
-    int n = 32;
-    while (n < s) n <<= 1;
-    if (direct) {
-        const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) ss_smem[i] = i < s ? ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i) : ~0ull;
-    } else {
-        const uint64_t* in = pairs + (int64_t)q * n_db + off;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) ss_smem[i] = i < s ? in[i] : ~0ull;
+// fill (n_q, B) -> offsets (n_q, B): rank of the first element of every bucket
+__global__ void __launch_bounds__(256) ss_offsets_kernel(const uint32_t* __restrict__ fill, int B, uint32_t* __restrict__ offsets) {
+    __shared__ uint32_t sh[kMaxBuckets];
+    const int q = blockIdx.x;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) sh[b] = min(fill[(int64_t)q * B + b], (uint32_t)kBucketCap);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (int b = 0; b < B; ++b) {
+            const uint32_t c = sh[b];
+            sh[b] = run;
+            run += c;
+        }
     }
     __syncthreads();
-    ss_bitonic(ss_smem, n);
+    for (int b = threadIdx.x; b < B; b += blockDim.x) offsets[(int64_t)q * B + b] = sh[b];
+}
+
+// direct != 0: B == 1, the pairs are built from the scores / keys themselves (short segments: no partition pass) and
+// staged in shared memory; otherwise the bucket is read straight from its (L2-resident) region, three times.
+// dynamic smem: kBucketCap keys (+ kBucketCap more when direct) + 2 * kBucketCap counters + 80 keys
+constexpr int kSortThreads = 256;
+__global__ void __launch_bounds__(kSortThreads, 8) ss_bucket_sort_kernel(const uint64_t* __restrict__ pairs, const void* __restrict__ src, int is_key, int direct,
+                                                             int64_t n_db, int B, const uint32_t* __restrict__ fill,
+                                                             const uint32_t* __restrict__ offsets, const uint64_t* __restrict__ splitters,
+                                                             uint32_t* __restrict__ vals) {
+    extern __shared__ uint64_t ss_smem[];
+    uint64_t* tmp = ss_smem;
+    uint64_t* red = tmp + kBucketCap;
+    uint32_t* cur = reinterpret_cast<uint32_t*>(red + 80);
+    const int b = blockIdx.x, q = blockIdx.y;
+    int s;
+    uint32_t off = 0u;
+    const uint64_t* a;
+    if (direct) {
+        s = (int)n_db;
+        uint64_t* stage = reinterpret_cast<uint64_t*>(cur + 2 * kBucketCap);
+        const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+        for (int i = threadIdx.x; i < s; i += blockDim.x) stage[i] = ss_composite(ss_load_key(seg, is_key, i), (uint32_t)i);
+        a = stage;
+    } else {
+        s = (int)min(fill[(int64_t)q * B + b], (uint32_t)kBucketCap);
+        off = offsets[(int64_t)q * B + b];
+        a = pairs + ((int64_t)q * B + b) * kBucketCap;
+    }
+    if (s <= 0) return;
+    __syncthreads();
+    int F = 64;
+    while (F < 2 * s) F <<= 1;
     uint32_t* out = vals + (int64_t)q * n_db + off;
-    for (int i = threadIdx.x; i < s; i += blockDim.x) out[i] = (uint32_t)ss_smem[i];
+    // an inner bucket lies between two splitters: its key range is known without looking at the keys
+    __shared__ uint64_t bnd[2];
+    const bool inner = !direct && b >= 1 && b + 1 < B;
+    if (inner && threadIdx.x < 2) bnd[threadIdx.x] = splitters[(int64_t)q * B + b - 1 + threadIdx.x] - threadIdx.x;
+    ss_interp_sort<2>(a, tmp, cur, red, s, F, false, inner ? bnd : nullptr, [&](int r, uint64_t x) { out[r] = (uint32_t)x; });
 }
 
 struct SsPlan {
-    int B, m, m_pow2, n_chunks;
+    int B, m, F_sample;
 };
 static SsPlan ss_plan(int64_t n_db) {
     SsPlan p;
-    p.B = n_db <= kBucketCap ? 1 : (int)((n_db + kBucketTarget - 1) / kBucketTarget);
+    p.B = n_db <= kBucketCap ? 1 : (int)((n_db + kBucketTarget - 1) / kBucketTarget);      // B == 1: direct in-smem sort
     if (p.B > kMaxBuckets) p.B = kMaxBuckets;
     int64_t m = (int64_t)p.B * kOversample;
     if (m > n_db) m = n_db;
     p.m = (int)m;
-    p.m_pow2 = 32;
-    while (p.m_pow2 < p.m) p.m_pow2 <<= 1;
-    p.n_chunks = (int)((n_db + kSsChunk - 1) / kSsChunk);
+    p.F_sample = 64;
+    while (p.F_sample < 2 * p.m) p.F_sample <<= 1;
     return p;
 }
 
@@ -508,8 +698,9 @@ extern "C" size_t mdir_rank_fast_workspace_bytes(int64_t n_db, int n_q) {
     if (n_db <= 0 || n_q <= 0) return 0;
     if (n_db > kSsMaxRows) return mdir_rank_workspace_bytes(n_db, n_q);
     const SsPlan p = ss_plan(n_db);
-    const size_t pairs = (size_t)n_db * n_q;
-    return align256((size_t)n_q * p.B * 8) + align256((size_t)n_q * p.B * p.n_chunks * 4) + align256(pairs * 8) + 2 * align256(pairs * 4);
+    const size_t n_pairs = (size_t)n_db * n_q;
+    return align256((size_t)n_q * p.B * 8) + 2 * align256((size_t)n_q * p.B * 4) + align256((size_t)n_q * sizeof(SsTable)) +
+           align256((size_t)n_q * p.B * kBucketCap * 8) + 2 * align256(n_pairs * 4);
 }
 
 extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, int64_t ranks_ld,
@@ -523,8 +714,10 @@ extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q,
     const size_t n_pairs = (size_t)n_db * n_q;
     uint8_t* w = (uint8_t*)ws;
     uint64_t* splitters = (uint64_t*)w;          w += align256((size_t)n_q * p.B * 8);
-    uint32_t* counts = (uint32_t*)w;             w += align256((size_t)n_q * p.B * p.n_chunks * 4);
-    uint64_t* pairs = (uint64_t*)w;              w += align256(n_pairs * 8);
+    uint32_t* fill = (uint32_t*)w;               w += align256((size_t)n_q * p.B * 4);
+    uint32_t* offsets = (uint32_t*)w;            w += align256((size_t)n_q * p.B * 4);
+    SsTable* table = (SsTable*)w;                w += align256((size_t)n_q * sizeof(SsTable));
+    uint64_t* pairs = (uint64_t*)w;              w += align256((size_t)n_q * p.B * kBucketCap * 8);
     uint32_t* vals = (uint32_t*)w;               w += align256(n_pairs * 4);
     uint32_t* keys_t = (uint32_t*)w;             // only for the (n_db, n_q) input layout
     const unsigned gx = (unsigned)((n_db + 31) / 32), gy = (unsigned)((n_q + 31) / 32);
@@ -536,25 +729,30 @@ extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q,
         src = keys_t;
         is_key = 1;
     }
-    const size_t scatter_smem = (size_t)kSsChunk * 8 + (size_t)p.B * 8 + (size_t)p.B * 8 + (size_t)kSsChunk * 2;
+    const size_t scatter_smem = (size_t)kSsChunk * 8 + (size_t)p.B * 20 + (size_t)kSsChunk * 2;
+    const size_t sort_smem = (size_t)kBucketCap * 8 + 80 * 8 + (size_t)2 * kBucketCap * 4 + (p.B == 1 ? (size_t)kBucketCap * 8 : 0);
+    const size_t spl_smem = (size_t)p.m * 16 + 80 * 8 + (size_t)p.F_sample * 4;
     static PerDeviceOnce once;
     if (once.first() != 0) {
         MDIR_CUDA(cudaFuncSetAttribute(ss_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)kSsChunk * 10 + (size_t)kMaxBuckets * 16)));
-        MDIR_CUDA(cudaFuncSetAttribute(ss_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxBuckets * kOversample * 8));
+                                       (int)((size_t)kSsChunk * 10 + (size_t)kMaxBuckets * 20)));
+        MDIR_CUDA(cudaFuncSetAttribute(ss_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)kMaxSample * 16 + 80 * 8 + (size_t)2 * kMaxSample * 4)));
+        MDIR_CUDA(cudaFuncSetAttribute(ss_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)kBucketCap * 16 + 80 * 8 + (size_t)2 * kBucketCap * 4)));
     }
     if (p.B > 1) {
-        ss_splitters_kernel<<<n_q, 512, (size_t)p.m_pow2 * 8, st>>>(src, is_key, n_db, p.B, p.m, p.m_pow2, splitters);
+        MDIR_CUDA(cudaMemsetAsync(fill, 0, (size_t)n_q * p.B * 4, st));
+        ss_splitters_kernel<<<n_q, 1024, spl_smem, st>>>(src, is_key, n_db, p.B, p.m, p.F_sample, splitters, table);
         MDIR_LAUNCH_CHECK();
-        ss_count_kernel<<<dim3(p.n_chunks, n_q), kSsThreads, (size_t)p.B * 12, st>>>(src, is_key, n_db, p.B, p.n_chunks, splitters, counts);
+        const int n_chunks = (int)((n_db + kSsChunk - 1) / kSsChunk);
+        ss_scatter_kernel<<<dim3(n_chunks, n_q), kSsThreads, scatter_smem, st>>>(src, is_key, n_db, p.B, splitters, table, fill, pairs, status);
         MDIR_LAUNCH_CHECK();
-        radix_scan_kernel<<<n_q, 1024, 0, st>>>(counts, p.n_chunks, p.B);
-        MDIR_LAUNCH_CHECK();
-        ss_scatter_kernel<<<dim3(p.n_chunks, n_q), kSsThreads, scatter_smem, st>>>(src, is_key, n_db, p.B, p.n_chunks, splitters, counts, pairs);
+        ss_offsets_kernel<<<n_q, 256, 0, st>>>(fill, p.B, offsets);
         MDIR_LAUNCH_CHECK();
     }
-    ss_bucket_sort_kernel<<<dim3(p.B, n_q), 256, (size_t)kBucketCap * 8, st>>>(pairs, src, is_key, p.B == 1 ? 1 : 0, n_db, p.B, p.n_chunks, counts,
-                                                                              vals, status);
+    ss_bucket_sort_kernel<<<dim3(p.B, n_q), kSortThreads, sort_smem, st>>>(pairs, src, is_key, p.B == 1 ? 1 : 0, n_db, p.B, fill, offsets, splitters,
+                                                                                       vals);
     MDIR_LAUNCH_CHECK();
     ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
     MDIR_LAUNCH_CHECK();

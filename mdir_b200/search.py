@@ -377,19 +377,35 @@ class Index:
     def ranks(self, q, max_pairs=1 << 28, precision="bf16"):
         """Full ranking: (N_db, N_q) int64 C-order on the device (== np.argsort(-scores, axis=0,
         kind='stable') of this index's scores at the given precision, see scores()).  Queries are processed in chunks of at most
-        max_pairs // N_db to bound the sort workspace (16 B per pair)."""
+        max_pairs // N_db to bound the sort workspace (~30 B per pair)."""
+        lib = _lib.lib()
         with torch.cuda.device(self.device):
             q32 = _as_dev_f32(q, self.device)
             nq_all = q32.shape[0]
             out = torch.empty((self.n, nq_all), dtype=torch.int64, device=self.device)
+            if nq_all == 0 or self.n == 0:
+                return out
             chunk = max(1, min(nq_all, max_pairs // max(self.n, 1)))
             chunk = max(1, min(chunk, 65535))
             ws = _rank_workspace(self.n, chunk, self.device)
             sc = torch.empty((chunk, self.n), dtype=torch.float32, device=self.device)
-            for q0 in range(0, nq_all, chunk):
+            starts = list(range(0, nq_all, chunk))
+            status = torch.zeros((len(starts),), dtype=torch.int32, device=self.device)
+            for c, q0 in enumerate(starts):
                 q1 = min(q0 + chunk, nq_all)
                 self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
-                _rank_scores(sc, self.n, q1 - q0, 1, out[:, q0:], nq_all, ws)
+                _lib.check(lib.mdir_rank_scores_fast(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
+                                                     _lib.ptr(status[c:]), _lib.stream()), "mdir_rank_scores_fast")
+            RANK_STATS["fast"] += len(starts)
+            # ONE read-back for the whole call, after everything is queued; a chunk whose sample sort could not stage a
+            # bucket is redone through the segmented radix sort
+            for c in [i for i, v in enumerate(status.cpu().tolist()) if v]:
+                q0 = starts[c]
+                q1 = min(q0 + chunk, nq_all)
+                RANK_STATS["fallback"] += 1
+                self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
+                _lib.check(lib.mdir_rank_scores(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws), _lib.stream()),
+                           "mdir_rank_scores")
             return out
 
 
