@@ -125,8 +125,11 @@ int mdir_lab_clahe_to_rgb(const float* rgb, const mdir_rgb_desc* descs, int n_im
  * (D, n) column-per-image layout (cirtorch/networks/imageretrievalnet.py:291).  */
 int mdir_pack_bf16(const float* src, int64_t n, int D, int src_is_Dxn, uint16_t* dst, void* stream);
 
-/* One streaming pass of the database against <= 128 resident queries on
- * tcgen05/TMEM tiles fed by TMA (256 db rows per tile, fp32 accumulate).
+/* One streaming pass of the database against <= 256 resident queries on
+ * tcgen05/TMEM tiles fed by TMA (256 db rows per tile, fp32 accumulate).  Up to 128 queries the TMEM
+ * accumulators are double / triple buffered (the HBM-bound serving shapes); 129..256 queries use all 512 TMEM
+ * columns for one tile: arithmetic intensity = n_q FLOP per database byte, above the ~214 FLOP/B ridge of this part,
+ * i.e. the tensor-bound shapes (database-side augmentation, all-pairs scores).
  *   mode MDIR_SCAN_DENSE   : write every score, out[q * dense_ld + row]
  *   mode MDIR_SCAN_SAMPLE  : only tiles t = j*sample_stride (j < n_sample), written
  *                            compactly: out[q * dense_ld + j*256 + r]

@@ -26,7 +26,7 @@ constexpr int kBlockKBytes = 128;               // one 128-byte swizzle row per 
                                                 //   64 bf16 (UMMA_K = 16) or 32 fp32/tf32 (UMMA_K = 8): 4 MMAs of 32 bytes either way
 constexpr int kKSteps = 4;
 constexpr int kABytes = kBlockM * kBlockKBytes;  // 32768
-constexpr int kMaxN = 128;
+constexpr int kMaxN = 256;               // queries resident per pass (UMMA N); the in-kernel threshold exchange handles <= 128
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
@@ -501,8 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         }
         if (emode == MDIR_SCAN_FILTER) {
             asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
-            const int t = threadIdx.x - 64;
-            if (t < p.n_q) {
+            for (int t = (int)threadIdx.x - 64; t < p.n_q; t += 128) {
                 p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + 1 + blockIdx.x] = cand_n[t];
                 if (p.mode == MDIR_SCAN_FUSED && blockIdx.x == 0) {
                     // no select kernel in this route: segment 0 and the segments of absent CTAs are empty
@@ -598,8 +597,11 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.split_stride = split_stride;
     p.chain = 1;
     p.kb_per_chain = p.num_k_blocks;
-    p.acc_bufs = p.n_pad <= 80 ? 3 : 2;
-    p.acc_stride = p.n_pad <= 80 ? 80 : 128;
+    // TMEM (512 columns): 3 tiles of 2 x 80 columns, 2 of 2 x 128, or -- 129..256 queries, the tensor-bound shapes
+    // (DBA, all-pairs): AI = n_q FLOP/B crosses the ~214 FLOP/B ridge -- ONE tile of 2 x 256 (the epilogue of a tile is
+    // then not overlapped with the next tile's MMAs: ~10 % of a D = 2048 tile)
+    p.acc_bufs = p.n_pad <= 80 ? 3 : (p.n_pad <= 128 ? 2 : 1);
+    p.acc_stride = p.n_pad <= 80 ? 80 : (p.n_pad <= 128 ? 128 : 256);
     p.kth = 0;
     p.grp_top = nullptr;
     p.sync = nullptr;
@@ -623,7 +625,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         p.n_work = n_sample;
     } else if (mode == MDIR_SCAN_FUSED) {
         // one sample tile per CTA, all CTAs co-resident (the in-kernel arrival counters rely on it)
-        MDIR_CHECK_ARG(tau_rw && fused_ws && cand && seg_counts && cap_l >= 1 && kth >= 1);
+        MDIR_CHECK_ARG(tau_rw && fused_ws && cand && seg_counts && cap_l >= 1 && kth >= 1 && n_q <= 128);
         const int sm_count = device_sm_count();
         MDIR_CHECK_ARG(sm_count > 0);
         int g = sm_count < kNumSMs ? sm_count : kNumSMs;
@@ -655,7 +657,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     if (p.n_work <= 0 && mode != MDIR_SCAN_FUSED) return 0;
 
     const int stage_bytes = kABytes + p.n_pad * 128;
-    int stages = (232448 - 1024 - 4096) / stage_bytes;
+    int stages = (232448 - 1024 - 8192) / stage_bytes;      // 8 KB left for the static shared arrays
     if (stages > kMaxStages) stages = kMaxStages;
     MDIR_CHECK_ARG(stages >= 2);
     p.num_stages = stages;
@@ -669,8 +671,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
 
     static PerDeviceOnce once;
     if (once.first() != 0) {
-        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
-        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 4096));
+        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 8192));
+        MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 8192));
     }
     const int n_ctas_wanted = p.chain > 1 ? p.n_tiles : p.n_work;
     const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (n_ctas_wanted < kNumSMs ? n_ctas_wanted : kNumSMs);
@@ -829,10 +831,11 @@ __global__ void __launch_bounds__(256) sum_partials_l2n_kernel(const float* __re
 // one), each on half of the SMs, instead of back to back on all of them: the chain of small kernels per block is
 // latency-bound, so two half-width chains finish in about the time of one.
 static void whiten_blocks(int n, int* n_blocks, int* block_rows) {
-    const int nblk = (n + kMaxN - 1) / kMaxN;
+    constexpr int kWhitenBlock = 128;           // descriptors per projection block (double-buffered TMEM accumulators)
+    const int nblk = (n + kWhitenBlock - 1) / kWhitenBlock;
     int rows = (n + nblk - 1) / nblk;
     rows = (rows + 15) & ~15;
-    if (rows > kMaxN) rows = kMaxN;
+    if (rows > kWhitenBlock) rows = kWhitenBlock;
     *n_blocks = (n + rows - 1) / rows;
     *block_rows = rows;
 }

@@ -9,6 +9,13 @@ from . import _lib
 from .search import Index, ShardedIndex, MAX_Q
 
 
+DBA_BLOCK = 4096      # rows augmented per search() call (32 scan passes; ONE status read-back per call instead of one per pass)
+# Queries resident per scan pass.  256 (all of TMEM for one tile, AI = 256 FLOP per database byte) is supported and
+# bit-identical, but measured SLOWER than 128 on B200 (1.46 ms vs 2 x 0.65 ms per 256 queries at 1M x 2048: three 64 KB
+# pipeline stages and no accumulator double-buffering cost more than the halved HBM traffic saves) -- tools/time_wide.py.
+DBA_QUERIES_PER_PASS = MAX_Q
+
+
 def _accumulate(index, idx, scores, alpha):
     n_q, n_qe = idx.shape
     acc = torch.empty((n_q, index.D), dtype=torch.float32, device=index.device)
@@ -49,15 +56,15 @@ def search_qe(index, q, k, alpha=3.0, n_qe=10, precision="fp32"):
 def dba(index, alpha=3.0, k_dba=10, rows=None):
     """Database-side augmentation of a single-GPU Index: every row replaced by the normalised
     alpha-weighted sum of its own top-k_dba neighbours (self included).  Returns a new Index.
-    Each block of 128 rows is one streaming pass of the database (HBM-bound form).
+    Every 128 rows are one streaming pass of the database (HBM-bound at 128 FLOP per database byte; see DBA_QUERIES_PER_PASS).
     rows: augment only the first `rows` rows (the others are copied unchanged) -- bounded benchmarks."""
     if index.db32 is None:
         raise _lib.MdirError("DBA needs the fp32 master copy (keep_fp32=True)")
     n_aug = index.n if rows is None else min(int(rows), index.n)
     out = torch.empty_like(index.db32) if n_aug == index.n else index.db32.clone()
-    for r0 in range(0, n_aug, MAX_Q):
-        r1 = min(r0 + MAX_Q, n_aug)
-        s, i = index.search(index.db32[r0:r1], k_dba, precision="fp32")
+    for r0 in range(0, n_aug, DBA_BLOCK):
+        r1 = min(r0 + DBA_BLOCK, n_aug)
+        s, i = index.search(index.db32[r0:r1], k_dba, precision="fp32", block_q=DBA_QUERIES_PER_PASS)
         out[r0:r1] = _add_l2n(_accumulate(index, i, s, alpha), None)
     return Index(out, device=index.device, keep_fp32=True, idx_base=index.idx_base)
 
@@ -90,9 +97,9 @@ def dba_sharded(sharded, alpha=3.0, k_dba=10):
     del pad
     full_index = Index(full, device=dev, keep_fp32=True, idx_base=0)
     out = torch.empty_like(local.db32)
-    for r0 in range(0, local.n, MAX_Q):
-        r1 = min(r0 + MAX_Q, local.n)
-        s, i = full_index.search(local.db32[r0:r1], k_dba, precision="fp32")
+    for r0 in range(0, local.n, DBA_BLOCK):
+        r1 = min(r0 + DBA_BLOCK, local.n)
+        s, i = full_index.search(local.db32[r0:r1], k_dba, precision="fp32", block_q=DBA_QUERIES_PER_PASS)
         out[r0:r1] = _add_l2n(_accumulate(full_index, i, s, alpha), None)
     new_local = Index(out, device=dev, keep_fp32=True, idx_base=local.idx_base)
     return ShardedIndex.from_local(new_local, sharded.group)

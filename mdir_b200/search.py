@@ -21,7 +21,8 @@ import torch
 from . import _lib
 
 TILE = 256            # MDIR_SCAN_TILE_ROWS
-MAX_Q = 128           # queries resident per scan pass
+MAX_Q = 128           # queries per scan pass on the serving path (double / triple buffered TMEM accumulators)
+MAX_Q_WIDE = 256      # queries per pass for tensor-bound work (search(block_q=256): DBA, all-pairs): all of TMEM for one tile
 N_SEGS = 149          # MDIR_CAND_SEGS: segment 0 = select kernel, 1 + c = scan CTA c
 CAP_S = 8192          # capacity of segment 0 (the >= kth sample rows that pass, incl. ties)
 CAP_L = 96            # capacity of each scan CTA's private segment
@@ -145,12 +146,12 @@ class Index:
             return None
         return n_sample, stride
 
-    def _fused_ok(self, kth):
+    def _fused_ok(self, kth, nq=1):
         """One-launch route (mdir_sim_scan_fused_bf16): each of the g persistent CTAs samples one tile, so the
         threshold is about the kth best of g*256 rows and ~1.25 * kth * n_tiles / g rows survive, spread over g
         segments.  Taken when that keeps the segments at most half full; larger k or databases use the
         three-launch route, whose sample grows with the database."""
-        if not self.fused:
+        if not self.fused or nq > MAX_Q:
             return False
         n_tiles = (self.n + TILE - 1) // TILE
         if self._sms is None:
@@ -166,8 +167,8 @@ class Index:
                                                  _lib.ptr(cnt), CAP_S, CAP_L, _lib.stream()), "mdir_sim_scan_bf16")
 
     def _cand_bufs(self):
-        return (self._buf("tau", (MAX_Q,), torch.int64), self._buf("cand", (MAX_Q, CAND_ROW), torch.int64),
-                self._buf("segcnt", (MAX_Q, N_SEGS), torch.int32))
+        return (self._buf("tau", (MAX_Q_WIDE,), torch.int64), self._buf("cand", (MAX_Q_WIDE, CAND_ROW), torch.int64),
+                self._buf("segcnt", (MAX_Q_WIDE, N_SEGS), torch.int32))
 
     def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore=None, caps=(CAP_S, CAP_L)):
         """rescore = (q32_block, k_out): fused exact fp32 re-scoring of the kth-long bf16 shortlist."""
@@ -192,7 +193,7 @@ class Index:
         lib = _lib.lib()
         nq = q16.shape[0]
         tau, cand, cnt = self._cand_bufs()       # the select kernel (re)initialises every segment counter
-        dense = self._buf("dense", (MAX_Q, max(self.n, 1)), torch.float32)
+        dense = self._buf("dense", (MAX_Q if nq <= MAX_Q else MAX_Q_WIDE, max(self.n, 1)), torch.float32)
         self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
                                        _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 0, _lib.stream()), "mdir_select_kth")
@@ -207,7 +208,7 @@ class Index:
             return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf, rescore)
         tau, cand, cnt = self._cand_bufs()       # the select / fused kernel (re)initialises every segment counter
         prof = getattr(self, "prof", None)       # bench.py: CUDA events around the dominant kernel, on its own stream
-        if self._fused_ok(kth):
+        if self._fused_ok(kth, nq):
             ws = self._ws.get("fused_ws")
             if ws is None:                       # zeroed once; the kernel re-arms its arrival counters itself
                 ws = torch.zeros((lib.mdir_sim_scan_fused_workspace_bytes(MAX_Q) // 4,), dtype=torch.int32, device=self.device)
@@ -222,7 +223,7 @@ class Index:
             return self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore, caps=(0, FUSED_CAP_L))
         n_sample, stride = plan
         rows = n_sample * TILE
-        sample = self._buf("sample", (MAX_Q, MAX_SAMPLE_TILES * TILE), torch.float32)
+        sample = self._buf("sample", (MAX_Q if nq <= MAX_Q else MAX_Q_WIDE, MAX_SAMPLE_TILES * TILE), torch.float32)
         ld = MAX_SAMPLE_TILES * TILE
         self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
@@ -235,14 +236,15 @@ class Index:
         self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore)
 
     # ------------------------------------------------------------------ public
-    def search(self, q, k, precision="fp32", shortlist=None, check=True, return_keys=False):
+    def search(self, q, k, precision="fp32", shortlist=None, check=True, return_keys=False, block_q=MAX_Q):
         """q: (N_q, D) fp32 (host or device).  Returns (scores (N_q,k) fp32, idx (N_q,k) int32) on
         the device, ordered by (score desc, index asc); idx = idx_base + local row, -1 padding.
 
         precision="bf16": exact top-k of the bf16-input / fp32-accumulate scores.
-        precision="fp32": bf16 shortlist of `shortlist` (default max(k+32, 1.25k)) per query, re-scored exactly in
-                          fp32 against the fp32 master copy, then top-k of those.
-        check=False skips the (synchronising) candidate-overflow check; call check_overflow() later."""
+        precision="fp32": bf16 shortlist of `shortlist` (default 1.25 k rounded up to 64) per query, re-scored exactly in
+                          fp32 against the fp32 master copy and extended until certified (mdir_topk_finalize_rescore).
+        check=False skips the (synchronising) status check; call check_overflow() later.
+        block_q: queries per scan pass, 128 (serving) or 256 (tensor-bound batches: the database is streamed half as often)."""
         lib = _lib.lib()
         with torch.cuda.device(self.device):
             q32 = _as_dev_f32(q, self.device)
@@ -269,8 +271,9 @@ class Index:
             out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
             out_k = torch.empty((nq_all, k), dtype=torch.int64, device=self.device) if return_keys else None
             self._ovf = self._buf("ovf", (max(nq_all, 1),), torch.int32)
-            for q0 in range(0, nq_all, MAX_Q):
-                q1 = min(q0 + MAX_Q, nq_all)
+            block_q = MAX_Q_WIDE if int(block_q) > MAX_Q else MAX_Q
+            for q0 in range(0, nq_all, block_q):
+                q1 = min(q0 + block_q, nq_all)
                 nq = q1 - q0
                 ovf = self._ovf[q0:q1]
                 bs, bi = out_s[q0:q1], out_i[q0:q1]
@@ -354,8 +357,9 @@ class Index:
                 out = torch.empty((nq_all, self.n), dtype=torch.float32, device=self.device)
             if precision == "bf16":
                 q16 = pack_bf16(q32)
-                for q0 in range(0, nq_all, MAX_Q):
-                    q1 = min(q0 + MAX_Q, nq_all)
+                step = MAX_Q
+                for q0 in range(0, nq_all, step):
+                    q1 = min(q0 + step, nq_all)
                     self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], self.n, None, None, None)
                 return out
             if precision not in ("tf32", "fp32"):
