@@ -163,9 +163,10 @@ int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int 
  * TMEM) and then the rest of the database exactly like MDIR_SCAN_FILTER.  Writes tau[q], the
  * candidate segments 1.. and ALL n_q * MDIR_CAND_SEGS segment counters (segment 0 stays empty).
  * ws: mdir_sim_scan_fused_workspace_bytes(n_q) bytes, 16-byte aligned, ZEROED ONCE by the caller
- * before first use (the kernel re-arms its counters itself).  Needs n_db >= 512 rows and the
- * whole grid co-resident (one CTA per SM, nothing else occupying the device); if an arrival
- * counter is not reached within ~4 s the segments report overflow instead of hanging.       */
+ * before first use (the kernel re-arms its counters itself).  Needs n_db >= 512 rows.  The launch is
+ * COOPERATIVE (cudaLaunchAttributeCooperative): the runtime guarantees the grid's co-residency, which
+ * the in-kernel rendezvous needs, or fails the launch; should an arrival counter still not be
+ * reached within ~4 s the segments report overflow instead of hanging.                        */
 size_t mdir_sim_scan_fused_workspace_bytes(int n_q);
 int mdir_sim_scan_fused_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
                              int kth, uint64_t* tau, uint32_t idx_base,

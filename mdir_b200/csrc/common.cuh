@@ -54,6 +54,16 @@ struct PerDeviceOnce {
         return 1;
     }
 };
+// Persistent-grid size for n_work equal work items on at most max_ctas SMs: the smallest grid that needs the same
+// number of rounds as max_ctas would (489 tiles on 148 SMs are 4 rounds either way; 123 CTAs x 4 rounds keep every
+// CTA busy to the end, where 148 CTAs leave 103 SMs idle during a last round that then runs at a third of the HBM rate).
+inline int balanced_grid(int64_t n_work, int max_ctas) {
+    if (n_work <= 0 || max_ctas <= 0) return 1;
+    if (n_work <= max_ctas) return (int)n_work;
+    const int64_t rounds = (n_work + max_ctas - 1) / max_ctas;
+    return (int)((n_work + rounds - 1) / rounds);
+}
+
 // SM count of the current device (cached per ordinal); 0 on error
 inline int device_sm_count() {
     static int cache[kMaxDevices] = {};

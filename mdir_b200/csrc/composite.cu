@@ -70,6 +70,7 @@ extern "C" int mdir_topk_plan(int64_t n_db, int kth, int sm_count, int* route, i
     if (n_tiles < 64) return 0;
     int64_t g = sm_count < 148 ? sm_count : 148;
     if (g > n_tiles / 2) g = n_tiles / 2;
+    g = balanced_grid(n_tiles, (int)g);          // the grid mdir_sim_scan_fused_bf16 launches
     if (g * 16 >= 2 * (int64_t)kth && 1.25 * kth * (double)n_tiles / ((double)g * (double)g) <= kFusedCapL / 2.0) {
         *route = 1;
         return 0;

@@ -631,6 +631,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         int g = sm_count < kNumSMs ? sm_count : kNumSMs;
         if (g > p.n_tiles / 2) g = p.n_tiles / 2;
         MDIR_CHECK_ARG(g >= 1);
+        g = balanced_grid(p.n_tiles, g);          // every CTA scans the same number of tiles (its sample tile included)
         p.n_sample = g;
         p.sample_stride = p.n_tiles / g;
         p.n_work = p.n_tiles - g;
@@ -675,7 +676,24 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 8192));
     }
     const int n_ctas_wanted = p.chain > 1 ? p.n_tiles : p.n_work;
-    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : (n_ctas_wanted < kNumSMs ? n_ctas_wanted : kNumSMs);
+    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : balanced_grid(n_ctas_wanted, kNumSMs);
+    if (mode == MDIR_SCAN_FUSED) {
+        // the in-kernel threshold exchange is a grid-wide rendezvous: launch COOPERATIVELY, so the runtime guarantees
+        // that all `grid` CTAs are co-resident (or fails the launch) instead of the kernel relying on an empty device
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MDIR_CUDA(cudaLaunchKernelEx(&cfg, sim_scan_kernel<false>, tmap_db, tmap_q, p));
+        MDIR_LAUNCH_CHECK();
+        return 0;
+    }
     if (tf32) sim_scan_kernel<true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     else sim_scan_kernel<false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(tmap_db, tmap_q, p);
     MDIR_LAUNCH_CHECK();

@@ -493,7 +493,22 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     __syncthreads();
     const uint64_t* res;       // ascending keys, at least min(k, cnt) valid
     int nres;
-    if (cnt <= 2 * kpow2 || cnt <= 1024) {
+    if (cnt <= 1024 && cnt + kpow2 <= smem_cap) {
+        // few candidates (small shards): rank-counting sort -- one pass, no barriers inside -- into the upper part of
+        // the staging area, then back, instead of ~45 barrier-separated bitonic stages
+        uint64_t mine = ~0ull;
+        int r = 0;
+        if ((int)threadIdx.x < cnt) {
+            mine = skeys[threadIdx.x];
+            for (int j = 0; j < cnt; ++j) r += skeys[j] < mine ? 1 : 0;          // keys are unique
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < cnt) skeys[r] = mine;
+        for (int i = cnt + threadIdx.x; i < cnt + kpow2 && i < smem_cap; i += blockDim.x) skeys[i] = ~0ull;
+        __syncthreads();
+        res = skeys;
+        nres = cnt;
+    } else if (cnt <= 2 * kpow2 || cnt <= 1024) {
         int n = 32;
         while (n < cnt) n <<= 1;
         for (int i = cnt + threadIdx.x; i < n; i += blockDim.x) skeys[i] = ~0ull;

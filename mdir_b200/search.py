@@ -45,6 +45,16 @@ def default_shortlist(k):
     return -(-(-(-5 * int(k) // 4)) // 64) * 64
 
 
+def balanced_grid(n_work, max_ctas):
+    """common.cuh:balanced_grid -- the smallest persistent grid that needs as many rounds as max_ctas CTAs would."""
+    if n_work <= 0 or max_ctas <= 0:
+        return 1
+    if n_work <= max_ctas:
+        return int(n_work)
+    rounds = -(-n_work // max_ctas)
+    return int(-(-n_work // rounds))
+
+
 def _as_dev_f32(x, device):
     if isinstance(x, np.ndarray):
         x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
@@ -156,7 +166,7 @@ class Index:
         n_tiles = (self.n + TILE - 1) // TILE
         if self._sms is None:
             self._sms = torch.cuda.get_device_properties(self.device).multi_processor_count
-        g = min(148, self._sms, n_tiles // 2)
+        g = balanced_grid(n_tiles, min(148, self._sms, n_tiles // 2))
         if n_tiles < 64 or g * 16 < 2 * kth:
             return False
         return 1.25 * kth * n_tiles / (g * g) <= FUSED_CAP_L / 2

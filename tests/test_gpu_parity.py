@@ -541,6 +541,17 @@ class ImageRetrievalNet(torch.nn.Module):
         self.norm = m.L2N()
         self.meta = {"pooling": pooling, "regional": False, "whitening": False, "out_channels": 64, "outputdim": 64}
 
+    def forward(self, x):                                     # imageretrievalnet.py:93-115 without whitening
+        o = self.norm(self.pool(self.features(x))).squeeze(-1).squeeze(-1)
+        return o.permute(1, 0)
+
+
+class CirNetwork:
+    """Shaped like mdir's CirNetwork (learning/network.py:72-89): .model + per-stage wrapper compositions."""
+
+    def __init__(self, model, comp):
+        self.model, self.wrappers, self.stage = model, {"eval": comp}, "eval"
+
 
 def test_batched_extract_vectors(m, golden):
     torch.manual_seed(3)
@@ -567,7 +578,7 @@ def test_batched_extract_vectors(m, golden):
         g = golden("head")
         lw = {"m": g["lw_m"][:64], "P": g["lw_P"][:64, :64]}
         comp = types.SimpleNamespace(wrappers=[m.CirtorchWhiten(lw, 32, DEV), m.CirMultiscaleAggregation(True, DEV)])
-        cirnet = types.SimpleNamespace(model=net, wrappers={"eval": comp}, stage="eval")
+        cirnet = CirNetwork(net, comp)
         vw = m.extract_vectors(cirnet, imgs, None, None, group=3, return_device=True)
         assert tuple(vw.shape) == (5, 32) and vw.is_cuda
         for i, im in enumerate(imgs):
@@ -599,7 +610,7 @@ def test_extract_vectors_matches_reference_extract_vectors(m, golden):
             # mdir's CirNetwork pattern: the eval wrappers carry the scales (msp rule) and the Lw whitening
             lw = {"m": g["lw_m"], "P": g["lw_P"]}
             comp = types.SimpleNamespace(wrappers=[m.CirtorchWhiten(lw, 32, DEV), m.CirMultiscaleAggregation(True, DEV)])
-            cirnet = types.SimpleNamespace(model=net, wrappers={"eval": comp}, stage="eval")
+            cirnet = CirNetwork(net, comp)
             v_wr = m.extract_vectors(cirnet, imgs, None, None, group=4, return_device=True)
     finally:
         torch.backends.cudnn.allow_tf32 = tf32
@@ -896,6 +907,8 @@ def test_bench_line_contract():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == "queries/s" and c["sample"]
     e = d["e2e"]
-    assert e["value"] > 1e4 and e["h2d_bytes_per_step"] == 70 * 2048 * 4 and e["d2h_bytes_per_step"] == 70 * 100 * 8
+    assert e["value"] > 1e4 and e["h2d_bytes_per_step"] == 70 * 2048 * 4 and e["d2h_bytes_per_step"] == 70 * 100 * 8 + 70 * 4
+    pc = d["parity_check"]                                     # the timed graphs' results against the independent ranking
+    assert pc["checked_queries"] == 8 * 70 and pc["mismatches"] == 0 and pc["certificate_failures"] == 0
     assert d["gpu_launches"] == 20 * 3                         # pack, fused scan, finalize+re-score per step
     assert "sm_mhz" in d["clocks"] or "error" in d["clocks"]
