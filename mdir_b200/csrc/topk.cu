@@ -373,22 +373,143 @@ __device__ __forceinline__ float rescore_row(const float* __restrict__ a, const 
     return warp_sum(acc);
 }
 
+// The k smallest of the cnt unique keys in skeys[0, cnt) (1024-thread block), sorted ascending into out[0, min(k, cnt))
+// (padded with ~0 up to kpow2), without the 8 MSB radix passes: candidates of one query share sign and exponent, so
+// ONE histogram over 1024 bins linear between the smallest and the largest key separates them; the bins up to the
+// one where the running count reaches k hold k + a few keys, which are compacted behind the list (skeys[cnt, cnt + 1024))
+// and rank-counted.  Returns false (nothing written) when those bins hold more than 1024 keys (massive ties): the
+// caller then takes the radix path.  scratch: 64 words.
+__device__ __forceinline__ bool topk_hist_select(uint64_t* skeys, int cnt, int k, int kpow2, uint64_t* out, uint32_t* hist, uint32_t* s_n,
+                                                 uint32_t* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t mn = 0xffffffffu, mx = 0u;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint32_t h = (uint32_t)(skeys[i] >> 32);
+        mn = min(mn, h);
+        mx = max(mx, h);
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) { scratch[w] = mn; scratch[32 + w] = mx; }
+    hist[threadIdx.x] = 0u;
+    if (threadIdx.x == 0) *s_n = 0u;
+    __syncthreads();
+    mn = scratch[lane];
+    mx = scratch[32 + lane];
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    const float scale = 1024.0f / ((float)(mx - mn) + 1.0f);
+    auto bin_of = [&](uint64_t key) { return min(1023, (int)((float)((uint32_t)(key >> 32) - mn) * scale)); };     // monotone in the key
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) atomicAdd(&hist[bin_of(skeys[i])], 1u);
+    __syncthreads();
+    // inclusive scan over the 1024 bins, one per thread
+    const uint32_t c = hist[threadIdx.x];
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();                                   // scratch (min / max) fully read
+    if (lane == 31) scratch[w] = incl;
+    __syncthreads();
+    uint32_t pre = 0;
+    for (int j = 0; j < w; ++j) pre += scratch[j];
+    incl += pre;
+    // the first bin where the running count reaches k: everything up to it is wanted
+    if (incl >= (uint32_t)k && incl - c < (uint32_t)k) { scratch[32] = threadIdx.x; scratch[33] = incl; }
+    if (threadIdx.x == 1023 && incl < (uint32_t)k) { scratch[32] = 1023u; scratch[33] = incl; }      // fewer than k keys in all
+    __syncthreads();
+    const int b_star = (int)scratch[32];
+    const int take = (int)scratch[33];
+    if (take > 1024) return false;
+    uint64_t* sel = skeys + cnt;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const uint64_t key = skeys[i];
+        if (bin_of(key) <= b_star) sel[atomicAdd(s_n, 1u)] = key;
+    }
+    for (int i = threadIdx.x; i < kpow2; i += blockDim.x) out[i] = ~0ull;
+    __syncthreads();
+    if ((int)threadIdx.x < take) {
+        const uint64_t mine = sel[threadIdx.x];
+        int r = 0;
+        for (int j = 0; j < take; ++j) r += sel[j] < mine ? 1 : 0;
+        if (r < kpow2) out[r] = mine;
+    }
+    __syncthreads();
+    return true;
+}
+
 // Rescore entries [j0, j0 + n) of the key list at shared-memory address `list` of cluster rank 0 (DSMEM when this
 // CTA is a helper): one warp per row, rows interleaved over the CS CTAs of the cluster.
+// fp32 dot products of TWO database rows with the staged query, both rows' loads in flight together
+__device__ __forceinline__ void rescore_row2(const float* __restrict__ a0, const float* __restrict__ a1, const float* qs, int D, int lane,
+                                             float& r0, float& r1) {
+    if ((D & 3) != 0) {
+        r0 = rescore_row(a0, qs, D, lane);
+        r1 = rescore_row(a1, qs, D, lane);
+        return;
+    }
+    const float4* p0 = reinterpret_cast<const float4*>(a0);
+    const float4* p1 = reinterpret_cast<const float4*>(a1);
+    const float4* b4 = reinterpret_cast<const float4*>(qs);
+    const int n4 = D >> 2;
+    float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+    int i = lane;
+    for (; i + 96 < n4; i += 128) {           // 2 x 4 independent 128-bit loads in flight per lane (4 KB per warp)
+        const float4 x0 = __ldg(p0 + i), x1 = __ldg(p0 + i + 32), x2 = __ldg(p0 + i + 64), x3 = __ldg(p0 + i + 96);
+        const float4 z0 = __ldg(p1 + i), z1 = __ldg(p1 + i + 32), z2 = __ldg(p1 + i + 64), z3 = __ldg(p1 + i + 96);
+        float4 y = b4[i];
+        s0a = fmaf(x0.x, y.x, s0a); s0a = fmaf(x0.y, y.y, s0a); s0a = fmaf(x0.z, y.z, s0a); s0a = fmaf(x0.w, y.w, s0a);
+        s1a = fmaf(z0.x, y.x, s1a); s1a = fmaf(z0.y, y.y, s1a); s1a = fmaf(z0.z, y.z, s1a); s1a = fmaf(z0.w, y.w, s1a);
+        y = b4[i + 32];
+        s0b = fmaf(x1.x, y.x, s0b); s0b = fmaf(x1.y, y.y, s0b); s0b = fmaf(x1.z, y.z, s0b); s0b = fmaf(x1.w, y.w, s0b);
+        s1b = fmaf(z1.x, y.x, s1b); s1b = fmaf(z1.y, y.y, s1b); s1b = fmaf(z1.z, y.z, s1b); s1b = fmaf(z1.w, y.w, s1b);
+        y = b4[i + 64];
+        s0a = fmaf(x2.x, y.x, s0a); s0a = fmaf(x2.y, y.y, s0a); s0a = fmaf(x2.z, y.z, s0a); s0a = fmaf(x2.w, y.w, s0a);
+        s1a = fmaf(z2.x, y.x, s1a); s1a = fmaf(z2.y, y.y, s1a); s1a = fmaf(z2.z, y.z, s1a); s1a = fmaf(z2.w, y.w, s1a);
+        y = b4[i + 96];
+        s0b = fmaf(x3.x, y.x, s0b); s0b = fmaf(x3.y, y.y, s0b); s0b = fmaf(x3.z, y.z, s0b); s0b = fmaf(x3.w, y.w, s0b);
+        s1b = fmaf(z3.x, y.x, s1b); s1b = fmaf(z3.y, y.y, s1b); s1b = fmaf(z3.z, y.z, s1b); s1b = fmaf(z3.w, y.w, s1b);
+    }
+    for (; i < n4; i += 32) {
+        const float4 x = __ldg(p0 + i), z = __ldg(p1 + i), y = b4[i];
+        s0a = fmaf(x.x, y.x, s0a); s0a = fmaf(x.y, y.y, s0a); s0a = fmaf(x.z, y.z, s0a); s0a = fmaf(x.w, y.w, s0a);
+        s1a = fmaf(z.x, y.x, s1a); s1a = fmaf(z.y, y.y, s1a); s1a = fmaf(z.z, y.z, s1a); s1a = fmaf(z.w, y.w, s1a);
+    }
+    r0 = warp_sum(s0a + s0b);
+    r1 = warp_sum(s1a + s1b);
+}
+
+// Rescore entries [j0, j0 + n) of the key list at shared-memory address `list` of cluster rank 0 (DSMEM when this
+// CTA is a helper): one warp per row, rows interleaved over the CS CTAs of the cluster, two rows of a warp in flight
+// together (a row is 4 * D bytes gathered from HBM: latency, not bandwidth, is what a warp waits for).
 template <int CS>
 __device__ __forceinline__ void rescore_share(uint64_t* local_list, uint32_t remote_list, bool remote, int j0, int n, int crank,
                                               const float* __restrict__ db32, int64_t n_db, uint32_t idx_base, const float* qs, int D) {
     const int lane = threadIdx.x & 31;
-    for (int j = (threadIdx.x >> 5) * CS + crank; j < n; j += 32 * CS) {
-        const uint64_t key = remote ? cluster_ld_u64(remote_list + 8u * (uint32_t)(j0 + j)) : local_list[j0 + j];
-        const uint32_t gi = (uint32_t)key;
-        const int64_t row = (int64_t)gi - (int64_t)idx_base;
-        uint64_t nkey = ~0ull;
-        if (key != ~0ull && row >= 0 && row < n_db) nkey = make_key(rescore_row(db32 + row * D, qs, D, lane), gi);
+    for (int j = (threadIdx.x >> 5) * CS + crank; j < n; j += 64 * CS) {
+        const int jb = j + 32 * CS;                       // this warp's second row of the round
+        const uint64_t key0 = remote ? cluster_ld_u64(remote_list + 8u * (uint32_t)(j0 + j)) : local_list[j0 + j];
+        uint64_t key1 = ~0ull;
+        if (jb < n) key1 = remote ? cluster_ld_u64(remote_list + 8u * (uint32_t)(j0 + jb)) : local_list[j0 + jb];
+        const uint32_t g0 = (uint32_t)key0, g1 = (uint32_t)key1;
+        const int64_t row0 = (int64_t)g0 - (int64_t)idx_base, row1 = (int64_t)g1 - (int64_t)idx_base;
+        const bool ok0 = key0 != ~0ull && row0 >= 0 && row0 < n_db, ok1 = key1 != ~0ull && row1 >= 0 && row1 < n_db;
+        float s0 = 0.f, s1 = 0.f;
+        if (ok0 && ok1) rescore_row2(db32 + row0 * D, db32 + row1 * D, qs, D, lane, s0, s1);
+        else if (ok0) s0 = rescore_row(db32 + row0 * D, qs, D, lane);
+        else if (ok1) s1 = rescore_row(db32 + row1 * D, qs, D, lane);
+        const uint64_t n0 = ok0 ? make_key(s0, g0) : ~0ull, n1 = ok1 ? make_key(s1, g1) : ~0ull;
         __syncwarp();
         if (lane == 0) {
-            if (remote) cluster_st_u64(remote_list + 8u * (uint32_t)(j0 + j), nkey);
-            else local_list[j0 + j] = nkey;
+            if (remote) {
+                cluster_st_u64(remote_list + 8u * (uint32_t)(j0 + j), n0);
+                if (jb < n) cluster_st_u64(remote_list + 8u * (uint32_t)(j0 + jb), n1);
+            } else {
+                local_list[j0 + j] = n0;
+                if (jb < n) local_list[j0 + jb] = n1;
+            }
         }
     }
 }
@@ -428,7 +549,8 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     __shared__ int s_ovf;
     __shared__ int s_hdr[3];                      // rank 0 -> helpers: {shortlist length, offset of the list in skeys, extension length}
     __shared__ uint64_t s_tkey;
-    __shared__ float s_red[32];
+    __shared__ float s_red[96];
+    __shared__ uint32_t hist_sel[1024];
     uint64_t* sorted = skeys + smem_cap;          // sl_cap entries: the sorted selection; with re-scoring the shortlist + its extension
     const int q = blockIdx.x / CS;
     const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
@@ -453,17 +575,25 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         return;
     }
     const uint64_t tau_in = tau ? tau[q] : ~0ull;
-    // segment offsets (exclusive scan of the clamped counts) by warp 0
+    // segment offsets (exclusive scan of the clamped counts) by warp 0; the (at most 5) count loads of a lane are all
+    // issued before the first is used
     if (threadIdx.x < 32) {
+        constexpr int kRounds = (MDIR_CAND_SEGS + 31) / 32;
+        uint32_t raw[kRounds];
+#pragma unroll
+        for (int i = 0; i < kRounds; ++i) {
+            const int sg = i * 32 + lane;
+            raw[i] = sg < n_seg ? seg_counts[(int64_t)q * n_seg + sg] : 0u;
+        }
         int run = 0, ovf = 0;
-        for (int s0 = 0; s0 < n_seg; s0 += 32) {
-            const int sg = s0 + lane;
+#pragma unroll
+        for (int i = 0; i < kRounds; ++i) {
+            const int sg = i * 32 + lane;
             int c = 0;
             if (sg < n_seg) {
-                const uint32_t raw = seg_counts[(int64_t)q * n_seg + sg];
                 const uint32_t cp = (uint32_t)(sg == 0 ? cap0 : cap_l);
-                if (raw > cp) ovf = 1;
-                c = (int)min(raw, cp);
+                if (raw[i] > cp) ovf = 1;
+                c = (int)min(raw[i], cp);
             }
             int incl = c;
 #pragma unroll
@@ -481,21 +611,29 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
     const int total = s_off[n_seg];
     const int cnt = min(total, smem_cap);
     const bool ovf_any = s_ovf || total > smem_cap;
-    {   // compaction: warp w copies segments w, w+32, ...
+    {   // compaction by OUTPUT slot: slot p belongs to the segment found by a binary search over the offsets, so every
+        // thread's loads are independent of each other (a warp-per-segment loop paid one global latency per segment)
         const uint64_t* row = cand + (int64_t)q * cand_row;
-        for (int sg = threadIdx.x >> 5; sg < n_seg; sg += 32) {
-            const int o = s_off[sg], c = s_off[sg + 1] - o;
-            const uint64_t* src = row + (sg == 0 ? 0 : (int64_t)cap0 + (int64_t)(sg - 1) * cap_l);
-            for (int i = lane; i < c; i += 32)
-                if (o + i < smem_cap) skeys[o + i] = src[i];
+        for (int p = threadIdx.x; p < cnt; p += blockDim.x) {
+            int lo = 0, hi = n_seg;                               // last segment with s_off[sg] <= p
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= p) lo = mid; else hi = mid;
+            }
+            const int64_t base = lo == 0 ? 0 : (int64_t)cap0 + (int64_t)(lo - 1) * cap_l;
+            skeys[p] = row[base + (p - s_off[lo])];
         }
     }
     __syncthreads();
     const uint64_t* res;       // ascending keys, at least min(k, cnt) valid
     int nres;
-    if (cnt <= 1024 && cnt + kpow2 <= smem_cap) {
-        // few candidates (small shards): rank-counting sort -- one pass, no barriers inside -- into the upper part of
-        // the staging area, then back, instead of ~45 barrier-separated bitonic stages
+    if (cnt > k + 96 && cnt + 1024 <= smem_cap &&
+        topk_hist_select(skeys, cnt, k, kpow2, sorted, hist_sel, &s_out, reinterpret_cast<uint32_t*>(s_red))) {
+        // the k best keys isolated by ONE histogram over bins linear between the extreme keys, then rank-counted
+        res = sorted;
+        nres = min(cnt, k);
+    } else if (cnt <= 1024 && cnt + kpow2 <= smem_cap) {
+        // few candidates: rank-counting sort (cnt^2 / 1024 comparisons per thread, no barriers inside)
         uint64_t mine = ~0ull;
         int r = 0;
         if ((int)threadIdx.x < cnt) {
@@ -594,9 +732,12 @@ __global__ void __launch_bounds__(1024) topk_finalize_kernel(const uint64_t* __r
         const uint64_t last16 = nk > 0 ? sl[nk - 1] : 0ull;          // worst bf16 key inside the shortlist
         float eps = 0.f;
         if (db_stats) {
-            q2 = block_sum(q2, s_red);
-            qt2 = block_sum(qt2, s_red);
-            qf2 = block_sum(qf2, s_red);
+            // one block reduction for the three sums
+            q2 = warp_sum(q2); qt2 = warp_sum(qt2); qf2 = warp_sum(qf2);
+            const int wi = threadIdx.x >> 5;
+            if (lane == 0) { s_red[wi] = q2; s_red[32 + wi] = qt2; s_red[64 + wi] = qf2; }
+            __syncthreads();
+            q2 = warp_sum(s_red[lane]); qt2 = warp_sum(s_red[32 + lane]); qf2 = warp_sum(s_red[64 + lane]);
             const float e_max = sqrtf(db_stats[0]), x_max = sqrtf(db_stats[1]);
             eps = e_max * sqrtf(qt2) + x_max * sqrtf(qf2) + 1.25f * (float)D * 5.9604645e-8f * x_max * sqrtf(q2);
             eps = eps * 1.001f + 1e-7f;                              // slack for evaluating the bound itself in fp32
@@ -839,9 +980,12 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
         MDIR_CHECK_ARG(db_stats == nullptr || tau != nullptr);          // the certificate compares against the filter threshold
         smem += (size_t)D * 4;
     }
+    // 227 KB per CTA minus the kernel's static arrays: the deepest selection (4096-row shortlist) leaves room for D <= 7168
+    constexpr int kFinalizeMaxSmem = 232448 - 7424;
+    MDIR_CHECK_ARG(smem <= (size_t)kFinalizeMaxSmem);
     static PerDeviceOnce once;
     if (once.first() != 0) {
-        const int max_smem = (16384 + 8192) * 8 + 8192 * 4;
+        const int max_smem = kFinalizeMaxSmem;
         MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
         MDIR_CUDA(cudaFuncSetAttribute(topk_finalize_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     }
