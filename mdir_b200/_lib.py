@@ -75,6 +75,8 @@ PROTOTYPES = {
     "mdir_rank_scores": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp]),
     "mdir_rank_fast_workspace_bytes": (_sz, [_i64, _i]),
     "mdir_rank_scores_fast": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp]),
+    "mdir_rank_hist_workspace_bytes": (_sz, [_i64, _i]),
+    "mdir_rank_scores_hist": (_i, [_vp, _i64, _i, _i, _vp, _i64, _vp, _vp, _vp]),
 }
 
 

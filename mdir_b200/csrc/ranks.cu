@@ -634,6 +634,343 @@ static SsPlan ss_plan(int64_t n_db) {
     return p;
 }
 
+
+// ============================================================================================================
+// Histogram-sort path (mdir_rank_scores_hist): the same two-level idea as the sample sort, with every per-key step cut
+// to a table lookup.  Similarity scores of one query are a smooth, near-Gaussian population: a 4096-cell histogram that
+// is LINEAR IN THE SCORE over mean +- 4 sigma (both from a strided sample; the end cells take the tails) separates
+// 100,000 rows into cells of <= ~80 rows.  Per query:
+//   1. hs_plan_kernel        sample statistics -> (hi, scale); exact cell histogram of the whole row in shared memory;
+//                            prefix sums; cell -> bucket table with bucket = floor(first rank of the cell / 2048), so a
+//                            bucket is a run of whole cells holding < 2048 + (largest cell) rows; exact start / size /
+//                            cell range of every bucket.  No sorting, no sampling error: the layout is exact.
+//   2. hs_scatter_kernel     per (query, 4096-row chunk): bucket = table[cell(score)] (one LDS, no search), pairs staged
+//                            in shared memory grouped by bucket, one global atomicAdd per (chunk, bucket) on a cursor
+//                            that starts at the bucket's exact offset: the pair array is compact (8 B per row) and the
+//                            runs are ~80 pairs long (full lines)
+//   3. hs_bucket_sort_kernel one CTA per bucket (<= 4096 rows, 8 per thread in registers): interpolation counting sort
+//                            with 4096 fine bins linear in the score over the bucket's cell range, exact rank inside a
+//                            fine bin by comparing (score key, row) composites; ranks leave coalesced
+//   4. ranks_transpose_kernel
+// Everything is monotone in the score key, so the result is bit-identical to the stable argsort.  A query whose
+// histogram has a bucket of more than 4096 rows (massive ties, a spike, heavy tails) is flagged in *status (bit 1) and
+// the caller re-runs the call through the sample sort, which splits ties by row.
+constexpr int kHsCells = 4096;
+constexpr int kHsT = 2048;                   // bucket = floor(first rank of the cell / kHsT)
+constexpr int kHsCap = 4096;                 // rows one CTA sorts
+constexpr int kHsF = 4096;                   // fine bins of the bucket sort
+constexpr int kHsFPad = kHsF + kHsF / 8;     // one pad word per 8 counters: a thread's 8 consecutive counters are conflict-free
+constexpr int kHsSortThreads = 512;
+constexpr int kHsPer = kHsCap / kHsSortThreads;            // 8 rows per thread
+constexpr int kHsPlanThreads = 512;
+constexpr int kHsChunk = 4096;
+constexpr int kHsScatterThreads = 256;
+constexpr int kHsItems = kHsChunk / kHsScatterThreads;     // 16
+constexpr int kHsMinRows = 1025, kHsMaxRows = 131072;
+constexpr int kHsMaxBuckets = kHsMaxRows / kHsT + 2;       // 66
+constexpr int kHsSample = 4096;
+static_assert(kHsMaxBuckets <= 256, "bucket ids are bytes");
+
+struct HsRange {
+    float hi, scale;          // cell(score) = clamp(int((hi - score) * scale), 0, kHsCells - 1); NaN -> last cell
+    uint32_t heavy;           // 1: some bucket exceeds kHsCap rows -> this query needs the sample sort
+    uint32_t pad;
+};
+struct HsBucket {
+    uint32_t start, size;     // first rank and number of rows
+    uint32_t cells;           // first non-empty cell | last non-empty cell << 16
+    uint32_t cursor;          // next free slot of the bucket in the pair array (scatter kernel)
+};
+
+static inline int hs_buckets(int64_t n_db) { return (int)(n_db / kHsT) + 2; }
+
+__device__ __forceinline__ float hs_pos(float score, float hi, float scale) { return __fmul_rn(__fsub_rn(hi, score), scale); }
+__device__ __forceinline__ int hs_cell(float score, float hi, float scale) {
+    const float v = hs_pos(score, hi, scale);
+    return (v == v) ? min(kHsCells - 1, max(0, (int)v)) : kHsCells - 1;
+}
+// every kernel goes through the KEY, so all of them see the same canonical score (-0 -> +0, one NaN)
+__device__ __forceinline__ int hs_cell_of_key(uint32_t key, float hi, float scale) { return hs_cell(key_score((uint64_t)key << 32), hi, scale); }
+
+// dynamic smem: kHsCells counters + 4 * B words
+__global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __restrict__ src, int is_key, int n_db, int B,
+                                                                 HsRange* __restrict__ range, uint8_t* __restrict__ table,
+                                                                 HsBucket* __restrict__ buckets, int32_t* __restrict__ status) {
+    extern __shared__ uint32_t hs_smem[];
+    uint32_t* hist = hs_smem;                 // kHsCells
+    uint32_t* st = hist + kHsCells;           // B: first rank of the bucket
+    uint32_t* sz = st + B;                    // B: rows
+    uint32_t* cf = sz + B;                    // B: first non-empty cell
+    uint32_t* cl = cf + B;                    // B: last non-empty cell
+    __shared__ float red[3][kHsPlanThreads / 32];
+    __shared__ uint32_t wsum[kHsPlanThreads / 32];
+    __shared__ float s_rng[2];
+    __shared__ uint32_t s_heavy;
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+    {   // ---- range from a strided sample: mean +- 4 sigma of its finite scores
+        float sum = 0.f, sq = 0.f, cnt = 0.f;
+        const int m = min(kHsSample, n_db);
+        for (int j = threadIdx.x; j < m; j += kHsPlanThreads) {
+            const int64_t i = (int64_t)j * n_db / m;
+            const float x = key_score((uint64_t)ss_load_key(seg, is_key, i) << 32);
+            if (fabsf(x) < INFINITY) { sum += x; sq = fmaf(x, x, sq); cnt += 1.f; }
+        }
+        sum = warp_sum(sum); sq = warp_sum(sq); cnt = warp_sum(cnt);
+        if (lane == 0) { red[0][w] = sum; red[1][w] = sq; red[2][w] = cnt; }
+        for (int c = threadIdx.x; c < kHsCells; c += kHsPlanThreads) hist[c] = 0u;
+        for (int b = threadIdx.x; b < B; b += kHsPlanThreads) { st[b] = 0xffffffffu; sz[b] = 0u; cf[b] = 0xffffu; cl[b] = 0u; }
+        if (threadIdx.x == 0) s_heavy = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f, b2 = 0.f, n = 0.f;
+            for (int k = 0; k < kHsPlanThreads / 32; ++k) { a += red[0][k]; b2 += red[1][k]; n += red[2][k]; }
+            const float mean = n > 0.f ? a / n : 0.f;
+            const float var = n > 0.f ? fmaxf(b2 / n - mean * mean, 0.f) : 0.f;
+            const float sd = sqrtf(var);
+            float hi = mean + 4.f * sd, scale = (float)kHsCells / (8.f * sd);
+            if (!(sd > 0.f) || !(scale < INFINITY) || !(fabsf(hi) < INFINITY)) { hi = mean; scale = 0.f; }     // one cell: flagged below
+            s_rng[0] = hi;
+            s_rng[1] = scale;
+        }
+        __syncthreads();
+    }
+    const float hi = s_rng[0], scale = s_rng[1];
+    // ---- exact cell histogram of the whole row (two 128-bit loads in flight per thread)
+    if ((n_db & 3) == 0 && (((uintptr_t)seg) & 15) == 0) {
+        const uint4* p4 = static_cast<const uint4*>(seg);
+        const int n4 = n_db >> 2;
+        auto add4 = [&](const uint4& v) {
+            const uint32_t k0 = is_key ? v.x : desc_key(__uint_as_float(v.x)), k1 = is_key ? v.y : desc_key(__uint_as_float(v.y));
+            const uint32_t k2 = is_key ? v.z : desc_key(__uint_as_float(v.z)), k3 = is_key ? v.w : desc_key(__uint_as_float(v.w));
+            atomicAdd(&hist[hs_cell_of_key(k0, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell_of_key(k1, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell_of_key(k2, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell_of_key(k3, hi, scale)], 1u);
+        };
+        int i = threadIdx.x;
+        for (; i + kHsPlanThreads < n4; i += 2 * kHsPlanThreads) {
+            const uint4 v0 = p4[i], v1 = p4[i + kHsPlanThreads];
+            add4(v0);
+            add4(v1);
+        }
+        if (i < n4) add4(p4[i]);
+    } else {
+        for (int i = threadIdx.x; i < n_db; i += kHsPlanThreads) atomicAdd(&hist[hs_cell_of_key(ss_load_key(seg, is_key, i), hi, scale)], 1u);
+    }
+    __syncthreads();
+    // ---- exclusive prefix over the cells: thread t owns cells [8t, 8t + 8)
+    constexpr int kPer = kHsCells / kHsPlanThreads;
+    static_assert(kPer == 8, "8 table bytes per thread");
+    uint32_t c[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) { c[k] = hist[threadIdx.x * kPer + k]; sum += c[k]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    uint32_t run = incl - sum;
+    for (int k = 0; k < w; ++k) run += wsum[k];
+    uint32_t packed[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int cell = threadIdx.x * kPer + k;
+        const uint32_t b = run / kHsT;                // < B by construction (run <= n_db)
+        packed[k >> 2] |= b << (8 * (k & 3));
+        if (c[k]) {
+            atomicMin(&st[b], run);
+            atomicAdd(&sz[b], c[k]);
+            atomicMin(&cf[b], (uint32_t)cell);
+            atomicMax(&cl[b], (uint32_t)cell);
+        }
+        run += c[k];
+    }
+    *reinterpret_cast<uint2*>(table + (int64_t)q * kHsCells + threadIdx.x * kPer) = make_uint2(packed[0], packed[1]);
+    __syncthreads();
+    HsBucket* bk = buckets + (int64_t)q * B;
+    for (int b = threadIdx.x; b < B; b += kHsPlanThreads) {
+        HsBucket o;
+        o.size = sz[b];
+        o.start = o.size ? st[b] : 0u;
+        o.cells = o.size ? (cf[b] | (cl[b] << 16)) : 0u;
+        o.cursor = o.start;
+        bk[b] = o;
+        if (o.size > (uint32_t)kHsCap) s_heavy = 1u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        HsRange r;
+        r.hi = hi; r.scale = scale; r.heavy = s_heavy; r.pad = 0u;
+        range[q] = r;
+        if (s_heavy) atomicOr(status, 2);
+    }
+}
+
+// static smem: 4096 pairs + 4096 bucket ids + the 4096-entry table: 44 KB, five CTAs per SM
+__global__ void __launch_bounds__(kHsScatterThreads, 5) hs_scatter_kernel(const void* __restrict__ src, int is_key, int n_db, int B,
+                                                                        const HsRange* __restrict__ range, const uint8_t* __restrict__ table,
+                                                                        HsBucket* __restrict__ buckets, uint2* __restrict__ pairs) {
+    __shared__ uint2 stage[kHsChunk];
+    __shared__ __align__(16) uint8_t tab[kHsCells];
+    __shared__ uint8_t sbucket[kHsChunk];
+    __shared__ uint32_t cnt[kHsMaxBuckets + 2];        // counts, then chunk-local bases
+    __shared__ uint32_t delta[kHsMaxBuckets + 2];      // slot in the pair array - local base (mod 2^32)
+    const int chunk = blockIdx.x, q = blockIdx.y;
+    const HsRange rg = range[q];
+    if (rg.heavy) return;
+    const int lane = threadIdx.x & 31;
+    {
+        static_assert(kHsCells / 16 == kHsScatterThreads, "one 16-byte table load per thread");
+        reinterpret_cast<uint4*>(tab)[threadIdx.x] = reinterpret_cast<const uint4*>(table + (int64_t)q * kHsCells)[threadIdx.x];
+        if (threadIdx.x < kHsMaxBuckets + 2) cnt[threadIdx.x] = 0u;
+    }
+    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
+    const int base = chunk * kHsChunk;
+    uint32_t key[kHsItems], where[kHsItems];                                     // where = bucket << 16 | rank inside (chunk, bucket)
+#pragma unroll
+    for (int it = 0; it < kHsItems; ++it) {
+        const int i = base + it * kHsScatterThreads + threadIdx.x;
+        key[it] = i < n_db ? ss_load_key(seg, is_key, i) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kHsItems; ++it) {
+        const int i = base + it * kHsScatterThreads + threadIdx.x;
+        where[it] = 0xffffffffu;
+        if (i < n_db) {
+            const uint32_t b = tab[hs_cell_of_key(key[it], rg.hi, rg.scale)];
+            where[it] = (b << 16) | atomicAdd(&cnt[b], 1u);                      // order inside a bucket is free: the bucket gets sorted
+        }
+    }
+    __syncthreads();
+    // exclusive scan of the B <= 66 counts by warp 0 (three per lane) + one global atomicAdd per non-empty (chunk, bucket)
+    if (threadIdx.x < 32) {
+        uint32_t c[3], g[3], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int b = 3 * lane + k;
+            c[k] = b < B ? cnt[b] : 0u;
+            g[k] = c[k] ? atomicAdd(&buckets[(int64_t)q * B + b].cursor, c[k]) : 0u;
+            sum += c[k];
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t lbase = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int b = 3 * lane + k;
+            if (b < B) { cnt[b] = lbase; delta[b] = g[k] - lbase; }
+            lbase += c[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kHsItems; ++it) {
+        if (where[it] != 0xffffffffu) {
+            const uint32_t b = where[it] >> 16;
+            const uint32_t l = cnt[b] + (where[it] & 0xffffu);
+            stage[l] = make_uint2((uint32_t)(base + it * kHsScatterThreads + threadIdx.x), key[it]);      // composite: key high, row low
+            sbucket[l] = (uint8_t)b;
+        }
+    }
+    __syncthreads();
+    const int n_valid = min(kHsChunk, n_db - base);
+    uint2* out = pairs + (int64_t)q * n_db;
+    for (int l = threadIdx.x; l < n_valid; l += kHsScatterThreads) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+}
+
+// One CTA per bucket.  dynamic smem: kHsCap keys + kHsFPad counters
+__global__ void __launch_bounds__(kHsSortThreads, 3) hs_bucket_sort_kernel(const uint2* __restrict__ pairs, int n_db, int B,
+                                                                          const HsRange* __restrict__ range,
+                                                                          const HsBucket* __restrict__ buckets, uint32_t* __restrict__ vals) {
+    extern __shared__ uint64_t hs_smem64[];
+    __shared__ uint32_t wsum[kHsSortThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x, q = blockIdx.y;
+    const HsRange rg = range[q];
+    if (rg.heavy) return;
+    const HsBucket bk = buckets[(int64_t)q * B + b];
+    const int n = (int)bk.size;
+    if (n == 0) return;
+    uint64_t* tmp = hs_smem64;
+    uint32_t* cur = reinterpret_cast<uint32_t*>(hs_smem64 + kHsCap);
+    const float c0 = (float)(bk.cells & 0xffffu);
+    const float fscale = (float)kHsF / (float)((bk.cells >> 16) - (bk.cells & 0xffffu) + 1u);
+    auto pad = [](int f) { return f + (f >> 3); };
+    for (int j = threadIdx.x; j < kHsFPad; j += kHsSortThreads) cur[j] = 0u;
+    const uint2* in = pairs + (int64_t)q * n_db + bk.start;
+    uint2 x[kHsPer];
+    int fr[kHsPer];
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k) {
+        const int i = threadIdx.x + kHsSortThreads * k;
+        if (i < n) x[k] = in[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k) {
+        const int i = threadIdx.x + kHsSortThreads * k;
+        fr[k] = -1;
+        if (i < n) {
+            const float v = hs_pos(key_score((uint64_t)x[k].y << 32), rg.hi, rg.scale);
+            // the same clamped cell position the plan used, refined: monotone non-decreasing in the key
+            const float vc = (v == v) ? fminf(fmaxf(v, 0.f), (float)(kHsCells - 1)) : (float)(kHsCells - 1);
+            fr[k] = min(kHsF - 1, max(0, (int)(__fmul_rn(__fsub_rn(vc, c0), fscale))));
+            atomicAdd(&cur[pad(fr[k])], 1u);
+        }
+    }
+    __syncthreads();
+    {   // exclusive scan: thread t owns fine bins [8t, 8t + 8)
+        uint32_t cc[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { cc[k] = cur[9 * threadIdx.x + k]; sum += cc[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        uint32_t run = incl - sum;
+        for (int k = 0; k < w; ++k) run += wsum[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { cur[9 * threadIdx.x + k] = run; run += cc[k]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k)
+        if (fr[k] >= 0) tmp[atomicAdd(&cur[pad(fr[k])], 1u)] = ((uint64_t)x[k].y << 32) | x[k].x;      // afterwards cur[f] = END of fine bin f
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k) {
+        if (fr[k] >= 0) {                          // fine bin -> exact rank, in place
+            const uint64_t me = ((uint64_t)x[k].y << 32) | x[k].x;
+            const int begin = fr[k] ? (int)cur[pad(fr[k] - 1)] : 0, end = (int)cur[pad(fr[k])];
+            int r = begin;
+            for (int j = begin; j < end; ++j) r += tmp[j] < me ? 1 : 0;
+            fr[k] = r;
+        }
+    }
+    __syncthreads();
+    // rows in rank order through the (now free) counter area, then out as one coalesced run
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k)
+        if (fr[k] >= 0) cur[fr[k]] = x[k].x;
+    __syncthreads();
+    uint32_t* out = vals + (int64_t)q * n_db + bk.start;
+    for (int i = threadIdx.x; i < n; i += kHsSortThreads) out[i] = cur[i];
+}
+
 }  // namespace mdir
 
 using namespace mdir;
@@ -753,6 +1090,61 @@ extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q,
     }
     ss_bucket_sort_kernel<<<dim3(p.B, n_q), kSortThreads, sort_smem, st>>>(pairs, src, is_key, p.B == 1 ? 1 : 0, n_db, p.B, fill, offsets, splitters,
                                                                                        vals);
+    MDIR_LAUNCH_CHECK();
+    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
+    MDIR_LAUNCH_CHECK();
+    return 0;
+}
+
+
+// ---- histogram-sort path ----------------------------------------------------------------------------------------
+static inline bool hs_eligible(int64_t n_db) { return n_db >= kHsMinRows && n_db <= kHsMaxRows; }
+
+extern "C" size_t mdir_rank_hist_workspace_bytes(int64_t n_db, int n_q) {
+    if (n_db <= 0 || n_q <= 0) return 0;
+    if (!hs_eligible(n_db)) return mdir_rank_fast_workspace_bytes(n_db, n_q);
+    const size_t n_pairs = (size_t)n_db * n_q;
+    const int B = hs_buckets(n_db);
+    return align256((size_t)n_q * sizeof(HsRange)) + align256((size_t)n_q * kHsCells) + align256((size_t)n_q * B * sizeof(HsBucket)) +
+           align256(n_pairs * 8) + 2 * align256(n_pairs * 4);
+}
+
+extern "C" int mdir_rank_scores_hist(const float* scores, int64_t n_db, int n_q, int query_major, int64_t* ranks, int64_t ranks_ld,
+                                     void* ws, int32_t* status, void* stream) {
+    MDIR_CHECK_ARG(scores && ranks && ws && status && n_db >= 1 && n_q >= 1 && ranks_ld >= n_q);
+    MDIR_CHECK_ARG(n_db < ((int64_t)1 << 32) && n_q <= 65535);
+    if (!hs_eligible(n_db)) return mdir_rank_scores_fast(scores, n_db, n_q, query_major, ranks, ranks_ld, ws, status, stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    MDIR_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    const size_t n_pairs = (size_t)n_db * n_q;
+    const int B = hs_buckets(n_db);
+    uint8_t* w = (uint8_t*)ws;
+    HsRange* range = (HsRange*)w;                w += align256((size_t)n_q * sizeof(HsRange));
+    uint8_t* table = w;                          w += align256((size_t)n_q * kHsCells);
+    HsBucket* buckets = (HsBucket*)w;            w += align256((size_t)n_q * B * sizeof(HsBucket));
+    uint2* pairs = (uint2*)w;                    w += align256(n_pairs * 8);
+    uint32_t* vals = (uint32_t*)w;               w += align256(n_pairs * 4);
+    uint32_t* keys_t = (uint32_t*)w;             // only for the (n_db, n_q) input layout
+    const unsigned gx = (unsigned)((n_db + 31) / 32), gy = (unsigned)((n_q + 31) / 32);
+    const void* src = scores;
+    int is_key = 0;
+    if (!query_major) {
+        keys_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, keys_t);
+        MDIR_LAUNCH_CHECK();
+        src = keys_t;
+        is_key = 1;
+    }
+    const size_t plan_smem = (size_t)(kHsCells + 4 * B) * 4;
+    const size_t sort_smem = (size_t)kHsCap * 8 + (size_t)kHsFPad * 4;
+    static PerDeviceOnce once;
+    if (once.first() != 0)
+        MDIR_CUDA(cudaFuncSetAttribute(hs_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    hs_plan_kernel<<<n_q, kHsPlanThreads, plan_smem, st>>>(src, is_key, (int)n_db, B, range, table, buckets, status);
+    MDIR_LAUNCH_CHECK();
+    const int n_chunks = (int)((n_db + kHsChunk - 1) / kHsChunk);
+    hs_scatter_kernel<<<dim3(n_chunks, n_q), kHsScatterThreads, 0, st>>>(src, is_key, (int)n_db, B, range, table, buckets, pairs);
+    MDIR_LAUNCH_CHECK();
+    hs_bucket_sort_kernel<<<dim3(B, n_q), kHsSortThreads, sort_smem, st>>>(pairs, (int)n_db, B, range, buckets, vals);
     MDIR_LAUNCH_CHECK();
     ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
     MDIR_LAUNCH_CHECK();

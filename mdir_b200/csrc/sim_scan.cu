@@ -31,6 +31,7 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kChainKBlocks = 4;        // k-blocks (16 MMAs) per chained accumulation chunk of the tf32 DENSE scan
+constexpr int kChainMaxN = 96;          // queries per launch of the chained scan (96 KB of running sums + 2 operand stages)
 constexpr int kMaxAccBufs = 3;          // accumulator tiles resident in TMEM (2 halves x acc_stride columns each)
 
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -127,8 +128,9 @@ struct ScanParams {
     // DENSE mode only: CHAINED accumulation.  The tensor core's fp32 accumulator truncates once per MMA, so a long K
     // loop drifts by up to (number of MMAs) x ulp(|score|) (~4.6e-5 relative at 3 x 2048 tf32 elements).  With
     // chain > 1 the K loop of a tile is cut into `chain` chunks of kb_per_chain k-blocks that the SAME CTA runs back
-    // to back; the epilogue of chunk c > 0 adds its TMEM partial to what chunk c-1 left in dense_out (one rounded
-    // fp32 add per chunk), which keeps the drift at (MMAs per chunk) x ulp.
+    // to back; the epilogue of a chunk adds its TMEM partial to a running sum the CTA keeps in SHARED memory behind the
+    // operand ring (256 rows x n_pad fp32, one rounded fp32 add per chunk; each thread owns its own entries, so no
+    // barrier), and the last chunk's epilogue writes sum + partial to dense_out.  Drift: (MMAs per chunk) x ulp.
     int chain, kb_per_chain;
     // FUSED mode only (threshold + filter in one launch): every CTA's first tile is a sample tile; the best two keys
     // of each 32-row group go to grp_top (n_q, grid, 8, 2); CTA q selects the kth smallest of query q's grid*16
@@ -143,7 +145,7 @@ struct ScanParams {
 constexpr int MDIR_SCAN_FUSED = 3;      // internal mode behind mdir_sim_scan_fused_bf16
 
 struct WorkItem {
-    int tile, ks, kb0, nkb, j, chunk;
+    int tile, ks, kb0, nkb, j, chunk, last;
 };
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j);
@@ -163,6 +165,7 @@ __device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
     }
     w.j = j;
     w.chunk = 0;
+    w.last = 1;
     return w;
 }
 
@@ -179,6 +182,7 @@ __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem&
         w.nkb = min(p.kb_per_chain, p.num_k_blocks - w.kb0);
         w.j = tile;
         w.chunk = c;
+        w.last = c == p.chain - 1 ? 1 : 0;
         return true;
     }
     int j = (int)blockIdx.x + it * (int)gridDim.x;
@@ -190,6 +194,7 @@ __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem&
             w.nkb = p.num_k_blocks;
             w.j = (int)blockIdx.x;
             w.chunk = 0;
+            w.last = 1;
             return true;
         }
         j -= (int)gridDim.x;
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         const int64_t cand_row = (int64_t)p.cap_s + (int64_t)kNumSMs * p.cap_l;
         const int64_t cand_seg_off = (int64_t)p.cap_s + (int64_t)blockIdx.x * p.cap_l;
         const int emode = p.mode == MDIR_SCAN_FUSED ? MDIR_SCAN_FILTER : p.mode;
+        float* chain_sum = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.num_stages * stage_bytes);
         WorkItem w;
         for (int it = 0; next_item(p, it, w); ++it) {
             const int b = it % p.acc_bufs;
@@ -463,21 +469,27 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     tmem_ld_wait();
                     if (emode != MDIR_SCAN_FILTER) {
                         // rows past the end of the database only exist in the compact SAMPLE buffer: mark them -inf
-                        if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
-                            if (w.chunk > 0) {
-                                // chained chunk: add to what this same thread stored for the previous chunk of the tile
+                        if (p.chain > 1) {
+                            // chained chunk: running sum of this thread's row in shared memory (column-major, 128 rows
+                            // per (half, column): conflict-free); only the last chunk touches dense_out
+                            float* sum = chain_sum + ((int64_t)(h * p.n_pad + c0) * 128 + quarter * 32 + lane);
+                            if (w.chunk == 0) {
 #pragma unroll
-                                for (int i = 0; i < 16; ++i)
-                                    if (c0 + i < p.n_q) {
-                                        float* o = dense_out + (int64_t)(c0 + i) * p.dense_ld + out_row;
-                                        *o = __fadd_rn(*o, __uint_as_float(v[i]));
-                                    }
-                            } else {
+                                for (int i = 0; i < 16; ++i) sum[i * 128] = __uint_as_float(v[i]);
+                            } else if (!w.last) {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) sum[i * 128] = __fadd_rn(sum[i * 128], __uint_as_float(v[i]));
+                            } else if (row_ok) {
 #pragma unroll
                                 for (int i = 0; i < 16; ++i)
                                     if (c0 + i < p.n_q)
-                                        dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
+                                        dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = __fadd_rn(sum[i * 128], __uint_as_float(v[i]));
                             }
+                        } else if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (c0 + i < p.n_q)
+                                    dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
                         }
                     } else if (row_ok) {
 #pragma unroll
@@ -615,6 +627,16 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         p.n_work = p.n_tiles * p.k_split;
         if (tf32 && p.k_split == 1 && p.num_k_blocks > 2 * kChainKBlocks) {
             // fp32-faithful path: at most 16 truncating MMAs per TMEM accumulation (see ScanParams::chain)
+            if (p.n_pad > kChainMaxN) {
+                // the running sums (256 x n_pad fp32) share the CTA's shared memory with the operand ring: wider query
+                // blocks go as two launches
+                const int n0 = ((n_q / 2) + 15) & ~15;
+                int rc = launch_scan(tf32, db, n_db, q, n0, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts,
+                                     cap_s, cap_l, stream);
+                if (rc) return rc;
+                return launch_scan(tf32, db, n_db, static_cast<const uint8_t*>(q) + (size_t)n0 * D * esz, n_q - n0, D, mode, sample_stride, n_sample,
+                                   dense_out + (int64_t)n0 * dense_ld, dense_ld, tau, idx_base, cand, seg_counts, cap_s, cap_l, stream);
+            }
             p.kb_per_chain = kChainKBlocks;
             p.chain = (p.num_k_blocks + kChainKBlocks - 1) / kChainKBlocks;
         }
@@ -658,11 +680,12 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     if (p.n_work <= 0 && mode != MDIR_SCAN_FUSED) return 0;
 
     const int stage_bytes = kABytes + p.n_pad * 128;
-    int stages = (232448 - 1024 - 8192) / stage_bytes;      // 8 KB left for the static shared arrays
+    const int chain_bytes = p.chain > 1 ? kBlockM * p.n_pad * 4 : 0;      // running sums of the chained tf32 DENSE scan
+    int stages = (232448 - 1024 - 8192 - chain_bytes) / stage_bytes;      // 8 KB left for the static shared arrays
     if (stages > kMaxStages) stages = kMaxStages;
     MDIR_CHECK_ARG(stages >= 2);
     p.num_stages = stages;
-    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + chain_bytes;
 
     CUtensorMap tmap_db, tmap_q;
     int rc = make_tmap(&tmap_db, tf32, db, (uint64_t)n_db, (uint64_t)D, kBlockM);

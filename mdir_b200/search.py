@@ -408,42 +408,59 @@ class Index:
             for c, q0 in enumerate(starts):
                 q1 = min(q0 + chunk, nq_all)
                 self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
-                _lib.check(lib.mdir_rank_scores_fast(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
-                                                     _lib.ptr(status[c:]), _lib.stream()), "mdir_rank_scores_fast")
+                _lib.check(lib.mdir_rank_scores_hist(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws),
+                                                     _lib.ptr(status[c:]), _lib.stream()), "mdir_rank_scores_hist")
             RANK_STATS["fast"] += len(starts)
-            # ONE read-back for the whole call, after everything is queued; a chunk whose sample sort could not stage a
-            # bucket is redone through the segmented radix sort
-            for c in [i for i, v in enumerate(status.cpu().tolist()) if v]:
+            # ONE read-back for the whole call, after everything is queued; a chunk the histogram sort flagged (a bucket
+            # of massive ties) is redone through the sample sort, and through the segmented radix sort if that cannot
+            # stage a bucket either
+            for c, st in enumerate(status.cpu().tolist()):
+                if not st:
+                    continue
                 q0 = starts[c]
                 q1 = min(q0 + chunk, nq_all)
-                RANK_STATS["fallback"] += 1
                 self.scores(q32[q0:q1], out=sc[:q1 - q0], precision=precision)
-                _lib.check(lib.mdir_rank_scores(_lib.ptr(sc), self.n, q1 - q0, 1, _lib.ptr(out[:, q0:]), nq_all, _lib.ptr(ws), _lib.stream()),
-                           "mdir_rank_scores")
+                _rank_scores_slow(sc, self.n, q1 - q0, 1, out[:, q0:], nq_all, ws, st)
             return out
 
 
-RANK_STATS = {"fast": 0, "fallback": 0}       # sample-sort calls / of those re-run through the radix path
+RANK_STATS = {"fast": 0, "sample_sort": 0, "fallback": 0}       # histogram-sort calls / re-run through the sample sort / through the radix sort
 
 
 def _rank_workspace(n_db, n_q, device):
     lib = _lib.lib()
-    return torch.empty(max(lib.mdir_rank_workspace_bytes(n_db, n_q), lib.mdir_rank_fast_workspace_bytes(n_db, n_q)) + 256,
+    return torch.empty(max(lib.mdir_rank_workspace_bytes(n_db, n_q), lib.mdir_rank_fast_workspace_bytes(n_db, n_q),
+                           lib.mdir_rank_hist_workspace_bytes(n_db, n_q)) + 256,
                        dtype=torch.uint8, device=device)
 
 
-def _rank_scores(scores, n_db, n_q, query_major, out, out_ld, ws):
-    """mdir_rank_scores_fast (sample sort), and the segmented radix sort when it reports a bucket it could not stage
-    (one status word read back per call: the price of never returning an incomplete ranking)."""
+def _rank_scores_slow(scores, n_db, n_q, query_major, out, out_ld, ws, status):
+    """The fallbacks behind a non-zero status word of mdir_rank_scores_hist: bit 1 -> sample sort (splits ties by row);
+    bit 0 (from the sample sort) -> segmented LSD radix sort, which always completes."""
     lib = _lib.lib()
-    status = torch.empty((1,), dtype=torch.int32, device=scores.device)
-    _lib.check(lib.mdir_rank_scores_fast(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.ptr(status),
-                                         _lib.stream()), "mdir_rank_scores_fast")
-    RANK_STATS["fast"] += 1
-    if int(status.item()) != 0:
+    if status & 2:
+        RANK_STATS["sample_sort"] += 1
+        st = torch.empty((1,), dtype=torch.int32, device=scores.device)
+        _lib.check(lib.mdir_rank_scores_fast(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.ptr(st),
+                                             _lib.stream()), "mdir_rank_scores_fast")
+        status = int(st.item())
+    if status & 1:
         RANK_STATS["fallback"] += 1
         _lib.check(lib.mdir_rank_scores(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.stream()),
                    "mdir_rank_scores")
+
+
+def _rank_scores(scores, n_db, n_q, query_major, out, out_ld, ws):
+    """mdir_rank_scores_hist (histogram sort), then the sample sort / the segmented radix sort when it reports a bucket it
+    could not stage (one status word read back per call: the price of never returning an incomplete ranking)."""
+    lib = _lib.lib()
+    status = torch.empty((1,), dtype=torch.int32, device=scores.device)
+    _lib.check(lib.mdir_rank_scores_hist(_lib.ptr(scores), n_db, n_q, query_major, _lib.ptr(out), out_ld, _lib.ptr(ws), _lib.ptr(status),
+                                         _lib.stream()), "mdir_rank_scores_hist")
+    RANK_STATS["fast"] += 1
+    st = int(status.item())
+    if st:
+        _rank_scores_slow(scores, n_db, n_q, query_major, out, out_ld, ws, st)
 
 
 def ranks_from_scores(scores, device="cuda", method="auto"):

@@ -304,19 +304,26 @@ def test_ranks_edge_cases(m):
         assert np.array_equal(m.ranks_from_scores(sc, method="radix").cpu().numpy(), ref), (n_db, n_q)
 
 
-@pytest.mark.parametrize("case", ["gauss", "all_equal", "ascending", "descending", "periodic", "two_values", "spike"])
-@pytest.mark.parametrize("n_db", [1024, 1025, 4993, 100000, 102400, 102401])
-def test_ranks_sample_sort_distributions(m, case, n_db):
-    """mdir_rank_scores_fast (splitters from a systematic sample, one partition pass, shared-memory bucket sorts) against
-    the stable argsort on distributions chosen to stress the splitters: massive ties (composite (score, row) keys keep the
-    buckets balanced), monotone data, data periodic in the row index (aliases with the systematic sample), a dense spike.
-    Whatever the sample does, the result is exact: a bucket that cannot be staged falls back to the radix sort."""
+@pytest.mark.parametrize("case", ["gauss", "gauss_outliers", "all_equal", "ascending", "descending", "periodic", "two_values", "spike", "heavy_tail"])
+@pytest.mark.parametrize("n_db", [1024, 1025, 4993, 100000, 102400, 102401, 131072, 131073])
+def test_ranks_sort_paths_distributions(m, case, n_db):
+    """The three ranking routes against the stable argsort on distributions chosen to stress them.  Histogram sort
+    (mdir_rank_scores_hist: 4096 cells linear in the score over mean +- 4 sigma of a strided sample): smooth populations,
+    outliers far outside the range, +-inf / NaN / +-0, monotone data, heavy tails.  Sample sort (mdir_rank_scores_fast:
+    splitters from a systematic sample, composite (score, row) keys): what the histogram sort flags -- massive ties,
+    two-valued data, a dense spike -- plus data periodic in the row index (aliases with the systematic sample).
+    Whatever the plans do, the result is exact: a bucket that cannot be staged falls through to the next route, the
+    segmented radix sort last."""
     from mdir_b200 import search
     rs = np.random.RandomState(n_db % 1000 + len(case))
     n_q = 3
     i = np.arange(n_db, dtype=np.float64)
     if case == "gauss":
         sc = rs.randn(n_db, n_q) * 0.05
+    elif case == "gauss_outliers":
+        sc = rs.randn(n_db, n_q) * 0.03
+        sc[rs.randint(0, n_db, 40), rs.randint(0, n_q, 40)] = rs.rand(40) * 2 - 1          # planted neighbours / far negatives
+        sc[[0, 1, 2, 3, 4, 5], 0] = [np.inf, -np.inf, np.nan, 0.0, -0.0, np.nan]
     elif case == "all_equal":
         sc = np.full((n_db, n_q), 0.25)
     elif case == "ascending":
@@ -328,6 +335,8 @@ def test_ranks_sample_sort_distributions(m, case, n_db):
         sc = np.stack([np.sin(2 * np.pi * i / period), (i % period) / period, ((i * 7) % period) / period], 1)
     elif case == "two_values":
         sc = (rs.rand(n_db, n_q) < 0.999).astype(np.float64)
+    elif case == "heavy_tail":
+        sc = rs.standard_cauchy((n_db, n_q)) * 0.01
     else:
         sc = rs.randn(n_db, n_q) * 1e-3
         sc[rs.rand(n_db, n_q) < 0.9] = 0.7
@@ -335,8 +344,12 @@ def test_ranks_sample_sort_distributions(m, case, n_db):
     before = dict(search.RANK_STATS)
     got = m.ranks_from_scores(sc).cpu().numpy()
     assert np.array_equal(got, oracle.ranks_from_scores(sc)), (case, n_db)
-    if case in ("gauss", "all_equal", "ascending", "descending", "two_values", "spike"):
-        assert search.RANK_STATS["fallback"] == before["fallback"], "the sample sort needed its fallback on %s" % case
+    if case in ("gauss", "gauss_outliers", "all_equal", "ascending", "descending", "two_values", "spike"):
+        assert search.RANK_STATS["fallback"] == before["fallback"], "the radix fallback was needed on %s" % case
+    if case in ("gauss", "gauss_outliers", "ascending", "descending") and 1025 <= n_db <= 131072:
+        assert search.RANK_STATS["sample_sort"] == before["sample_sort"], "the histogram sort flagged %s" % case
+    if case in ("all_equal", "two_values", "spike") and 4096 < n_db <= 131072:        # up to 4096 rows are one bucket, ties or not
+        assert search.RANK_STATS["sample_sort"] == before["sample_sort"] + 1, "the histogram sort should hand %s to the sample sort" % case
 
 
 # ------------------------------------------------------------------ similarity + search
