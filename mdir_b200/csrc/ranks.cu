@@ -200,24 +200,67 @@ __global__ void __launch_bounds__(kScatterThreads, 4) radix_scatter_kernel(const
     }
 }
 
-// vals (n_q, n_db) u32 -> ranks (n_db, n_q) int64
-__global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __restrict__ vals, int64_t n_db, int n_q,
-                                                              int64_t* __restrict__ ranks, int64_t ranks_ld) {
-    __shared__ uint32_t tile[32][33];
-    const int64_t r0 = (int64_t)blockIdx.x * 32;
-    const int q0 = blockIdx.y * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int r = ty; r < 32; r += 8) {
-        const int q = q0 + r;
-        const int64_t row = r0 + tx;
-        tile[r][tx] = (q < n_q && row < n_db) ? vals[(int64_t)q * n_db + row] : 0u;
+// vals (n_q, n_db) u32 -> ranks (n_db, n_q) int64, on 64 x 64 tiles: a warp reads 64 consecutive rows of one query (256 B) and writes one row's 64
+// consecutive queries (512 B, 16-byte streaming stores).
+// vec != 0: n_db even, vals 8-byte aligned, ranks 16-byte aligned, ranks_ld even.
+__global__ void __launch_bounds__(256) ranks_transpose64_kernel(const uint32_t* __restrict__ vals, int64_t n_db, int n_q,
+                                                                int64_t* __restrict__ ranks, int64_t ranks_ld, int vec) {
+    __shared__ uint32_t tile[64][65];                 // [query][row]
+    const int64_t r0 = (int64_t)blockIdx.x * 64;
+    const int q0 = blockIdx.y * 64;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (vec) {
+        const int64_t row = r0 + 2 * lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ql = w + 8 * i, q = q0 + ql;
+            uint2 v = make_uint2(0u, 0u);
+            if (q < n_q && row < n_db) v = *reinterpret_cast<const uint2*>(vals + (int64_t)q * n_db + row);      // n_db even: row + 1 < n_db too
+            tile[ql][2 * lane] = v.x;
+            tile[ql][2 * lane + 1] = v.y;
+        }
+        __syncthreads();
+        const int q = q0 + 2 * lane;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = w + 8 * i;
+            const int64_t r = r0 + rl;
+            if (r < n_db) {
+                int64_t* dst = ranks + r * ranks_ld + q;
+                if (q + 1 < n_q) {
+                    const longlong2 o = make_longlong2((long long)tile[2 * lane][rl], (long long)tile[2 * lane + 1][rl]);
+                    __stcs(reinterpret_cast<longlong2*>(dst), o);
+                } else if (q < n_q) {
+                    __stcs(dst, (int64_t)tile[2 * lane][rl]);
+                }
+            }
+        }
+    } else {
+        for (int i = w; i < 64; i += 8) {
+            const int q = q0 + i;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t row = r0 + lane + 32 * h;
+                tile[i][lane + 32 * h] = (q < n_q && row < n_db) ? vals[(int64_t)q * n_db + row] : 0u;
+            }
+        }
+        __syncthreads();
+        for (int i = w; i < 64; i += 8) {
+            const int64_t r = r0 + i;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int q = q0 + lane + 32 * h;
+                if (r < n_db && q < n_q) ranks[r * ranks_ld + q] = (int64_t)tile[lane + 32 * h][i];
+            }
+        }
     }
-    __syncthreads();
-    for (int r = ty; r < 32; r += 8) {
-        const int64_t row = r0 + r;
-        const int q = q0 + tx;
-        if (row < n_db && q < n_q) ranks[row * ranks_ld + q] = (int64_t)tile[tx][r];
-    }
+}
+
+static int launch_ranks_transpose(const uint32_t* vals, int64_t n_db, int n_q, int64_t* ranks, int64_t ranks_ld, cudaStream_t st) {
+    const int vec = ((n_db & 1) == 0 && (ranks_ld & 1) == 0 && (((uintptr_t)vals) & 7) == 0 && (((uintptr_t)ranks) & 15) == 0) ? 1 : 0;
+    ranks_transpose64_kernel<<<dim3((unsigned)((n_db + 63) / 64), (unsigned)((n_q + 63) / 64)), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld, vec);
+    MDIR_LAUNCH_CHECK();
+    return 0;
 }
 
 
@@ -240,7 +283,7 @@ __global__ void __launch_bounds__(256) ranks_transpose_kernel(const uint32_t* __
 //                            inside the ~0.5-element bins by comparison): O(n) for the smooth key distributions of
 //                            similarity scores, O(n^2 / 256) per CTA at worst (never wrong); row indices land at their
 //                            final ranks (query-major u32)
-//   5. ranks_transpose_kernel (n_q, n_db) u32 -> (n_db, n_q) int64, the reference's layout
+//   5. ranks_transpose64_kernel (n_q, n_db) u32 -> (n_db, n_q) int64, the reference's layout
 // Traffic per pair: scores 4 + pairs 8 written + 8 read + ranks 4 + transpose 4 + 8 = 36 B, against ~100 B for the four
 // radix passes.  A bucket that overflows its region (probability ~1e-9 per bucket for a random row order) raises
 // *status and the caller re-runs mdir_rank_scores.
@@ -651,7 +694,7 @@ static SsPlan ss_plan(int64_t n_db) {
 //   3. hs_bucket_sort_kernel one CTA per bucket (<= 4096 rows, 8 per thread in registers): interpolation counting sort
 //                            with 4096 fine bins linear in the score over the bucket's cell range, exact rank inside a
 //                            fine bin by comparing (score key, row) composites; ranks leave coalesced
-//   4. ranks_transpose_kernel
+//   4. ranks_transpose64_kernel
 // Everything is monotone in the score key, so the result is bit-identical to the stable argsort.  A query whose
 // histogram has a bucket of more than 4096 rows (massive ties, a spike, heavy tails) is flagged in *status (bit 1) and
 // the caller re-runs the call through the sample sort, which splits ties by row.
@@ -663,9 +706,9 @@ constexpr int kHsFPad = kHsF + kHsF / 8;     // one pad word per 8 counters: a t
 constexpr int kHsSortThreads = 512;
 constexpr int kHsPer = kHsCap / kHsSortThreads;            // 8 rows per thread
 constexpr int kHsPlanThreads = 512;
-constexpr int kHsChunk = 4096;
+constexpr int kHsChunk = 2048;
 constexpr int kHsScatterThreads = 256;
-constexpr int kHsItems = kHsChunk / kHsScatterThreads;     // 16
+constexpr int kHsItems = kHsChunk / kHsScatterThreads;     // 8
 constexpr int kHsMinRows = 1025, kHsMaxRows = 131072;
 constexpr int kHsMaxBuckets = kHsMaxRows / kHsT + 2;       // 66
 constexpr int kHsSample = 4096;
@@ -684,18 +727,37 @@ struct HsBucket {
 
 static inline int hs_buckets(int64_t n_db) { return (int)(n_db / kHsT) + 2; }
 
+// Position of a score on the cell axis.  Monotone non-increasing in the score (every operation is a correctly rounded,
+// monotone fp32 operation), equal for +0 / -0, NaN for NaN: consistent with the order of the score keys.
 __device__ __forceinline__ float hs_pos(float score, float hi, float scale) { return __fmul_rn(__fsub_rn(hi, score), scale); }
 __device__ __forceinline__ int hs_cell(float score, float hi, float scale) {
     const float v = hs_pos(score, hi, scale);
     return (v == v) ? min(kHsCells - 1, max(0, (int)v)) : kHsCells - 1;
 }
-// every kernel goes through the KEY, so all of them see the same canonical score (-0 -> +0, one NaN)
-__device__ __forceinline__ int hs_cell_of_key(uint32_t key, float hi, float scale) { return hs_cell(key_score((uint64_t)key << 32), hi, scale); }
+
+// scores (n_db, n_q) -> (n_q, n_db), values untouched
+__global__ void __launch_bounds__(256) scores_transpose_kernel(const float* __restrict__ scores, int64_t n_db, int n_q, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int q0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t row = r0 + r;
+        const int q = q0 + tx;
+        tile[r][tx] = (row < n_db && q < n_q) ? scores[row * n_q + q] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int q = q0 + r;
+        const int64_t row = r0 + tx;
+        if (q < n_q && row < n_db) out[(int64_t)q * n_db + row] = tile[tx][r];
+    }
+}
 
 // dynamic smem: kHsCells counters + 4 * B words
-__global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __restrict__ src, int is_key, int n_db, int B,
-                                                                 HsRange* __restrict__ range, uint8_t* __restrict__ table,
-                                                                 HsBucket* __restrict__ buckets, int32_t* __restrict__ status) {
+__global__ void __launch_bounds__(kHsPlanThreads, 4) hs_plan_kernel(const float* __restrict__ src, int n_db, int B,
+                                                                    HsRange* __restrict__ range, uint8_t* __restrict__ table,
+                                                                    HsBucket* __restrict__ buckets, int32_t* __restrict__ status) {
     extern __shared__ uint32_t hs_smem[];
     uint32_t* hist = hs_smem;                 // kHsCells
     uint32_t* st = hist + kHsCells;           // B: first rank of the bucket
@@ -708,18 +770,23 @@ __global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __r
     __shared__ uint32_t s_heavy;
     const int q = blockIdx.x;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
-    {   // ---- range from a strided sample: mean +- 4 sigma of its finite scores
-        float sum = 0.f, sq = 0.f, cnt = 0.f;
+    const float* seg = src + (int64_t)q * n_db;
+    {   // ---- range from a strided sample: mean +- 4 sigma of its finite scores (all 8 loads of a thread in flight)
+        constexpr int kS = kHsSample / kHsPlanThreads;
         const int m = min(kHsSample, n_db);
-        for (int j = threadIdx.x; j < m; j += kHsPlanThreads) {
-            const int64_t i = (int64_t)j * n_db / m;
-            const float x = key_score((uint64_t)ss_load_key(seg, is_key, i) << 32);
-            if (fabsf(x) < INFINITY) { sum += x; sq = fmaf(x, x, sq); cnt += 1.f; }
+        float xs[kS];
+#pragma unroll
+        for (int k = 0; k < kS; ++k) {
+            const int j = threadIdx.x + k * kHsPlanThreads;
+            xs[k] = j < m ? seg[(int64_t)j * n_db / m] : INFINITY;
         }
+        float sum = 0.f, sq = 0.f, cnt = 0.f;
+#pragma unroll
+        for (int k = 0; k < kS; ++k)
+            if (fabsf(xs[k]) < INFINITY) { sum += xs[k]; sq = fmaf(xs[k], xs[k], sq); cnt += 1.f; }
         sum = warp_sum(sum); sq = warp_sum(sq); cnt = warp_sum(cnt);
         if (lane == 0) { red[0][w] = sum; red[1][w] = sq; red[2][w] = cnt; }
-        for (int c = threadIdx.x; c < kHsCells; c += kHsPlanThreads) hist[c] = 0u;
+        for (int c = threadIdx.x; c < kHsCells / 4; c += kHsPlanThreads) reinterpret_cast<uint4*>(hist)[c] = make_uint4(0u, 0u, 0u, 0u);
         for (int b = threadIdx.x; b < B; b += kHsPlanThreads) { st[b] = 0xffffffffu; sz[b] = 0u; cf[b] = 0xffffu; cl[b] = 0u; }
         if (threadIdx.x == 0) s_heavy = 0u;
         __syncthreads();
@@ -737,35 +804,39 @@ __global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __r
         __syncthreads();
     }
     const float hi = s_rng[0], scale = s_rng[1];
-    // ---- exact cell histogram of the whole row (two 128-bit loads in flight per thread)
+    // ---- exact cell histogram of the whole row (four 128-bit loads in flight per thread)
     if ((n_db & 3) == 0 && (((uintptr_t)seg) & 15) == 0) {
-        const uint4* p4 = static_cast<const uint4*>(seg);
+        const float4* p4 = reinterpret_cast<const float4*>(seg);
         const int n4 = n_db >> 2;
-        auto add4 = [&](const uint4& v) {
-            const uint32_t k0 = is_key ? v.x : desc_key(__uint_as_float(v.x)), k1 = is_key ? v.y : desc_key(__uint_as_float(v.y));
-            const uint32_t k2 = is_key ? v.z : desc_key(__uint_as_float(v.z)), k3 = is_key ? v.w : desc_key(__uint_as_float(v.w));
-            atomicAdd(&hist[hs_cell_of_key(k0, hi, scale)], 1u);
-            atomicAdd(&hist[hs_cell_of_key(k1, hi, scale)], 1u);
-            atomicAdd(&hist[hs_cell_of_key(k2, hi, scale)], 1u);
-            atomicAdd(&hist[hs_cell_of_key(k3, hi, scale)], 1u);
+        auto add4 = [&](const float4& v) {
+            atomicAdd(&hist[hs_cell(v.x, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell(v.y, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell(v.z, hi, scale)], 1u);
+            atomicAdd(&hist[hs_cell(v.w, hi, scale)], 1u);
         };
         int i = threadIdx.x;
-        for (; i + kHsPlanThreads < n4; i += 2 * kHsPlanThreads) {
-            const uint4 v0 = p4[i], v1 = p4[i + kHsPlanThreads];
+        for (; i + 3 * kHsPlanThreads < n4; i += 4 * kHsPlanThreads) {
+            const float4 v0 = p4[i], v1 = p4[i + kHsPlanThreads], v2 = p4[i + 2 * kHsPlanThreads], v3 = p4[i + 3 * kHsPlanThreads];
             add4(v0);
             add4(v1);
+            add4(v2);
+            add4(v3);
         }
-        if (i < n4) add4(p4[i]);
+        for (; i < n4; i += kHsPlanThreads) add4(p4[i]);
     } else {
-        for (int i = threadIdx.x; i < n_db; i += kHsPlanThreads) atomicAdd(&hist[hs_cell_of_key(ss_load_key(seg, is_key, i), hi, scale)], 1u);
+        for (int i = threadIdx.x; i < n_db; i += kHsPlanThreads) atomicAdd(&hist[hs_cell(seg[i], hi, scale)], 1u);
     }
     __syncthreads();
     // ---- exclusive prefix over the cells: thread t owns cells [8t, 8t + 8)
     constexpr int kPer = kHsCells / kHsPlanThreads;
     static_assert(kPer == 8, "8 table bytes per thread");
     uint32_t c[kPer], sum = 0;
+    {
+        const uint4 lo = reinterpret_cast<const uint4*>(hist)[2 * threadIdx.x], hi4 = reinterpret_cast<const uint4*>(hist)[2 * threadIdx.x + 1];
+        c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi4.x; c[5] = hi4.y; c[6] = hi4.z; c[7] = hi4.w;
+    }
 #pragma unroll
-    for (int k = 0; k < kPer; ++k) { c[k] = hist[threadIdx.x * kPer + k]; sum += c[k]; }
+    for (int k = 0; k < kPer; ++k) sum += c[k];
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -775,7 +846,10 @@ __global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __r
     if (lane == 31) wsum[w] = incl;
     __syncthreads();
     uint32_t run = incl - sum;
-    for (int k = 0; k < w; ++k) run += wsum[k];
+    {
+        const uint32_t mine = lane < kHsPlanThreads / 32 ? wsum[lane] : 0u;      // sum of the warps before this one
+        run += warp_sum_int((int)(lane < w ? mine : 0u));
+    }
     uint32_t packed[2] = {0u, 0u};
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
@@ -811,8 +885,9 @@ __global__ void __launch_bounds__(kHsPlanThreads) hs_plan_kernel(const void* __r
     }
 }
 
-// static smem: 4096 pairs + 4096 bucket ids + the 4096-entry table: 44 KB, five CTAs per SM
-__global__ void __launch_bounds__(kHsScatterThreads, 5) hs_scatter_kernel(const void* __restrict__ src, int is_key, int n_db, int B,
+// static smem: 2048 pairs + 2048 bucket ids + the 4096-entry table: 23 KB, eight CTAs per SM.
+// pairs: (row, raw fp32 score bits); the sort kernel turns the score into its key.
+__global__ void __launch_bounds__(kHsScatterThreads, 8) hs_scatter_kernel(const float* __restrict__ src, int n_db, int B,
                                                                         const HsRange* __restrict__ range, const uint8_t* __restrict__ table,
                                                                         HsBucket* __restrict__ buckets, uint2* __restrict__ pairs) {
     __shared__ uint2 stage[kHsChunk];
@@ -824,26 +899,27 @@ __global__ void __launch_bounds__(kHsScatterThreads, 5) hs_scatter_kernel(const 
     const HsRange rg = range[q];
     if (rg.heavy) return;
     const int lane = threadIdx.x & 31;
+    const float* seg = src + (int64_t)q * n_db;
+    const int base = chunk * kHsChunk;
+    float sc[kHsItems];
+#pragma unroll
+    for (int it = 0; it < kHsItems; ++it) {
+        const int i = base + it * kHsScatterThreads + threadIdx.x;
+        sc[it] = i < n_db ? seg[i] : 0.f;
+    }
     {
         static_assert(kHsCells / 16 == kHsScatterThreads, "one 16-byte table load per thread");
         reinterpret_cast<uint4*>(tab)[threadIdx.x] = reinterpret_cast<const uint4*>(table + (int64_t)q * kHsCells)[threadIdx.x];
         if (threadIdx.x < kHsMaxBuckets + 2) cnt[threadIdx.x] = 0u;
     }
-    const void* seg = static_cast<const uint8_t*>(src) + (int64_t)q * n_db * 4;
-    const int base = chunk * kHsChunk;
-    uint32_t key[kHsItems], where[kHsItems];                                     // where = bucket << 16 | rank inside (chunk, bucket)
-#pragma unroll
-    for (int it = 0; it < kHsItems; ++it) {
-        const int i = base + it * kHsScatterThreads + threadIdx.x;
-        key[it] = i < n_db ? ss_load_key(seg, is_key, i) : 0u;
-    }
     __syncthreads();
+    uint32_t where[kHsItems];                                                    // bucket << 16 | rank inside (chunk, bucket)
 #pragma unroll
     for (int it = 0; it < kHsItems; ++it) {
         const int i = base + it * kHsScatterThreads + threadIdx.x;
         where[it] = 0xffffffffu;
         if (i < n_db) {
-            const uint32_t b = tab[hs_cell_of_key(key[it], rg.hi, rg.scale)];
+            const uint32_t b = tab[hs_cell(sc[it], rg.hi, rg.scale)];
             where[it] = (b << 16) | atomicAdd(&cnt[b], 1u);                      // order inside a bucket is free: the bucket gets sorted
         }
     }
@@ -878,14 +954,18 @@ __global__ void __launch_bounds__(kHsScatterThreads, 5) hs_scatter_kernel(const 
         if (where[it] != 0xffffffffu) {
             const uint32_t b = where[it] >> 16;
             const uint32_t l = cnt[b] + (where[it] & 0xffffu);
-            stage[l] = make_uint2((uint32_t)(base + it * kHsScatterThreads + threadIdx.x), key[it]);      // composite: key high, row low
+            stage[l] = make_uint2((uint32_t)(base + it * kHsScatterThreads + threadIdx.x), __float_as_uint(sc[it]));
             sbucket[l] = (uint8_t)b;
         }
     }
     __syncthreads();
     const int n_valid = min(kHsChunk, n_db - base);
     uint2* out = pairs + (int64_t)q * n_db;
-    for (int l = threadIdx.x; l < n_valid; l += kHsScatterThreads) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+#pragma unroll
+    for (int it = 0; it < kHsItems; ++it) {
+        const int l = it * kHsScatterThreads + threadIdx.x;
+        if (l < n_valid) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+    }
 }
 
 // One CTA per bucket.  dynamic smem: kHsCap keys + kHsFPad counters
@@ -905,27 +985,29 @@ __global__ void __launch_bounds__(kHsSortThreads, 3) hs_bucket_sort_kernel(const
     uint32_t* cur = reinterpret_cast<uint32_t*>(hs_smem64 + kHsCap);
     const float c0 = (float)(bk.cells & 0xffffu);
     const float fscale = (float)kHsF / (float)((bk.cells >> 16) - (bk.cells & 0xffffu) + 1u);
-    auto pad = [](int f) { return f + (f >> 3); };
-    for (int j = threadIdx.x; j < kHsFPad; j += kHsSortThreads) cur[j] = 0u;
     const uint2* in = pairs + (int64_t)q * n_db + bk.start;
     uint2 x[kHsPer];
-    int fr[kHsPer];
 #pragma unroll
     for (int k = 0; k < kHsPer; ++k) {
         const int i = threadIdx.x + kHsSortThreads * k;
         if (i < n) x[k] = in[i];
     }
+    static_assert(kHsFPad % 4 == 0, "128-bit zeroing");
+    for (int j = threadIdx.x; j < kHsFPad / 4; j += kHsSortThreads) reinterpret_cast<uint4*>(cur)[j] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
+    int fr[kHsPer];              // fine bin, then the row's position in tmp, then its rank
 #pragma unroll
     for (int k = 0; k < kHsPer; ++k) {
         const int i = threadIdx.x + kHsSortThreads * k;
         fr[k] = -1;
         if (i < n) {
-            const float v = hs_pos(key_score((uint64_t)x[k].y << 32), rg.hi, rg.scale);
+            const float sc = __uint_as_float(x[k].y);
+            const float v = hs_pos(sc, rg.hi, rg.scale);
             // the same clamped cell position the plan used, refined: monotone non-decreasing in the key
             const float vc = (v == v) ? fminf(fmaxf(v, 0.f), (float)(kHsCells - 1)) : (float)(kHsCells - 1);
             fr[k] = min(kHsF - 1, max(0, (int)(__fmul_rn(__fsub_rn(vc, c0), fscale))));
-            atomicAdd(&cur[pad(fr[k])], 1u);
+            x[k].y = desc_key(sc);
+            atomicAdd(&cur[fr[k] + (fr[k] >> 3)], 1u);
         }
     }
     __syncthreads();
@@ -942,22 +1024,40 @@ __global__ void __launch_bounds__(kHsSortThreads, 3) hs_bucket_sort_kernel(const
         if (lane == 31) wsum[w] = incl;
         __syncthreads();
         uint32_t run = incl - sum;
-        for (int k = 0; k < w; ++k) run += wsum[k];
+        {
+            const uint32_t mine = lane < kHsSortThreads / 32 ? wsum[lane] : 0u;
+            run += (uint32_t)warp_sum_int((int)(lane < w ? mine : 0u));
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) { cur[9 * threadIdx.x + k] = run; run += cc[k]; }
     }
     __syncthreads();
+    uint32_t pos[kHsPer];
 #pragma unroll
     for (int k = 0; k < kHsPer; ++k)
-        if (fr[k] >= 0) tmp[atomicAdd(&cur[pad(fr[k])], 1u)] = ((uint64_t)x[k].y << 32) | x[k].x;      // afterwards cur[f] = END of fine bin f
+        if (fr[k] >= 0) {
+            pos[k] = atomicAdd(&cur[fr[k] + (fr[k] >> 3)], 1u);                  // afterwards cur[f] = END of fine bin f
+            tmp[pos[k]] = ((uint64_t)x[k].y << 32) | x[k].x;
+        }
     __syncthreads();
+    // exact rank = first slot of the fine bin + the number of smaller composites in it: alone in the bin (the usual case)
+    // -> its own slot; two rows -> one comparison with the other slot; more (ties) -> a loop over the bin
 #pragma unroll
     for (int k = 0; k < kHsPer; ++k) {
-        if (fr[k] >= 0) {                          // fine bin -> exact rank, in place
-            const uint64_t me = ((uint64_t)x[k].y << 32) | x[k].x;
-            const int begin = fr[k] ? (int)cur[pad(fr[k] - 1)] : 0, end = (int)cur[pad(fr[k])];
-            int r = begin;
-            for (int j = begin; j < end; ++j) r += tmp[j] < me ? 1 : 0;
+        if (fr[k] >= 0) {
+            const int f = fr[k];
+            const int end = (int)cur[f + (f >> 3)];
+            const int begin = f ? (int)cur[f - 1 + ((f - 1) >> 3)] : 0;
+            const int c = end - begin;
+            int r = (int)pos[k];
+            if (c == 2) {
+                const uint64_t me = ((uint64_t)x[k].y << 32) | x[k].x;
+                r = begin + (tmp[2 * begin + 1 - r] < me ? 1 : 0);
+            } else if (c > 2) {
+                const uint64_t me = ((uint64_t)x[k].y << 32) | x[k].x;
+                r = begin;
+                for (int j = begin; j < end; ++j) r += tmp[j] < me ? 1 : 0;
+            }
             fr[k] = r;
         }
     }
@@ -968,7 +1068,11 @@ __global__ void __launch_bounds__(kHsSortThreads, 3) hs_bucket_sort_kernel(const
         if (fr[k] >= 0) cur[fr[k]] = x[k].x;
     __syncthreads();
     uint32_t* out = vals + (int64_t)q * n_db + bk.start;
-    for (int i = threadIdx.x; i < n; i += kHsSortThreads) out[i] = cur[i];
+#pragma unroll
+    for (int k = 0; k < kHsPer; ++k) {
+        const int i = threadIdx.x + kHsSortThreads * k;
+        if (i < n) out[i] = cur[i];
+    }
 }
 
 }  // namespace mdir
@@ -1024,8 +1128,7 @@ extern "C" int mdir_rank_scores(const float* scores, int64_t n_db, int n_q, int 
         vin = vout;
         vout = (vout == vA) ? vB : vA;
     }
-    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vin, n_db, n_q, ranks, ranks_ld);
-    MDIR_LAUNCH_CHECK();
+    { const int rc = launch_ranks_transpose(vin, n_db, n_q, ranks, ranks_ld, st); if (rc) return rc; }
     return 0;
 }
 
@@ -1091,8 +1194,7 @@ extern "C" int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q,
     ss_bucket_sort_kernel<<<dim3(p.B, n_q), kSortThreads, sort_smem, st>>>(pairs, src, is_key, p.B == 1 ? 1 : 0, n_db, p.B, fill, offsets, splitters,
                                                                                        vals);
     MDIR_LAUNCH_CHECK();
-    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
-    MDIR_LAUNCH_CHECK();
+    { const int rc = launch_ranks_transpose(vals, n_db, n_q, ranks, ranks_ld, st); if (rc) return rc; }
     return 0;
 }
 
@@ -1126,27 +1228,24 @@ extern "C" int mdir_rank_scores_hist(const float* scores, int64_t n_db, int n_q,
     uint32_t* vals = (uint32_t*)w;               w += align256(n_pairs * 4);
     uint32_t* keys_t = (uint32_t*)w;             // only for the (n_db, n_q) input layout
     const unsigned gx = (unsigned)((n_db + 31) / 32), gy = (unsigned)((n_q + 31) / 32);
-    const void* src = scores;
-    int is_key = 0;
+    const float* src = scores;
     if (!query_major) {
-        keys_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, keys_t);
+        scores_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(scores, n_db, n_q, reinterpret_cast<float*>(keys_t));
         MDIR_LAUNCH_CHECK();
-        src = keys_t;
-        is_key = 1;
+        src = reinterpret_cast<const float*>(keys_t);
     }
     const size_t plan_smem = (size_t)(kHsCells + 4 * B) * 4;
     const size_t sort_smem = (size_t)kHsCap * 8 + (size_t)kHsFPad * 4;
     static PerDeviceOnce once;
     if (once.first() != 0)
         MDIR_CUDA(cudaFuncSetAttribute(hs_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
-    hs_plan_kernel<<<n_q, kHsPlanThreads, plan_smem, st>>>(src, is_key, (int)n_db, B, range, table, buckets, status);
+    hs_plan_kernel<<<n_q, kHsPlanThreads, plan_smem, st>>>(src, (int)n_db, B, range, table, buckets, status);
     MDIR_LAUNCH_CHECK();
     const int n_chunks = (int)((n_db + kHsChunk - 1) / kHsChunk);
-    hs_scatter_kernel<<<dim3(n_chunks, n_q), kHsScatterThreads, 0, st>>>(src, is_key, (int)n_db, B, range, table, buckets, pairs);
+    hs_scatter_kernel<<<dim3(n_chunks, n_q), kHsScatterThreads, 0, st>>>(src, (int)n_db, B, range, table, buckets, pairs);
     MDIR_LAUNCH_CHECK();
     hs_bucket_sort_kernel<<<dim3(B, n_q), kHsSortThreads, sort_smem, st>>>(pairs, (int)n_db, B, range, buckets, vals);
     MDIR_LAUNCH_CHECK();
-    ranks_transpose_kernel<<<dim3(gx, gy), 256, 0, st>>>(vals, n_db, n_q, ranks, ranks_ld);
-    MDIR_LAUNCH_CHECK();
+    { const int rc = launch_ranks_transpose(vals, n_db, n_q, ranks, ranks_ld, st); if (rc) return rc; }
     return 0;
 }
