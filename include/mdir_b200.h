@@ -154,6 +154,13 @@ int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int 
                        const uint64_t* tau, uint32_t idx_base,
                        uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream);
 
+/* Dense bf16 scores of ANY number of queries in one launch: out (n_q, n_db) fp32 query-major with pitch dense_ld
+ * (np.dot(vecs.T, qvecs).T, cirscore.py:69).  Work items are (256-row tile, 128-query block) pairs, the blocks of a
+ * tile adjacent in the persistent round-robin, so the database is streamed from HBM once and the kernel ramps up once
+ * instead of once per 128 queries (the all-pairs / full-ranks shapes, BASELINE config C3).                          */
+int mdir_sim_scan_dense_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
+                             float* dense_out, int64_t dense_ld, void* stream);
+
 /* Threshold + filter in ONE launch (the large-database route of the top-k search; replaces the
  * SAMPLE scan -> mdir_select_kth -> FILTER scan chain and its two extra launches).  Every
  * persistent CTA first scans one sample tile (tiles c * (n_tiles / grid)), publishes the two best

@@ -132,6 +132,9 @@ struct ScanParams {
     // operand ring (256 rows x n_pad fp32, one rounded fp32 add per chunk; each thread owns its own entries, so no
     // barrier), and the last chunk's epilogue writes sum + partial to dense_out.  Drift: (MMAs per chunk) x ulp.
     int chain, kb_per_chain;
+    // DENSE mode only: more than one block of n_pad queries in ONE launch (work item = (tile, query block), the blocks
+    // of a tile adjacent in the round-robin so that its database rows are read from HBM once): n_q_total queries in all
+    int n_qblocks, n_q_total;
     // FUSED mode only (threshold + filter in one launch): every CTA's first tile is a sample tile; the best two keys
     // of each 32-row group go to grp_top (n_q, grid, 8, 2); CTA q selects the kth smallest of query q's grid*16
     // values as the threshold, published through tau_rw; sync = {arrivals 1, arrivals 2, unused, exits}
@@ -145,18 +148,25 @@ struct ScanParams {
 constexpr int MDIR_SCAN_FUSED = 3;      // internal mode behind mdir_sim_scan_fused_bf16
 
 struct WorkItem {
-    int tile, ks, kb0, nkb, j, chunk, last;
+    int tile, ks, kb0, nkb, j, chunk, last, qb;
 };
 
 __device__ __forceinline__ int tile_of_work(const ScanParams& p, int j);
 
 __device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
     WorkItem w;
+    w.qb = 0;
     if (p.mode == MDIR_SCAN_DENSE && p.k_split > 1) {
         w.tile = j / p.k_split;
         w.ks = j - w.tile * p.k_split;
         w.kb0 = w.ks * p.kb_per_split;
         w.nkb = min(p.kb_per_split, p.num_k_blocks - w.kb0);
+    } else if (p.mode == MDIR_SCAN_DENSE && p.n_qblocks > 1) {
+        w.tile = j / p.n_qblocks;
+        w.qb = j - w.tile * p.n_qblocks;
+        w.ks = 0;
+        w.kb0 = 0;
+        w.nkb = p.num_k_blocks;
     } else {
         w.tile = tile_of_work(p, j);
         w.ks = 0;
@@ -178,6 +188,7 @@ __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem&
         if (tile >= p.n_tiles) return false;
         w.tile = tile;
         w.ks = 0;
+        w.qb = 0;
         w.kb0 = c * p.kb_per_chain;
         w.nkb = min(p.kb_per_chain, p.num_k_blocks - w.kb0);
         w.j = tile;
@@ -190,6 +201,7 @@ __device__ __forceinline__ bool next_item(const ScanParams& p, int it, WorkItem&
         if (it == 0) {
             w.tile = (int)blockIdx.x * p.sample_stride;
             w.ks = 0;
+            w.qb = 0;
             w.kb0 = 0;
             w.nkb = p.num_k_blocks;
             w.j = (int)blockIdx.x;
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                     mbar_expect_tx(fb, stage_bytes);
                     constexpr int kElemsPerBlock = TF32 ? 32 : 64;
                     tma_load_2d(a_dst, &tmap_db, fb, kb * kElemsPerBlock, row0, p.db_hint);
-                    tma_load_2d(a_dst + kABytes, &tmap_q, fb, kb * kElemsPerBlock, 0, kEvictLast);
+                    tma_load_2d(a_dst + kABytes, &tmap_q, fb, kb * kElemsPerBlock, w.qb * p.n_pad, kEvictLast);
                     if (++stage == p.num_stages) { stage = 0; phase ^= 1u; }
                 }
             }
@@ -349,7 +361,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
             const int b = it % p.acc_bufs;
             const uint32_t acc_phase = (uint32_t)(it / p.acc_bufs) & 1u;
             const int tile = w.tile;
-            float* dense_out = p.dense_out + (int64_t)w.ks * p.split_stride;
+            float* dense_out = p.dense_out + (int64_t)w.ks * p.split_stride + (int64_t)w.qb * p.n_pad * p.dense_ld;
+            const int nq_here = p.n_qblocks > 1 ? min(p.n_pad, p.n_q_total - w.qb * p.n_pad) : p.n_q;     // queries of this item's block
             mbar_wait(smem_u32(&tmem_full_bar[b]), acc_phase);
             tc_fence_after();
             if (p.mode == MDIR_SCAN_FUSED && it == 0) {
@@ -488,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                         } else if (row_ok || p.mode == MDIR_SCAN_SAMPLE) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i)
-                                if (c0 + i < p.n_q)
+                                if (c0 + i < nq_here)
                                     dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
                         }
                     } else if (row_ok) {
@@ -586,7 +599,7 @@ using namespace mdir;
 static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, int n_q, int D, int mode, int sample_stride, int n_sample,
                        float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base, uint64_t* cand,
                        uint32_t* seg_counts, int cap_s, int cap_l, void* stream, int k_split = 1, int64_t split_stride = 0,
-                       int kth = 0, uint32_t* fused_ws = nullptr, uint64_t* tau_rw = nullptr) {
+                       int kth = 0, uint32_t* fused_ws = nullptr, uint64_t* tau_rw = nullptr, int n_q_total = 0) {
     const int esz = tf32 ? 4 : 2;
     MDIR_CHECK_ARG(db && q && n_db >= 1 && n_q >= 1 && n_q <= kMaxN && D >= 16 / esz && (D % (16 / esz)) == 0);
     MDIR_CHECK_ARG((((uintptr_t)db | (uintptr_t)q) & 15) == 0);
@@ -609,6 +622,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.split_stride = split_stride;
     p.chain = 1;
     p.kb_per_chain = p.num_k_blocks;
+    p.n_qblocks = 1;
+    p.n_q_total = n_q;
     // TMEM (512 columns): 3 tiles of 2 x 80 columns, 2 of 2 x 128, or -- 129..256 queries, the tensor-bound shapes
     // (DBA, all-pairs): AI = n_q FLOP/B crosses the ~214 FLOP/B ridge -- ONE tile of 2 x 256 (the epilogue of a tile is
     // then not overlapped with the next tile's MMAs: ~10 % of a D = 2048 tile)
@@ -625,6 +640,14 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
             p.k_split = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // every split gets >= 1 k-block
         }
         p.n_work = p.n_tiles * p.k_split;
+        if (n_q_total > n_q) {
+            // several blocks of n_pad queries in one launch (bf16, no split-K): one ramp instead of one per block
+            MDIR_CHECK_ARG(!tf32 && k_split == 1 && n_q == p.n_pad);
+            p.n_q_total = n_q_total;
+            p.n_qblocks = (n_q_total + p.n_pad - 1) / p.n_pad;
+            MDIR_CHECK_ARG((int64_t)p.n_tiles * p.n_qblocks < ((int64_t)1 << 30));
+            p.n_work = p.n_tiles * p.n_qblocks;
+        }
         if (tf32 && p.k_split == 1 && p.num_k_blocks > 2 * kChainKBlocks) {
             // fp32-faithful path: at most 16 truncating MMAs per TMEM accumulation (see ScanParams::chain)
             if (p.n_pad > kChainMaxN) {
@@ -690,7 +713,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     CUtensorMap tmap_db, tmap_q;
     int rc = make_tmap(&tmap_db, tf32, db, (uint64_t)n_db, (uint64_t)D, kBlockM);
     if (rc) return rc;
-    rc = make_tmap(&tmap_q, tf32, q, (uint64_t)n_q, (uint64_t)D, (uint32_t)p.n_pad);
+    rc = make_tmap(&tmap_q, tf32, q, (uint64_t)p.n_q_total, (uint64_t)D, (uint32_t)p.n_pad);
     if (rc) return rc;
 
     static PerDeviceOnce once;
@@ -728,6 +751,14 @@ extern "C" int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16
                                   uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
     return launch_scan(false, db, n_db, q, n_q, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts,
                        cap_s, cap_l, stream);
+}
+
+extern "C" int mdir_sim_scan_dense_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, float* dense_out, int64_t dense_ld,
+                                        void* stream) {
+    // all of a (possibly > 128-query) block of queries in ONE launch: (tile, 128-query block) work items
+    const int blk = n_q < 128 ? n_q : 128;
+    return launch_scan(false, db, n_db, q, blk, D, MDIR_SCAN_DENSE, 0, 0, dense_out, dense_ld, nullptr, 0, nullptr, nullptr, 0, 0, stream, 1, 0, 0,
+                       nullptr, nullptr, n_q > blk ? n_q : 0);
 }
 
 extern "C" size_t mdir_sim_scan_fused_workspace_bytes(int n_q) {

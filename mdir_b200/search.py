@@ -22,6 +22,7 @@ from . import _lib
 
 TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries per scan pass on the serving path (double / triple buffered TMEM accumulators)
+DENSE_LAUNCH_Q = 1 << 20   # queries per mdir_sim_scan_dense_bf16 launch ((tile, query block) work items are counted in 30 bits)
 MAX_Q_WIDE = 256      # queries per pass for tensor-bound work (search(block_q=256): DBA, all-pairs): all of TMEM for one tile
 N_SEGS = 149          # MDIR_CAND_SEGS: segment 0 = select kernel, 1 + c = scan CTA c
 CAP_S = 8192          # capacity of segment 0 (the >= kth sample rows that pass, incl. ties)
@@ -367,10 +368,16 @@ class Index:
                 out = torch.empty((nq_all, self.n), dtype=torch.float32, device=self.device)
             if precision == "bf16":
                 q16 = pack_bf16(q32)
-                step = MAX_Q
-                for q0 in range(0, nq_all, step):
-                    q1 = min(q0 + step, nq_all)
-                    self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], self.n, None, None, None)
+                if nq_all > MAX_Q and out.stride(0) >= self.n and self.n > 0:
+                    # every 128-query block in one launch (one kernel ramp, the database streamed once)
+                    for q0 in range(0, nq_all, DENSE_LAUNCH_Q):
+                        q1 = min(q0 + DENSE_LAUNCH_Q, nq_all)
+                        _lib.check(lib.mdir_sim_scan_dense_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16[q0:q1]), q1 - q0, self.D,
+                                                                _lib.ptr(out[q0:q1]), out.stride(0), _lib.stream()), "mdir_sim_scan_dense_bf16")
+                    return out
+                for q0 in range(0, nq_all, MAX_Q):
+                    q1 = min(q0 + MAX_Q, nq_all)
+                    self._scan(q16[q0:q1], 0, 0, 0, out[q0:q1], out.stride(0), None, None, None)
                 return out
             if precision not in ("tf32", "fp32"):
                 raise ValueError("precision must be 'bf16', 'tf32' or 'fp32'")

@@ -397,6 +397,26 @@ def test_tf32_and_fp32_faithful_scores(m, golden):
     np.testing.assert_allclose(idx2.scores(q2, precision="bf16").cpu().numpy().T, ref, rtol=0, atol=2e-3)
 
 
+@pytest.mark.parametrize("n_db,n_q,D", [(777, 129, 64), (5000, 300, 128), (33000, 1024, 64), (100, 257, 512)])
+def test_dense_scores_one_launch_equals_per_block_launches(m, n_db, n_q, D):
+    """mdir_sim_scan_dense_bf16 ((tile, 128-query block) work items, one launch) against one mdir_sim_scan_bf16 launch per
+    128-query block: the same MMAs in the same order, so the scores are bit-identical; ragged last block and last tile."""
+    import torch
+    db = synth.descriptors(n_db, D, 3)
+    q = synth.descriptors(n_q, D, 4)
+    index = m.Index(db, device=DEV, keep_fp32=False)
+    one = index.scores(q, precision="bf16")
+    ref = torch.full((n_q, n_db), float("nan"), device=DEV)
+    for q0 in range(0, n_q, 128):
+        ref[q0:q0 + 128] = index.scores(q[q0:q0 + 128], precision="bf16")
+    assert torch.equal(one, ref)
+    assert np.abs(one.cpu().numpy() - (q @ db.T)).max() < 2e-3
+    # a pitched output (column block of a wider array)
+    wide = torch.zeros((n_q, n_db + 8), device=DEV)
+    index.scores(q, out=wide[:, :n_db], precision="bf16")
+    assert torch.equal(wide[:, :n_db], ref) and float(wide[:, n_db:].abs().max()) == 0.0
+
+
 def _assert_same_order(got, ref_i, ref_v, tol):
     """got (k, nq) vs the reference ranking ref_i / ref_v (k_ref >= k rows, best first): every position where the
     indices differ must hold a row that the REFERENCE places within `tol` of that position's reference score
