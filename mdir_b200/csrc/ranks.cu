@@ -705,7 +705,7 @@ constexpr int kHsF = 4096;                   // fine bins of the bucket sort
 constexpr int kHsFPad = kHsF + kHsF / 8;     // one pad word per 8 counters: a thread's 8 consecutive counters are conflict-free
 constexpr int kHsSortThreads = 512;
 constexpr int kHsPer = kHsCap / kHsSortThreads;            // 8 rows per thread
-constexpr int kHsPlanThreads = 512;
+constexpr int kHsPlanThreads = 256;          // 8 CTAs per SM: 1,024 queries are one wave
 constexpr int kHsChunk = 2048;
 constexpr int kHsScatterThreads = 256;
 constexpr int kHsItems = kHsChunk / kHsScatterThreads;     // 8
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(256) scores_transpose_kernel(const float* __re
 }
 
 // dynamic smem: kHsCells counters + 4 * B words
-__global__ void __launch_bounds__(kHsPlanThreads, 4) hs_plan_kernel(const float* __restrict__ src, int n_db, int B,
+__global__ void __launch_bounds__(kHsPlanThreads, 8) hs_plan_kernel(const float* __restrict__ src, int n_db, int B,
                                                                     HsRange* __restrict__ range, uint8_t* __restrict__ table,
                                                                     HsBucket* __restrict__ buckets, int32_t* __restrict__ status) {
     extern __shared__ uint32_t hs_smem[];
@@ -827,13 +827,14 @@ __global__ void __launch_bounds__(kHsPlanThreads, 4) hs_plan_kernel(const float*
         for (int i = threadIdx.x; i < n_db; i += kHsPlanThreads) atomicAdd(&hist[hs_cell(seg[i], hi, scale)], 1u);
     }
     __syncthreads();
-    // ---- exclusive prefix over the cells: thread t owns cells [8t, 8t + 8)
+    // ---- exclusive prefix over the cells: thread t owns cells [16t, 16t + 16)
     constexpr int kPer = kHsCells / kHsPlanThreads;
-    static_assert(kPer == 8, "8 table bytes per thread");
+    static_assert(kPer == 16, "16 table bytes per thread");
     uint32_t c[kPer], sum = 0;
-    {
-        const uint4 lo = reinterpret_cast<const uint4*>(hist)[2 * threadIdx.x], hi4 = reinterpret_cast<const uint4*>(hist)[2 * threadIdx.x + 1];
-        c[0] = lo.x; c[1] = lo.y; c[2] = lo.z; c[3] = lo.w; c[4] = hi4.x; c[5] = hi4.y; c[6] = hi4.z; c[7] = hi4.w;
+#pragma unroll
+    for (int k4 = 0; k4 < kPer / 4; ++k4) {
+        const uint4 v = reinterpret_cast<const uint4*>(hist)[(kPer / 4) * threadIdx.x + k4];
+        c[4 * k4] = v.x; c[4 * k4 + 1] = v.y; c[4 * k4 + 2] = v.z; c[4 * k4 + 3] = v.w;
     }
 #pragma unroll
     for (int k = 0; k < kPer; ++k) sum += c[k];
@@ -850,7 +851,7 @@ __global__ void __launch_bounds__(kHsPlanThreads, 4) hs_plan_kernel(const float*
         const uint32_t mine = lane < kHsPlanThreads / 32 ? wsum[lane] : 0u;      // sum of the warps before this one
         run += warp_sum_int((int)(lane < w ? mine : 0u));
     }
-    uint32_t packed[2] = {0u, 0u};
+    uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int k = 0; k < kPer; ++k) {
         const int cell = threadIdx.x * kPer + k;
@@ -864,7 +865,7 @@ __global__ void __launch_bounds__(kHsPlanThreads, 4) hs_plan_kernel(const float*
         }
         run += c[k];
     }
-    *reinterpret_cast<uint2*>(table + (int64_t)q * kHsCells + threadIdx.x * kPer) = make_uint2(packed[0], packed[1]);
+    *reinterpret_cast<uint4*>(table + (int64_t)q * kHsCells + threadIdx.x * kPer) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     __syncthreads();
     HsBucket* bk = buckets + (int64_t)q * B;
     for (int b = threadIdx.x; b < B; b += kHsPlanThreads) {
