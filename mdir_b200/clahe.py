@@ -25,10 +25,18 @@ _DESC_DTYPE = np.dtype([("src_off", np.int64), ("dst_off", np.int64), ("H", np.i
                         ("src_pitch", np.int32), ("dst_pitch", np.int32)])
 
 
+_DESC_CACHE = {}          # (device, descriptor bytes) -> device copy: a regular batch re-uses its table call after call
+
+
 def _launch(sbase, dbase, descs_np, dev, max_h, max_w, clip_limit, grid):
     lib = _lib.lib()
     n = descs_np.shape[0]
-    descs_d = torch.from_numpy(descs_np.view(np.uint8).reshape(-1)).to(dev)
+    key = (str(dev), descs_np.tobytes())
+    descs_d = _DESC_CACHE.get(key)
+    if descs_d is None:
+        if len(_DESC_CACHE) >= 16:
+            _DESC_CACHE.clear()
+        descs_d = _DESC_CACHE[key] = torch.from_numpy(descs_np.view(np.uint8).reshape(-1).copy()).to(dev)
     tiles_x, tiles_y = int(grid[0]), int(grid[1])
     ws = torch.empty(lib.mdir_clahe_workspace_bytes(n, tiles_x, tiles_y), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):

@@ -92,18 +92,21 @@ __device__ __forceinline__ void hist_chunk_full(uint32_t* h, const uint32_t (&w)
     }
 }
 
-__global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restrict__ src, const mdir_image_desc* __restrict__ descs,
-                                                        const ClahePrep* __restrict__ prep, uint8_t* __restrict__ luts) {
-    __shared__ uint32_t whist[8][256];
-    __shared__ int red_i[8];
-    __shared__ int scan_w[8];
+constexpr int kLutThreads = 128;          // 4 warps, one private histogram each: a 96 x 128 tile is 96 pixels per thread, so
+constexpr int kLutWarps = kLutThreads / 32; // the per-tile epilogue (merge, clip, scan, LUT) is paid by 4 warps instead of 8
+
+__global__ void __launch_bounds__(kLutThreads) clahe_lut_kernel(const uint8_t* __restrict__ src, const mdir_image_desc* __restrict__ descs,
+                                                                const ClahePrep* __restrict__ prep, uint8_t* __restrict__ luts) {
+    __shared__ __align__(16) uint32_t whist[kLutWarps][256];
+    __shared__ int red_i[kLutWarps];
+    __shared__ int scan_w[kLutWarps];
     const int img = blockIdx.z;
     const int ty = blockIdx.y, tx = blockIdx.x;
     const int tiles_x = gridDim.x, tiles_y = gridDim.y;
     const mdir_image_desc d = descs[img];
     const ClahePrep g = prep[img];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 8 * 256; i += 256) (&whist[0][0])[i] = 0u;
+    for (int i = threadIdx.x; i < kLutWarps * 64; i += kLutThreads) reinterpret_cast<uint4*>(&whist[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
 
     const uint8_t* base = src + d.src_off;
@@ -119,13 +122,13 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
         const int cpr = g.tw >> 4;
         const int total = g.th * cpr;
         const uint8_t* tb = base + (int64_t)y0 * d.src_pitch + x0;
-        const int step_r = 256 / cpr, step_c = 256 - step_r * cpr;
+        const int step_r = kLutThreads / cpr, step_c = kLutThreads - step_r * cpr;
         int r = (int)threadIdx.x / cpr, c = (int)threadIdx.x - r * cpr;
-        for (int c0 = threadIdx.x; c0 < total; c0 += 4 * 256) {
-            uint32_t wv[4][4];
+        for (int c0 = threadIdx.x; c0 < total; c0 += 6 * kLutThreads) {
+            uint32_t wv[6][4];                     // six 16-byte loads in flight per thread
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (c0 + u * 256 < total) {
+            for (int u = 0; u < 6; ++u) {
+                if (c0 + u * kLutThreads < total) {
                     const uint4 q = *reinterpret_cast<const uint4*>(tb + (int64_t)r * d.src_pitch + 16 * c);
                     wv[u][0] = q.x; wv[u][1] = q.y; wv[u][2] = q.z; wv[u][3] = q.w;
                 }
@@ -134,22 +137,22 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
                 if (c >= cpr) { c -= cpr; ++r; }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (c0 + u * 256 < total) hist_chunk_full(myh, wv[u]);
+            for (int u = 0; u < 6; ++u)
+                if (c0 + u * kLutThreads < total) hist_chunk_full(myh, wv[u]);
         }
     } else if (vw > 0) {
         // 16-byte chunks: cpr per tile row (rows start at arbitrary alignment), 4 loads in flight per thread
         const int cpr = (vw + 15) / 16 + 1;
         const int total = g.th * cpr;
-        // chunk ci = (row r, chunk-in-row c); consecutive chunks of a thread are 256 apart: advance (r, c) instead of dividing
-        const int step_r = 256 / cpr, step_c = 256 - step_r * cpr;
+        // chunk ci = (row r, chunk-in-row c); consecutive chunks of a thread are kLutThreads apart: advance (r, c) instead of dividing
+        const int step_r = kLutThreads / cpr, step_c = kLutThreads - step_r * cpr;
         int r = (int)threadIdx.x / cpr, c = (int)threadIdx.x - r * cpr;
-        for (int c0 = threadIdx.x; c0 < total; c0 += 4 * 256) {
+        for (int c0 = threadIdx.x; c0 < total; c0 += 4 * kLutThreads) {
             uint32_t wv[4][4];
             int jlo[4], jhi[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const int ci = c0 + u * 256;
+                const int ci = c0 + u * kLutThreads;
                 jlo[u] = 0; jhi[u] = 0;
                 if (ci < total) {
                     const uint8_t* rowp = base + (int64_t)reflect101(y0 + r, d.H) * d.src_pitch;
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     const int rw = g.tw - vw;
     if (rw > 0) {
         const int total = g.th * rw;
-        for (int i = threadIdx.x; i < total; i += 256) {
+        for (int i = threadIdx.x; i < total; i += kLutThreads) {
             const int r = i / rw, c = vw + (i - r * rw);
             const uint8_t* rowp = base + (int64_t)reflect101(y0 + r, d.H) * d.src_pitch;
             atomicAdd(&myh[rowp[reflect101(x0 + c, d.W)]], 1u);
@@ -194,55 +197,85 @@ __global__ void __launch_bounds__(256) clahe_lut_kernel(const uint8_t* __restric
     }
     __syncthreads();
 
-    const int i = threadIdx.x;
-    int h = 0;
+    // thread t owns bins 2t and 2t + 1
+    const int i0 = 2 * threadIdx.x;
+    int h0 = 0, h1 = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) h += (int)whist[k][i];
-
+    for (int k = 0; k < kLutWarps; ++k) {
+        const uint2 v = *reinterpret_cast<const uint2*>(&whist[k][i0]);
+        h0 += (int)v.x;
+        h1 += (int)v.y;
+    }
     const int clip_limit = g.clip_limit;
     if (clip_limit > 0) {
-        int excess = max(h - clip_limit, 0);
-        h = min(h, clip_limit);
-        int s = warp_sum_int(excess);
+        const int excess = max(h0 - clip_limit, 0) + max(h1 - clip_limit, 0);
+        h0 = min(h0, clip_limit);
+        h1 = min(h1, clip_limit);
+        const int s = warp_sum_int(excess);
         if (lane == 0) red_i[w] = s;
         __syncthreads();
         int clipped = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) clipped += red_i[k];
+        for (int k = 0; k < kLutWarps; ++k) clipped += red_i[k];
         const int redist = clipped / 256;
-        int residual = clipped - redist * 256;
-        h += redist;
+        const int residual = clipped - redist * 256;
+        h0 += redist;
+        h1 += redist;
         if (residual != 0) {
             const int step = max(256 / residual, 1);
-            if ((i % step) == 0 && (i / step) < residual) h += 1;
+            if ((i0 % step) == 0 && (i0 / step) < residual) h0 += 1;
+            if (((i0 + 1) % step) == 0 && ((i0 + 1) / step) < residual) h1 += 1;
         }
     }
     // inclusive scan over the 256 bins
-    int s = h;
+    int s = h0 + h1;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, s, o);
+        const int t = __shfl_up_sync(0xffffffffu, s, o);
         if (lane >= o) s += t;
     }
     if (lane == 31) scan_w[w] = s;
     __syncthreads();
-    int pre = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-        if (k < w) pre += scan_w[k];
-    s += pre;
-    int q = __float2int_rn(__fmul_rn((float)s, g.lut_scale));
-    q = min(max(q, 0), 255);
-    luts[(((int64_t)img * tiles_y + ty) * tiles_x + tx) * 256 + i] = (uint8_t)q;
+    for (int k = 0; k < kLutWarps; ++k)
+        if (k < w) s += scan_w[k];
+    int q1 = __float2int_rn(__fmul_rn((float)s, g.lut_scale));
+    int q0 = __float2int_rn(__fmul_rn((float)(s - h1), g.lut_scale));
+    q0 = min(max(q0, 0), 255);
+    q1 = min(max(q1, 0), 255);
+    uint8_t* lut = luts + (((int64_t)img * tiles_y + ty) * tiles_x + tx) * 256;
+    *reinterpret_cast<uchar2*>(lut + i0) = make_uchar2((unsigned char)q0, (unsigned char)q1);
 }
 
-__global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                           const mdir_image_desc* __restrict__ descs, const ClahePrep* __restrict__ prep,
-                                                           const uint8_t* __restrict__ luts) {
-    __shared__ float4 lutf[256];          // the four contributing LUTs, pre-converted: one LDS.128 per pixel
+constexpr int kInterpThreads = 128;
+constexpr int kLutRep = 8;                // copies of the interleaved LUT: lane l reads copy l & 7, its own 16-byte bank group
+
+__global__ void __launch_bounds__(kInterpThreads, 6) clahe_interp_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                        const mdir_image_desc* __restrict__ descs, const ClahePrep* __restrict__ prep,
+                                                                        const uint8_t* __restrict__ luts) {
+    // the four contributing LUTs, pre-converted and interleaved: one LDS.128 per pixel.  Pixel values are arbitrary, so a
+    // single copy costs a quarter-warp of lanes up to 8 serialised 16-byte bank groups; with one copy per lane-mod-8 every
+    // quarter-warp access is conflict-free whatever the image holds (32 KB, built once per cell)
+    __shared__ float4 lutf[256 * kLutRep];
+    __shared__ float4 lut1[256];
     const int img = blockIdx.z;
     const int cy = blockIdx.y, cx = blockIdx.x;
     const int tiles_x = (int)gridDim.x - 1, tiles_y = (int)gridDim.y - 1;
+    // the LUT bytes first: their addresses need nothing but the block index, so these loads are in flight while the
+    // image descriptor arrives and the cell geometry is worked out
+    uint32_t lb[256 / kInterpThreads][4];
+    {
+        const int ty1 = max(cy - 1, 0), ty2 = min(cy, tiles_y - 1);
+        const int tx1 = max(cx - 1, 0), tx2 = min(cx, tiles_x - 1);
+        const uint8_t* L = luts + (int64_t)img * tiles_y * tiles_x * 256;
+        const uint8_t* l11 = L + (ty1 * tiles_x + tx1) * 256, *l12 = L + (ty1 * tiles_x + tx2) * 256;
+        const uint8_t* l21 = L + (ty2 * tiles_x + tx1) * 256, *l22 = L + (ty2 * tiles_x + tx2) * 256;
+#pragma unroll
+        for (int k = 0; k < 256 / kInterpThreads; ++k) {
+            const int v = threadIdx.x + k * kInterpThreads;
+            lb[k][0] = l11[v]; lb[k][1] = l12[v]; lb[k][2] = l21[v]; lb[k][3] = l22[v];
+        }
+    }
     const mdir_image_desc d = descs[img];
     const ClahePrep g = prep[img];
     // nominal pixel ranges of this cell: raw tile index floor(x/tw - 0.5) == cx - 1.  The exact fp32
@@ -256,14 +289,13 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     xe = min(xe, d.W); ye = min(ye, d.H);
     if (xs >= xe || ys >= ye) return;
 
-    {
-        const int ty1 = max(cy - 1, 0), ty2 = min(cy, tiles_y - 1);
-        const int tx1 = max(cx - 1, 0), tx2 = min(cx, tiles_x - 1);
-        const uint8_t* L = luts + (int64_t)img * tiles_y * tiles_x * 256;
-        const int v = threadIdx.x;
-        lutf[v] = make_float4((float)L[(ty1 * tiles_x + tx1) * 256 + v], (float)L[(ty1 * tiles_x + tx2) * 256 + v],
-                              (float)L[(ty2 * tiles_x + tx1) * 256 + v], (float)L[(ty2 * tiles_x + tx2) * 256 + v]);
-    }
+    // one copy first (lane-consecutive 16-byte stores), then the kLutRep copies with lanes again on consecutive
+    // addresses: entry v of copy c lives at lutf[v * kLutRep + c]
+#pragma unroll
+    for (int k = 0; k < 256 / kInterpThreads; ++k)
+        lut1[threadIdx.x + k * kInterpThreads] = make_float4((float)lb[k][0], (float)lb[k][1], (float)lb[k][2], (float)lb[k][3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256 * kLutRep; i += kInterpThreads) lutf[i] = lut1[i / kLutRep];
     __syncthreads();
 
     const float inv_tw = g.inv_tw;
@@ -281,18 +313,18 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
     const uint8_t* sbase = src + d.src_off;
     uint8_t* dbase = dst + d.dst_off;
     const bool vec_ok = (((uintptr_t)sbase | (uintptr_t)dbase | (uintptr_t)d.src_pitch | (uintptr_t)d.dst_pitch) & 7) == 0;
+    uint32_t lane_off;      // opaque to the optimiser, so that (x & 0x7f80) | lane_off stays ONE three-input LOP3 per pixel
+    asm volatile("mov.u32 %0, %1;" : "=r"(lane_off) : "r"((threadIdx.x & (kLutRep - 1)) * 16u));
+    static_assert(kLutRep == 8, "entry stride 128 bytes");
 
     // thread -> (group of 8 consecutive pixels, row slot); a thread keeps its x-group for all rows so the
     // 8 column weights live in registers.  Groups are aligned to 8 in image coordinates.
     const int xs8 = xs & ~7;
     const int n_groups = (xe - xs8 + 7) >> 3;
-    const int gpp = min(n_groups, 256);                 // groups per pass
-    const int rows_pp = 256 / gpp;                      // rows per pass
+    const int gpp = min(n_groups, kInterpThreads);      // groups per pass
+    const int rows_pp = kInterpThreads / gpp;           // rows per pass
     const int gslot = threadIdx.x % gpp, rslot = threadIdx.x / gpp;
     if (rslot >= rows_pp) return;
-    // 4 or 6 rows in flight per thread, whichever leaves fewer idle row slots in the last sweep over the cell
-    const int n_rows = ye - ys;
-    const bool six_rows = ((n_rows + 6 * rows_pp - 1) / (6 * rows_pp)) * 6 <= ((n_rows + 4 * rows_pp - 1) / (4 * rows_pp)) * 4;
     for (int g0 = gslot; g0 < n_groups; g0 += gpp) {
         const int x8 = xs8 + g0 * 8;
         float xa[8], xa1[8];
@@ -309,62 +341,72 @@ __global__ void __launch_bounds__(256) clahe_interp_kernel(const uint8_t* __rest
         if (!mine) continue;
         const bool in_row = x8 + 7 < d.W;
         const bool full = (mine == 0xffu) && in_row;
-        auto rows = [&](auto U_) {
-        constexpr int U = decltype(U_)::value;
-        for (int yb = ys + rslot; yb < ye; yb += U * rows_pp) {
-            uint2 pix[U];
-            // U row loads in flight
+        // one row of 8 pixels: OpenCV's association (l11*xa1 + l12*xa)*ya1 + (l21*xa1 + l22*xa)*ya with individually
+        // rounded fp32 operations, round-half-even through the 1.5 * 2^23 magic add (0 <= res < 255.5: the byte cannot wrap)
+        auto blend_row = [&](const uint2 pix, const float ya, const float ya1) {
+            uint32_t q[8];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int y = yb + u * rows_pp;
-                pix[u] = make_uint2(0u, 0u);
-                if (y < ye) {
-                    const uint8_t* srow = sbase + (int64_t)y * d.src_pitch;
-                    if (vec_ok && in_row) {
-                        pix[u] = *reinterpret_cast<const uint2*>(srow + x8);
-                    } else {
+            for (int e = 0; e < 8; ++e) {
+                const uint32_t pw = e < 4 ? pix.x : pix.y;
+                // byte offset of entry (pixel value, this lane's copy): value * 128 + (lane & 7) * 16 -- one PRMT, one multiply-add
+                const uint32_t off = __byte_perm(pw, 0u, 0x4440u + (e & 3)) * 128u + lane_off;
+                const float4 l = *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(lutf) + off);
+                const float top = __fadd_rn(__fmul_rn(l.x, xa1[e]), __fmul_rn(l.y, xa[e]));
+                const float bot = __fadd_rn(__fmul_rn(l.z, xa1[e]), __fmul_rn(l.w, xa[e]));
+                const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
+                q[e] = __float_as_uint(__fadd_rn(res, 12582912.0f));
+            }
+            // low bytes of the eight magic-added floats -> two words
+            return make_uint2(__byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410),
+                              __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410));
+        };
+        if (vec_ok && full) {
+            // the common case: whole aligned groups; four rows in flight
+            constexpr int U = 4;
+            const uint8_t* sp = sbase + x8;
+            uint8_t* dp = dbase + x8;
+            uint2 pix[U], nxt[U];
+            auto load_rows = [&](uint2 (&p)[U], int yb) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e)
-                            if (x8 + e < d.W) {
-                                const uint32_t b = (uint32_t)srow[x8 + e] << (8 * (e & 3));
-                                if (e < 4) pix[u].x |= b; else pix[u].y |= b;
-                            }
+                for (int u = 0; u < U; ++u) {
+                    const int y = yb + u * rows_pp;
+                    if (y < ye) p[u] = *reinterpret_cast<const uint2*>(sp + (int64_t)y * d.src_pitch);
+                }
+            };
+            load_rows(pix, ys + rslot);
+            for (int yb = ys + rslot; yb < ye; yb += U * rows_pp) {
+                load_rows(nxt, yb + U * rows_pp);            // the next sweep's rows are in flight while this one is blended
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int y = yb + u * rows_pp;
+                    if (y < ye) {
+                        const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
+                        const float ya = __fsub_rn(tyf, floorf(tyf));             // rows [ys, ye) are all owned (monotone)
+                        *reinterpret_cast<uint2*>(dp + (int64_t)y * d.dst_pitch) = blend_row(pix[u], ya, __fsub_rn(1.0f, ya));
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < U; ++u) pix[u] = nxt[u];
             }
+        } else {
+            for (int y = ys + rslot; y < ye; y += rows_pp) {
+                const uint8_t* srow = sbase + (int64_t)y * d.src_pitch;
+                uint2 pix = make_uint2(0u, 0u);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int y = yb + u * rows_pp;
-                if (y >= ye) continue;
+                for (int e = 0; e < 8; ++e)
+                    if (x8 + e < d.W) {
+                        const uint32_t b = (uint32_t)srow[x8 + e] << (8 * (e & 3));
+                        if (e < 4) pix.x |= b; else pix.y |= b;
+                    }
                 const float tyf = __fsub_rn(__fmul_rn((float)y, inv_th), 0.5f);
-                const float fly = floorf(tyf);
-                if ((int)fly != cy - 1) continue;
-                const float ya = __fsub_rn(tyf, fly);
-                const float ya1 = __fsub_rn(1.0f, ya);
-                uint32_t outw[2] = {0u, 0u};
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const uint32_t pw = e < 4 ? pix[u].x : pix[u].y;
-                    const float4 l = lutf[(pw >> (8 * (e & 3))) & 0xffu];
-                    const float top = __fadd_rn(__fmul_rn(l.x, xa1[e]), __fmul_rn(l.y, xa[e]));
-                    const float bot = __fadd_rn(__fmul_rn(l.z, xa1[e]), __fmul_rn(l.w, xa[e]));
-                    const float res = __fadd_rn(__fmul_rn(top, ya1), __fmul_rn(bot, ya));
-                    // round-half-even via the 1.5*2^23 magic constant; 0 <= res < 255.5 so the byte cannot wrap
-                    const uint32_t q = __float_as_uint(__fadd_rn(res, 12582912.0f)) & 0xffu;
-                    outw[e >> 2] |= (uint32_t)q << (8 * (e & 3));
-                }
+                const float ya = __fsub_rn(tyf, floorf(tyf));
+                const uint2 o = blend_row(pix, ya, __fsub_rn(1.0f, ya));
                 uint8_t* drow = dbase + (int64_t)y * d.dst_pitch;
-                if (vec_ok && full) {
-                    *reinterpret_cast<uint2*>(drow + x8) = make_uint2(outw[0], outw[1]);
-                } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if (mine & (1u << e)) drow[x8 + e] = (uint8_t)(outw[e >> 2] >> (8 * (e & 3)));
-                }
+                for (int e = 0; e < 8; ++e)
+                    if (mine & (1u << e)) drow[x8 + e] = (uint8_t)((e < 4 ? o.x : o.y) >> (8 * (e & 3)));
             }
         }
-        };
-        if (six_rows) rows(std::integral_constant<int, 6>{}); else rows(std::integral_constant<int, 4>{});
     }
 }
 
@@ -398,9 +440,9 @@ extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_
     for (int i0 = 0; i0 < n_img; i0 += chunk) {
         const int n = (n_img - i0) < chunk ? (n_img - i0) : chunk;
         uint8_t* l = luts + (size_t)i0 * tiles_x * tiles_y * 256;
-        clahe_lut_kernel<<<dim3(tiles_x, tiles_y, n), 256, 0, st>>>(src, descs + i0, prep + i0, l);
+        clahe_lut_kernel<<<dim3(tiles_x, tiles_y, n), kLutThreads, 0, st>>>(src, descs + i0, prep + i0, l);
         MDIR_LAUNCH_CHECK();
-        clahe_interp_kernel<<<dim3(tiles_x + 1, tiles_y + 1, n), 256, 0, st>>>(src, dst, descs + i0, prep + i0, l);
+        clahe_interp_kernel<<<dim3(tiles_x + 1, tiles_y + 1, n), kInterpThreads, 0, st>>>(src, dst, descs + i0, prep + i0, l);
         MDIR_LAUNCH_CHECK();
     }
     return 0;
