@@ -780,6 +780,7 @@ def side_measurements(torch, mdir_b200, dev):
                     "note": "floor = 12 B/pair (4 B score + 8 B int64 rank) at the measured HBM peak"}
         del idx, db, r
     out["c3_full"] = c3_full_measurement(torch, mdir_b200, dev, g)
+    out["similarity_gemm"] = gemm_measurement(torch, dev, g)
     # SURVEY.md 8d CPU baselines beside `head` and `clahe`: the reference's torch-CPU head and OpenCV CLAHE on this host,
     # as shipped (3 torch threads / 1 cv2 thread) and on all cores
     try:
@@ -792,6 +793,47 @@ def side_measurements(torch, mdir_b200, dev):
         out["cpu_baselines_error"] = repr(exc)
     out.update(training_side_measurements(torch, mdir_b200, dev, g, ev))
     return out
+
+
+def gemm_measurement(torch, dev, g):
+    """north_star: "similarity GEMM at >= 60 % of bf16 tensor peak".  The dense bf16 contraction alone
+    (mdir_sim_scan_dense_bf16: tcgen05 / TMEM / TMA, (256-row tile, 128-query block) work items in one launch), as TFLOP/s
+    against the measured sustained cuBLAS bf16 figure: the C3 shape (512-D: output-write-bound, 4 B out per 1,024 FLOP)
+    and the tensor-bound 2048-D shape of the R1M / DBA descriptors."""
+    from mdir_b200.search import Index
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    tf_sus, tf_burst = 1397.3, 1657.2
+    if os.path.exists(path):
+        with open(path) as fh:
+            pk = json.load(fh)
+            tf_sus, tf_burst = float(pk.get("bf16_tflops_sustained", tf_sus)), float(pk.get("bf16_tflops", tf_burst))
+    res = {"metric": "dense bf16 similarity GEMM, fp32 scores written query-major (device-resident operands)", "unit": "TFLOP/s",
+           "peak_sustained": tf_sus, "peak_burst": tf_burst, "shapes": []}
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for n_db, D, nq in ((100000, 512, 1024), (100000, 2048, 4096)):
+        db = torch.randn((n_db, D), device=dev, generator=g)
+        db = db / db.norm(dim=1, keepdim=True)
+        q = torch.randn((nq, D), device=dev, generator=g)
+        q = q / q.norm(dim=1, keepdim=True)
+        idx = Index(db, device=dev, keep_fp32=False)
+        sc = torch.empty((nq, n_db), dtype=torch.float32, device=dev)
+        for _ in range(3):
+            idx.scores(q, out=sc, precision="bf16")
+        torch.cuda.synchronize()
+        ev[0].record()
+        for _ in range(10):
+            idx.scores(q, out=sc, precision="bf16")
+        ev[1].record()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1]) / 10
+        tf = 2.0 * nq * n_db * D / (ms * 1e-3) / 1e12
+        res["shapes"].append({"shape": "%d q x %d db x %d-D" % (nq, n_db, D), "ms": ms, "tflops": tf, "frac_of_sustained": tf / tf_sus,
+                              "frac_of_burst": tf / tf_burst, "output_TB_per_s": nq * n_db * 4 / (ms * 1e-3) / 1e12})
+        del idx, db, q, sc
+    res["value"] = res["shapes"][-1]["tflops"]
+    res["frac_of_sustained"] = res["shapes"][-1]["frac_of_sustained"]
+    res["note"] = "ms includes the fp32 -> bf16 pack of the queries; ncu tensor-pipe evidence: profiles/r02_ncu_full_dense_gemm.json"
+    return res
 
 
 def c3_full_measurement(torch, mdir_b200, dev, g):
