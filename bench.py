@@ -341,12 +341,17 @@ def run_ours(args):
     # the whole step (pack q, fused threshold+filter scan, finalize + certified fp32 re-score, [exchange + merge]) captured
     # once per query batch into a CUDA graph whose static query buffer already holds that batch: every timed step is ONE
     # graph replay, and consecutive steps search different queries
-    deferred = world > 1 and getattr(target, "_mb", None) is not None
+    # N > 1: the graph holds the local part of the step; the NVLink push + merge of step t is launched on a second stream
+    # and runs while step t+1 scans (GraphedSearch(overlap=True)); every step's merged result is produced, none skipped
+    overlap = world > 1 and getattr(target, "_mb", None) is not None
+    deferred = False
     graphs = []
     for b in range(N_BATCHES):
-        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", deferred=deferred)
+        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", overlap=overlap)
         gb.q.copy_(q_bank[b])
+        gb.used = False
         graphs.append(gb)
+    exch_stream = torch.cuda.Stream(device=dev) if overlap else None
     gs = GraphedSearch(target, N_Q, TOPK, precision="fp32")          # synchronous exchange: the blocking e2e loop
     # the same step with a CUDA event pair around the dominant kernel inside the graph: used only to read that
     # kernel's duration (the two event-record nodes cost ~8 us per step, so `value` is timed on the plain graphs)
@@ -367,10 +372,23 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def run_steps(n):
+        cur = torch.cuda.current_stream(dev)
         for t in range(n):
-            graphs[t % N_BATCHES].graph.replay()
-        if deferred:
-            graphs[(n - 1) % N_BATCHES].drain()
+            gb = graphs[t % N_BATCHES]
+            if not overlap:
+                gb.graph.replay()
+                continue
+            if gb.used:
+                cur.wait_event(gb.done)                    # the previous exchange of this graph has read its key buffer
+            gb.graph.replay()
+            gb.local_done.record(cur)
+            with torch.cuda.stream(exch_stream):
+                exch_stream.wait_event(gb.local_done)
+                gb.exchange()
+                gb.done.record(exch_stream)
+            gb.used = True
+        if overlap:
+            cur.wait_stream(exch_stream)                   # the timed region ends when the last step's merge is done
 
     # ---- warm-up ---------------------------------------------------------------------------------
     run_steps(max(args.warmup, 3))
@@ -458,9 +476,7 @@ def run_ours(args):
     K_EXT = TOPK + 16
     timed, flagged = [], 0
     for b in range(N_BATCHES):
-        graphs[b].graph.replay()
-        if deferred:
-            graphs[b].drain()
+        graphs[b]()                                        # replay (+ this step's exchange and merge at N > 1)
         torch.cuda.synchronize()
         timed.append((graphs[b].out[0].clone(), graphs[b].out[1].clone()))
         flagged += int(graphs[b].status.ne(0).sum().item())
@@ -494,7 +510,7 @@ def run_ours(args):
     parity = {"checked_queries": N_BATCHES * N_Q, "mismatches": violations, "swaps_inside_2e-6_reference_gaps": swaps,
               "certificate_failures": flagged, "certificate_counters": dict(index.cert),
               "reference": "independent: per shard dense 3xTF32 scores of every row -> exact top-%d select -> fp64 re-scoring (torch), shards merged on the host" % (K_EXT + 48),
-              "timed_route": ("deferred NVLink exchange graph" if deferred else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
+              "timed_route": ("CUDA graph of the local step + NVLink exchange/merge kernel on a second stream" if overlap else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
     if nccl_equal is not None:
         parity["p2p_route_equals_nccl_allgather_route"] = nccl_equal
         flag = torch.tensor([violations, 0 if nccl_equal else 1], device=dev)
@@ -529,14 +545,14 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK),
                    "distinct_query_batches": N_BATCHES, "db_rows_per_gpu": hi - lo,
                    "sharding": "db rows contiguous over %d GPU(s); %s" % (world, "single shard" if world == 1 else (
-                       ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); the merge of "
-                        "step t runs inside step t+1, one drain after the last step") % (N_Q * TOPK * 8) if deferred else
+                       ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); the exchange + "
+                        "merge of step t runs on a second stream while step t+1 scans") % (N_Q * TOPK * 8) if overlap else
                        "ncclAllGather of %d B of keys per rank + merge kernel" % (N_Q * TOPK * 8))),
                    "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
         "clocks": sampler.summary(),
         "e2e": {"value": N_Q * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": N_Q * DIM * 4, "d2h_bytes_per_step": N_Q * TOPK * 8 + N_Q * 4,
                 "ms_per_step": e2e_s / args.steps * 1e3, "blocking_ms_per_step": e2e_blocking_s / args.steps * 1e3, "steps_redone_exactly": pipe.n_recovered,
-                "timing": "wall clock around %d steps of SearchPipeline (per step: H2D of the pinned queries, graph replay, D2H of scores/idx/status, host read of the result; %d steps in flight%s); blocking_ms_per_step = the same with a synchronize after every step" % (args.steps, pipe.depth, ", deferred NVLink exchange" if pipe.deferred else "")},
+                "timing": "wall clock around %d steps of SearchPipeline (per step: H2D of the pinned queries, graph replay, D2H of scores/idx/status, host read of the result; %d steps in flight%s); blocking_ms_per_step = the same with a synchronize after every step" % (args.steps, pipe.depth, ", NVLink exchange overlapped with the next scan" if pipe.overlap else "")},
         "e2e_cold_db_ms": {"pack_fp32_to_bf16_and_certificate_stats_ms": pack_ms,
                            "note": "one-off index build for this shard; host->device upload of the fp32 rows would add %.1f GB over PCIe" % ((hi - lo) * DIM * 4 / 1e9)},
         "gpu_launches": int(launches), "gpu_launches_note": "%d libmdir_b200 kernels per step, replayed from one CUDA graph per step" % launches_per_step,

@@ -215,8 +215,12 @@ extern "C" int mdir_shard_exchange_merge(const uint64_t* local_keys, int n_q, in
     for (int r = 0; r < world; ++r) MDIR_CHECK_ARG(mbs.base[r] != nullptr);
     const size_t smem = (size_t)world * k * 8;
     static PerDeviceOnce once;
-    if (once.first() != 0)
+    if (once.first() != 0) {
         MDIR_CUDA(cudaFuncSetAttribute(shard_exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        // the same L1 / shared-memory split as the scan kernel: CTAs of kernels with different carve-outs cannot share an
+        // SM, and this kernel is meant to run beside the next step's scan (SearchPipeline overlap mode)
+        MDIR_CUDA(cudaFuncSetAttribute(shard_exchange_merge_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     shard_exchange_merge_kernel<<<n_q, 256, smem, (cudaStream_t)stream>>>(local_keys, n_q, k, rank, world, max_q, max_k, mode, mbs, out_scores, out_idx,
                                                                           local_status, out_status);
     MDIR_LAUNCH_CHECK();

@@ -796,19 +796,27 @@ class GraphedSearch:
         gs.check_overflow()            # after a sync: True -> rerun through index.search()
     """
 
-    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None, deferred=False):
+    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None, deferred=False, overlap=False):
         """deferred=True (ShardedIndex with peer-memory mailboxes): every replay pushes its keys and returns the merged
-        result of the PREVIOUS replay (see ShardedIndex.search); drain() returns the last one."""
+        result of the PREVIOUS replay (see ShardedIndex.search); drain() returns the last one.
+        overlap=True (same precondition): the graph holds only the LOCAL part of the step (pack, scan, finalize -> this
+        shard's sorted keys); exchange() launches the NVLink push + merge kernel for those keys on whatever stream is
+        current -- a side stream in SearchPipeline, so that the exchange of step t runs while the scan of step t+1
+        streams the shard (the scan grid leaves SMs free for it) and its latency leaves the step's critical path."""
         self.index = index
         self.local = index.local if isinstance(index, ShardedIndex) else index
         dev = self.local.device
         self.n_q, self.k, self.precision, self.shortlist = int(n_q), int(k), precision, shortlist
-        self.deferred = bool(deferred) and isinstance(index, ShardedIndex) and index.world > 1
+        sharded = isinstance(index, ShardedIndex) and index.world > 1
+        self.overlap = bool(overlap) and sharded and index._mb is not None and self.k <= index.P2P_MAX_K and self.n_q <= index.P2P_MAX_Q
+        self.deferred = bool(deferred) and sharded and not self.overlap
         self.q = torch.zeros((n_q, self.local.D), dtype=torch.float32, device=dev)
         self.local.prof = None
         extra = {"exchange": "deferred"} if self.deferred else {}
 
         def step():
+            if self.overlap:
+                return self.local.search(self.q, self.k, precision=self.precision, shortlist=self.shortlist, check=False, return_keys=True)
             return index.search(self.q, self.k, precision=self.precision, shortlist=self.shortlist, check=False, **extra)
 
         with torch.cuda.device(dev):
@@ -822,17 +830,32 @@ class GraphedSearch:
             self.local.prof = prof
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.out = step()
+                res = step()
                 self.ovf = self.local._ovf[:n_q].clone()      # this graph's own copy of the LOCAL status words of this step
-                # status words of the step whose result `out` holds: the world's OR for a sharded index (in deferred
-                # mode that is the previous step, like `out`)
-                self.status = index._status[:n_q].clone() if isinstance(index, ShardedIndex) and index.world > 1 else self.ovf
+                if self.overlap:
+                    self.keys = res[2]
+                    self.out = (torch.empty((n_q, self.k), dtype=torch.float32, device=dev), torch.empty((n_q, self.k), dtype=torch.int32, device=dev))
+                    self.status = torch.zeros((n_q,), dtype=torch.int32, device=dev)
+                else:
+                    self.out = res
+                    # status words of the step whose result `out` holds: the world's OR for a sharded index (in deferred
+                    # mode that is the previous step, like `out`)
+                    self.status = index._status[:n_q].clone() if sharded else self.ovf
             self.local.prof = None
+            if self.overlap:
+                self.local_done, self.done = torch.cuda.Event(), torch.cuda.Event()
+
+    def exchange(self):
+        """overlap mode: push this graph's keys to every peer and merge the world's (synchronous exchange of THIS step) on
+        the current stream, into `out` / `status`.  Every rank calls it once per replay, in the same order."""
+        self.index._exchange(self.keys, self.n_q, self.k, 0, self.out[0], self.out[1], self.ovf, self.status)
 
     def __call__(self, q=None):
         if q is not None:
             self.q.copy_(q, non_blocking=True)
         self.graph.replay()
+        if self.overlap:
+            self.exchange()
         return self.out
 
     def drain(self):
@@ -862,33 +885,38 @@ class SearchPipeline:
     whose candidate lists overflowed is transparently redone through index.search() (exact recovery).
     With a ShardedIndex every rank must submit the same sequence (the all-gather is inside the graphs)."""
 
-    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None):
-        """deferred (default: on for a ShardedIndex with peer-memory mailboxes): the merge of step t runs inside the
-        replay of step t+1 (or in a drain when nothing follows), hiding the exchange behind the next scan.
-        depth = steps in flight (default 2; 3 when deferred, because result(t) then needs replay t+1 finished and the
-        host still wants a whole step of slack to queue the next one)."""
+    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None, overlap=None):
+        """overlap (default: on for a ShardedIndex with peer-memory mailboxes): the graphs hold the local part of a step;
+        the NVLink exchange + merge of step t runs on its own stream while the compute stream already scans step t+1
+        (GraphedSearch(overlap=True)) -- results are those of the SAME ticket, nothing lags.
+        deferred (the earlier scheme, kept selectable): the merge of step t runs inside the replay of step t+1 (or in a
+        drain when nothing follows).  depth = steps in flight (default 2; 3 for the two sharded schemes)."""
         self.index = index
         self.local = index.local if isinstance(index, ShardedIndex) else index
         dev = self.local.device
         self.n_q, self.k = int(n_q), int(k)
         self.precision, self.shortlist = precision, shortlist
         sharded = isinstance(index, ShardedIndex) and index.world > 1
+        p2p_ok = sharded and index._mb is not None and self.k <= index.P2P_MAX_K and self.n_q <= index.P2P_MAX_Q
+        if overlap is None:
+            overlap = p2p_ok and not deferred
+        self.overlap = bool(overlap) and p2p_ok
         if deferred is None:
-            deferred = sharded and index._mb is not None and self.k <= index.P2P_MAX_K and self.n_q <= index.P2P_MAX_Q
-        self.deferred = bool(deferred) and sharded
-        self.depth = int(depth) if depth else (3 if self.deferred else 2)
+            deferred = False
+        self.deferred = bool(deferred) and p2p_ok and not self.overlap
+        self.depth = int(depth) if depth else (3 if (self.deferred or self.overlap) else 2)
         self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None,
-                                     deferred=self.deferred) for s in range(self.depth)]
+                                     deferred=self.deferred, overlap=self.overlap) for s in range(self.depth)]
         with torch.cuda.device(dev):
-            self.compute, self.h2d, self.d2h = (torch.cuda.Stream(device=dev) for _ in range(3))
+            self.compute, self.h2d, self.d2h, self.exch = (torch.cuda.Stream(device=dev) for _ in range(4))
             self.slots = []
             for _ in range(self.depth):
                 self.slots.append({
                     "scores": torch.empty((self.n_q, self.k), dtype=torch.float32).pin_memory(),
                     "idx": torch.empty((self.n_q, self.k), dtype=torch.int32).pin_memory(),
                     "ovf": torch.zeros((self.n_q,), dtype=torch.int32).pin_memory(),
-                    "up": torch.cuda.Event(), "done": torch.cuda.Event(), "down": torch.cuda.Event(),
-                    "q": None, "pending": False, "merged": False})
+                    "up": torch.cuda.Event(), "done": torch.cuda.Event(), "down": torch.cuda.Event(), "local": torch.cuda.Event(),
+                    "q": None, "pending": False, "merged": False, "used": False})
             if self.deferred:
                 self.drain_out = (torch.empty((self.n_q, self.k), dtype=torch.float32, device=dev),
                                   torch.empty((self.n_q, self.k), dtype=torch.int32, device=dev))
@@ -924,9 +952,19 @@ class SearchPipeline:
             slot["up"].record()
         with torch.cuda.stream(self.compute):
             self.compute.wait_event(slot["up"])
+            if self.overlap and slot["used"]:
+                self.compute.wait_event(slot["done"])      # this graph's key buffer: its previous exchange has read it
             gs.graph.replay()
-            slot["done"].record()
-        slot["q"], slot["pending"], slot["merged"] = q, True, False
+            if self.overlap:
+                slot["local"].record()
+            else:
+                slot["done"].record()
+        if self.overlap:
+            with torch.cuda.stream(self.exch):             # exchange + merge of THIS ticket, behind the next ticket's scan
+                self.exch.wait_event(slot["local"])
+                gs.exchange()
+                slot["done"].record()
+        slot["q"], slot["pending"], slot["merged"], slot["used"] = q, True, False, True
         self.d2h.wait_event(slot["done"])
         if not self.deferred:
             self._download(slot, gs.out, gs.status)
@@ -962,6 +1000,8 @@ class SearchPipeline:
             if sharded and bool((slot["ovf"] & STATUS_PEER_TIMEOUT).any()):
                 raise _lib.MdirError("SearchPipeline: a peer rank did not deliver its keys for ticket %d within the bounded wait" % ticket)
             # exact recovery, ordered after everything already queued on the compute stream (shared workspaces)
+            if self.overlap:
+                self.compute.wait_stream(self.exch)
             with torch.cuda.stream(self.compute):
                 if sharded:
                     s, i = self.index.search_collective_recovery(slot["q"], self.k, precision=self.precision, shortlist=self.shortlist)

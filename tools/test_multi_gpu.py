@@ -84,10 +84,27 @@ def main():
     torch.cuda.synchronize()
     good &= torch.equal(i_last, refs[4][1]) and torch.equal(s_last, refs[4][0])
     check("deferred-exchange graph: step t returns step t-1, drain returns the last", good)
-    pipe = mdir_b200.SearchPipeline(sharded, nq, k)
+    # overlapped exchange: the graph holds the local step, the push + merge of the same ticket runs on a second stream
+    go = GraphedSearch(sharded, nq, k, overlap=True)
+    good = go.overlap
+    for b in range(5):
+        s_o, i_o = go(batches[b])
+        torch.cuda.synchronize()
+        good &= torch.equal(i_o, refs[b][1]) and torch.equal(s_o, refs[b][0]) and not go.check_overflow()
+    check("overlap-mode graph (local step graph + exchange kernel) == single", good)
     hb = [b.cpu().pin_memory() for b in batches]
+    pipe_o = mdir_b200.SearchPipeline(sharded, nq, k)
+    outs = [(s.copy(), i.copy()) for s, i in pipe_o.map(hb * 3)]
+    good = pipe_o.overlap and not pipe_o.deferred and len(outs) == 15
+    for b in range(15):
+        good &= bool(np.array_equal(outs[b][1], refs[b % 5][1].cpu().numpy()) and np.array_equal(outs[b][0], refs[b % 5][0].cpu().numpy()))
+    t_a = pipe_o.submit(hb[0])
+    sa, ia = pipe_o.result(t_a)
+    good &= bool(np.array_equal(ia, refs[0][1].cpu().numpy()))
+    check("SearchPipeline over the sharded index (exchange overlapped with the next scan) == single, in order", good)
+    pipe = mdir_b200.SearchPipeline(sharded, nq, k, deferred=True)
     outs = [(s.copy(), i.copy()) for s, i in pipe.map(hb)]
-    good = pipe.deferred and len(outs) == 5
+    good = pipe.deferred and not pipe.overlap and len(outs) == 5
     for b in range(5):
         good &= bool(np.array_equal(outs[b][1], refs[b][1].cpu().numpy()) and np.array_equal(outs[b][0], refs[b][0].cpu().numpy()))
     t_a = pipe.submit(hb[0])
