@@ -161,6 +161,15 @@ int mdir_sim_scan_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int 
 int mdir_sim_scan_dense_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D,
                              float* dense_out, int64_t dense_ld, void* stream);
 
+/* mdir_sim_scan_bf16 for more than 128 queries in ONE launch (SAMPLE / FILTER: up to 1,024; DENSE: any number): work
+ * items are (tile, 128-query block) pairs, so a database tile is read from HBM once for all its query blocks and the
+ * scan of a large query batch (DBA, all-pairs ranking) becomes tensor-bound.  tau, cand, seg_counts, dense_out are
+ * indexed by the query's position in q exactly as for mdir_sim_scan_bf16; results are bit-identical to per-block launches. */
+int mdir_sim_scan_wide_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode,
+                            int sample_stride, int n_sample, float* dense_out, int64_t dense_ld,
+                            const uint64_t* tau, uint32_t idx_base, uint64_t* cand, uint32_t* seg_counts,
+                            int cap_s, int cap_l, void* stream);
+
 /* Threshold + filter in ONE launch (the large-database route of the top-k search; replaces the
  * SAMPLE scan -> mdir_select_kth -> FILTER scan chain and its two extra launches).  Every
  * persistent CTA first scans one sample tile (tiles c * (n_tiles / grid)), publishes the two best

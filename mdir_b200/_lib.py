@@ -38,6 +38,7 @@ PROTOTYPES = {
     "mdir_pack_bf16": (_i, [_vp, _i64, _i, _i, _vp, _vp]),
     "mdir_sim_scan_bf16": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),
     "mdir_sim_scan_dense_bf16": (_i, [_vp, _i64, _vp, _i, _i, _vp, _i64, _vp]),
+    "mdir_sim_scan_wide_bf16": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),
     "mdir_sim_scan_fused_workspace_bytes": (_sz, [_i]),
     "mdir_sim_scan_fused_bf16": (_i, [_vp, _i64, _vp, _i, _i, _i, _vp, _u32, _vp, _vp, _i, _i, _vp, _vp]),
     "mdir_sim_scan_tf32": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _i, _vp, _i64, _vp, _u32, _vp, _vp, _i, _i, _vp]),

@@ -32,6 +32,7 @@ constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;
 constexpr uint32_t kTmemCols = 512;
 constexpr int kChainKBlocks = 4;        // k-blocks (16 MMAs) per chained accumulation chunk of the tf32 DENSE scan
+constexpr int kMaxWideQ = 1024;          // queries of one wide FILTER / SAMPLE launch (their filter state lives in shared memory)
 constexpr int kChainMaxN = 96;          // queries per launch of the chained scan (96 KB of running sums + 2 operand stages)
 constexpr int kMaxAccBufs = 3;          // accumulator tiles resident in TMEM (2 halves x acc_stride columns each)
 
@@ -162,12 +163,18 @@ __device__ __forceinline__ WorkItem decode_work(const ScanParams& p, int j) {
         w.ks = j - w.tile * p.k_split;
         w.kb0 = w.ks * p.kb_per_split;
         w.nkb = min(p.kb_per_split, p.num_k_blocks - w.kb0);
-    } else if (p.mode == MDIR_SCAN_DENSE && p.n_qblocks > 1) {
-        w.tile = j / p.n_qblocks;
-        w.qb = j - w.tile * p.n_qblocks;
+    } else if (p.n_qblocks > 1) {
+        // wide launch: work item = (tile-level item, query block), the blocks of a tile adjacent in the round-robin
+        const int jt = j / p.n_qblocks;
+        w.qb = j - jt * p.n_qblocks;
+        w.tile = tile_of_work(p, jt);
         w.ks = 0;
         w.kb0 = 0;
         w.nkb = p.num_k_blocks;
+        w.j = jt;
+        w.chunk = 0;
+        w.last = 1;
+        return w;
     } else {
         w.tile = tile_of_work(p, j);
         w.ks = 0;
@@ -251,14 +258,26 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     __shared__ __align__(8) uint64_t tmem_full_bar[kMaxAccBufs];
     __shared__ __align__(8) uint64_t tmem_empty_bar[kMaxAccBufs];
     __shared__ uint32_t tmem_base_s;
-    __shared__ uint64_t tau_s[kMaxN];
-    __shared__ float tau_f[kMaxN];
-    __shared__ uint32_t cand_n[kMaxN];     // candidates this CTA has appended per query (CTA-private list: no global atomics)
+    __shared__ uint64_t tau_s0[kMaxN];
+    __shared__ float tau_f0[kMaxN];
+    __shared__ uint32_t cand_n0[kMaxN];    // candidates this CTA has appended per query (CTA-private list: no global atomics)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_bytes = (uint32_t)p.n_pad * 128u;
     const uint32_t stage_bytes = (uint32_t)kABytes + b_bytes;
+    // per-query filter state: the static arrays for one block of queries; behind the operand ring for a wide launch
+    // (n_qblocks blocks of n_pad queries: thresholds and counters of all n_q_total queries stay resident)
+    uint64_t* tau_s = tau_s0;
+    float* tau_f = tau_f0;
+    uint32_t* cand_n = cand_n0;
+    const int n_state = p.n_qblocks > 1 ? p.n_qblocks * p.n_pad : kMaxN;
+    if (p.n_qblocks > 1 && p.mode == MDIR_SCAN_FILTER) {
+        uint8_t* wide = smem_raw + (smem_base - smem_u32(smem_raw)) + (uint32_t)p.num_stages * stage_bytes;
+        tau_s = reinterpret_cast<uint64_t*>(wide);
+        tau_f = reinterpret_cast<float*>(tau_s + n_state);
+        cand_n = reinterpret_cast<uint32_t*>(tau_f + n_state);
+    }
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_db) : "memory");
@@ -281,8 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
     if (p.mode == MDIR_SCAN_FUSED) {
         for (int c = threadIdx.x; c < kMaxN; c += kThreads) cand_n[c] = 0u;
     } else if (p.mode == MDIR_SCAN_FILTER) {
-        for (int c = threadIdx.x; c < kMaxN; c += kThreads) {
-            uint64_t t = c < p.n_q ? p.tau[c] : 0ull;
+        for (int c = threadIdx.x; c < n_state; c += kThreads) {
+            uint64_t t = c < p.n_q_total ? p.tau[c] : 0ull;
             tau_s[c] = t;
             tau_f[c] = ((uint32_t)(t >> 32) == 0xffffffffu) ? -INFINITY : key_score(t);
             cand_n[c] = 0u;
@@ -506,15 +525,16 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                                     dense_out[(int64_t)(c0 + i) * p.dense_ld + out_row] = row_ok ? __uint_as_float(v[i]) : -INFINITY;
                         }
                     } else if (row_ok) {
+                        const int qo = w.qb * p.n_pad + c0;               // first query of these 16 columns
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const float s = __uint_as_float(v[i]);
-                            if (s >= tau_f[c0 + i] && c0 + i < p.n_q) {
+                            if (s >= tau_f[qo + i] && c0 + i < nq_here) {
                                 const uint64_t key = make_key(s, gidx);
-                                if (key <= tau_s[c0 + i]) {
-                                    const uint32_t pos = atomicAdd(&cand_n[c0 + i], 1u);      // shared memory, rare
+                                if (key <= tau_s[qo + i]) {
+                                    const uint32_t pos = atomicAdd(&cand_n[qo + i], 1u);      // shared memory, rare
                                     if (pos < (uint32_t)p.cap_l)
-                                        p.cand[(int64_t)(c0 + i) * cand_row + cand_seg_off + pos] = key;
+                                        p.cand[(int64_t)(qo + i) * cand_row + cand_seg_off + pos] = key;
                                 }
                             }
                         }
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
         }
         if (emode == MDIR_SCAN_FILTER) {
             asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps only
-            for (int t = (int)threadIdx.x - 64; t < p.n_q; t += 128) {
+            for (int t = (int)threadIdx.x - 64; t < p.n_q_total; t += 128) {
                 p.seg_counts[(int64_t)t * MDIR_CAND_SEGS + 1 + blockIdx.x] = cand_n[t];
                 if (p.mode == MDIR_SCAN_FUSED && blockIdx.x == 0) {
                     // no select kernel in this route: segment 0 and the segments of absent CTAs are empty
@@ -625,6 +645,15 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     p.kb_per_chain = p.num_k_blocks;
     p.n_qblocks = 1;
     p.n_q_total = n_q;
+    if (n_q_total > n_q) {
+        // several blocks of n_pad queries in one launch (bf16, no split-K): one ramp instead of one per block, and the
+        // database tile of a work item is re-read from L2, not HBM, by the other query blocks
+        MDIR_CHECK_ARG(!tf32 && k_split == 1 && n_q == p.n_pad && mode != MDIR_SCAN_FUSED);
+        p.n_q_total = n_q_total;
+        p.n_qblocks = (n_q_total + p.n_pad - 1) / p.n_pad;
+        MDIR_CHECK_ARG(p.n_qblocks * p.n_pad <= kMaxWideQ || mode == MDIR_SCAN_DENSE);
+        MDIR_CHECK_ARG((int64_t)p.n_tiles * p.n_qblocks < ((int64_t)1 << 30));
+    }
     // TMEM (512 columns): 3 tiles of 2 x 80 columns, 2 of 2 x 128, or -- 129..256 queries, the tensor-bound shapes
     // (DBA, all-pairs): AI = n_q FLOP/B crosses the ~214 FLOP/B ridge -- ONE tile of 2 x 256 (the epilogue of a tile is
     // then not overlapped with the next tile's MMAs: ~10 % of a D = 2048 tile)
@@ -641,14 +670,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
             p.k_split = (p.num_k_blocks + p.kb_per_split - 1) / p.kb_per_split;     // every split gets >= 1 k-block
         }
         p.n_work = p.n_tiles * p.k_split;
-        if (n_q_total > n_q) {
-            // several blocks of n_pad queries in one launch (bf16, no split-K): one ramp instead of one per block
-            MDIR_CHECK_ARG(!tf32 && k_split == 1 && n_q == p.n_pad);
-            p.n_q_total = n_q_total;
-            p.n_qblocks = (n_q_total + p.n_pad - 1) / p.n_pad;
-            MDIR_CHECK_ARG((int64_t)p.n_tiles * p.n_qblocks < ((int64_t)1 << 30));
-            p.n_work = p.n_tiles * p.n_qblocks;
-        }
+        if (n_q_total > n_q) p.n_work = p.n_tiles * p.n_qblocks;
         if (tf32 && p.k_split == 1 && p.num_k_blocks > 2 * kChainKBlocks) {
             // fp32-faithful path: at most 16 truncating MMAs per TMEM accumulation (see ScanParams::chain)
             if (p.n_pad > kChainMaxN) {
@@ -668,7 +690,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CHECK_ARG(dense_out && n_sample >= 1 && sample_stride >= 1);
         MDIR_CHECK_ARG((int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
         MDIR_CHECK_ARG(dense_ld >= (int64_t)n_sample * kBlockM);
-        p.n_work = n_sample;
+        p.n_work = n_sample * p.n_qblocks;
     } else if (mode == MDIR_SCAN_FUSED) {
         // one sample tile per CTA, all CTAs co-resident (the in-kernel arrival counters rely on it)
         MDIR_CHECK_ARG(tau_rw && fused_ws && cand && seg_counts && cap_l >= 1 && kth >= 1 && n_q <= 128);
@@ -689,7 +711,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CHECK_ARG(tau && cand && seg_counts && cap_s >= 0 && cap_l >= 1);
         MDIR_CHECK_ARG(n_sample >= 0 && (n_sample == 0 || sample_stride >= 2));
         MDIR_CHECK_ARG(n_sample == 0 || (int64_t)(n_sample - 1) * sample_stride < p.n_tiles);
-        p.n_work = p.n_tiles - n_sample;
+        p.n_work = (p.n_tiles - n_sample) * p.n_qblocks;
     }
     p.dense_out = dense_out;
     p.dense_ld = dense_ld;
@@ -704,7 +726,8 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
     if (p.n_work <= 0 && mode != MDIR_SCAN_FUSED) return 0;
 
     const int stage_bytes = kABytes + p.n_pad * 128;
-    const int chain_bytes = p.chain > 1 ? kBlockM * p.n_pad * 4 : 0;      // running sums of the chained tf32 DENSE scan
+    int chain_bytes = p.chain > 1 ? kBlockM * p.n_pad * 4 : 0;            // running sums of the chained tf32 DENSE scan
+    if (p.n_qblocks > 1 && mode == MDIR_SCAN_FILTER) chain_bytes = p.n_qblocks * p.n_pad * 16;      // wide FILTER: per-query thresholds + counters
     int stages = (232448 - 1024 - 8192 - chain_bytes) / stage_bytes;      // 8 KB left for the static shared arrays
     if (stages > kMaxStages) stages = kMaxStages;
     MDIR_CHECK_ARG(stages >= 2);
@@ -723,7 +746,14 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         MDIR_CUDA(cudaFuncSetAttribute(sim_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 8192));
     }
     const int n_ctas_wanted = p.chain > 1 ? p.n_tiles : p.n_work;
-    const int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : balanced_grid(n_ctas_wanted, kNumSMs);
+    int grid = mode == MDIR_SCAN_FUSED ? p.n_sample : balanced_grid(n_ctas_wanted, kNumSMs);
+    if (p.n_qblocks > 1) {
+        // CTA c takes items c, c + grid, ...: with grid coprime to the number of query blocks it meets every block equally
+        // often (148 CTAs and 8 blocks would give each CTA only two of them -- and each query's candidates only a
+        // quarter of the per-CTA segments, four times as full)
+        auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+        while (grid > 1 && gcd(grid, p.n_qblocks) != 1) --grid;
+    }
     if (mode == MDIR_SCAN_FUSED) {
         // the in-kernel threshold exchange is a grid-wide rendezvous: launch COOPERATIVELY, so the runtime guarantees
         // that all `grid` CTAs are co-resident (or fails the launch) instead of the kernel relying on an empty device
@@ -762,6 +792,16 @@ extern "C" int mdir_sim_scan_dense_bf16(const uint16_t* db, int64_t n_db, const 
     const int blk = n_q < blk_max ? n_q : blk_max;
     return launch_scan(false, db, n_db, q, blk, D, MDIR_SCAN_DENSE, 0, 0, dense_out, dense_ld, nullptr, 0, nullptr, nullptr, 0, 0, stream, 1, 0, 0,
                        nullptr, nullptr, n_q > blk ? n_q : 0);
+}
+
+extern "C" int mdir_sim_scan_wide_bf16(const uint16_t* db, int64_t n_db, const uint16_t* q, int n_q, int D, int mode, int sample_stride,
+                                       int n_sample, float* dense_out, int64_t dense_ld, const uint64_t* tau, uint32_t idx_base,
+                                       uint64_t* cand, uint32_t* seg_counts, int cap_s, int cap_l, void* stream) {
+    // mdir_sim_scan_bf16 for 129 .. 1024 queries in one launch (DENSE: any number): blocks of 128 queries per work item
+    MDIR_CHECK_ARG(n_q >= 1 && (mode == MDIR_SCAN_DENSE || n_q <= kMaxWideQ));
+    const int blk = n_q < 128 ? n_q : 128;
+    return launch_scan(false, db, n_db, q, blk, D, mode, sample_stride, n_sample, dense_out, dense_ld, tau, idx_base, cand, seg_counts, cap_s,
+                       cap_l, stream, 1, 0, 0, nullptr, nullptr, n_q > blk ? n_q : 0);
 }
 
 extern "C" size_t mdir_sim_scan_fused_workspace_bytes(int n_q) {

@@ -6,14 +6,16 @@ alpha = 3, n_qe = 10, k_dba = 10, negative similarities clamped to 0, self inclu
 import torch
 
 from . import _lib
-from .search import Index, ShardedIndex, MAX_Q
+from .search import Index, ShardedIndex, WIDE_Q
 
 
-DBA_BLOCK = 4096      # rows augmented per search() call (32 scan passes; ONE status read-back per call instead of one per pass)
-# Queries resident per scan pass.  256 (all of TMEM for one tile, AI = 256 FLOP per database byte) is supported and
-# bit-identical, but measured SLOWER than 128 on B200 (1.46 ms vs 2 x 0.65 ms per 256 queries at 1M x 2048: three 64 KB
-# pipeline stages and no accumulator double-buffering cost more than the halved HBM traffic saves) -- tools/time_wide.py.
-DBA_QUERIES_PER_PASS = MAX_Q
+DBA_BLOCK = 4096      # rows augmented per search() call (four wide scan passes; ONE status read-back per call instead of one per pass)
+# Queries per scan pass: 1,024 as one WIDE launch (8 blocks of 128 queries per 256-row database tile, the blocks of a
+# tile adjacent in the persistent round-robin): the tile comes from HBM once and from L2 seven times, so the pass is
+# bound by the tensor pipe / L2 -> shared-memory ingest instead of HBM (128 queries per pass: AI = 128 FLOP per database
+# byte, under the ~214 FLOP/B ridge).  One 256-query tile (all of TMEM) was the earlier attempt and measured slower
+# than 2 x 128: three 64 KB stages and no accumulator double-buffering -- tools/time_wide.py.
+DBA_QUERIES_PER_PASS = WIDE_Q
 
 
 def _accumulate(index, idx, scores, alpha):
@@ -56,7 +58,7 @@ def search_qe(index, q, k, alpha=3.0, n_qe=10, precision="fp32"):
 def dba(index, alpha=3.0, k_dba=10, rows=None):
     """Database-side augmentation of a single-GPU Index: every row replaced by the normalised
     alpha-weighted sum of its own top-k_dba neighbours (self included).  Returns a new Index.
-    Every 128 rows are one streaming pass of the database (HBM-bound at 128 FLOP per database byte; see DBA_QUERIES_PER_PASS).
+    Every 1,024 rows are one wide pass over the database (see DBA_QUERIES_PER_PASS).
     rows: augment only the first `rows` rows (the others are copied unchanged) -- bounded benchmarks."""
     if index.db32 is None:
         raise _lib.MdirError("DBA needs the fp32 master copy (keep_fp32=True)")

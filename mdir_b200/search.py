@@ -23,7 +23,8 @@ from . import _lib
 TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries per scan pass on the serving path (double / triple buffered TMEM accumulators)
 DENSE_LAUNCH_Q = 1 << 20   # queries per mdir_sim_scan_dense_bf16 launch ((tile, query block) work items are counted in 30 bits)
-MAX_Q_WIDE = 256      # queries per pass for tensor-bound work (search(block_q=256): DBA, all-pairs): all of TMEM for one tile
+MAX_Q_WIDE = 256      # rows of the default candidate buffers
+WIDE_Q = 1024         # queries per WIDE launch (search(block_q=1024): DBA, all-pairs): 8 blocks of 128 per database tile
 N_SEGS = 149          # MDIR_CAND_SEGS: segment 0 = select kernel, 1 + c = scan CTA c
 CAP_S = 8192          # capacity of segment 0 (the >= kth sample rows that pass, incl. ties)
 CAP_L = 96            # capacity of each scan CTA's private segment
@@ -173,13 +174,17 @@ class Index:
         return 1.25 * kth * n_tiles / (g * g) <= FUSED_CAP_L / 2
 
     def _scan(self, q16, mode, stride, n_sample, dense, dense_ld, tau, cand, cnt):
-        _lib.check(_lib.lib().mdir_sim_scan_bf16(_lib.ptr(self.db16), self.n, _lib.ptr(q16), q16.shape[0], self.D, mode, stride,
-                                                 n_sample, _lib.ptr(dense), dense_ld, _lib.ptr(tau), self.idx_base, _lib.ptr(cand),
-                                                 _lib.ptr(cnt), CAP_S, CAP_L, _lib.stream()), "mdir_sim_scan_bf16")
+        # more than 128 queries: one WIDE launch, work items = (tile, 128-query block) -- one kernel ramp, and a database
+        # tile comes from HBM once for all the blocks (the tensor-bound regime: DBA, all-pairs)
+        fn = _lib.lib().mdir_sim_scan_wide_bf16 if q16.shape[0] > MAX_Q else _lib.lib().mdir_sim_scan_bf16
+        _lib.check(fn(_lib.ptr(self.db16), self.n, _lib.ptr(q16), q16.shape[0], self.D, mode, stride,
+                      n_sample, _lib.ptr(dense), dense_ld, _lib.ptr(tau), self.idx_base, _lib.ptr(cand),
+                      _lib.ptr(cnt), CAP_S, CAP_L, _lib.stream()), "mdir_sim_scan_bf16")
 
-    def _cand_bufs(self):
-        return (self._buf("tau", (MAX_Q_WIDE,), torch.int64), self._buf("cand", (MAX_Q_WIDE, CAND_ROW), torch.int64),
-                self._buf("segcnt", (MAX_Q_WIDE, N_SEGS), torch.int32))
+    def _cand_bufs(self, nq=MAX_Q_WIDE):
+        rows = MAX_Q_WIDE if nq <= MAX_Q_WIDE else WIDE_Q
+        return (self._buf("tau", (rows,), torch.int64), self._buf("cand", (rows, CAND_ROW), torch.int64),
+                self._buf("segcnt", (rows, N_SEGS), torch.int32))
 
     def _finalize(self, cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore=None, caps=(CAP_S, CAP_L)):
         """rescore = (q32_block, k_out): fused exact fp32 re-scoring of the kth-long bf16 shortlist."""
@@ -203,8 +208,8 @@ class Index:
         emits exactly kth keys, so nothing can overflow here)."""
         lib = _lib.lib()
         nq = q16.shape[0]
-        tau, cand, cnt = self._cand_bufs()       # the select kernel (re)initialises every segment counter
-        dense = self._buf("dense", (MAX_Q if nq <= MAX_Q else MAX_Q_WIDE, max(self.n, 1)), torch.float32)
+        tau, cand, cnt = self._cand_bufs(nq)     # the select kernel (re)initialises every segment counter
+        dense = self._buf("dense", (MAX_Q if nq <= MAX_Q else (MAX_Q_WIDE if nq <= MAX_Q_WIDE else WIDE_Q), max(self.n, 1)), torch.float32)
         self._scan(q16, 0, 0, 0, dense, self.n, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(dense), self.n, self.n, nq, kth, 0, self.idx_base, _lib.ptr(tau),
                                        _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 0, _lib.stream()), "mdir_select_kth")
@@ -217,7 +222,7 @@ class Index:
         plan = self._plan(kth)
         if plan is None:
             return self._dense_block(q16, kth, out_scores, out_idx, out_keys, ovf, rescore)
-        tau, cand, cnt = self._cand_bufs()       # the select / fused kernel (re)initialises every segment counter
+        tau, cand, cnt = self._cand_bufs(nq)     # the select / fused kernel (re)initialises every segment counter
         prof = getattr(self, "prof", None)       # bench.py: CUDA events around the dominant kernel, on its own stream
         if self._fused_ok(kth, nq):
             ws = self._ws.get("fused_ws")
@@ -234,8 +239,12 @@ class Index:
             return self._finalize(cand, cnt, nq, kth, out_scores, out_idx, out_keys, tau, ovf, rescore, caps=(0, FUSED_CAP_L))
         n_sample, stride = plan
         rows = n_sample * TILE
-        sample = self._buf("sample", (MAX_Q if nq <= MAX_Q else MAX_Q_WIDE, MAX_SAMPLE_TILES * TILE), torch.float32)
-        ld = MAX_SAMPLE_TILES * TILE
+        if nq <= MAX_Q_WIDE:
+            sample = self._buf("sample", (MAX_Q if nq <= MAX_Q else MAX_Q_WIDE, MAX_SAMPLE_TILES * TILE), torch.float32)
+            ld = MAX_SAMPLE_TILES * TILE
+        else:
+            sample = self._buf("sample_wide", (WIDE_Q, rows), torch.float32)
+            ld = rows
         self._scan(q16, 1, stride, n_sample, sample, ld, None, None, None)
         _lib.check(lib.mdir_select_kth(_lib.ptr(sample), ld, rows, nq, kth, stride, self.idx_base, _lib.ptr(tau),
                                        _lib.ptr(cand), CAND_ROW, _lib.ptr(cnt), N_SEGS, CAP_S, 1, _lib.stream()), "mdir_select_kth")
@@ -255,7 +264,8 @@ class Index:
         precision="fp32": bf16 shortlist of `shortlist` (default 1.25 k rounded up to 64) per query, re-scored exactly in
                           fp32 against the fp32 master copy and extended until certified (mdir_topk_finalize_rescore).
         check=False skips the (synchronising) status check; call check_overflow() later.
-        block_q: queries per scan pass, 128 (serving) or 256 (tensor-bound batches: the database is streamed half as often)."""
+        block_q: queries per scan pass, 128 (serving) up to 1,024 (tensor-bound batches -- DBA, all-pairs: one WIDE launch,
+        (tile, 128-query block) work items, the database streamed from HBM once per 1,024 queries)."""
         lib = _lib.lib()
         with torch.cuda.device(self.device):
             q32 = _as_dev_f32(q, self.device)
@@ -282,7 +292,7 @@ class Index:
             out_i = torch.empty((nq_all, k), dtype=torch.int32, device=self.device)
             out_k = torch.empty((nq_all, k), dtype=torch.int64, device=self.device) if return_keys else None
             self._ovf = self._buf("ovf", (max(nq_all, 1),), torch.int32)
-            block_q = MAX_Q_WIDE if int(block_q) > MAX_Q else MAX_Q
+            block_q = max(MAX_Q, min(WIDE_Q, int(block_q)))
             for q0 in range(0, nq_all, block_q):
                 q1 = min(q0 + block_q, nq_all)
                 nq = q1 - q0

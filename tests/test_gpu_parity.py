@@ -417,6 +417,24 @@ def test_dense_scores_one_launch_equals_per_block_launches(m, n_db, n_q, D):
     assert torch.equal(wide[:, :n_db], ref) and float(wide[:, n_db:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n_db,n_q,D,k", [(70000, 300, 64, 10), (120000, 1024, 128, 10), (40000, 1500, 64, 100), (3000, 700, 64, 10)])
+def test_wide_search_equals_per_block_search(m, n_db, n_q, D, k):
+    """search(block_q=1024): SAMPLE and FILTER scans as ONE wide launch per 1,024 queries ((tile, 128-query block) work
+    items, per-query filter state of all the blocks in shared memory) against the 128-queries-per-pass route: identical
+    indices and scores, both precisions; ragged last block, several wide passes, the dense route of a small database."""
+    import torch
+    db = synth.descriptors(n_db, D, 5, clusters=40)
+    q = synth.descriptors(n_q, D, 6)
+    index = m.Index(db, device=DEV)
+    index.fused = False                                    # the three-launch route for both (the one-launch route is <= 128 queries)
+    for prec in ("bf16", "fp32"):
+        s_ref, i_ref = index.search(q, k, precision=prec)
+        s_w, i_w = index.search(q, k, precision=prec, block_q=1024)
+        assert torch.equal(i_w, i_ref) and torch.equal(s_w, s_ref), prec
+    ref_i, ref_v = oracle.topk_from_scores(oracle.scores(db.T, q[:64].T), k)
+    assert (i_w[:64].cpu().numpy().T == ref_i).mean() > 0.99
+
+
 def _assert_same_order(got, ref_i, ref_v, tol):
     """got (k, nq) vs the reference ranking ref_i / ref_v (k_ref >= k rows, best first): every position where the
     indices differ must hold a row that the REFERENCE places within `tol` of that position's reference score

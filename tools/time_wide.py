@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Tensor-bound shapes of the similarity scan: 256 resident queries per pass.
-   python tools/time_wide.py            # FILTER/top-k scan at 1M x 2048 (DBA inner loop) and C3 (100k x 512), N = 128 vs 256"""
+"""Tensor-bound shapes of the similarity scan: 128 queries per pass against WIDE launches (256 / 1,024 queries per pass as
+(tile, 128-query block) work items).
+   python tools/time_wide.py            # top-10 search at 1M x 2048 (DBA inner loop) and C3 (100k x 512)"""
 import os
 import sys
 
@@ -33,7 +34,7 @@ for n_db, D, nq_total, reps in ((1001001, 2048, 4096, 3), (100000, 512, 10240, 3
     db = unit(n_db, D)
     idx = Index(db, device=dev, keep_fp32=False)
     q = db[:nq_total].clone()
-    for blk in (128, 256):
+    for blk in (128, 256, 1024):
         s0, i0 = idx.search(q[:512], 10, precision="bf16", block_q=blk)
         ms = timeit(lambda: idx.search(q, 10, precision="bf16", block_q=blk, check=False), reps)
         fl = 2.0 * nq_total * n_db * D
@@ -42,7 +43,7 @@ for n_db, D, nq_total, reps in ((1001001, 2048, 4096, 3), (100000, 512, 10240, 3
         if blk == 128:
             ref = (s0.clone(), i0.clone())
         else:
-            print("  256/pass == 128/pass:", bool(torch.equal(ref[1], i0) and torch.equal(ref[0], s0)))
+            print("  %d/pass == 128/pass:" % blk, bool(torch.equal(ref[1], i0) and torch.equal(ref[0], s0)))
     if D == 512:
         sc = torch.empty((nq_total, n_db), dtype=torch.float32, device=dev)
         ms = timeit(lambda: idx.scores(q, out=sc), reps)
