@@ -11,7 +11,8 @@ from mdir_b200.search import Index  # noqa: E402
 
 dev = "cuda:0"
 g = torch.Generator(device=dev).manual_seed(1)
-for n_db, D, nq in ((100000, 512, 1024), (100000, 2048, 1024), (100000, 2048, 4096)):
+SHAPES = ((100000, 512, 1024), (100000, 2048, 1024), (100000, 2048, 4096))
+for n_db, D, nq in (SHAPES if len(sys.argv) < 2 else [SHAPES[int(sys.argv[1])]]):
     db = torch.randn((n_db, D), device=dev, generator=g)
     db /= db.norm(dim=1, keepdim=True)
     q = torch.randn((nq, D), device=dev, generator=g)
