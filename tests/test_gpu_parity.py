@@ -873,7 +873,12 @@ def test_mining_larger_pool_and_exhaustion(m):
     pos, dist = m.mine_hard_negatives(q.T.copy(), pool.T.copy(), qc, pc, nnum, device=DEV)
     ref_pos, ref_dist = oracle.mine_negatives(q.T, pool.T, qc, pc, nnum)
     pos = pos.cpu().numpy()
-    assert np.mean(pos == ref_pos) > 0.995            # fp32 summation-order noise may swap near-equal scores
+    # fp32 summation-order noise may swap near-equal scores: wherever the picks differ, the reference's own scores of
+    # the two pool images must lie within 4e-6 of each other (a measured bound, not a quota of free mismatches)
+    sc_ref = np.dot(pool, q.T)
+    qi, ji = np.nonzero(pos != ref_pos)
+    assert np.all(np.abs(sc_ref[pos[qi, ji], qi] - sc_ref[ref_pos[qi, ji], qi]) <= 4e-6), "mining picks differ outside fp32 noise"
+    assert len(qi) <= 0.01 * pos.size
     got_c = pc[pos]
     assert not np.any(got_c == qc[:, None]) and all(len(set(r)) == nnum for r in got_c)
     same = (pos == ref_pos)
