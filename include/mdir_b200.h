@@ -290,11 +290,11 @@ int mdir_rank_scores_fast(const float* scores, int64_t n_db, int n_q, int query_
 /* The same result through a histogram sort, the fastest route for smooth score populations (1,025 .. 131,072 rows per
  * query; other lengths are forwarded to mdir_rank_scores_fast): per query an exact 4096-cell histogram linear in the
  * score over mean +- 4 sigma gives a cell -> bucket table and the exact offset of every bucket (runs of whole cells of
- * ~256 rows); one scatter pass (bucket = one table lookup per row) fills a compact pair array; one WARP per bucket
- * finishes with an interpolation counting sort in shared memory.  *status (device int32) is cleared first; bit 1
- * (value 2) is set when some query has a bucket of more than 512 rows (massive ties, spikes): ranks is then incomplete
- * and the caller re-runs mdir_rank_scores_fast (bit 0, value 1, keeps its meaning when the call was forwarded).
- * ws: mdir_rank_hist_workspace_bytes() bytes.                                                                       */
+ * ~2,048 rows); one scatter pass (bucket = one table lookup per row) fills a compact pair array; one CTA per bucket
+ * finishes with an interpolation counting sort in shared memory; a 64 x 64 tiled transpose writes the int64 ranks.
+ * *status (device int32) is cleared first; bit 1 (value 2) is set when some query has a bucket of more than 4,096 rows
+ * (massive ties, spikes): ranks is then incomplete and the caller re-runs mdir_rank_scores_fast (bit 0, value 1, keeps
+ * its meaning when the call was forwarded).  ws: mdir_rank_hist_workspace_bytes() bytes.                            */
 size_t mdir_rank_hist_workspace_bytes(int64_t n_db, int n_q);
 int mdir_rank_scores_hist(const float* scores, int64_t n_db, int n_q, int query_major,
                           int64_t* ranks, int64_t ranks_ld, void* ws, int32_t* status, void* stream);
