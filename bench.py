@@ -341,13 +341,14 @@ def run_ours(args):
     # the whole step (pack q, fused threshold+filter scan, finalize + certified fp32 re-score, [exchange + merge]) captured
     # once per query batch into a CUDA graph whose static query buffer already holds that batch: every timed step is ONE
     # graph replay, and consecutive steps search different queries
-    # N > 1: the graph holds the local part of the step; the NVLink push + merge of step t is launched on a second stream
-    # and runs while step t+1 scans (GraphedSearch(overlap=True)); every step's merged result is produced, none skipped
+    # N > 1: one graph holds pack + scan, a second one finalize + certified re-score; the second graph and the NVLink
+    # push + merge of step t are launched on a second stream and run while step t+1 scans (GraphedSearch(overlap=True,
+    # split=True)); every step's merged result is produced, none skipped
     overlap = world > 1 and getattr(target, "_mb", None) is not None
     deferred = False
     graphs = []
     for b in range(N_BATCHES):
-        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", overlap=overlap)
+        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", overlap=overlap, split=True)
         gb.q.copy_(q_bank[b])
         gb.used = False
         graphs.append(gb)
@@ -510,7 +511,7 @@ def run_ours(args):
     parity = {"checked_queries": N_BATCHES * N_Q, "mismatches": violations, "swaps_inside_2e-6_reference_gaps": swaps,
               "certificate_failures": flagged, "certificate_counters": dict(index.cert),
               "reference": "independent: per shard dense 3xTF32 scores of every row -> exact top-%d select -> fp64 re-scoring (torch), shards merged on the host" % (K_EXT + 48),
-              "timed_route": ("CUDA graph of the local step + NVLink exchange/merge kernel on a second stream" if overlap else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
+              "timed_route": ("CUDA graph of pack + scan; finalize graph + NVLink exchange/merge kernel on a second stream" if overlap else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
     if nccl_equal is not None:
         parity["p2p_route_equals_nccl_allgather_route"] = nccl_equal
         flag = torch.tensor([violations, 0 if nccl_equal else 1], device=dev)
@@ -545,8 +546,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK),
                    "distinct_query_batches": N_BATCHES, "db_rows_per_gpu": hi - lo,
                    "sharding": "db rows contiguous over %d GPU(s); %s" % (world, "single shard" if world == 1 else (
-                       ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); the exchange + "
-                        "merge of step t runs on a second stream while step t+1 scans") % (N_Q * TOPK * 8) if overlap else
+                       ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); finalize, exchange and "
+                        "merge of step t run on a second stream while step t+1 scans") % (N_Q * TOPK * 8) if overlap else
                        "ncclAllGather of %d B of keys per rank + merge kernel" % (N_Q * TOPK * 8))),
                    "l2": "inputs larger than L2: %.2f GB bf16 shard streamed per step vs 126 MB L2" % ((hi - lo) * DIM * 2 / 1e9)},
         "clocks": sampler.summary(),

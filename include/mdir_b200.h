@@ -34,6 +34,15 @@ int         mdir_device_check(void);
 /* number of kernels this library has launched in this process (for bench accounting) */
 uint64_t    mdir_launch_count(void);
 
+/* Process-wide SM-partitioning knobs, read at launch time (so a value set around a CUDA-graph capture is baked into
+ * that graph): MDIR_TUNE_SCAN_MAX_CTAS caps the persistent grid of mdir_sim_scan_fused_bf16 (0 = all SMs),
+ * MDIR_TUNE_FINALIZE_CLUSTER = 0 keeps mdir_topk_finalize_rescore on single CTAs.  A serving pipeline that runs the
+ * finalize + exchange of step t beside the scan of step t + 1 uses both so that the two kernels fit at once.        */
+#define MDIR_TUNE_SCAN_MAX_CTAS 1
+#define MDIR_TUNE_FINALIZE_CLUSTER 2
+#define MDIR_TUNE_FINALIZE_STAGE_CAP 3   /* keys staged per query by finalize (0 = everything the segments can hold); more -> overflow bit */
+int         mdir_tune(int key, int value);
+
 /* ---------------------------------------------------------------- pooling ---
  * kind: 0 = GeM, 1 = MAC, 2 = SPoC.
  * Replaces LF.gem / LF.mac / LF.spoc

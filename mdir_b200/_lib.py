@@ -25,6 +25,7 @@ PROTOTYPES = {
     "mdir_last_error": (C.c_char_p, []),
     "mdir_device_check": (_i, []),
     "mdir_launch_count": (_u64, []),
+    "mdir_tune": (_i, [_i, _i]),
     "mdir_pool": (_i, [_i, _vp, _vp, _vp, _i, _i, _i, _f, _f, _vp, _vp]),
     "mdir_l2n": (_i, [_vp, _i, _i, _i, _f, _vp, _vp]),
     "mdir_ms_aggregate": (_i, [_vp, _i, _i, _i, _f, _f, _vp, _vp, _vp]),

@@ -27,6 +27,11 @@ int fail_arg(const char* what);
     } while (0)
 
 extern unsigned long long g_launches;   // kernels launched by this library (bench.py's gpu_launches)
+// SM-partitioning knobs (mdir_tune): a serving pipeline that runs finalize + exchange of step t beside the scan of step
+// t + 1 caps the scan's persistent grid and keeps finalize off thread-block clusters, so that both fit at once
+extern int g_scan_max_ctas;            // 0 = no cap
+extern int g_finalize_cluster;         // 1 = 2-CTA clusters when SMs are idle (default)
+extern int g_finalize_stage_cap;       // 0 = stage everything the segments can hold (<= 16384 keys); else at most this many
 
 #define MDIR_LAUNCH_CHECK()                                               \
     do {                                                                  \

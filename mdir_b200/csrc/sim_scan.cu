@@ -697,6 +697,7 @@ static int launch_scan(bool tf32, const void* db, int64_t n_db, const void* q, i
         const int sm_count = device_sm_count();
         MDIR_CHECK_ARG(sm_count > 0);
         int g = sm_count < kNumSMs ? sm_count : kNumSMs;
+        if (g_scan_max_ctas > 0 && g > g_scan_max_ctas) g = g_scan_max_ctas;      // leave SMs to a concurrent finalize (mdir_tune)
         if (g > p.n_tiles / 2) g = p.n_tiles / 2;
         MDIR_CHECK_ARG(g >= 1);
         g = balanced_grid(p.n_tiles, g);          // every CTA scans the same number of tiles (its sample tile included)

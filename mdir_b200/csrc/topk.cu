@@ -970,6 +970,8 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
     int64_t want = (int64_t)cap0 + (int64_t)(n_seg - 1) * cap_l;
     int smem_cap = 1024;
     while (smem_cap < want && smem_cap < 16384) smem_cap <<= 1;
+    // mdir_tune: a smaller staging area (two CTAs fit on an SM); a query with more candidates raises the overflow bit
+    if (g_finalize_stage_cap > 0 && smem_cap > g_finalize_stage_cap) smem_cap = g_finalize_stage_cap;
     if (smem_cap < 2 * kpow2) smem_cap = 2 * kpow2;
     // with re-scoring the selection area also takes the certified extension of the shortlist (as many keys again)
     const int sl_cap = db32 ? 2 * kpow2 : kpow2;
@@ -992,7 +994,7 @@ static int launch_finalize(const uint64_t* cand, int64_t cand_row, const uint32_
     const int sm_count = device_sm_count();
     // fp32 re-scoring gathers shortlist x D x 4 bytes per query from one CTA; while the batch leaves SMs idle, a
     // 2-CTA cluster per query splits those rows (rank 1 reads / writes the shortlist through distributed shared memory)
-    if (db32 && 2 * n_q <= sm_count) {
+    if (db32 && g_finalize_cluster && 2 * n_q <= sm_count) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * n_q);
         cfg.blockDim = dim3(1024);

@@ -135,7 +135,7 @@ class Index:
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, name, shape, dtype):
-        key = (name, tuple(shape), dtype)
+        key = (getattr(self, "_ws_tag", None), name, tuple(shape), dtype)      # _ws_tag: a private workspace set (GraphedSearch(split=True))
         b = self._ws.get(key)
         if b is None:
             b = torch.empty(shape, dtype=dtype, device=self.device)
@@ -806,7 +806,8 @@ class GraphedSearch:
         gs.check_overflow()            # after a sync: True -> rerun through index.search()
     """
 
-    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None, deferred=False, overlap=False):
+    def __init__(self, index, n_q, k, precision="fp32", shortlist=None, prof=None, deferred=False, overlap=False, split=False,
+                 scan_ctas=0, fin_chunk=0, fin_stage=0):
         """deferred=True (ShardedIndex with peer-memory mailboxes): every replay pushes its keys and returns the merged
         result of the PREVIOUS replay (see ShardedIndex.search); drain() returns the last one.
         overlap=True (same precondition): the graph holds only the LOCAL part of the step (pack, scan, finalize -> this
@@ -823,6 +824,20 @@ class GraphedSearch:
         self.q = torch.zeros((n_q, self.local.D), dtype=torch.float32, device=dev)
         self.local.prof = None
         extra = {"exchange": "deferred"} if self.deferred else {}
+        # split=True (overlap mode, one-launch scan route, fp32): TWO graphs with a private candidate workspace --
+        # `graph` = pack + scan, `back` = finalize + certified re-score -- so that the pipeline can run the finalize (and
+        # the exchange) of ticket t on the side stream while the compute stream scans ticket t+1
+        k_eff = min(self.k, self.local.n)
+        self.kth = max(k_eff, min(self.local.n, int(shortlist or default_shortlist(self.k))))
+        self.split = (bool(split) and self.overlap and precision == "fp32" and self.local.db32 is not None and k_eff == self.k
+                      and self.n_q <= MAX_Q and self.local._fused_ok(self.kth, self.n_q))
+        # SM partition of the split mode: the scan's persistent grid capped at scan_ctas (0 = all SMs), finalize launched
+        # in slices of fin_chunk queries on single CTAs (0 = one launch, 2-CTA clusters) -- together at most 148 SMs, so
+        # that the side stream's finalize finds room while the compute stream scans
+        self.scan_ctas, self.fin_chunk, self.fin_stage = int(scan_ctas), int(fin_chunk), int(fin_stage)
+        if self.split:
+            self._init_split(prof)
+            return
 
         def step():
             if self.overlap:
@@ -855,9 +870,74 @@ class GraphedSearch:
             if self.overlap:
                 self.local_done, self.done = torch.cuda.Event(), torch.cuda.Event()
 
+    def _init_split(self, prof):
+        loc, dev, nq, k = self.local, self.local.device, self.n_q, self.k
+        lib = _lib.lib()
+        loc._ws_tag = ("graph", id(self))
+        try:
+            tau, cand, cnt = loc._cand_bufs(nq)
+            ovf = loc._buf("ovf", (max(nq, 1),), torch.int32)
+        finally:
+            loc._ws_tag = None
+        ws = loc._ws.get("fused_ws")
+        if ws is None:                           # zeroed once; the kernel re-arms its arrival counters itself
+            ws = torch.zeros((lib.mdir_sim_scan_fused_workspace_bytes(MAX_Q) // 4,), dtype=torch.int32, device=dev)
+            loc._ws["fused_ws"] = ws
+        self.q16 = torch.empty((nq, loc.D), dtype=torch.bfloat16, device=dev)
+        self.keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        self.local_out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
+        self.out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
+        self.status = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        self.ovf = ovf[:nq]
+
+        def front():
+            _lib.check(lib.mdir_pack_bf16(_lib.ptr(self.q), nq, loc.D, 0, _lib.ptr(self.q16), _lib.stream()), "mdir_pack_bf16")
+            if prof is not None:
+                prof.begin()
+            lib.mdir_tune(1, self.scan_ctas)
+            try:
+                _lib.check(lib.mdir_sim_scan_fused_bf16(_lib.ptr(loc.db16), loc.n, _lib.ptr(self.q16), nq, loc.D, self.kth, _lib.ptr(tau),
+                                                        loc.idx_base, _lib.ptr(cand), _lib.ptr(cnt), 0, FUSED_CAP_L, _lib.ptr(ws),
+                                                        _lib.stream()), "mdir_sim_scan_fused_bf16")
+            finally:
+                lib.mdir_tune(1, 0)
+            if prof is not None:
+                prof.end(loc.n * loc.D * 2)
+
+        def back():
+            chunk = self.fin_chunk if self.fin_chunk > 0 else nq
+            lib.mdir_tune(2, 0 if self.fin_chunk > 0 else 1)
+            lib.mdir_tune(3, self.fin_stage)
+            try:
+                for q0 in range(0, nq, chunk):
+                    q1 = min(q0 + chunk, nq)
+                    loc._finalize(cand[q0:q1], cnt[q0:q1], q1 - q0, self.kth, self.local_out[0][q0:q1], self.local_out[1][q0:q1],
+                                  self.keys[q0:q1], tau[q0:q1], self.ovf[q0:q1], (self.q[q0:q1], k), caps=(0, FUSED_CAP_L))
+            finally:
+                lib.mdir_tune(2, 1)
+                lib.mdir_tune(3, 0)
+
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    front()
+                    back()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph, self.back = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                front()
+            with torch.cuda.graph(self.back):
+                back()
+            self.local_done, self.done = torch.cuda.Event(), torch.cuda.Event()
+
     def exchange(self):
         """overlap mode: push this graph's keys to every peer and merge the world's (synchronous exchange of THIS step) on
         the current stream, into `out` / `status`.  Every rank calls it once per replay, in the same order."""
+        if getattr(self, "split", False):
+            self.back.replay()                   # finalize + certified re-score of the scan this graph's front part ran
         self.index._exchange(self.keys, self.n_q, self.k, 0, self.out[0], self.out[1], self.ovf, self.status)
 
     def __call__(self, q=None):
@@ -895,7 +975,7 @@ class SearchPipeline:
     whose candidate lists overflowed is transparently redone through index.search() (exact recovery).
     With a ShardedIndex every rank must submit the same sequence (the all-gather is inside the graphs)."""
 
-    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None, overlap=None):
+    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None, overlap=None, split=True):
         """overlap (default: on for a ShardedIndex with peer-memory mailboxes): the graphs hold the local part of a step;
         the NVLink exchange + merge of step t runs on its own stream while the compute stream already scans step t+1
         (GraphedSearch(overlap=True)) -- results are those of the SAME ticket, nothing lags.
@@ -916,7 +996,7 @@ class SearchPipeline:
         self.deferred = bool(deferred) and p2p_ok and not self.overlap
         self.depth = int(depth) if depth else (3 if (self.deferred or self.overlap) else 2)
         self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None,
-                                     deferred=self.deferred, overlap=self.overlap) for s in range(self.depth)]
+                                     deferred=self.deferred, overlap=self.overlap, split=split) for s in range(self.depth)]
         with torch.cuda.device(dev):
             self.compute, self.h2d, self.d2h, self.exch = (torch.cuda.Stream(device=dev) for _ in range(4))
             self.slots = []

@@ -92,6 +92,13 @@ def main():
         torch.cuda.synchronize()
         good &= torch.equal(i_o, refs[b][1]) and torch.equal(s_o, refs[b][0]) and not go.check_overflow()
     check("overlap-mode graph (local step graph + exchange kernel) == single", good)
+    gsplit = GraphedSearch(sharded, nq, k, overlap=True, split=True)
+    good = True
+    for b in range(5):
+        s_o, i_o = gsplit(batches[b])
+        torch.cuda.synchronize()
+        good &= torch.equal(i_o, refs[b][1]) and torch.equal(s_o, refs[b][0]) and not gsplit.check_overflow()
+    check("split graphs (scan | finalize + exchange, private candidate workspace; split=%s) == single" % gsplit.split, good)
     hb = [b.cpu().pin_memory() for b in batches]
     pipe_o = mdir_b200.SearchPipeline(sharded, nq, k)
     outs = [(s.copy(), i.copy()) for s, i in pipe_o.map(hb * 3)]

@@ -83,7 +83,23 @@ def run_overlap(n, guard=True):
 
 
 res["local-step graph + exchange on a second stream"] = timed(run_overlap)
-res["same, without the key-buffer guard wait"] = timed(lambda n: run_overlap(n, False))
+go = graphs(overlap=True, split=True)
+assert all(g_.split for g_ in go)
+res["scan graph; finalize graph + exchange on a second stream"] = timed(run_overlap)
+for scan_ctas, fin_chunk, fin_stage in [tuple(int(v) for v in x.split(":")) for x in os.environ.get("MDIR_SM_SPLITS", "").split(",") if x]:
+    del go
+    go = graphs(overlap=True, split=True, scan_ctas=scan_ctas, fin_chunk=fin_chunk, fin_stage=fin_stage)
+    res["same, scan <= %d CTAs, finalize %d q/launch on single CTAs staging %d keys" % (scan_ctas, fin_chunk, fin_stage)] = timed(run_overlap)
+    flagged = sum(int(g_.status.ne(0).sum().item()) for g_ in go)
+    if flagged:
+        res["   (flagged queries in the last replays: %d)" % flagged] = 0.0
+for scan_ctas, fin_chunk, fin_stage in [tuple(int(v) for v in x.split(":")) for x in os.environ.get("MDIR_SM_SPLITS", "").split(",") if x]:
+    del go
+    go = graphs(overlap=True, split=True, scan_ctas=scan_ctas, fin_chunk=fin_chunk, fin_stage=fin_stage)
+    res["same, scan <= %d CTAs, finalize %d q/launch on single CTAs staging %d keys" % (scan_ctas, fin_chunk, fin_stage)] = timed(run_overlap)
+    flagged = sum(int(g_.status.ne(0).sum().item()) for g_ in go)
+    if flagged:
+        res["   (flagged queries in the last replays: %d)" % flagged] = 0.0
 if rank == 0:
     for k_, v in res.items():
         print("world %d, %d rows/rank: %-55s %.1f us per step (max over ranks)" % (world, hi - lo, k_, v))
