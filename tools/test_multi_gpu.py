@@ -92,13 +92,31 @@ def main():
         torch.cuda.synchronize()
         good &= torch.equal(i_o, refs[b][1]) and torch.equal(s_o, refs[b][0]) and not go.check_overflow()
     check("overlap-mode graph (local step graph + exchange kernel) == single", good)
-    gsplit = GraphedSearch(sharded, nq, k, overlap=True, split=True)
-    good = True
+    # split graphs need the one-launch scan route on every shard: a database of 40,000 rows per rank
+    n_big = 40000 * world
+    db_big = synth.descriptors(n_big, 64, 181, clusters=200)
+    lo_b, hi_b = ShardedIndex.shard_bounds(n_big, world, rank)
+    sh_big = ShardedIndex(db_big[lo_b:hi_b], idx_base=lo_b, device=dev)
+    single_big = mdir_b200.Index(db_big, device=dev)
+    gsplit = GraphedSearch(sh_big, nq, k, overlap=True, split=True)
+    good = gsplit.split
     for b in range(5):
-        s_o, i_o = gsplit(batches[b])
+        qb = torch.from_numpy(synth.planted_queries(db_big, nq, 220 + b)[0]).to(dev)
+        s_ref, i_ref = single_big.search(qb, k)
+        s_o, i_o = gsplit(qb)
         torch.cuda.synchronize()
-        good &= torch.equal(i_o, refs[b][1]) and torch.equal(s_o, refs[b][0]) and not gsplit.check_overflow()
+        good &= torch.equal(i_o, i_ref) and torch.equal(s_o, s_ref) and not gsplit.check_overflow()
     check("split graphs (scan | finalize + exchange, private candidate workspace; split=%s) == single" % gsplit.split, good)
+    pipe_s = mdir_b200.SearchPipeline(sh_big, nq, k)
+    hq = [torch.from_numpy(synth.planted_queries(db_big, nq, 220 + b)[0]).pin_memory() for b in range(7)]
+    outs_s = [(s_.copy(), i_.copy()) for s_, i_ in pipe_s.map(hq)]
+    good = all(g_.split for g_ in pipe_s.graphs)
+    for b in range(7):
+        s_ref, i_ref = single_big.search(hq[b], k)
+        good &= bool(np.array_equal(outs_s[b][1], i_ref.cpu().numpy()) and np.array_equal(outs_s[b][0], s_ref.cpu().numpy()))
+    check("SearchPipeline with split graphs == single, in order", good)
+    sh_big.close()
+    del single_big, gsplit, pipe_s
     hb = [b.cpu().pin_memory() for b in batches]
     pipe_o = mdir_b200.SearchPipeline(sharded, nq, k)
     outs = [(s.copy(), i.copy()) for s, i in pipe_o.map(hb * 3)]
