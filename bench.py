@@ -612,6 +612,8 @@ def c5_measurements(torch, dist, world, rank, target, index, q_dev, args):
                            "" if world == 1 else " + one all-reduce of the expansion"),
                        "value": N_Q / (ms * 1e-3), "unit": "queries/s", "ms_per_batch": ms, "n_gpus": world}
     full = world > 1 or args.full_dba
+    if not full:
+        qe.dba(index, 3.0, 10, rows=4096)                # warm: the wide candidate / sample workspaces are allocated on first use
     barrier()
     t0 = time.perf_counter()
     if full:
