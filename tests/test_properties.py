@@ -52,3 +52,69 @@ def test_default_shortlist_monotone():
         s = default_shortlist(k)
         assert s >= 1.25 * k and s % 64 == 0 and s >= prev          # whole rounds of the 2 x 32 re-scoring warps
         prev = s
+
+
+# ---- histogram-sort route of the full ranking (csrc/ranks.cu: hs_plan / hs_scatter / hs_bucket_sort) -------------------
+def _hs_rank_restatement(s, cells=4096, t_rows=2048, fine=4096, hi=None, scale=None):
+    """numpy restatement (fp32 arithmetic, one operation at a time like the kernels' __fsub_rn / __fmul_rn) of how the
+    histogram sort orders one query's scores: cell -> bucket (= floor(first rank of the cell / t_rows)) -> fine bin
+    inside the bucket's cell range -> (score key, row) composite.  Returns the permutation it produces."""
+    s = np.asarray(s, dtype=np.float32)
+    n = s.shape[0]
+    keys = make_keys_host(s, np.arange(n))                                # (desc key << 32) | row: the order to reproduce
+    fin = s[np.isfinite(s)]
+    if hi is None:
+        m = np.float32(fin.mean()) if fin.size else np.float32(0)
+        sd = np.float32(fin.std()) if fin.size else np.float32(0)
+        hi, scale = np.float32(m + np.float32(4) * sd), (np.float32(cells) / (np.float32(8) * sd) if sd > 0 else np.float32(0))
+    canon = np.where(s == 0, np.float32(0), s)                            # the key's canonical score: -0 -> +0
+    with np.errstate(invalid="ignore", over="ignore"):
+        v = ((np.float32(hi) - canon).astype(np.float32) * np.float32(scale)).astype(np.float32)
+    nan = np.isnan(v)
+    vt = np.where(nan, 0, np.clip(v, -2.0 ** 31, 2.0 ** 31 - 128)).astype(np.int64)      # cvt.rzi saturates
+    cell = np.where(nan, cells - 1, np.clip(vt, 0, cells - 1))
+    counts = np.bincount(cell, minlength=cells)
+    excl = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    bucket_of_cell = excl // t_rows
+    bucket = bucket_of_cell[cell]
+    vc = np.where(nan, np.float32(cells - 1), np.clip(v, np.float32(0), np.float32(cells - 1))).astype(np.float32)
+    fbin = np.zeros(n, dtype=np.int64)
+    for b in np.unique(bucket):
+        sel = bucket == b
+        c0, c1 = cell[sel].min(), cell[sel].max()
+        fs = np.float32(fine) / np.float32(c1 - c0 + 1)
+        f = ((vc[sel] - np.float32(c0)).astype(np.float32) * fs).astype(np.float32)
+        fbin[sel] = np.clip(f.astype(np.int64), 0, fine - 1)
+    # the kernels place by (bucket, fine bin) and settle the rest by comparing composites
+    return np.lexsort((keys, fbin, bucket)), np.argsort(keys, kind="stable"), bucket, fbin, keys
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.one_of(st.floats(-2, 2, width=32), st.floats(width=32, allow_nan=True, allow_infinity=True),
+                          st.sampled_from([0.0, -0.0, 0.25, 0.25, 1e-30, -1e-30, float("inf"), float("-inf"), float("nan")])),
+                min_size=2, max_size=400), st.integers(0, 3))
+def test_hist_sort_bucket_and_bin_are_monotone_in_the_key(vals, mode):
+    s = np.asarray(vals, dtype=np.float32)
+    kw = {}
+    if mode == 1:                                   # a range far off the data: everything lands in the end cells
+        kw = {"hi": np.float32(1e3), "scale": np.float32(1e-2)}
+    elif mode == 2:                                 # tiny buckets and few fine bins: many boundaries
+        kw = {"cells": 64, "t_rows": 8, "fine": 16}
+    elif mode == 3:                                 # huge scale: saturating conversions
+        kw = {"hi": np.float32(0.5), "scale": np.float32(3e38)}
+    got, ref, bucket, fbin, keys = _hs_rank_restatement(s, **kw)
+    assert np.array_equal(got, ref)                                        # == the stable descending argsort
+    order = ref
+    assert np.all(np.diff(bucket[order]) >= 0)                             # bucket is monotone along the key order
+    same_bucket = np.diff(bucket[order]) == 0
+    assert np.all(np.diff(fbin[order])[same_bucket] >= 0)                  # and so is the fine bin inside a bucket
+
+
+def test_hist_sort_restatement_on_similarity_like_scores():
+    rs = np.random.RandomState(3)
+    s = (rs.randn(100000) * 0.044).astype(np.float32)
+    s[rs.randint(0, s.size, 50)] = rs.rand(50).astype(np.float32)           # planted neighbours
+    s[:6] = [np.inf, -np.inf, np.nan, 0.0, -0.0, np.nan]
+    got, ref, bucket, _, _ = _hs_rank_restatement(s)
+    assert np.array_equal(got, ref) and np.array_equal(ref, oracle.ranks_from_scores(s[:, None])[:, 0])
+    assert np.bincount(bucket).max() <= 4096                                # what one CTA sorts: no query of this shape is flagged

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Dense bf16 similarity GEMM alone (mdir_sim_scan_dense_bf16: tcgen05 / TMEM / TMA), as TFLOP/s against the sustained
 bf16 peak: the C3 shape (1,024 of the 10,000 queries x 100,000 x 512) and a 2048-D variant.
-    python tools/time_gemm.py            (MDIR_DENSE_BLK=256: 256 queries per work item)"""
+    python tools/time_gemm.py [shape index]"""
 import os
 import sys
 
@@ -30,6 +30,6 @@ for n_db, D, nq in (SHAPES if len(sys.argv) < 2 else [SHAPES[int(sys.argv[1])]])
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 10
     tf = 2.0 * nq * n_db * D / (ms * 1e-3) / 1e12
-    print("dense GEMM %d q x %d db x %d-D (blk %s): %.3f ms (incl. the query pack), %.0f TFLOP/s = %.3f of 1397.3 sustained; output %.2f TB/s" %
-          (nq, n_db, D, os.environ.get("MDIR_DENSE_BLK", "128"), ms, tf, tf / 1397.3, nq * n_db * 4 / (ms * 1e-3) / 1e12))
+    print("dense GEMM %d q x %d db x %d-D: %.3f ms (incl. the query pack), %.0f TFLOP/s = %.3f of 1397.3 sustained; output %.2f TB/s" %
+          (nq, n_db, D, ms, tf, tf / 1397.3, nq * n_db * 4 / (ms * 1e-3) / 1e12))
     del idx, db, q, out
