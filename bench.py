@@ -344,14 +344,16 @@ def run_ours(args):
     # N > 1: one graph holds pack + scan, a second one finalize + certified re-score; the second graph and the NVLink
     # push + merge of step t are launched on a second stream and run while step t+1 scans (GraphedSearch(overlap=True,
     # split=True)); every step's merged result is produced, none skipped
-    overlap = world > 1 and getattr(target, "_mb", None) is not None
+    # N = 1: one graph per step (the split was measured there too -- tools/time_split_1gpu.py: 660 us as one graph,
+    # 664-705 us split: capping the scan grid costs what hiding finalize gains)
     deferred = False
     graphs = []
     for b in range(N_BATCHES):
-        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", overlap=overlap, split=True)
+        gb = GraphedSearch(target, N_Q, TOPK, precision="fp32", overlap=(world > 1 and getattr(target, "_mb", None) is not None), split=True)
         gb.q.copy_(q_bank[b])
         gb.used = False
         graphs.append(gb)
+    overlap = all(gb.overlap for gb in graphs)
     exch_stream = torch.cuda.Stream(device=dev) if overlap else None
     gs = GraphedSearch(target, N_Q, TOPK, precision="fp32")          # synchronous exchange: the blocking e2e loop
     # the same step with a CUDA event pair around the dominant kernel inside the graph: used only to read that
@@ -511,7 +513,7 @@ def run_ours(args):
     parity = {"checked_queries": N_BATCHES * N_Q, "mismatches": violations, "swaps_inside_2e-6_reference_gaps": swaps,
               "certificate_failures": flagged, "certificate_counters": dict(index.cert),
               "reference": "independent: per shard dense 3xTF32 scores of every row -> exact top-%d select -> fp64 re-scoring (torch), shards merged on the host" % (K_EXT + 48),
-              "timed_route": ("CUDA graph of pack + scan; finalize graph + NVLink exchange/merge kernel on a second stream" if overlap else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
+              "timed_route": (("CUDA graph of pack + scan; finalize graph%s on a second stream" % (" + NVLink exchange/merge kernel" if world > 1 else "")) if overlap else "CUDA graph") + ", %d distinct query batches" % N_BATCHES}
     if nccl_equal is not None:
         parity["p2p_route_equals_nccl_allgather_route"] = nccl_equal
         flag = torch.tensor([violations, 0 if nccl_equal else 1], device=dev)
@@ -545,6 +547,9 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_step": N_Q, "topk": TOPK, "shortlist": default_shortlist(TOPK),
                    "distinct_query_batches": N_BATCHES, "db_rows_per_gpu": hi - lo,
+                   "pipeline": ("step = CUDA graph {pack, scan} on the compute stream + CUDA graph {finalize, certified re-score}%s on a second stream, "
+                                "overlapping the next step's scan%s" % (" + exchange/merge kernel" if world > 1 else "", ""))
+                               if overlap else "one CUDA graph per step",
                    "sharding": "db rows contiguous over %d GPU(s); %s" % (world, "single shard" if world == 1 else (
                        ("%d B of keys per rank pushed to every peer over NVLink by the merge kernel itself (no NCCL call on the step); finalize, exchange and "
                         "merge of step t run on a second stream while step t+1 scans") % (N_Q * TOPK * 8) if overlap else

@@ -24,6 +24,7 @@ TILE = 256            # MDIR_SCAN_TILE_ROWS
 MAX_Q = 128           # queries per scan pass on the serving path (double / triple buffered TMEM accumulators)
 DENSE_LAUNCH_Q = 1 << 20   # queries per mdir_sim_scan_dense_bf16 launch ((tile, query block) work items are counted in 30 bits)
 MAX_Q_WIDE = 256      # rows of the default candidate buffers
+SINGLE_GPU_SCAN_CTAS = 140   # split serving graphs on one GPU: SMs the scan keeps; the other 8 run finalize of the previous ticket
 WIDE_Q = 1024         # queries per WIDE launch (search(block_q=1024): DBA, all-pairs): 8 blocks of 128 per database tile
 N_SEGS = 149          # MDIR_CAND_SEGS: segment 0 = select kernel, 1 + c = scan CTA c
 CAP_S = 8192          # capacity of segment 0 (the >= kth sample rows that pass, incl. ties)
@@ -819,6 +820,7 @@ class GraphedSearch:
         dev = self.local.device
         self.n_q, self.k, self.precision, self.shortlist = int(n_q), int(k), precision, shortlist
         sharded = isinstance(index, ShardedIndex) and index.world > 1
+        self._has_exchange = sharded
         self.overlap = bool(overlap) and sharded and index._mb is not None and self.k <= index.P2P_MAX_K and self.n_q <= index.P2P_MAX_Q
         self.deferred = bool(deferred) and sharded and not self.overlap
         self.q = torch.zeros((n_q, self.local.D), dtype=torch.float32, device=dev)
@@ -829,8 +831,10 @@ class GraphedSearch:
         # the exchange) of ticket t on the side stream while the compute stream scans ticket t+1
         k_eff = min(self.k, self.local.n)
         self.kth = max(k_eff, min(self.local.n, int(shortlist or default_shortlist(self.k))))
-        self.split = (bool(split) and self.overlap and precision == "fp32" and self.local.db32 is not None and k_eff == self.k
-                      and self.n_q <= MAX_Q and self.local._fused_ok(self.kth, self.n_q))
+        self.split = (bool(split) and (self.overlap or (bool(overlap) and not sharded)) and precision == "fp32" and self.local.db32 is not None
+                      and k_eff == self.k and self.n_q <= MAX_Q and self.local._fused_ok(self.kth, self.n_q))
+        if self.split and not sharded:
+            self.overlap = True                  # a single GPU: no exchange, but the finalize half still runs on the side stream
         # SM partition of the split mode: the scan's persistent grid capped at scan_ctas (0 = all SMs), finalize launched
         # in slices of fin_chunk queries on single CTAs (0 = one launch, 2-CTA clusters) -- together at most 148 SMs, so
         # that the side stream's finalize finds room while the compute stream scans
@@ -886,9 +890,12 @@ class GraphedSearch:
         self.q16 = torch.empty((nq, loc.D), dtype=torch.bfloat16, device=dev)
         self.keys = torch.empty((nq, k), dtype=torch.int64, device=dev)
         self.local_out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
-        self.out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
-        self.status = torch.zeros((nq,), dtype=torch.int32, device=dev)
         self.ovf = ovf[:nq]
+        if self._has_exchange:
+            self.out = (torch.empty((nq, k), dtype=torch.float32, device=dev), torch.empty((nq, k), dtype=torch.int32, device=dev))
+            self.status = torch.zeros((nq,), dtype=torch.int32, device=dev)
+        else:
+            self.out, self.status = self.local_out, self.ovf
 
         def front():
             _lib.check(lib.mdir_pack_bf16(_lib.ptr(self.q), nq, loc.D, 0, _lib.ptr(self.q16), _lib.stream()), "mdir_pack_bf16")
@@ -938,7 +945,8 @@ class GraphedSearch:
         the current stream, into `out` / `status`.  Every rank calls it once per replay, in the same order."""
         if getattr(self, "split", False):
             self.back.replay()                   # finalize + certified re-score of the scan this graph's front part ran
-        self.index._exchange(self.keys, self.n_q, self.k, 0, self.out[0], self.out[1], self.ovf, self.status)
+        if self._has_exchange:
+            self.index._exchange(self.keys, self.n_q, self.k, 0, self.out[0], self.out[1], self.ovf, self.status)
 
     def __call__(self, q=None):
         if q is not None:
@@ -975,7 +983,8 @@ class SearchPipeline:
     whose candidate lists overflowed is transparently redone through index.search() (exact recovery).
     With a ShardedIndex every rank must submit the same sequence (the all-gather is inside the graphs)."""
 
-    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None, overlap=None, split=True):
+    def __init__(self, index, n_q, k, depth=None, precision="fp32", shortlist=None, prof=None, deferred=None, overlap=None, split=True,
+                 scan_ctas=None):
         """overlap (default: on for a ShardedIndex with peer-memory mailboxes): the graphs hold the local part of a step;
         the NVLink exchange + merge of step t runs on its own stream while the compute stream already scans step t+1
         (GraphedSearch(overlap=True)) -- results are those of the SAME ticket, nothing lags.
@@ -994,9 +1003,21 @@ class SearchPipeline:
         if deferred is None:
             deferred = False
         self.deferred = bool(deferred) and p2p_ok and not self.overlap
-        self.depth = int(depth) if depth else (3 if (self.deferred or self.overlap) else 2)
+        # a single GPU has no exchange, but the split graphs still move finalize + re-score of ticket t beside the scan of
+        # ticket t+1: the scan's persistent grid is capped (SINGLE_GPU_SCAN_CTAS of 148 SMs; the stream stays HBM-bound)
+        # so that the finalize CTAs find SMs
+        # -- measured on the R1M shape: 660 us per step as one graph, 664-705 us split (tools/time_split_1gpu.py): the capped
+        # scan loses what the hidden finalize gains, so this stays opt-in (split="single")
+        single_split = (not sharded) and split == "single" and overlap is not False and not deferred
+        if scan_ctas is None:
+            scan_ctas = SINGLE_GPU_SCAN_CTAS if single_split else 0
+        n_graphs = int(depth) if depth else (3 if (self.deferred or self.overlap or single_split) else 2)
         self.graphs = [GraphedSearch(index, n_q, k, precision=precision, shortlist=shortlist, prof=prof if s == 0 else None,
-                                     deferred=self.deferred, overlap=self.overlap, split=split) for s in range(self.depth)]
+                                     deferred=self.deferred, overlap=self.overlap or single_split, split=split, scan_ctas=scan_ctas)
+                       for s in range(n_graphs)]
+        if single_split:
+            self.overlap = all(g.split for g in self.graphs)
+        self.depth = n_graphs
         with torch.cuda.device(dev):
             self.compute, self.h2d, self.d2h, self.exch = (torch.cuda.Stream(device=dev) for _ in range(4))
             self.slots = []

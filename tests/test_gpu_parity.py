@@ -577,6 +577,16 @@ def test_graphed_search_replays(m):
         s2, i2 = index.search(q, 100)
         assert torch.equal(i, i2) and torch.equal(s, s2)
         assert np.array_equal(i.cpu().numpy()[:, 0], src)
+    # split graphs on one GPU: pack + scan | finalize + certified re-score, private candidate workspace, capped scan grid
+    for scan_ctas in (0, 140, 64):
+        gsp = GraphedSearch(index, n_q=70, k=100, overlap=True, split=True, scan_ctas=scan_ctas)
+        assert gsp.split and gsp.overlap
+        for seed in (4, 5):
+            q, src = synth.planted_queries(db, 70, seed)
+            s, i = gsp(torch.from_numpy(q).pin_memory())
+            torch.cuda.synchronize()
+            s2, i2 = index.search(q, 100)
+            assert not gsp.check_overflow() and torch.equal(i, i2) and torch.equal(s, s2), scan_ctas
 
 
 # ------------------------------------------------------------------ batched extract_vectors (section 8f, f2)
