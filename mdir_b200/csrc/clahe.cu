@@ -12,7 +12,7 @@
 //            single LDS.128; the bilinear blend uses individually rounded fp32 mul/add in
 //            OpenCV's association (no FMA contraction) and round-half-even; a thread owns 8
 //            consecutive pixels (64-bit loads/stores, 4 rows in flight).
-//  The batch is processed in chunks of <= 48 MB of pixels so that pass 2 re-reads from L2.
+//  The whole batch is one pair of launches (both kernels are instruction-bound; the second read of the source hides).
 #include <type_traits>
 
 #include "common.cuh"
@@ -92,6 +92,19 @@ __device__ __forceinline__ void hist_chunk_full(uint32_t* h, const uint32_t (&w)
     }
 }
 
+// the same for the fast path: hists = the CTA's histograms (static shared memory: its address rides in the ATOMS
+// immediate), wofs = this warp's byte offset: one shift + one three-input LOP3 per pixel before the ATOMS
+__device__ __forceinline__ void hist_chunk_full_ofs(uint32_t* hists, uint32_t wofs, const uint32_t (&w)[4]) {
+    char* hb = reinterpret_cast<char*>(hists);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        atomicAdd(reinterpret_cast<uint32_t*>(hb + (((w[k] << 2) & 0x3fcu) | wofs)), 1u);
+        atomicAdd(reinterpret_cast<uint32_t*>(hb + (((w[k] >> 6) & 0x3fcu) | wofs)), 1u);
+        atomicAdd(reinterpret_cast<uint32_t*>(hb + (((w[k] >> 14) & 0x3fcu) | wofs)), 1u);
+        atomicAdd(reinterpret_cast<uint32_t*>(hb + (((w[k] >> 22) & 0x3fcu) | wofs)), 1u);
+    }
+}
+
 constexpr int kLutThreads = 128;          // 4 warps, one private histogram each: a 96 x 128 tile is 96 pixels per thread, so
 constexpr int kLutWarps = kLutThreads / 32; // the per-tile epilogue (merge, clip, scan, LUT) is paid by 4 warps instead of 8
 
@@ -138,7 +151,7 @@ __global__ void __launch_bounds__(kLutThreads) clahe_lut_kernel(const uint8_t* _
             }
 #pragma unroll
             for (int u = 0; u < 6; ++u)
-                if (c0 + u * kLutThreads < total) hist_chunk_full(myh, wv[u]);
+                if (c0 + u * kLutThreads < total) hist_chunk_full_ofs(&whist[0][0], (uint32_t)w * 1024u, wv[u]);
         }
     } else if (vw > 0) {
         // 16-byte chunks: cpr per tile row (rows start at arbitrary alignment), 4 loads in flight per thread
@@ -432,10 +445,12 @@ extern "C" int mdir_clahe_u8(const uint8_t* src, uint8_t* dst, const mdir_image_
     clahe_prep_kernel<<<(n_img + 255) / 256, 256, 0, st>>>(descs, n_img, clip, tiles_x, tiles_y, prep);
     MDIR_LAUNCH_CHECK();
 
-    // Both passes read the source; processing the batch in chunks of <= ~48 MB of pixels lets the
-    // interpolation pass of a chunk hit L2 (126 MB) for the pixels its LUT pass just streamed.
+    // Both passes read the source.  Chunks of <= 48 MB of pixels (so that the second pass re-reads from L2) were the
+    // round-1 schedule; both kernels are instruction-bound now, the second read from HBM hides under them, and fewer,
+    // larger launches win: 0.312 -> 0.277 ms per 256 images of 768 x 1024 in one pass.  The chunk loop only bounds the
+    // grid for enormous batches (1 GB of pixels per pass).
     const int64_t px = (int64_t)max_H * max_W;
-    int chunk = (int)((int64_t)48 * 1024 * 1024 / (px > 0 ? px : 1));
+    int chunk = (int)((int64_t)1024 * 1024 * 1024 / (px > 0 ? px : 1));
     if (chunk < 1) chunk = 1;
     for (int i0 = 0; i0 < n_img; i0 += chunk) {
         const int n = (n_img - i0) < chunk ? (n_img - i0) : chunk;
