@@ -886,14 +886,13 @@ __global__ void __launch_bounds__(kHsPlanThreads, 8) hs_plan_kernel(const float*
     }
 }
 
-// static smem: 2048 pairs + 2048 bucket ids + the 4096-entry table: 23 KB, eight CTAs per SM.
+// static smem: 2048 pairs + the 4096-entry table: 21 KB, eight CTAs per SM.
 // pairs: (row, raw fp32 score bits); the sort kernel turns the score into its key.
 __global__ void __launch_bounds__(kHsScatterThreads, 8) hs_scatter_kernel(const float* __restrict__ src, int n_db, int B,
                                                                         const HsRange* __restrict__ range, const uint8_t* __restrict__ table,
                                                                         HsBucket* __restrict__ buckets, uint2* __restrict__ pairs) {
     __shared__ uint2 stage[kHsChunk];
     __shared__ __align__(16) uint8_t tab[kHsCells];
-    __shared__ uint8_t sbucket[kHsChunk];
     __shared__ uint32_t cnt[kHsMaxBuckets + 2];        // counts, then chunk-local bases
     __shared__ uint32_t delta[kHsMaxBuckets + 2];      // slot in the pair array - local base (mod 2^32)
     const int chunk = blockIdx.x, q = blockIdx.y;
@@ -956,16 +955,18 @@ __global__ void __launch_bounds__(kHsScatterThreads, 8) hs_scatter_kernel(const 
             const uint32_t b = where[it] >> 16;
             const uint32_t l = cnt[b] + (where[it] & 0xffffu);
             stage[l] = make_uint2((uint32_t)(base + it * kHsScatterThreads + threadIdx.x), __float_as_uint(sc[it]));
-            sbucket[l] = (uint8_t)b;
         }
     }
     __syncthreads();
+    // copy-out by run: warp w takes buckets w, w + 8, ...; the staged pairs of a bucket are contiguous and go to
+    // contiguous slots, so a run costs three broadcast loads and then one LDS.64 + one coalesced store per 32 pairs (a
+    // per-pair bucket id / offset lookup cost a third of the kernel's shared-memory wavefronts)
     const int n_valid = min(kHsChunk, n_db - base);
     uint2* out = pairs + (int64_t)q * n_db;
-#pragma unroll
-    for (int it = 0; it < kHsItems; ++it) {
-        const int l = it * kHsScatterThreads + threadIdx.x;
-        if (l < n_valid) out[(uint32_t)l + delta[sbucket[l]]] = stage[l];
+    for (int b = (int)(threadIdx.x >> 5); b < B; b += kHsScatterThreads / 32) {
+        const int l0 = (int)cnt[b], l1 = b + 1 < B ? (int)cnt[b + 1] : n_valid;
+        const uint32_t d = delta[b];
+        for (int l = l0 + lane; l < l1; l += 32) out[(uint32_t)l + d] = stage[l];
     }
 }
 
