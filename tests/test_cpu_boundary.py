@@ -172,6 +172,27 @@ def test_topk_route_planner_c_equals_python(libpath):
                 assert (r.value, ns.value, st.value) == want, (n_db, kth, sms, want, (r.value, ns.value, st.value))
 
 
+def test_tune_knobs_and_workspace_sizes_are_host_only(libpath):
+    """Host-only entry points of the round-2 additions answer without a GPU: the SM-partition knobs validate their
+    arguments, and the three ranking routes report workspace sizes that grow with the problem (the histogram sort
+    needs a compact 8 B/pair array, the sample sort over-provisioned bucket regions)."""
+    import ctypes as C
+    l = C.CDLL(libpath)
+    l.mdir_tune.argtypes = [C.c_int, C.c_int]
+    assert l.mdir_tune(1, 98) == 0 and l.mdir_tune(1, 0) == 0
+    assert l.mdir_tune(2, 0) == 0 and l.mdir_tune(2, 1) == 0
+    assert l.mdir_tune(3, 4096) == 0 and l.mdir_tune(3, 0) == 0
+    assert l.mdir_tune(2, 7) != 0 and l.mdir_tune(99, 0) != 0 and l.mdir_tune(1, -1) != 0
+    for fn in ("mdir_rank_workspace_bytes", "mdir_rank_fast_workspace_bytes", "mdir_rank_hist_workspace_bytes"):
+        f = getattr(l, fn)
+        f.argtypes, f.restype = [C.c_int64, C.c_int], C.c_size_t
+        assert f(0, 5) == 0 and f(100000, 0) == 0
+        assert 0 < f(100000, 64) < f(100000, 128) < f(200000, 128)
+    hist, fast = l.mdir_rank_hist_workspace_bytes, l.mdir_rank_fast_workspace_bytes
+    assert hist(100000, 1024) >= 100000 * 1024 * 16                       # pairs 8 B + ranks 4 B + transposed scores 4 B
+    assert hist(500, 8) == fast(500, 8) and hist(200000, 8) == fast(200000, 8)      # lengths the histogram sort forwards
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` runs on the host alone and prints exactly one JSON line with the contract's keys."""
     import json
