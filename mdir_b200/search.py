@@ -923,6 +923,9 @@ class GraphedSearch:
             finally:
                 lib.mdir_tune(2, 1)
                 lib.mdir_tune(3, 0)
+            if self._has_exchange:
+                # the NVLink push + merge of these keys rides in the same graph: one launch per ticket on the side stream
+                self.index._exchange(self.keys, nq, k, 0, self.out[0], self.out[1], self.ovf, self.status)
 
         with torch.cuda.device(dev):
             side = torch.cuda.Stream(device=dev)
@@ -944,7 +947,8 @@ class GraphedSearch:
         """overlap mode: push this graph's keys to every peer and merge the world's (synchronous exchange of THIS step) on
         the current stream, into `out` / `status`.  Every rank calls it once per replay, in the same order."""
         if getattr(self, "split", False):
-            self.back.replay()                   # finalize + certified re-score of the scan this graph's front part ran
+            self.back.replay()                   # finalize + certified re-score (+ exchange and merge) of this graph's scan
+            return
         if self._has_exchange:
             self.index._exchange(self.keys, self.n_q, self.k, 0, self.out[0], self.out[1], self.ovf, self.status)
 
