@@ -463,7 +463,10 @@ __global__ void __launch_bounds__(kThreads, 1) sim_scan_kernel(const __grid_cons
                             }
                             asm volatile("bar.sync 1, 128;" ::: "memory");
                         }
-                        if (et == 0) result = sel_prefix;       // only the publishing thread reads it (it also rewrites it next round)
+                        // only the publishing thread reads it (it also rewrites it next round).  volatile: the compiler
+                        // otherwise loads sel_prefix on every thread and selects by predicate -- harmless, but the other
+                        // threads' speculative read then races with this thread's next-round store (racecheck)
+                        if (et == 0) result = *reinterpret_cast<volatile uint32_t*>(&sel_prefix);
                     }
                     if (et == 0) {
                         p.tau_rw[q] = sel_ok ? (((uint64_t)result << 32) | 0xffffffffull) : 0ull;
