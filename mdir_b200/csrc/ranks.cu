@@ -305,6 +305,7 @@ struct SsTable {                        // written by ss_splitters_kernel, read 
 };
 // Monotone (non-decreasing) in the composite key: keys ascend as scores descend; NaN (last) -> last cell.
 __device__ __forceinline__ int ss_cell(float score, float hi, float scale) {
+    if (scale == 0.f) return 0;          // one cell = the full splitter range; (hi - inf) * 0 would be NaN and send +-inf to the last cell
     const float v = (hi - score) * scale;
     return (v == v) ? min(kTab - 1, max(0, (int)v)) : kTab - 1;
 }
@@ -879,6 +880,9 @@ __global__ void __launch_bounds__(kHsPlanThreads, 8) hs_plan_kernel(const float*
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+        // scale == 0 (a constant row, or no finite spread): (hi - s) * 0 is NaN for an infinite s, which would send +inf to
+        // the LAST cell; such a row goes to the sample sort whatever its size
+        if (!(scale > 0.f)) s_heavy = 1u;
         HsRange r;
         r.hi = hi; r.scale = scale; r.heavy = s_heavy; r.pad = 0u;
         range[q] = r;

@@ -304,6 +304,18 @@ def test_ranks_edge_cases(m):
         assert np.array_equal(m.ranks_from_scores(sc, method="radix").cpu().numpy(), ref), (n_db, n_q)
 
 
+def test_ranks_constant_rows_with_infinities(m):
+    """A constant score row has no finite spread: the histogram sort's scale is 0 and (hi - inf) * 0 would be NaN -- such
+    queries must be handed to the sample sort whatever their length (found by the CPU property test of the plan)."""
+    for n_db in (1500, 3000, 4096, 9000):
+        sc = np.full((n_db, 4), 0.25, dtype=np.float32)
+        sc[[3, 700, n_db - 1], 0] = np.inf
+        sc[[5, 9], 1] = -np.inf
+        sc[[1, 2, 1000], 2] = [np.inf, -np.inf, np.nan]
+        sc[:, 3] = np.inf
+        assert np.array_equal(m.ranks_from_scores(sc).cpu().numpy(), oracle.ranks_from_scores(sc)), n_db
+
+
 @pytest.mark.parametrize("case", ["gauss", "gauss_outliers", "all_equal", "ascending", "descending", "periodic", "two_values", "spike", "heavy_tail"])
 @pytest.mark.parametrize("n_db", [1024, 1025, 4993, 100000, 102400, 102401, 131072, 131073])
 def test_ranks_sort_paths_distributions(m, case, n_db):

@@ -102,6 +102,9 @@ def test_hist_sort_bucket_and_bin_are_monotone_in_the_key(vals, mode):
         kw = {"cells": 64, "t_rows": 8, "fine": 16}
     elif mode == 3:                                 # huge scale: saturating conversions
         kw = {"hi": np.float32(0.5), "scale": np.float32(3e38)}
+    fin = s[np.isfinite(s)]
+    if mode in (0, 2) and not (fin.size and np.float32(fin.std()) > 0):
+        return          # no finite spread: scale = 0, the plan kernel flags the query (hs_plan_kernel) and the sample sort takes it
     got, ref, bucket, fbin, keys = _hs_rank_restatement(s, **kw)
     assert np.array_equal(got, ref)                                        # == the stable descending argsort
     order = ref
