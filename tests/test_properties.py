@@ -121,3 +121,62 @@ def test_hist_sort_restatement_on_similarity_like_scores():
     got, ref, bucket, _, _ = _hs_rank_restatement(s)
     assert np.array_equal(got, ref) and np.array_equal(ref, oracle.ranks_from_scores(s[:, None])[:, 0])
     assert np.bincount(bucket).max() <= 4096                                # what one CTA sorts: no query of this shape is flagged
+
+
+# ---- sample-sort route (csrc/ranks.cu: ss_splitters / ss_scatter): the score -> bucket-range table -----------------------
+def _ss_bucket_restatement(s, B, k_tab=1024, oversample=32):
+    """numpy fp32 restatement of how the sample sort buckets one query's scores: splitters = order statistics of a
+    systematic sample of (score key, row) composites; a table over k_tab cells linear in the score narrows the binary
+    search to [lower[cell], lower[cell + 1]].  Returns (bucket by the narrowed search, bucket by the full search)."""
+    s = np.asarray(s, dtype=np.float32)
+    n = s.shape[0]
+    keys = make_keys_host(s, np.arange(n))
+    m = min(B * oversample, n)
+    samp = np.sort(keys[(np.arange(m, dtype=np.int64) * n) // m])
+    spl = np.array([samp[(b * m) // B] for b in range(1, B)], dtype=np.uint64)               # B - 1 splitters
+    canon = np.where(s == 0, np.float32(0), s)
+    sc_of = lambda kk: keys_to_host(np.asarray([kk], dtype=np.uint64))[0][0] if (int(kk) >> 32) != 0xffffffff else np.float32(np.nan)
+    hi, lo = np.float32(sc_of(samp[0])), np.float32(sc_of(samp[-1]))
+    with np.errstate(invalid="ignore", over="ignore"):
+        rng = np.float32(hi - lo)
+        scale = np.float32(k_tab) / np.float32(rng * np.float32(1.0001)) if (rng > 0 and np.isfinite(rng)) else np.float32(0)
+
+        def cell(x):
+            x = np.asarray(x, dtype=np.float32)
+            if scale == 0:
+                return np.zeros(x.shape, dtype=np.int64)
+            v = ((hi - x).astype(np.float32) * scale).astype(np.float32)
+            nan = np.isnan(v)
+            vt = np.where(nan, 0, np.clip(v, -2.0 ** 31, 2.0 ** 31 - 128)).astype(np.int64)
+            return np.where(nan, k_tab - 1, np.clip(vt, 0, k_tab - 1))
+
+        spl_sc = np.array([sc_of(k_) for k_ in spl], dtype=np.float32)
+        hist = np.bincount(cell(spl_sc) + 1, minlength=k_tab + 2)
+        lower = np.cumsum(hist)                                                                # lower[j] = splitters in cells < j
+        c = cell(canon)
+    full = np.searchsorted(spl, keys, side="right")
+    narrowed = np.empty(n, dtype=np.int64)
+    for i in range(n):
+        a, b = int(lower[c[i]]), int(lower[c[i] + 1])
+        narrowed[i] = a + np.searchsorted(spl[a:b], keys[i], side="right")
+    return narrowed, full
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.one_of(st.floats(-2, 2, width=32), st.floats(width=32, allow_nan=True, allow_infinity=True),
+                          st.sampled_from([0.0, -0.0, 0.25, 0.25, 0.25, float("inf"), float("-inf"), float("nan")])),
+                min_size=8, max_size=300), st.integers(2, 9))
+def test_sample_sort_table_never_narrows_the_search_wrongly(vals, B):
+    narrowed, full = _ss_bucket_restatement(vals, B)
+    assert np.array_equal(narrowed, full)
+
+
+def test_sample_sort_table_zero_spread_sample_with_infinite_rows():
+    """The regression behind ss_cell's `scale == 0 -> cell 0`: a constant row whose +-inf entries the systematic sample
+    misses.  Without it (hi - inf) * 0 = NaN sent those rows through the last cell to the last bucket."""
+    s = np.full(1500, 0.25, dtype=np.float32)
+    s[[3, 700, 1499]] = np.inf
+    s[[5, 9]] = -np.inf
+    s[11] = np.nan
+    narrowed, full = _ss_bucket_restatement(s, 4)
+    assert np.array_equal(narrowed, full) and narrowed[3] == 0 and narrowed[5] == 3 and narrowed[11] == 3
