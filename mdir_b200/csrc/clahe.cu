@@ -1,17 +1,18 @@
 // CLAHE on batches of ragged 8UC1 images, bit-exact against cv2.createCLAHE(...).apply
 // (algorithm: SURVEY.md App. A; oracle/oracle.py:clahe_u8).
 //
-//  kernel 1  clahe_lut_kernel    one CTA per (tile, image): the tile is read as aligned 16-byte
-//            chunks (4 in flight per thread), per-warp private uint32 histograms in shared memory
+//  kernel 1  clahe_lut_kernel    one CTA of 128 threads per (tile, image): the tile is read as aligned 16-byte
+//            chunks (6 in flight per thread), per-warp private uint32 histograms in shared memory
 //            updated with unit-increment atomics (ATOMS.POPC.INC; run-length aggregation and per-lane
-//            byte counters were both tried and lost), clip-limit redistribution, block scan,
-//            LUT = sat_u8(rint(cdf * 255/area)).
-//  kernel 2  clahe_interp_kernel one CTA per interpolation cell (the rectangle between four
+//            byte counters were both tried and lost; one shift + one LOP3 per pixel before the ATOMS),
+//            clip-limit redistribution, block scan (two bins per thread), LUT = sat_u8(rint(cdf * 255/area)).
+//  kernel 2  clahe_interp_kernel one CTA of 128 threads per interpolation cell (the rectangle between four
 //            tile centres, where the four contributing LUTs are fixed): the four LUTs are
-//            interleaved into one float4[256] table in shared memory so each pixel costs a
-//            single LDS.128; the bilinear blend uses individually rounded fp32 mul/add in
-//            OpenCV's association (no FMA contraction) and round-half-even; a thread owns 8
-//            consecutive pixels (64-bit loads/stores, 4 rows in flight).
+//            interleaved into one float4[256] table in shared memory, kept in 8 copies (lane l reads
+//            copy l & 7: conflict-free whatever the pixel values), so each pixel costs a single LDS.128;
+//            the bilinear blend uses individually rounded fp32 mul/add in OpenCV's association (no FMA
+//            contraction) and round-half-even; a thread owns 8 consecutive pixels (64-bit loads/stores,
+//            4 rows in flight, the next sweep's rows requested before the current one is blended).
 //  The whole batch is one pair of launches (both kernels are instruction-bound; the second read of the source hides).
 #include <type_traits>
 
